@@ -1,0 +1,933 @@
+/*
+ * mldsa_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).  See mldsa_oracle.h.
+ *
+ * Scalar C restatement of the ML-DSA hot path of integritychain/fips204 v0.4.6.  Every function
+ * cites the reference file:line it follows.  Nothing here is copied: the reference is Rust with
+ * const generics and iterator closures, this is plain C over int32_t[256].
+ *
+ * Parity status: PINNED.  tests/test_oracle_*.py run this file against all 180 ACVP vectors, the
+ * tests/messages.rs KAT (pk, sk, sig), tests/integration.rs::bad_sig, the src/lib.rs:536-545 pk[0]
+ * pins, the zeta KAT (src/helpers.rs:194-196) and the src/conversion.rs:423-488 leaf KATs.
+ * sha2 (HashML-DSA pre-hash) has no reference KAT and is pinned against hashlib only.
+ *
+ * Documented divergence (SURVEY.md 8a note R): the reference's inv_ntt leaves its sum path
+ * unreduced and could wrap an i32 on a >10-sigma input alignment; this oracle pre-reduces the
+ * inputs of inv_ntt to (-q, q) so it is always mod-q correct.  Outputs agree wherever the
+ * reference does not overflow (i.e. on every vector and every input anyone will ever see).
+ */
+#include "mldsa_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define Q 8380417
+#define D 13
+#define QINV 58728449 /* helpers.rs:157 */
+
+/* ------------------------------------------------------------------------------------------
+ * Keccak-f[1600], SHAKE128/256 (FIPS 202).  Crate sha3 ^0.10.2 in the reference (hashing.rs:6-27).
+ * ---------------------------------------------------------------------------------------- */
+static const uint64_t KRC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+static const int KROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43,
+                             25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+
+static inline uint64_t rol64(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+
+void oracle_keccak_f1600(uint64_t a[25])
+{
+    for (int rnd = 0; rnd < 24; rnd++) {
+        uint64_t c[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; x++) {
+            uint64_t d = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+            for (int y = 0; y < 25; y += 5) a[x + y] ^= d;
+        }
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++)
+                b[y + 5 * ((2 * x + 3 * y) % 5)] = rol64(a[x + 5 * y], KROT[x + 5 * y]);
+        for (int y = 0; y < 25; y += 5)
+            for (int x = 0; x < 5; x++)
+                a[x + y] = b[x + y] ^ (~b[(x + 1) % 5 + y] & b[(x + 2) % 5 + y]);
+        a[0] ^= KRC[rnd];
+    }
+}
+
+typedef struct {
+    uint64_t s[25];
+    unsigned rate; /* bytes */
+    unsigned pos;  /* absorb: bytes absorbed in current block; squeeze: bytes consumed of block */
+    int squeezing;
+} xof_t;
+
+static void xof_init(xof_t *x, unsigned rate)
+{
+    memset(x, 0, sizeof *x);
+    x->rate = rate;
+}
+static void xof_absorb(xof_t *x, const uint8_t *in, size_t len)
+{
+    for (size_t i = 0; i < len; i++) {
+        x->s[x->pos >> 3] ^= (uint64_t)in[i] << (8 * (x->pos & 7));
+        if (++x->pos == x->rate) {
+            oracle_keccak_f1600(x->s);
+            x->pos = 0;
+        }
+    }
+}
+static void xof_finish(xof_t *x)
+{
+    x->s[x->pos >> 3] ^= (uint64_t)0x1F << (8 * (x->pos & 7));
+    x->s[(x->rate - 1) >> 3] ^= (uint64_t)0x80 << (8 * ((x->rate - 1) & 7));
+    x->pos = x->rate; /* forces a permutation before the first squeeze byte */
+    x->squeezing = 1;
+}
+static void xof_squeeze(xof_t *x, uint8_t *out, size_t len)
+{
+    if (!x->squeezing) xof_finish(x);
+    for (size_t i = 0; i < len; i++) {
+        if (x->pos == x->rate) {
+            oracle_keccak_f1600(x->s);
+            x->pos = 0;
+        }
+        out[i] = (uint8_t)(x->s[x->pos >> 3] >> (8 * (x->pos & 7)));
+        x->pos++;
+    }
+}
+
+void oracle_shake128(const uint8_t *in, size_t inlen, uint8_t *out, size_t outlen)
+{
+    xof_t x;
+    xof_init(&x, 168);
+    xof_absorb(&x, in, inlen);
+    xof_squeeze(&x, out, outlen);
+}
+void oracle_shake256(const uint8_t *in, size_t inlen, uint8_t *out, size_t outlen)
+{
+    xof_t x;
+    xof_init(&x, 136);
+    xof_absorb(&x, in, inlen);
+    xof_squeeze(&x, out, outlen);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SHA-256 / SHA-512 (FIPS 180-4).  Crate sha2 ^0.10.8 in the reference (hashing.rs:324-338).
+ * ---------------------------------------------------------------------------------------- */
+static const uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+static inline uint32_t ror32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+static void sha256_block(uint32_t h[8], const uint8_t *p)
+{
+    uint32_t w[64], a[8];
+    for (int i = 0; i < 16; i++)
+        w[i] = (uint32_t)p[4 * i] << 24 | (uint32_t)p[4 * i + 1] << 16 | (uint32_t)p[4 * i + 2] << 8 | p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = ror32(w[i - 15], 7) ^ ror32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = ror32(w[i - 2], 17) ^ ror32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    memcpy(a, h, sizeof a);
+    for (int i = 0; i < 64; i++) {
+        uint32_t S1 = ror32(a[4], 6) ^ ror32(a[4], 11) ^ ror32(a[4], 25);
+        uint32_t ch = (a[4] & a[5]) ^ (~a[4] & a[6]);
+        uint32_t t1 = a[7] + S1 + ch + K256[i] + w[i];
+        uint32_t S0 = ror32(a[0], 2) ^ ror32(a[0], 13) ^ ror32(a[0], 22);
+        uint32_t mj = (a[0] & a[1]) ^ (a[0] & a[2]) ^ (a[1] & a[2]);
+        uint32_t t2 = S0 + mj;
+        a[7] = a[6]; a[6] = a[5]; a[5] = a[4]; a[4] = a[3] + t1;
+        a[3] = a[2]; a[2] = a[1]; a[1] = a[0]; a[0] = t1 + t2;
+    }
+    for (int i = 0; i < 8; i++) h[i] += a[i];
+}
+
+void oracle_sha256(const uint8_t *in, size_t inlen, uint8_t out[32])
+{
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint8_t buf[128];
+    size_t full = inlen / 64, rem = inlen % 64;
+    for (size_t i = 0; i < full; i++) sha256_block(h, in + 64 * i);
+    memset(buf, 0, sizeof buf);
+    if (rem) memcpy(buf, in + 64 * full, rem);
+    buf[rem] = 0x80;
+    size_t tot = (rem < 56) ? 64 : 128;
+    uint64_t bits = (uint64_t)inlen * 8;
+    for (int i = 0; i < 8; i++) buf[tot - 1 - i] = (uint8_t)(bits >> (8 * i));
+    sha256_block(h, buf);
+    if (tot == 128) sha256_block(h, buf + 64);
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(h[i] >> 24); out[4 * i + 1] = (uint8_t)(h[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(h[i] >> 8); out[4 * i + 3] = (uint8_t)h[i];
+    }
+}
+
+static const uint64_t K512[80] = {
+    0x428a2f98d728ae22ULL, 0x7137449123ef65cdULL, 0xb5c0fbcfec4d3b2fULL, 0xe9b5dba58189dbbcULL, 0x3956c25bf348b538ULL,
+    0x59f111f1b605d019ULL, 0x923f82a4af194f9bULL, 0xab1c5ed5da6d8118ULL, 0xd807aa98a3030242ULL, 0x12835b0145706fbeULL,
+    0x243185be4ee4b28cULL, 0x550c7dc3d5ffb4e2ULL, 0x72be5d74f27b896fULL, 0x80deb1fe3b1696b1ULL, 0x9bdc06a725c71235ULL,
+    0xc19bf174cf692694ULL, 0xe49b69c19ef14ad2ULL, 0xefbe4786384f25e3ULL, 0x0fc19dc68b8cd5b5ULL, 0x240ca1cc77ac9c65ULL,
+    0x2de92c6f592b0275ULL, 0x4a7484aa6ea6e483ULL, 0x5cb0a9dcbd41fbd4ULL, 0x76f988da831153b5ULL, 0x983e5152ee66dfabULL,
+    0xa831c66d2db43210ULL, 0xb00327c898fb213fULL, 0xbf597fc7beef0ee4ULL, 0xc6e00bf33da88fc2ULL, 0xd5a79147930aa725ULL,
+    0x06ca6351e003826fULL, 0x142929670a0e6e70ULL, 0x27b70a8546d22ffcULL, 0x2e1b21385c26c926ULL, 0x4d2c6dfc5ac42aedULL,
+    0x53380d139d95b3dfULL, 0x650a73548baf63deULL, 0x766a0abb3c77b2a8ULL, 0x81c2c92e47edaee6ULL, 0x92722c851482353bULL,
+    0xa2bfe8a14cf10364ULL, 0xa81a664bbc423001ULL, 0xc24b8b70d0f89791ULL, 0xc76c51a30654be30ULL, 0xd192e819d6ef5218ULL,
+    0xd69906245565a910ULL, 0xf40e35855771202aULL, 0x106aa07032bbd1b8ULL, 0x19a4c116b8d2d0c8ULL, 0x1e376c085141ab53ULL,
+    0x2748774cdf8eeb99ULL, 0x34b0bcb5e19b48a8ULL, 0x391c0cb3c5c95a63ULL, 0x4ed8aa4ae3418acbULL, 0x5b9cca4f7763e373ULL,
+    0x682e6ff3d6b2b8a3ULL, 0x748f82ee5defb2fcULL, 0x78a5636f43172f60ULL, 0x84c87814a1f0ab72ULL, 0x8cc702081a6439ecULL,
+    0x90befffa23631e28ULL, 0xa4506cebde82bde9ULL, 0xbef9a3f7b2c67915ULL, 0xc67178f2e372532bULL, 0xca273eceea26619cULL,
+    0xd186b8c721c0c207ULL, 0xeada7dd6cde0eb1eULL, 0xf57d4f7fee6ed178ULL, 0x06f067aa72176fbaULL, 0x0a637dc5a2c898a6ULL,
+    0x113f9804bef90daeULL, 0x1b710b35131c471bULL, 0x28db77f523047d84ULL, 0x32caab7b40c72493ULL, 0x3c9ebe0a15c9bebcULL,
+    0x431d67c49c100d4cULL, 0x4cc5d4becb3e42b6ULL, 0x597f299cfc657e2aULL, 0x5fcb6fab3ad6faecULL, 0x6c44198c4a475817ULL};
+static inline uint64_t ror64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+
+static void sha512_block(uint64_t h[8], const uint8_t *p)
+{
+    uint64_t w[80], a[8];
+    for (int i = 0; i < 16; i++) {
+        w[i] = 0;
+        for (int j = 0; j < 8; j++) w[i] = (w[i] << 8) | p[8 * i + j];
+    }
+    for (int i = 16; i < 80; i++) {
+        uint64_t s0 = ror64(w[i - 15], 1) ^ ror64(w[i - 15], 8) ^ (w[i - 15] >> 7);
+        uint64_t s1 = ror64(w[i - 2], 19) ^ ror64(w[i - 2], 61) ^ (w[i - 2] >> 6);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    memcpy(a, h, sizeof a);
+    for (int i = 0; i < 80; i++) {
+        uint64_t S1 = ror64(a[4], 14) ^ ror64(a[4], 18) ^ ror64(a[4], 41);
+        uint64_t ch = (a[4] & a[5]) ^ (~a[4] & a[6]);
+        uint64_t t1 = a[7] + S1 + ch + K512[i] + w[i];
+        uint64_t S0 = ror64(a[0], 28) ^ ror64(a[0], 34) ^ ror64(a[0], 39);
+        uint64_t mj = (a[0] & a[1]) ^ (a[0] & a[2]) ^ (a[1] & a[2]);
+        uint64_t t2 = S0 + mj;
+        a[7] = a[6]; a[6] = a[5]; a[5] = a[4]; a[4] = a[3] + t1;
+        a[3] = a[2]; a[2] = a[1]; a[1] = a[0]; a[0] = t1 + t2;
+    }
+    for (int i = 0; i < 8; i++) h[i] += a[i];
+}
+
+void oracle_sha512(const uint8_t *in, size_t inlen, uint8_t out[64])
+{
+    uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                     0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    uint8_t buf[256];
+    size_t full = inlen / 128, rem = inlen % 128;
+    for (size_t i = 0; i < full; i++) sha512_block(h, in + 128 * i);
+    memset(buf, 0, sizeof buf);
+    if (rem) memcpy(buf, in + 128 * full, rem);
+    buf[rem] = 0x80;
+    size_t tot = (rem < 112) ? 128 : 256;
+    uint64_t bits = (uint64_t)inlen * 8;
+    for (int i = 0; i < 8; i++) buf[tot - 1 - i] = (uint8_t)(bits >> (8 * i));
+    sha512_block(h, buf);
+    if (tot == 256) sha512_block(h, buf + 128);
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) out[8 * i + j] = (uint8_t)(h[i] >> (56 - 8 * j));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Parameter sets (lib.rs:639-653, 681-695, 723-737; derived sizes lib.rs:129-131)
+ * ---------------------------------------------------------------------------------------- */
+static int bitlen(int x) { int n = 0; while (x) { n++; x >>= 1; } return n; } /* helpers.rs:82 */
+
+int oracle_get_params(int ps, oracle_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->ps = ps;
+    switch (ps) {
+    case 44: p->k = 4; p->l = 4; p->eta = 2; p->tau = 39; p->lambda_div4 = 32; p->gamma1 = 1 << 17; p->gamma2 = (Q - 1) / 88; p->omega = 80; break;
+    case 65: p->k = 6; p->l = 5; p->eta = 4; p->tau = 49; p->lambda_div4 = 48; p->gamma1 = 1 << 19; p->gamma2 = (Q - 1) / 32; p->omega = 55; break;
+    case 87: p->k = 8; p->l = 7; p->eta = 2; p->tau = 60; p->lambda_div4 = 64; p->gamma1 = 1 << 19; p->gamma2 = (Q - 1) / 32; p->omega = 75; break;
+    default: return -1;
+    }
+    p->beta = p->tau * p->eta;
+    p->eta_bits = bitlen(2 * p->eta);
+    p->z_bits = 1 + bitlen(p->gamma1 - 1);
+    p->w1_bits = bitlen((Q - 1) / (2 * p->gamma2) - 1);
+    p->pk_len = 32 + 32 * p->k * (bitlen(Q - 1) - D);
+    p->sk_len = 128 + 32 * ((p->k + p->l) * p->eta_bits + D * p->k);
+    p->sig_len = p->lambda_div4 + p->l * 32 * p->z_bits + p->omega + p->k;
+    p->w1_len = 32 * p->k * p->w1_bits;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Field helpers (helpers.rs)
+ * ---------------------------------------------------------------------------------------- */
+/* helpers.rs:156-165: a * 2^-32 mod q, result in (-q, q) */
+int32_t oracle_mont_reduce(int64_t a)
+{
+    int32_t t = (int32_t)((uint32_t)a * (uint32_t)QINV);
+    return (int32_t)((a - (int64_t)t * Q) >> 32);
+}
+#define mont oracle_mont_reduce
+
+/* helpers.rs:61-67 */
+static inline int32_t partial_reduce32(int32_t a) { return a - ((a + (1 << 22)) >> 23) * Q; }
+/* helpers.rs:70-76 */
+static inline int32_t full_reduce32(int32_t a)
+{
+    int32_t x = partial_reduce32(a);
+    return x + ((x >> 31) & Q);
+}
+/* helpers.rs:84-91 */
+static inline int32_t center_mod(int32_t m)
+{
+    int32_t t = full_reduce32(m);
+    return t - ((((Q / 2) - t) >> 31) & Q);
+}
+/* helpers.rs:131-135 (to_mont): a * 2^32 mod q.  Realised as mont(a * (2^64 mod q)); only the
+ * residue class matters downstream. */
+static inline int32_t to_mont1(int32_t a) { return mont((int64_t)a * 2365951); }
+
+/* helpers.rs:171-184: tab[brv8(i)] = zeta^i * 2^32 mod q, residues in [0, q) */
+static int32_t ZETA_MONT[256];
+static pthread_once_t zeta_once = PTHREAD_ONCE_INIT;
+static void zeta_init(void)
+{
+    int64_t x = 1;
+    for (int i = 0; i < 256; i++) {
+        int r = 0;
+        for (int b = 0; b < 8; b++) r |= ((i >> b) & 1) << (7 - b);
+        ZETA_MONT[r] = (int32_t)((x << 32) % Q);
+        x = (x * 1753) % Q;
+    }
+}
+int32_t oracle_zeta_mont(int i)
+{
+    pthread_once(&zeta_once, zeta_init);
+    return ZETA_MONT[i & 255];
+}
+
+/* ntt.rs:14-76.  No reduction after add/sub: outputs are the reference's exact representatives. */
+void oracle_ntt_raw(int32_t w[256])
+{
+    pthread_once(&zeta_once, zeta_init);
+    int m = 0;
+    for (int len = 128; len >= 1; len >>= 1)
+        for (int start = 0; start < 256; start += 2 * len) {
+            int64_t z = ZETA_MONT[++m];
+            for (int j = start; j < start + len; j++) {
+                int32_t t = mont(z * w[j + len]);
+                w[j + len] = w[j] - t;
+                w[j] = w[j] + t;
+            }
+        }
+}
+
+/* ntt.rs:85-161.  Output canonical [0, q).  Inputs must satisfy 256*|w| < 2^31 (|w| < q is enough);
+ * callers below pre-reduce (see header note on the documented divergence). */
+#define F_MONT 16382 /* 256^-1 * 2^32 mod q, ntt.rs:88 */
+void oracle_inv_ntt(int32_t w[256])
+{
+    pthread_once(&zeta_once, zeta_init);
+    int m = 256;
+    for (int len = 1; len < 256; len <<= 1)
+        for (int start = 0; start < 256; start += 2 * len) {
+            int64_t z = -ZETA_MONT[--m];
+            for (int j = start; j < start + len; j++) {
+                int32_t t = w[j];
+                w[j] = t + w[j + len];
+                w[j + len] = mont(z * (t - w[j + len]));
+            }
+        }
+    for (int i = 0; i < 256; i++) w[i] = full_reduce32(mont((int64_t)F_MONT * w[i]));
+}
+
+void oracle_ntt_batch(int32_t *w, size_t n) { for (size_t i = 0; i < n; i++) oracle_ntt_raw(w + 256 * i); }
+void oracle_inv_ntt_batch(int32_t *w, size_t n) { for (size_t i = 0; i < n; i++) oracle_inv_ntt(w + 256 * i); }
+
+static void inv_ntt_safe(int32_t w[256])
+{
+    for (int i = 0; i < 256; i++) w[i] = partial_reduce32(w[i]);
+    oracle_inv_ntt(w);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Samplers (hashing.rs) and leaf conversions (conversion.rs)
+ * ---------------------------------------------------------------------------------------- */
+/* hashing.rs:111-146 + conversion.rs:40-61 */
+void oracle_rej_ntt_poly(const uint8_t seed34[34], int32_t out[256])
+{
+    xof_t x;
+    xof_init(&x, 168);
+    xof_absorb(&x, seed34, 34);
+    int j = 0;
+    while (j < 256) {
+        uint8_t b[3];
+        xof_squeeze(&x, b, 3);
+        int32_t z = ((int32_t)(b[2] & 0x7F) << 16) | ((int32_t)b[1] << 8) | b[0];
+        if (z < Q) out[j++] = z;
+    }
+}
+void oracle_expand_a_batch(const uint8_t *seed34, size_t n, int32_t *out)
+{
+    for (size_t i = 0; i < n; i++) oracle_rej_ntt_poly(seed34 + 34 * i, out + 256 * i);
+}
+
+/* conversion.rs:80-111: returns 1 and writes *r when accepted */
+static int coeff_from_half_byte(int eta, int b, int32_t *r)
+{
+    if (eta == 2 && b < 15) { *r = 2 - (b % 5); return 1; }
+    if (eta == 4 && b < 9) { *r = 4 - b; return 1; }
+    return 0;
+}
+/* hashing.rs:158-213 */
+void oracle_rej_bounded_poly(int eta, const uint8_t seed66[66], int32_t out[256])
+{
+    xof_t x;
+    xof_init(&x, 136);
+    xof_absorb(&x, seed66, 66);
+    int j = 0;
+    while (j < 256) {
+        uint8_t z;
+        int32_t v;
+        xof_squeeze(&x, &z, 1);
+        if (coeff_from_half_byte(eta, z & 15, &v)) out[j++] = v;
+        if (j < 256 && coeff_from_half_byte(eta, z >> 4, &v)) out[j++] = v;
+    }
+}
+
+/* conversion.rs:143-182 (bit_pack; simple_bit_pack is the a == 0 case, conversion.rs:120-134) */
+void oracle_bit_pack(const int32_t w[256], int a, int b, uint8_t *out)
+{
+    int c = bitlen(a + b);
+    uint64_t acc = 0;
+    int nb = 0, o = 0;
+    for (int i = 0; i < 256; i++) {
+        uint32_t v = (a > 0) ? (uint32_t)(b - w[i]) : (uint32_t)w[i];
+        acc |= (uint64_t)(v & ((1u << c) - 1)) << nb;
+        nb += c;
+        while (nb >= 8) { out[o++] = (uint8_t)acc; acc >>= 8; nb -= 8; }
+    }
+}
+/* conversion.rs:227-262 (bit_unpack; its range check is tautological, SURVEY 8a note T) */
+void oracle_bit_unpack(const uint8_t *in, int a, int b, int32_t w[256])
+{
+    int c = bitlen(a + b);
+    uint64_t acc = 0;
+    int nb = 0, o = 0;
+    for (int i = 0; i < 32 * c; i++) {
+        acc |= (uint64_t)in[i] << nb;
+        nb += 8;
+        while (nb >= c) {
+            int32_t v = (int32_t)(acc & ((1u << c) - 1));
+            w[o++] = (a == 0) ? v : b - v;
+            acc >>= c;
+            nb -= c;
+        }
+    }
+}
+
+/* conversion.rs:277-328 */
+static void hint_bit_pack(int k, int omega, const int32_t *h, uint8_t *y)
+{
+    memset(y, 0, (size_t)(omega + k));
+    int idx = 0;
+    for (int i = 0; i < k; i++) {
+        for (int j = 0; j < 256; j++)
+            if (h[256 * i + j] != 0) y[idx++] = (uint8_t)j;
+        y[omega + i] = (uint8_t)idx;
+    }
+}
+/* conversion.rs:340-414: the three malformed-input exits (:357, :373, :398) */
+int oracle_hint_bit_unpack(int k, int omega, const uint8_t *y, int32_t *h)
+{
+    memset(h, 0, sizeof(int32_t) * 256 * (size_t)k);
+    int idx = 0;
+    for (int i = 0; i < k; i++) {
+        int lim = y[omega + i];
+        if (lim < idx || lim > omega) return -1;
+        int first = idx;
+        while (idx < lim) {
+            if (idx > first && y[idx - 1] >= y[idx]) return -1;
+            h[256 * i + y[idx]] = 1;
+            idx++;
+        }
+    }
+    for (int i = idx; i < omega; i++)
+        if (y[i] != 0) return -1;
+    return 0;
+}
+
+/* hashing.rs:281-313: always squeezes from SHAKE256(rho || LE16(nonce)), BitUnpack(gamma1-1, gamma1) */
+void oracle_expand_mask_poly(int gamma1, const uint8_t rho64[64], uint16_t nonce, int32_t out[256])
+{
+    uint8_t seed[66], v[640];
+    memcpy(seed, rho64, 64);
+    seed[64] = (uint8_t)nonce;
+    seed[65] = (uint8_t)(nonce >> 8);
+    int c = 1 + bitlen(gamma1 - 1);
+    oracle_shake256(seed, 66, v, (size_t)(32 * c));
+    oracle_bit_unpack(v, gamma1 - 1, gamma1, out);
+}
+
+/* hashing.rs:43-100 */
+void oracle_sample_in_ball(int tau, const uint8_t *ctilde, size_t clen, int32_t c[256])
+{
+    xof_t x;
+    uint8_t s[8], j;
+    memset(c, 0, 256 * sizeof(int32_t));
+    xof_init(&x, 136);
+    xof_absorb(&x, ctilde, clen);
+    xof_squeeze(&x, s, 8);
+    for (int i = 256 - tau; i < 256; i++) {
+        do xof_squeeze(&x, &j, 1); while (j > i);
+        c[i] = c[j];
+        int idx = i + tau - 256;
+        c[j] = 1 - 2 * ((s[idx >> 3] >> (idx & 7)) & 1);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * High / low bits and hints (high_low.rs)
+ * ---------------------------------------------------------------------------------------- */
+void oracle_power2round(int32_t r, int32_t *r1, int32_t *r0) /* high_low.rs:26-31; r in [0,q) */
+{
+    *r1 = (r + (1 << (D - 1)) - 1) >> D;
+    *r0 = r - (*r1 << D);
+}
+void oracle_decompose(int gamma2, int32_t r, int32_t *r1o, int32_t *r0o) /* high_low.rs:66-96 */
+{
+    int32_t rp = full_reduce32(r), r1 = (rp + 127) >> 7;
+    if (gamma2 == (Q - 1) / 88) {
+        r1 = (r1 * 11275 + (1 << 23)) >> 24;
+        r1 ^= ((43 - r1) >> 31) & r1;
+    } else {
+        r1 = (r1 * 1025 + (1 << 21)) >> 22;
+        r1 &= 15;
+    }
+    int32_t r0 = rp - r1 * 2 * gamma2;
+    r0 -= (((Q - 1) / 2 - r0) >> 31) & Q;
+    *r1o = r1;
+    *r0o = r0;
+}
+static inline int32_t high_bits(int g2, int32_t r) { int32_t a, b; oracle_decompose(g2, r, &a, &b); return a; }
+static inline int32_t low_bits(int g2, int32_t r) { int32_t a, b; oracle_decompose(g2, r, &a, &b); return b; }
+int oracle_make_hint(int gamma2, int32_t z, int32_t r) /* high_low.rs:134-144 */
+{
+    return high_bits(gamma2, r) != high_bits(gamma2, r + z);
+}
+int32_t oracle_use_hint(int gamma2, int h, int32_t r) /* high_low.rs:155-192 */
+{
+    int32_t r1, r0;
+    oracle_decompose(gamma2, r, &r1, &r0);
+    if (!h) return r1;
+    if (gamma2 == (Q - 1) / 88) {
+        if (r0 > 0) return r1 == 43 ? 0 : r1 + 1;
+        return r1 == 0 ? 43 : r1 - 1;
+    }
+    return r0 > 0 ? (r1 + 1) & 15 : (r1 - 1) & 15;
+}
+
+static int32_t inf_norm(const int32_t *w, int npoly) /* helpers.rs:138-147 */
+{
+    int32_t m = 0;
+    for (int i = 0; i < 256 * npoly; i++) {
+        int32_t v = center_mod(w[i]);
+        if (v < 0) v = -v;
+        if (v > m) m = v;
+    }
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Scheme (ml_dsa.rs).  Polynomial vectors are flat int32_t[n][256].
+ * ---------------------------------------------------------------------------------------- */
+#define KMAX 8
+#define LMAX 7
+
+/* hashing.rs:225-239: A[r][s] = RejNTTPoly(rho || s || r) (column byte first) */
+static void expand_a(const oracle_params *p, const uint8_t rho[32], int32_t *A /* k*l*256 */)
+{
+    uint8_t seed[34];
+    memcpy(seed, rho, 32);
+    for (int r = 0; r < p->k; r++)
+        for (int s = 0; s < p->l; s++) {
+            seed[32] = (uint8_t)s;
+            seed[33] = (uint8_t)r;
+            oracle_rej_ntt_poly(seed, A + 256 * (r * p->l + s));
+        }
+}
+
+/* helpers.rs:100-114: w_hat[i] = sum_j mont(A[i][j] * to_mont(u_hat[j])) */
+static void mat_vec_mul(const oracle_params *p, const int32_t *A, const int32_t *u_hat, int32_t *w_hat)
+{
+    int32_t um[LMAX * 256];
+    for (int i = 0; i < 256 * p->l; i++) um[i] = to_mont1(u_hat[i]);
+    for (int i = 0; i < p->k; i++)
+        for (int n = 0; n < 256; n++) {
+            int32_t acc = 0;
+            for (int j = 0; j < p->l; j++)
+                acc += mont((int64_t)A[256 * (i * p->l + j) + n] * um[256 * j + n]);
+            w_hat[256 * i + n] = acc;
+        }
+}
+
+/* encodings.rs:18-40 */
+static void pk_encode(const oracle_params *p, const uint8_t rho[32], const int32_t *t1, uint8_t *pk)
+{
+    memcpy(pk, rho, 32);
+    for (int i = 0; i < p->k; i++) oracle_bit_pack(t1 + 256 * i, 0, 1023, pk + 32 + 320 * i);
+}
+
+/* ml_dsa.rs:57-134 (key_gen_internal) followed by SerDes::into_bytes (lib.rs:427-493), i.e. bytes out.
+ * The reference's struct pre-computation (ml_dsa.rs:108-127) has no effect on the bytes and is skipped. */
+int oracle_keygen(int ps, const uint8_t xi[32], uint8_t *pk, uint8_t *sk)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    uint8_t in[34], seeds[128], seed66[66];
+    memcpy(in, xi, 32);
+    in[32] = (uint8_t)p.k;
+    in[33] = (uint8_t)p.l;
+    oracle_shake256(in, 34, seeds, 128); /* rho[32] || rho'[64] || K[32]  (ml_dsa.rs:68-74) */
+    const uint8_t *rho = seeds, *rhop = seeds + 32, *capk = seeds + 96;
+
+    int32_t s1[LMAX * 256], s2[KMAX * 256], s1h[LMAX * 256], t[KMAX * 256], t1[KMAX * 256], t0[KMAX * 256];
+    int32_t *A = malloc(sizeof(int32_t) * 256 * (size_t)(p.k * p.l));
+    memcpy(seed66, rhop, 64);
+    seed66[65] = 0;
+    for (int r = 0; r < p.l; r++) { seed66[64] = (uint8_t)r; oracle_rej_bounded_poly(p.eta, seed66, s1 + 256 * r); }          /* hashing.rs:260 */
+    for (int r = 0; r < p.k; r++) { seed66[64] = (uint8_t)(r + p.l); oracle_rej_bounded_poly(p.eta, seed66, s2 + 256 * r); } /* hashing.rs:266 */
+
+    expand_a(&p, rho, A);
+    memcpy(s1h, s1, sizeof(int32_t) * 256 * (size_t)p.l);
+    for (int i = 0; i < p.l; i++) oracle_ntt_raw(s1h + 256 * i);
+    mat_vec_mul(&p, A, s1h, t);
+    for (int i = 0; i < p.k; i++) inv_ntt_safe(t + 256 * i);
+    for (int i = 0; i < 256 * p.k; i++) {
+        int32_t v = full_reduce32(t[i] + s2[i]);
+        oracle_power2round(v, &t1[i], &t0[i]);
+    }
+    free(A);
+
+    uint8_t tr[64];
+    pk_encode(&p, rho, t1, pk);
+    oracle_shake256(pk, (size_t)p.pk_len, tr, 64); /* ml_dsa.rs:99-101 */
+
+    /* encodings.rs:94-152 */
+    uint8_t *o = sk;
+    memcpy(o, rho, 32); memcpy(o + 32, capk, 32); memcpy(o + 64, tr, 64);
+    o += 128;
+    for (int i = 0; i < p.l; i++, o += 32 * p.eta_bits) oracle_bit_pack(s1 + 256 * i, p.eta, p.eta, o);
+    for (int i = 0; i < p.k; i++, o += 32 * p.eta_bits) oracle_bit_pack(s2 + 256 * i, p.eta, p.eta, o);
+    for (int i = 0; i < p.k; i++, o += 32 * D) oracle_bit_pack(t0 + 256 * i, (1 << (D - 1)) - 1, 1 << (D - 1), o);
+    return 0;
+}
+
+/* encodings.rs:168-224 (sk_decode): never fails (note T) */
+typedef struct {
+    const uint8_t *rho, *capk, *tr;
+    int32_t s1[LMAX * 256], s2[KMAX * 256], t0[KMAX * 256];
+} sk_parts;
+static void sk_decode(const oracle_params *p, const uint8_t *sk, sk_parts *o)
+{
+    o->rho = sk; o->capk = sk + 32; o->tr = sk + 64;
+    const uint8_t *q = sk + 128;
+    for (int i = 0; i < p->l; i++, q += 32 * p->eta_bits) oracle_bit_unpack(q, p->eta, p->eta, o->s1 + 256 * i);
+    for (int i = 0; i < p->k; i++, q += 32 * p->eta_bits) oracle_bit_unpack(q, p->eta, p->eta, o->s2 + 256 * i);
+    for (int i = 0; i < p->k; i++, q += 32 * D) oracle_bit_unpack(q, (1 << (D - 1)) - 1, 1 << (D - 1), o->t0 + 256 * i);
+}
+
+/* ml_dsa.rs:502-563 (private_to_public_key) + into_bytes: pk bytes from sk bytes */
+int oracle_sk_to_pk(int ps, const uint8_t *sk, uint8_t *pk)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    sk_parts *k = malloc(sizeof *k);
+    int32_t *A = malloc(sizeof(int32_t) * 256 * (size_t)(p.k * p.l));
+    int32_t t[KMAX * 256], t1[KMAX * 256], t0;
+    sk_decode(&p, sk, k);
+    expand_a(&p, k->rho, A);
+    for (int i = 0; i < p.l; i++) oracle_ntt_raw(k->s1 + 256 * i);
+    mat_vec_mul(&p, A, k->s1, t);
+    for (int i = 0; i < p.k; i++) inv_ntt_safe(t + 256 * i);
+    for (int i = 0; i < 256 * p.k; i++) oracle_power2round(full_reduce32(t[i] + k->s2[i]), &t1[i], &t0);
+    pk_encode(&p, k->rho, t1, pk);
+    free(A);
+    free(k);
+    return 0;
+}
+
+static const uint8_t OID_PREFIX[10] = {0x06, 0x09, 0x60, 0x86, 0x48, 0x01, 0x65, 0x03, 0x04, 0x02};
+
+/* mu = H(tr || M') with the three framings of ml_dsa.rs:185-196 / :386-397 */
+static int compute_mu(int framing, int ph, const uint8_t tr[64], const uint8_t *msg, size_t mlen,
+                      const uint8_t *ctx, size_t ctxlen, uint8_t mu[64])
+{
+    xof_t x;
+    xof_init(&x, 136);
+    xof_absorb(&x, tr, 64);
+    if (framing == 1) {
+        xof_absorb(&x, msg, mlen);
+    } else if (framing == 0) {
+        uint8_t hd[2] = {0, (uint8_t)ctxlen};
+        xof_absorb(&x, hd, 2);
+        xof_absorb(&x, ctx, ctxlen);
+        xof_absorb(&x, msg, mlen);
+    } else if (framing == 2) {
+        uint8_t hd[2] = {1, (uint8_t)ctxlen}, oid[11], phm[64];
+        size_t plen;
+        memcpy(oid, OID_PREFIX, 10);
+        if (ph == 0) { oid[10] = 0x01; oracle_sha256(msg, mlen, phm); plen = 32; }        /* hashing.rs:319-329 */
+        else if (ph == 1) { oid[10] = 0x03; oracle_sha512(msg, mlen, phm); plen = 64; }   /* hashing.rs:330-340 */
+        else if (ph == 2) { oid[10] = 0x0B; oracle_shake128(msg, mlen, phm, 32); plen = 32; } /* hashing.rs:341-352 */
+        else return -1;
+        xof_absorb(&x, hd, 2);
+        xof_absorb(&x, ctx, ctxlen);
+        xof_absorb(&x, oid, 11);
+        xof_absorb(&x, phm, plen);
+    } else {
+        return -1;
+    }
+    xof_squeeze(&x, mu, 64);
+    return 0;
+}
+
+/* ml_dsa.rs:153-337 (sign_internal) on canonical sk bytes (expand_private, ml_dsa.rs:445-469, folded in).
+ * Returns 0, -1 bad parameter, -2 ctx too long (lib.rs:274). */
+int oracle_sign(int ps, int framing, int ph, const uint8_t *sk, const uint8_t *msg, size_t mlen,
+                const uint8_t *ctx, size_t ctxlen, const uint8_t rnd[32], uint8_t *sig, uint32_t *iters)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    if (ctxlen > 255) return -2;
+    const int K = p.k, L = p.l;
+    sk_parts *key = malloc(sizeof *key);
+    int32_t *A = malloc(sizeof(int32_t) * 256 * (size_t)(K * L));
+    int32_t y[LMAX * 256], yh[LMAX * 256], w[KMAX * 256], w1[KMAX * 256], c[256], z[LMAX * 256];
+    int32_t tmp[KMAX * 256], cs2[KMAX * 256], ct0[KMAX * 256], h[KMAX * 256], r0[KMAX * 256];
+    uint8_t mu[64], rhopp[64], buf[128], ctilde[64], w1enc[64 + 1024];
+    int rc = 0;
+
+    sk_decode(&p, sk, key);
+    /* ml_dsa.rs:447-453: s1_hat, s2_hat, t0_hat in Montgomery form */
+    for (int i = 0; i < L; i++) oracle_ntt_raw(key->s1 + 256 * i);
+    for (int i = 0; i < K; i++) { oracle_ntt_raw(key->s2 + 256 * i); oracle_ntt_raw(key->t0 + 256 * i); }
+    for (int i = 0; i < 256 * L; i++) key->s1[i] = to_mont1(key->s1[i]);
+    for (int i = 0; i < 256 * K; i++) { key->s2[i] = to_mont1(key->s2[i]); key->t0[i] = to_mont1(key->t0[i]); }
+
+    expand_a(&p, key->rho, A); /* ml_dsa.rs:181 */
+    if (compute_mu(framing, ph, key->tr, msg, mlen, ctx, ctxlen, mu)) { rc = -1; goto out; }
+    memcpy(buf, key->capk, 32); memcpy(buf + 32, rnd, 32); memcpy(buf + 64, mu, 64);
+    oracle_shake256(buf, 128, rhopp, 64); /* ml_dsa.rs:199-201 */
+
+    uint16_t kappa = 0;
+    uint32_t trips = 0;
+    for (;;) { /* ml_dsa.rs:212-330 */
+        trips++;
+        for (int r = 0; r < L; r++) oracle_expand_mask_poly(p.gamma1, rhopp, (uint16_t)(kappa + r), y + 256 * r);
+        kappa = (uint16_t)(kappa + L);
+        memcpy(yh, y, sizeof(int32_t) * 256 * (size_t)L);
+        for (int i = 0; i < L; i++) oracle_ntt_raw(yh + 256 * i);
+        mat_vec_mul(&p, A, yh, w);
+        for (int i = 0; i < K; i++) inv_ntt_safe(w + 256 * i);
+
+        for (int i = 0; i < 256 * K; i++) w1[i] = high_bits(p.gamma2, w[i]);
+        memcpy(w1enc, mu, 64);
+        for (int i = 0; i < K; i++) /* encodings.rs:338-360 */
+            oracle_bit_pack(w1 + 256 * i, 0, (Q - 1) / (2 * p.gamma2) - 1, w1enc + 64 + 32 * p.w1_bits * i);
+        oracle_shake256(w1enc, (size_t)(64 + p.w1_len), ctilde, (size_t)p.lambda_div4);
+
+        oracle_sample_in_ball(p.tau, ctilde, (size_t)p.lambda_div4, c);
+        oracle_ntt_raw(c);
+
+        for (int l = 0; l < L; l++) { /* ml_dsa.rs:243-250, 263-265 */
+            for (int n = 0; n < 256; n++) tmp[n] = mont((int64_t)c[n] * key->s1[256 * l + n]);
+            inv_ntt_safe(tmp);
+            for (int n = 0; n < 256; n++) z[256 * l + n] = partial_reduce32(y[256 * l + n] + tmp[n]);
+        }
+        for (int k = 0; k < K; k++) { /* ml_dsa.rs:253-260, 268-272 */
+            for (int n = 0; n < 256; n++) cs2[256 * k + n] = mont((int64_t)c[n] * key->s2[256 * k + n]);
+            inv_ntt_safe(cs2 + 256 * k);
+            for (int n = 0; n < 256; n++)
+                r0[256 * k + n] = low_bits(p.gamma2, partial_reduce32(w[256 * k + n] - cs2[256 * k + n]));
+        }
+        if (inf_norm(z, L) >= p.gamma1 - p.beta || inf_norm(r0, K) >= p.gamma2 - p.beta) continue; /* :277-283 */
+
+        int hsum = 0;
+        for (int k = 0; k < K; k++) { /* ml_dsa.rs:288-306 */
+            for (int n = 0; n < 256; n++) ct0[256 * k + n] = mont((int64_t)c[n] * key->t0[256 * k + n]);
+            inv_ntt_safe(ct0 + 256 * k);
+            for (int n = 0; n < 256; n++) {
+                int i = 256 * k + n;
+                h[i] = oracle_make_hint(p.gamma2, Q - ct0[i], partial_reduce32(w[i] - cs2[i] + ct0[i]));
+                hsum += h[i];
+            }
+        }
+        if (inf_norm(ct0, K) >= p.gamma2 || hsum > p.omega) continue; /* ml_dsa.rs:312-319 */
+        break;
+    }
+    if (iters) *iters = trips;
+
+    /* ml_dsa.rs:334-336 + encodings.rs:238-276 */
+    memcpy(sig, ctilde, (size_t)p.lambda_div4);
+    for (int i = 0; i < 256 * L; i++) z[i] = center_mod(z[i]);
+    for (int l = 0; l < L; l++)
+        oracle_bit_pack(z + 256 * l, p.gamma1 - 1, p.gamma1, sig + p.lambda_div4 + 32 * p.z_bits * l);
+    hint_bit_pack(K, p.omega, h, sig + p.lambda_div4 + 32 * p.z_bits * L);
+out:
+    memset(key, 0, sizeof *key);
+    free(key);
+    free(A);
+    return rc;
+}
+
+/* ml_dsa.rs:351-437 (verify_internal) on canonical pk bytes (expand_public, ml_dsa.rs:477-498, folded in).
+ * Returns 1 (valid) or 0.  ctx > 255 -> 0 (lib.rs:368-370).  Negative only for a bad parameter set. */
+int oracle_verify(int ps, int framing, int ph, const uint8_t *pk, const uint8_t *msg, size_t mlen,
+                  const uint8_t *ctx, size_t ctxlen, const uint8_t *sig)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    if (ctxlen > 255) return 0;
+    const int K = p.k, L = p.l;
+    int32_t z[LMAX * 256], zh[LMAX * 256], h[KMAX * 256], t1[KMAX * 256], c[256], w[KMAX * 256], w1[KMAX * 256];
+    uint8_t tr[64], mu[64], w1enc[64 + 1024], ctp[64];
+
+    /* encodings.rs:292-328 */
+    const uint8_t *ctilde = sig;
+    for (int l = 0; l < L; l++)
+        oracle_bit_unpack(sig + p.lambda_div4 + 32 * p.z_bits * l, p.gamma1 - 1, p.gamma1, z + 256 * l);
+    if (oracle_hint_bit_unpack(K, p.omega, sig + p.lambda_div4 + 32 * p.z_bits * L, h)) return 0;
+
+    /* expand_public: pk_decode, tr = H(pk), t1*2^d in NTT/Montgomery form */
+    for (int i = 0; i < K; i++) oracle_bit_unpack(pk + 32 + 320 * i, 0, 1023, t1 + 256 * i);
+    oracle_shake256(pk, (size_t)p.pk_len, tr, 64);
+    for (int i = 0; i < 256 * K; i++) t1[i] <<= D;
+    for (int i = 0; i < K; i++) oracle_ntt_raw(t1 + 256 * i);
+    for (int i = 0; i < 256 * K; i++) t1[i] = to_mont1(t1[i]);
+
+    if (compute_mu(framing, ph, tr, msg, mlen, ctx, ctxlen, mu)) return -1;
+    oracle_sample_in_ball(p.tau, ctilde, (size_t)p.lambda_div4, c);
+
+    int32_t *A = malloc(sizeof(int32_t) * 256 * (size_t)(K * L));
+    expand_a(&p, pk, A);
+    memcpy(zh, z, sizeof(int32_t) * 256 * (size_t)L);
+    for (int i = 0; i < L; i++) oracle_ntt_raw(zh + 256 * i);
+    mat_vec_mul(&p, A, zh, w);
+    free(A);
+    oracle_ntt_raw(c);
+    for (int k = 0; k < K; k++) { /* ml_dsa.rs:407-416 */
+        for (int n = 0; n < 256; n++) w[256 * k + n] -= mont((int64_t)c[n] * t1[256 * k + n]);
+        inv_ntt_safe(w + 256 * k);
+    }
+    for (int i = 0; i < 256 * K; i++) w1[i] = oracle_use_hint(p.gamma2, h[i], w[i]); /* ml_dsa.rs:420-422 */
+    memcpy(w1enc, mu, 64);
+    for (int i = 0; i < K; i++)
+        oracle_bit_pack(w1 + 256 * i, 0, (Q - 1) / (2 * p.gamma2) - 1, w1enc + 64 + 32 * p.w1_bits * i);
+    oracle_shake256(w1enc, (size_t)(64 + p.w1_len), ctp, (size_t)p.lambda_div4);
+
+    int left = inf_norm(z, L) < p.gamma1 - p.beta; /* ml_dsa.rs:434-436 */
+    int right = memcmp(ctilde, ctp, (size_t)p.lambda_div4) == 0;
+    return left && right;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Threaded batch runners: one scalar instance per thread, contiguous lane ranges.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int op, ps, framing, rc;
+    size_t lo, hi;
+    const uint8_t *a, *msgs, *ctx, *rnd, *sigin;
+    size_t a_stride;
+    const uint64_t *msg_off;
+    const uint32_t *ctx_off;
+    uint8_t *o1, *o2;
+    uint32_t *iters;
+} job_t;
+
+static void *job_main(void *arg)
+{
+    job_t *j = arg;
+    oracle_params p;
+    oracle_get_params(j->ps, &p);
+    for (size_t i = j->lo; i < j->hi; i++) {
+        const uint8_t *m = j->msgs ? j->msgs + j->msg_off[i] : NULL;
+        size_t mlen = j->msgs ? (size_t)(j->msg_off[i + 1] - j->msg_off[i]) : 0;
+        const uint8_t *cx = (j->ctx && j->ctx_off) ? j->ctx + j->ctx_off[i] : NULL;
+        size_t clen = (j->ctx && j->ctx_off) ? (size_t)(j->ctx_off[i + 1] - j->ctx_off[i]) : 0;
+        int rc = 0;
+        if (j->op == 0) {
+            rc = oracle_keygen(j->ps, j->a + 32 * i, j->o1 + (size_t)p.pk_len * i, j->o2 + (size_t)p.sk_len * i);
+        } else if (j->op == 1) {
+            rc = oracle_sign(j->ps, j->framing, 0, j->a + j->a_stride * i, m, mlen, cx, clen, j->rnd + 32 * i,
+                             j->o1 + (size_t)p.sig_len * i, j->iters ? j->iters + i : NULL);
+        } else {
+            int v = oracle_verify(j->ps, j->framing, 0, j->a + j->a_stride * i, m, mlen, cx, clen,
+                                  j->sigin + (size_t)p.sig_len * i);
+            if (v < 0) rc = v; else j->o1[i] = (uint8_t)v;
+        }
+        if (rc) j->rc = rc;
+    }
+    return NULL;
+}
+
+static int run_jobs(job_t *proto, int nthreads, size_t n)
+{
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > n && n > 0) nthreads = (int)n;
+    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
+    job_t *jobs = malloc(sizeof(job_t) * (size_t)nthreads);
+    int rc = 0;
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = *proto;
+        jobs[t].lo = n * (size_t)t / (size_t)nthreads;
+        jobs[t].hi = n * (size_t)(t + 1) / (size_t)nthreads;
+        jobs[t].rc = 0;
+        if (nthreads == 1) job_main(&jobs[t]);
+        else pthread_create(&th[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) {
+        if (nthreads > 1) pthread_join(th[t], NULL);
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    free(th);
+    free(jobs);
+    return rc;
+}
+
+int oracle_keygen_batch(int ps, int nthreads, size_t n, const uint8_t *xi, uint8_t *pk, uint8_t *sk)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    job_t j = {0};
+    j.op = 0; j.ps = ps; j.a = xi; j.o1 = pk; j.o2 = sk;
+    return run_jobs(&j, nthreads, n);
+}
+int oracle_sign_batch(int ps, int framing, int nthreads, size_t n, const uint8_t *sk, size_t sk_stride,
+                      const uint8_t *msgs, const uint64_t *msg_off, const uint8_t *ctx, const uint32_t *ctx_off,
+                      const uint8_t *rnd, uint8_t *sig, uint32_t *iters)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    job_t j = {0};
+    j.op = 1; j.ps = ps; j.framing = framing; j.a = sk; j.a_stride = sk_stride; j.msgs = msgs; j.msg_off = msg_off;
+    j.ctx = ctx; j.ctx_off = ctx_off; j.rnd = rnd; j.o1 = sig; j.iters = iters;
+    return run_jobs(&j, nthreads, n);
+}
+int oracle_verify_batch(int ps, int framing, int nthreads, size_t n, const uint8_t *pk, size_t pk_stride,
+                        const uint8_t *msgs, const uint64_t *msg_off, const uint8_t *ctx, const uint32_t *ctx_off,
+                        const uint8_t *sig, uint8_t *ok)
+{
+    oracle_params p;
+    if (oracle_get_params(ps, &p)) return -1;
+    job_t j = {0};
+    j.op = 2; j.ps = ps; j.framing = framing; j.a = pk; j.a_stride = pk_stride; j.msgs = msgs; j.msg_off = msg_off;
+    j.ctx = ctx; j.ctx_off = ctx_off; j.sigin = sig; j.o1 = ok;
+    return run_jobs(&j, nthreads, n);
+}
