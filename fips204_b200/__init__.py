@@ -1,0 +1,276 @@
+"""fips204_b200 -- B200-native batched ML-DSA (FIPS 204), a drop-in for the hot path of the Rust crate
+integritychain/fips204.
+
+Host-side mirror of the reference's public surface (src/lib.rs:116-614, src/traits.rs):
+
+    from fips204_b200 import ml_dsa_44, ml_dsa_65, ml_dsa_87
+    pk, sk = ml_dsa_65.try_keygen()                      # lib.rs:195      KeyGen::try_keygen
+    pk, sk = ml_dsa_65.try_keygen_with_rng(rng)          # lib.rs:230
+    pk, sk = ml_dsa_65.KG.keygen_from_seed(xi)           # lib.rs:247
+    sig = sk.try_sign(msg, ctx)                          # traits.rs:156   Signer::try_sign
+    sig = sk.try_sign_with_rng(rng, msg, ctx)            # lib.rs:268
+    sig = sk.try_sign_with_seed(seed, msg, ctx)          # traits.rs:228
+    ok  = pk.verify(msg, sig, ctx)                       # lib.rs:364      Verifier::verify
+    sk.into_bytes(); ml_dsa_65.PrivateKey.try_from_bytes(b)   # lib.rs:417-494  SerDes
+
+plus the batch entry points the engine exists for (keygen_batch / sign_batch / verify_batch), all of
+which call hand-written sm_100a CUDA through the C ABI of include/mldsa_b200.h.  Single operations
+are batches of one.  There is no CPU fallback: without the CUDA library every call raises.
+
+Error behaviour follows the reference: signing with |ctx| > 255 raises ValueError("ML-DSA.Sign: ctx
+too long") (lib.rs:274), an RNG failure raises ValueError("... random number generator failed")
+(lib.rs:283, ml_dsa.rs:41), verify never raises for malformed input and returns False (lib.rs:368-370).
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import MldsaError
+
+__all__ = ["ml_dsa_44", "ml_dsa_65", "ml_dsa_87", "MldsaError", "micro", "device_count", "kernel_launches"]
+
+
+def device_count():
+    return _lib.lib().mldsa_device_count()
+
+
+def kernel_launches():
+    return int(_lib.lib().mldsa_kernel_launches())
+
+
+class OsRng:
+    """Default RNG (the reference's `default-rng` feature binds OsRng, traits.rs:44-47)."""
+
+    def try_fill_bytes(self, n):
+        return os.urandom(n)
+
+
+def _draw(rng, n, what):
+    # exactly ONE 32-byte draw per keygen (ml_dsa.rs:40-41) / per sign (lib.rs:282-283), in lane order
+    try:
+        b = rng.try_fill_bytes(n) if hasattr(rng, "try_fill_bytes") else rng(n)
+    except Exception as e:  # noqa: BLE001 - mirrors map_err(|_| "...") of the reference
+        raise ValueError(what) from e
+    if b is None or len(b) != n:
+        raise ValueError(what)
+    return bytes(b)
+
+
+def _u8(a, shape=None):
+    arr = np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray, memoryview)) else np.asarray(a, dtype=np.uint8)
+    arr = np.ascontiguousarray(arr)
+    if shape is not None:
+        arr = arr.reshape(shape)
+    return arr
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _ragged(items, off_dtype):
+    off = np.zeros(len(items) + 1, dtype=off_dtype)
+    if len(items):
+        off[1:] = np.cumsum([len(x) for x in items])
+    blob = np.frombuffer(b"".join(bytes(x) for x in items) or b"\0", dtype=np.uint8)
+    return blob, off
+
+
+class _ParamSet:
+    """One of the reference's per-parameter-set modules (src/lib.rs:639-653, 681-695, 723-737)."""
+
+    def __init__(self, ps, k, l, pk_len, sk_len, sig_len):
+        self.PS, self.K, self.L = ps, k, l
+        self.PK_LEN, self.SK_LEN, self.SIG_LEN = pk_len, sk_len, sig_len
+        mod = self
+
+        class PublicKey:
+            __slots__ = ("_b",)
+
+            def __init__(self, b):
+                self._b = bytes(b)
+
+            @staticmethod
+            def try_from_bytes(b):  # lib.rs:469-474; never fails on a correctly sized array (SURVEY 8a note T)
+                if len(b) != mod.PK_LEN:
+                    raise ValueError("incorrect public key length")
+                return PublicKey(b)
+
+            def into_bytes(self):  # lib.rs:477-493
+                return self._b
+
+            def verify(self, message, sig, ctx=b""):  # lib.rs:364-380
+                if len(ctx) > 255 or len(sig) != mod.SIG_LEN:
+                    return False
+                return bool(mod.verify_batch(self._b, [message], [sig], ctxs=[ctx], shared_key=True)[0])
+
+            def __eq__(self, o):
+                return isinstance(o, PublicKey) and o._b == self._b
+
+        class PrivateKey:
+            __slots__ = ("_b",)
+
+            def __init__(self, b):
+                self._b = bytes(b)
+
+            @staticmethod
+            def try_from_bytes(b):  # lib.rs:420-424
+                if len(b) != mod.SK_LEN:
+                    raise ValueError("incorrect private key length")
+                return PrivateKey(b)
+
+            def into_bytes(self):  # lib.rs:427-463
+                return self._b
+
+            def try_sign(self, message, ctx=b""):  # traits.rs:156
+                return self.try_sign_with_rng(OsRng(), message, ctx)
+
+            def try_sign_with_rng(self, rng, message, ctx=b""):  # lib.rs:268-296
+                if len(ctx) > 255:
+                    raise ValueError("ML-DSA.Sign: ctx too long")
+                rnd = _draw(rng, 32, "ML-DSA.Sign: random number generator failed")
+                return self.try_sign_with_seed(rnd, message, ctx)
+
+            def try_sign_with_seed(self, seed, message, ctx=b""):  # traits.rs:228-232 (DummyRng)
+                if len(ctx) > 255:
+                    raise ValueError("ML-DSA.Sign: ctx too long")
+                return mod.sign_batch(self._b, [message], seed, ctxs=[ctx], shared_key=True)[0].tobytes()
+
+        class KG:
+            @staticmethod
+            def try_keygen():  # traits.rs:44
+                return mod.try_keygen()
+
+            @staticmethod
+            def try_keygen_with_rng(rng):  # lib.rs:241-244
+                return mod.try_keygen_with_rng(rng)
+
+            @staticmethod
+            def keygen_from_seed(xi):  # lib.rs:247-250
+                if len(xi) != 32:
+                    raise ValueError("xi must be 32 bytes")
+                pk, sk = mod.keygen_batch(xi)
+                return PublicKey(pk[0].tobytes()), PrivateKey(sk[0].tobytes())
+
+        self.PublicKey, self.PrivateKey, self.KG = PublicKey, PrivateKey, KG
+
+    # ----- single-op module functions (lib.rs:195, :230) -----
+    def try_keygen(self):
+        return self.try_keygen_with_rng(OsRng())
+
+    def try_keygen_with_rng(self, rng):
+        xi = _draw(rng, 32, "KeyGen: Random number generator failed")  # ml_dsa.rs:41
+        return self.KG.keygen_from_seed(xi)
+
+    def _internal_sign(self, sk, message, ctx, rnd):  # lib.rs:586-594 (ACVP interface)
+        if len(ctx) > 255:
+            raise ValueError("_internal_sign: ctx too long")
+        return self.sign_batch(sk.into_bytes(), [message], rnd, shared_key=True, framing=1)[0].tobytes()
+
+    def _internal_verify(self, pk, message, sig, ctx=b""):  # lib.rs:605-612
+        if len(ctx) > 255:
+            return False
+        return bool(self.verify_batch(pk.into_bytes(), [message], [sig], shared_key=True, framing=1)[0])
+
+    # ----- batch entry points (the engine) -----
+    def keygen_batch(self, xis, dev=0):
+        """xis: n x 32 seed bytes -> (pk[n, PK_LEN], sk[n, SK_LEN]) uint8 arrays."""
+        xi = _u8(xis).reshape(-1, 32)
+        n = xi.shape[0]
+        pk = np.empty((n, self.PK_LEN), dtype=np.uint8)
+        sk = np.empty((n, self.SK_LEN), dtype=np.uint8)
+        _lib.check(_lib.lib().mldsa_keygen_batch(self.PS, dev, n, _ptr(xi), _ptr(pk), _ptr(sk)))
+        return pk, sk
+
+    def keygen_batch_with_rng(self, rng, n, dev=0):
+        xi = b"".join(_draw(rng, 32, "KeyGen: Random number generator failed") for _ in range(n))
+        return self.keygen_batch(xi, dev)
+
+    def sign_batch(self, sks, msgs, rnds, ctxs=None, shared_key=False, framing=0, dev=0, want_iters=False):
+        """sks: n x SK_LEN (or one key with shared_key), msgs: list of bytes, rnds: n x 32."""
+        n = len(msgs)
+        sk = _u8(sks)
+        if sk.size != (1 if shared_key else n) * self.SK_LEN:
+            raise ValueError("incorrect private key length")
+        rnd = _u8(rnds)
+        if rnd.size != 32 * n:
+            raise ValueError("rnd must be n x 32 bytes")
+        mb, mo = _ragged(msgs, np.uint64)
+        cb = co = None
+        if ctxs is not None:
+            if len(ctxs) != n:
+                raise ValueError("ctxs must have n entries")
+            if any(len(c) > 255 for c in ctxs):
+                raise ValueError("ML-DSA.Sign: ctx too long")
+            cb, co = _ragged(ctxs, np.uint32)
+        sig = np.empty((n, self.SIG_LEN), dtype=np.uint8)
+        iters = np.zeros(n, dtype=np.uint32)
+        rc = _lib.lib().mldsa_sign_batch(self.PS, dev, framing, n, _ptr(sk), 0 if shared_key else self.SK_LEN,
+                                         _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(rnd), _ptr(sig), _ptr(iters))
+        if rc == -2:
+            raise ValueError("ML-DSA.Sign: ctx too long")
+        _lib.check(rc)
+        return (sig, iters) if want_iters else sig
+
+    def sign_batch_with_rng(self, rng, sks, msgs, ctxs=None, **kw):
+        rnd = b"".join(_draw(rng, 32, "ML-DSA.Sign: random number generator failed") for _ in range(len(msgs)))
+        return self.sign_batch(sks, msgs, rnd, ctxs, **kw)
+
+    def verify_batch(self, pks, msgs, sigs, ctxs=None, shared_key=False, framing=0, dev=0):
+        """-> uint8[n], 1 = valid.  Never raises for malformed signatures (lib.rs:368-370)."""
+        n = len(msgs)
+        pk = _u8(pks)
+        if pk.size != (1 if shared_key else n) * self.PK_LEN:
+            raise ValueError("incorrect public key length")
+        if isinstance(sigs, (list, tuple)):
+            sg = _u8(b"".join(bytes(s) for s in sigs))
+        else:
+            sg = _u8(sigs)
+        if sg.size != n * self.SIG_LEN:
+            raise ValueError("incorrect signature length")
+        mb, mo = _ragged(msgs, np.uint64)
+        cb = co = None
+        if ctxs is not None:
+            cb, co = _ragged(ctxs, np.uint32)
+        ok = np.zeros(n, dtype=np.uint8)
+        _lib.check(_lib.lib().mldsa_verify_batch(self.PS, dev, framing, n, _ptr(pk), 0 if shared_key else self.PK_LEN,
+                                                 _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(sg), _ptr(ok)))
+        return ok
+
+
+ml_dsa_44 = _ParamSet(44, 4, 4, 1312, 2560, 2420)
+ml_dsa_65 = _ParamSet(65, 6, 5, 1952, 4032, 3309)
+ml_dsa_87 = _ParamSet(87, 8, 7, 2592, 4896, 4627)
+PARAM_SETS = {44: ml_dsa_44, 65: ml_dsa_65, 87: ml_dsa_87}
+
+
+class micro:
+    """Leaf entry points of BASELINE config 2 (src/ntt.rs, src/hashing.rs:111-146) and the SHAKE hook."""
+
+    @staticmethod
+    def ntt(polys, dev=0):
+        a = np.ascontiguousarray(polys, dtype=np.int32).copy()
+        _lib.check(_lib.lib().mldsa_ntt_batch(dev, a.size // 256, _ptr(a)))
+        return a
+
+    @staticmethod
+    def inv_ntt(polys, dev=0):
+        a = np.ascontiguousarray(polys, dtype=np.int32).copy()
+        _lib.check(_lib.lib().mldsa_intt_batch(dev, a.size // 256, _ptr(a)))
+        return a
+
+    @staticmethod
+    def expand_a(seeds34, dev=0):
+        s = _u8(seeds34).reshape(-1, 34)
+        out = np.empty((s.shape[0], 256), dtype=np.int32)
+        _lib.check(_lib.lib().mldsa_expand_a_batch(dev, s.shape[0], _ptr(s), _ptr(out)))
+        return out
+
+    @staticmethod
+    def shake(bits, rows, out_len, dev=0):
+        r = np.ascontiguousarray(rows, dtype=np.uint8)
+        n, in_len = r.shape
+        out = np.empty((n, out_len), dtype=np.uint8)
+        _lib.check(_lib.lib().mldsa_shake_batch(dev, bits, n, _ptr(r), in_len, _ptr(out), out_len))
+        return out

@@ -1,0 +1,73 @@
+"""ctypes binding of the C-ABI library (include/mldsa_b200.h).  There is NO CPU fallback: if the CUDA
+library is missing or a call fails, an exception is raised."""
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+SO_PATH = HERE / "libmldsa_b200.so"
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+sz = C.c_size_t
+vp = C.c_void_p
+
+# every symbol include/mldsa_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "mldsa_device_count": (C.c_int, []),
+    "mldsa_strerror": (C.c_char_p, [C.c_int]),
+    "mldsa_last_cuda_error": (C.c_char_p, []),
+    "mldsa_sizes": (C.c_int, [C.c_int, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]),
+    "mldsa_host_alloc": (vp, [sz]),
+    "mldsa_host_free": (None, [vp]),
+    "mldsa_keygen_batch": (C.c_int, [C.c_int, C.c_int, sz, vp, vp, vp]),
+    "mldsa_keygen_batch_dev": (C.c_int, [C.c_int, vp, sz, vp, vp, vp]),
+    "mldsa_sign_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
+    "mldsa_sign_batch_dev": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
+    "mldsa_verify_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
+    "mldsa_verify_batch_dev": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
+    "mldsa_ntt_batch": (C.c_int, [C.c_int, sz, vp]),
+    "mldsa_intt_batch": (C.c_int, [C.c_int, sz, vp]),
+    "mldsa_expand_a_batch": (C.c_int, [C.c_int, sz, vp, vp]),
+    "mldsa_ntt_batch_dev": (C.c_int, [vp, sz, vp]),
+    "mldsa_intt_batch_dev": (C.c_int, [vp, sz, vp]),
+    "mldsa_expand_a_batch_dev": (C.c_int, [vp, sz, vp, vp]),
+    "mldsa_shake_batch": (C.c_int, [C.c_int, C.c_int, sz, vp, sz, vp, sz]),
+    "mldsa_set_workspace_limit": (None, [sz]),
+    "mldsa_kernel_launches": (C.c_uint64, []),
+    "mldsa_last_sign_rounds": (C.c_int, []),
+}
+
+_lib = None
+
+
+class MldsaError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__(f"mldsa error {code}: {detail}")
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built (python -m fips204_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not SO_PATH.exists():
+            raise ImportError(f"{SO_PATH} is missing: build it with `python -m fips204_b200.build` "
+                              "(there is no CPU fallback)")
+        l = C.CDLL(str(SO_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        l = lib()
+        msg = l.mldsa_strerror(rc).decode()
+        if rc == -3:
+            msg += ": " + l.mldsa_last_cuda_error().decode()
+        raise MldsaError(rc, msg)

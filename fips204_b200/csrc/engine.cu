@@ -1,0 +1,668 @@
+// engine.cu -- host runtime and the extern "C" boundary (include/mldsa_b200.h).
+//
+// One lazily created context per CUDA device (mutex-guarded): a work stream, a cached device arena
+// that is carved into the per-call scratch (and, for the host-pointer entry points, the staged
+// inputs/outputs), and a small pinned mailbox.  Batches are cut into chunks that fit the workspace
+// limit; every chunk runs the kernel pipeline of k_keygen / k_sign / k_verify.  Calls are
+// synchronous and re-entrant; calls on different devices run concurrently from different threads.
+#include "engine.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/mldsa_b200.h"
+#include "params.h"
+
+namespace mldsa {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static thread_local std::string t_cuda_err;
+static thread_local int t_last_rounds = 0;
+static std::atomic<size_t> g_ws_limit{0};
+
+static int cuda_fail(cudaError_t e, const char* what)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    t_cuda_err = buf;
+    cudaGetLastError();  // clear the sticky-less error state
+    return e == cudaErrorMemoryAllocation ? E_NOMEM : E_CUDA;
+}
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct PSInfo {
+    int K, L, zbits, w1len;
+    size_t pk, sk, sig;
+};
+static bool ps_info(int ps, PSInfo& o)
+{
+    switch (ps) {
+    case 44: o = {4, 4, 18, 768, 1312, 2560, 2420}; return true;
+    case 65: o = {6, 5, 20, 768, 1952, 4032, 3309}; return true;
+    case 87: o = {8, 7, 20, 1024, 2592, 4896, 4627}; return true;
+    }
+    return false;
+}
+
+struct DeviceCtx {
+    std::mutex mu;
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    uint32_t* mailbox = nullptr;  // pinned, 16 words
+
+    int init(int d)
+    {
+        if (dev == d) return OK;
+        CK(cudaSetDevice(d));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 64, cudaHostAllocDefault));
+        dev = d;
+        return OK;
+    }
+    // Grow the arena to at least `bytes`.  `keep` bytes at its start (inputs already staged by a host
+    // entry point) survive a reallocation.
+    int reserve(size_t bytes, size_t keep = 0)
+    {
+        if (bytes <= arena_bytes) return OK;
+        const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+        uint8_t* fresh = nullptr;
+        if (keep == 0 && arena) {
+            cudaFree(arena);
+            arena = nullptr;
+            arena_bytes = 0;
+        }
+        CK(cudaMalloc(reinterpret_cast<void**>(&fresh), want));
+        if (arena) {
+            cudaError_t e = cudaMemcpy(fresh, arena, keep, cudaMemcpyDeviceToDevice);
+            cudaFree(arena);
+            if (e != cudaSuccess) {
+                cudaFree(fresh);
+                arena = nullptr;
+                arena_bytes = 0;
+                return cuda_fail(e, "arena grow");
+            }
+        }
+        arena = fresh;
+        arena_bytes = want;
+        return OK;
+    }
+};
+
+constexpr int MAX_DEV = 64;
+static DeviceCtx g_ctx[MAX_DEV];
+
+// bump allocator over the arena, 256-byte granules
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(uint8_t* b) : base(b) {}
+    template <class T> T* take(size_t count)
+    {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 255) & ~size_t(255);
+        return p;
+    }
+};
+static size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+static size_t workspace_budget(size_t arena_bytes)
+{
+    size_t lim = g_ws_limit.load();
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
+    free_b += arena_bytes;  // the cached arena is ours to reuse
+    size_t def = free_b / 10 * 6;
+    const size_t cap = size_t(64) << 30;
+    if (def > cap) def = cap;
+    if (lim == 0 || lim > free_b / 10 * 9) lim = lim == 0 ? def : free_b / 10 * 9;
+    if (lim < (size_t(64) << 20)) lim = size_t(64) << 20;
+    return lim;
+}
+
+// ---- workspace carving per operation ------------------------------------------------------------
+static size_t keygen_ws_bytes(const PSInfo& p, size_t n)
+{
+    return pad256(n * 128) + pad256(n * (size_t)(p.K + p.L) * 256) + pad256(n * (size_t)p.K * p.L * 1024);
+}
+static KeygenWs keygen_carve(Carver& c, const PSInfo& p, size_t n)
+{
+    KeygenWs w;
+    w.seeds = c.take<uint8_t>(n * 128);
+    w.s = c.take<int8_t>(n * (size_t)(p.K + p.L) * 256);
+    w.A = c.take<int32_t>(n * (size_t)p.K * p.L * 256);
+    return w;
+}
+static size_t verify_ws_bytes(const PSInfo& p, size_t n, bool shared)
+{
+    const size_t nk = shared ? 1 : n;
+    return pad256(nk * (size_t)p.K * p.L * 1024) + pad256((size_t)p.K * 1024) + pad256(64) +
+           pad256(n * (size_t)(64 + p.w1len)) + pad256(n * (size_t)SIB_BYTES) + pad256(n);
+}
+static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n, bool shared)
+{
+    const size_t nk = shared ? 1 : n;
+    VerifyWs w;
+    w.A = c.take<int32_t>(nk * (size_t)p.K * p.L * 256);
+    w.t1h = c.take<int32_t>((size_t)p.K * 256);
+    w.tr = c.take<uint8_t>(64);
+    w.mw1 = c.take<uint8_t>(n * (size_t)(64 + p.w1len));
+    w.sib = c.take<uint8_t>(n * (size_t)SIB_BYTES);
+    w.pre_ok = c.take<uint8_t>(n);
+    return w;
+}
+static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared)
+{
+    const size_t nk = shared ? 1 : n;
+    return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
+           pad256(n * (size_t)p.K * 1024) + pad256(n * (size_t)p.L * 32 * p.zbits) + pad256(n * (size_t)(64 + p.w1len)) +
+           2 * pad256(n * 64) + pad256(n * (size_t)SIB_BYTES) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) +
+           pad256(16);
+}
+static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox)
+{
+    const size_t nk = shared ? 1 : n;
+    SignWs w;
+    w.A = c.take<int32_t>(nk * (size_t)p.K * p.L * 256);
+    w.s1h = c.take<int32_t>(nk * (size_t)p.L * 256);
+    w.s2h = c.take<int32_t>(nk * (size_t)p.K * 256);
+    w.t0h = c.take<int32_t>(nk * (size_t)p.K * 256);
+    w.w = c.take<int32_t>(n * (size_t)p.K * 256);
+    w.yraw = c.take<uint8_t>(n * (size_t)p.L * 32 * p.zbits);
+    w.mw1 = c.take<uint8_t>(n * (size_t)(64 + p.w1len));
+    w.rhopp = c.take<uint8_t>(n * 64);
+    w.ctilde = c.take<uint8_t>(n * 64);
+    w.sib = c.take<uint8_t>(n * (size_t)SIB_BYTES);
+    w.kappa = c.take<uint32_t>(n);
+    w.done = c.take<uint8_t>(n);
+    w.act[0] = c.take<uint32_t>(n);
+    w.act[1] = c.take<uint32_t>(n);
+    w.nact = c.take<uint32_t>(4);
+    w.h_nact = mailbox;
+    return w;
+}
+
+static size_t pick_chunk(size_t arena_bytes, size_t n, size_t fixed_bytes, size_t per_lane_bytes)
+{
+    const size_t budget = workspace_budget(arena_bytes);
+    size_t room = budget > fixed_bytes ? budget - fixed_bytes : 0;
+    size_t chunk = room / (per_lane_bytes + 64);
+    if (chunk < 256) chunk = 256;
+    if (chunk > n) chunk = n;
+    return chunk;
+}
+
+// =================================================================================================
+// device-pointer cores (current device must already be set; ctx locked by the caller)
+// =================================================================================================
+static int keygen_core(DeviceCtx& cx, cudaStream_t st, int ps, size_t n, const uint8_t* d_xi, uint8_t* d_pk,
+                       uint8_t* d_sk, size_t arena_skip)
+{
+    PSInfo p;
+    if (!ps_info(ps, p)) return E_PARAM;
+    const size_t per_lane = keygen_ws_bytes(p, 1024) / 1024 + 1;
+    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip, per_lane);
+    int rc = cx.reserve(arena_skip + keygen_ws_bytes(p, chunk), arena_skip);
+    if (rc) return rc;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        Carver c(cx.arena + arena_skip);
+        KeygenWs ws = keygen_carve(c, p, m);
+        CK(keygen_run(ps, st, m, d_xi + 32 * lo, d_pk + p.pk * lo, d_sk + p.sk * lo, ws));
+        // rho', K, s1, s2 are secret: zero the scratch (mirrors ZeroizeOnDrop, src/types.rs:19)
+        CK(cudaMemsetAsync(ws.seeds, 0, m * 128, st));
+        CK(cudaMemsetAsync(ws.s, 0, m * (size_t)(p.K + p.L) * 256, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
+static int verify_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t n, const uint8_t* d_pk,
+                       size_t pk_stride, const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
+                       const uint32_t* d_ctx_off, const uint8_t* d_sig, uint8_t* d_ok, size_t arena_skip)
+{
+    PSInfo p;
+    if (!ps_info(ps, p)) return E_PARAM;
+    const bool shared = pk_stride == 0;
+    const size_t per_lane = (verify_ws_bytes(p, 1024, shared) - (shared ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
+    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + verify_ws_bytes(p, 0, shared), per_lane);
+    int rc = cx.reserve(arena_skip + verify_ws_bytes(p, chunk, shared), arena_skip);
+    if (rc) return rc;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        Carver c(cx.arena + arena_skip);
+        VerifyWs ws = verify_carve(c, p, m, shared);
+        MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
+        CK(verify_run(ps, st, m, d_pk + pk_stride * lo, pk_stride, md, d_sig + p.sig * lo, d_ok + lo, ws));
+    }
+    CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
+static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t n, const uint8_t* d_sk,
+                     size_t sk_stride, const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
+                     const uint32_t* d_ctx_off, const uint8_t* d_rnd, uint8_t* d_sig, uint32_t* d_iters,
+                     size_t arena_skip)
+{
+    PSInfo p;
+    if (!ps_info(ps, p)) return E_PARAM;
+    const bool shared = sk_stride == 0;
+    const size_t fixed = sign_ws_bytes(p, 0, shared);
+    const size_t per_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? fixed : 0)) / 1024 + 1;
+    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + fixed, per_lane);
+    int rc = cx.reserve(arena_skip + sign_ws_bytes(p, chunk, shared), arena_skip);
+    if (rc) return rc;
+    t_last_rounds = 0;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        Carver c(cx.arena + arena_skip);
+        SignWs ws = sign_carve(c, p, m, shared, cx.mailbox);
+        ws.h_nact[1] = 0;
+        MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
+        int rounds = 0;
+        cudaError_t e = sign_run(ps, st, m, d_sk + sk_stride * lo, sk_stride, md, d_rnd + 32 * lo, d_sig + p.sig * lo,
+                                 d_iters ? d_iters + lo : nullptr, ws, &rounds);
+        t_last_rounds += rounds;
+        // zero everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop)
+        cudaMemsetAsync(cx.arena + arena_skip, 0, c.off, st);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(st);
+            if (ws.h_nact[1] == CTX_ERR_MARK) return E_CTX;
+            return cuda_fail(e, "sign_run");
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
+static DeviceCtx* lock_ctx(int dev, std::unique_lock<std::mutex>& lk, int& rc)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || dev < 0 || dev >= ndev || dev >= MAX_DEV) {
+        rc = E_PARAM;
+        return nullptr;
+    }
+    DeviceCtx& cx = g_ctx[dev];
+    lk = std::unique_lock<std::mutex>(cx.mu);
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        rc = E_CUDA;
+        return nullptr;
+    }
+    rc = cx.init(dev);
+    return rc ? nullptr : &cx;
+}
+static DeviceCtx* lock_current(std::unique_lock<std::mutex>& lk, int& rc)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        rc = E_CUDA;
+        return nullptr;
+    }
+    return lock_ctx(dev, lk, rc);
+}
+
+static bool check_msgs(size_t n, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx,
+                       const uint32_t* ctx_off)
+{
+    if (!msg_off) return false;
+    if (!msgs && n && msg_off[n] != msg_off[0]) return false;
+    if ((ctx == nullptr) != (ctx_off == nullptr)) return ctx_off == nullptr || ctx_off[n] == ctx_off[0];
+    return true;
+}
+
+}  // namespace mldsa
+
+using namespace mldsa;
+
+extern "C" {
+
+int mldsa_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+const char* mldsa_strerror(int code)
+{
+    switch (code) {
+    case MLDSA_OK: return "ok";
+    case MLDSA_E_PARAM: return "bad parameter";
+    case MLDSA_E_CTX: return "ML-DSA.Sign: ctx too long";
+    case MLDSA_E_CUDA: return "CUDA error";
+    case MLDSA_E_NOMEM: return "out of device memory";
+    case MLDSA_E_UNSUPPORTED: return "not supported";
+    }
+    return "unknown error";
+}
+const char* mldsa_last_cuda_error(void) { return t_cuda_err.c_str(); }
+
+int mldsa_sizes(int ps, size_t* pk_len, size_t* sk_len, size_t* sig_len)
+{
+    PSInfo p;
+    if (!ps_info(ps, p)) return E_PARAM;
+    if (pk_len) *pk_len = p.pk;
+    if (sk_len) *sk_len = p.sk;
+    if (sig_len) *sig_len = p.sig;
+    return OK;
+}
+
+void* mldsa_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void mldsa_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
+uint64_t mldsa_kernel_launches(void) { return g_launches.load(); }
+int mldsa_last_sign_rounds(void) { return t_last_rounds; }
+
+// ---------------------------------------------------------------- device-pointer entry points
+int mldsa_keygen_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_xi, uint8_t* d_pk, uint8_t* d_sk)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (n && (!d_xi || !d_pk || !d_sk))) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_current(lk, rc);
+    if (!cx) return rc;
+    return keygen_core(*cx, stream ? (cudaStream_t)stream : cx->stream, ps, n, d_xi, d_pk, d_sk, 0);
+}
+
+int mldsa_sign_batch_dev(int ps, void* stream, int framing, size_t n, const uint8_t* d_sk, size_t sk_stride,
+                         const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
+                         const uint32_t* d_ctx_off, const uint8_t* d_rnd, uint8_t* d_sig, uint32_t* d_iters)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return framing == 2 ? E_UNSUPPORTED : E_PARAM;
+    if (sk_stride != 0 && sk_stride != p.sk) return E_PARAM;
+    if (n && (!d_sk || !d_msg_off || !d_rnd || !d_sig)) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_current(lk, rc);
+    if (!cx) return rc;
+    return sign_core(*cx, stream ? (cudaStream_t)stream : cx->stream, ps, framing, n, d_sk, sk_stride, d_msgs,
+                     d_msg_off, d_ctx, d_ctx_off, d_rnd, d_sig, d_iters, 0);
+}
+
+int mldsa_verify_batch_dev(int ps, void* stream, int framing, size_t n, const uint8_t* d_pk, size_t pk_stride,
+                           const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
+                           const uint32_t* d_ctx_off, const uint8_t* d_sig, uint8_t* d_ok)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return framing == 2 ? E_UNSUPPORTED : E_PARAM;
+    if (pk_stride != 0 && pk_stride != p.pk) return E_PARAM;
+    if (n && (!d_pk || !d_msg_off || !d_sig || !d_ok)) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_current(lk, rc);
+    if (!cx) return rc;
+    return verify_core(*cx, stream ? (cudaStream_t)stream : cx->stream, ps, framing, n, d_pk, pk_stride, d_msgs,
+                       d_msg_off, d_ctx, d_ctx_off, d_sig, d_ok, 0);
+}
+
+int mldsa_ntt_batch_dev(void* stream, size_t n, int32_t* d_polys)
+{
+    if (n && !d_polys) return E_PARAM;
+    CK(launch_ntt((cudaStream_t)stream, d_polys, n, false));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return OK;
+}
+int mldsa_intt_batch_dev(void* stream, size_t n, int32_t* d_polys)
+{
+    if (n && !d_polys) return E_PARAM;
+    CK(launch_ntt((cudaStream_t)stream, d_polys, n, true));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return OK;
+}
+int mldsa_expand_a_batch_dev(void* stream, size_t n, const uint8_t* d_seed34, int32_t* d_out)
+{
+    if (n && (!d_seed34 || !d_out)) return E_PARAM;
+    CK(launch_expand_a_seed34((cudaStream_t)stream, d_seed34, n, d_out));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return OK;
+}
+
+// ---------------------------------------------------------------- host-pointer entry points
+// Inputs are staged into the device arena chunk by chunk, results copied back.  (Pinned caller
+// buffers -- mldsa_host_alloc -- make these copies true async DMA.)
+
+int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (n && (!xi || !pk || !sk))) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    const size_t io_lane = 32 + p.pk + p.sk;
+    const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, keygen_ws_bytes(p, 1024) / 1024 + io_lane + 1);
+    const size_t io = pad256(chunk * 32) + pad256(chunk * p.pk) + pad256(chunk * p.sk);
+    rc = cx->reserve(io + keygen_ws_bytes(p, chunk));
+    if (rc) return rc;
+    cudaStream_t st = cx->stream;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        Carver c(cx->arena);
+        uint8_t* d_xi = c.take<uint8_t>(chunk * 32);
+        uint8_t* d_pk = c.take<uint8_t>(chunk * p.pk);
+        uint8_t* d_sk = c.take<uint8_t>(chunk * p.sk);
+        CK(cudaMemcpyAsync(d_xi, xi + 32 * lo, m * 32, cudaMemcpyHostToDevice, st));
+        rc = keygen_core(*cx, st, ps, m, d_xi, d_pk, d_sk, io);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(pk + p.pk * lo, d_pk, m * p.pk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sk + p.sk * lo, d_sk, m * p.sk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(d_xi, 0, m * 32, st));
+        CK(cudaMemsetAsync(d_sk, 0, m * p.sk, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return OK;
+}
+
+// stage the ragged message / ctx slices of lanes [lo, lo+m) and build a MsgDesc whose offsets are
+// the caller's absolute ones (the base pointers are rebased instead)
+struct StagedMsgs {
+    const uint8_t* d_msgs;
+    const uint64_t* d_msg_off;
+    const uint8_t* d_ctx;
+    const uint32_t* d_ctx_off;
+};
+
+int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
+                     const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                     uint8_t* sig, uint32_t* iters)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return framing == 2 ? E_UNSUPPORTED : E_PARAM;
+    if (sk_stride != 0 && sk_stride != p.sk) return E_PARAM;
+    if (n && (!sk || !rnd || !sig || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
+    if (n == 0) return OK;
+    if (ctx_off)
+        for (size_t i = 0; i < n; i++)
+            if (ctx_off[i + 1] - ctx_off[i] > 255) return E_CTX;  // src/lib.rs:274
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    const bool shared = sk_stride == 0;
+    const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
+    const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
+    const size_t fixed = sign_ws_bytes(p, 0, shared) + (shared ? pad256(p.sk) : 0);
+    const size_t ws_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? sign_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
+    const size_t io_lane = (shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + 2 * avg_msg + 2 * avg_ctx;
+    size_t chunk = pick_chunk(cx->arena_bytes, n, fixed, ws_lane + io_lane);
+    cudaStream_t st = cx->stream;
+    for (size_t lo = 0; lo < n;) {
+        size_t m = n - lo < chunk ? n - lo : chunk;
+        const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
+        const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
+        const size_t io = pad256(shared ? p.sk : m * p.sk) + pad256(m * 32) + pad256(m * p.sig) + pad256(m * 4) +
+                          pad256((m + 1) * 8) + pad256((m + 1) * 4) + pad256(mbytes + 8) + pad256(cbytes + 8);
+        rc = cx->reserve(io + sign_ws_bytes(p, m, shared));
+        if (rc) return rc;
+        Carver c(cx->arena);
+        uint8_t* d_sk = c.take<uint8_t>(shared ? p.sk : m * p.sk);
+        uint8_t* d_rnd = c.take<uint8_t>(m * 32);
+        uint8_t* d_sig = c.take<uint8_t>(m * p.sig);
+        uint32_t* d_it = c.take<uint32_t>(m);
+        uint64_t* d_mo = c.take<uint64_t>(m + 1);
+        uint32_t* d_co = c.take<uint32_t>(m + 1);
+        uint8_t* d_m = c.take<uint8_t>(mbytes + 8);
+        uint8_t* d_c = c.take<uint8_t>(cbytes + 8);
+        CK(cudaMemcpyAsync(d_sk, sk + sk_stride * lo, shared ? p.sk : m * p.sk, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_rnd, rnd + 32 * lo, m * 32, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (mbytes) CK(cudaMemcpyAsync(d_m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, st));
+        if (ctx_off) {
+            CK(cudaMemcpyAsync(d_co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, st));
+            if (cbytes) CK(cudaMemcpyAsync(d_c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, st));
+        }
+        rc = sign_core(*cx, st, ps, framing, m, d_sk, sk_stride, d_m - msg_off[lo], d_mo, ctx_off ? d_c - ctx_off[lo] : nullptr,
+                       ctx_off ? d_co : nullptr, d_rnd, d_sig, d_it, c.off);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(sig + p.sig * lo, d_sig, m * p.sig, cudaMemcpyDeviceToHost, st));
+        if (iters) CK(cudaMemcpyAsync(iters + lo, d_it, m * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(d_sk, 0, shared ? p.sk : m * p.sk, st));
+        CK(cudaMemsetAsync(d_rnd, 0, m * 32, st));
+        CK(cudaStreamSynchronize(st));
+        lo += m;
+    }
+    return OK;
+}
+
+int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk, size_t pk_stride,
+                       const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                       const uint8_t* sig, uint8_t* ok)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return framing == 2 ? E_UNSUPPORTED : E_PARAM;
+    if (pk_stride != 0 && pk_stride != p.pk) return E_PARAM;
+    if (n && (!pk || !sig || !ok || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    const bool shared = pk_stride == 0;
+    const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
+    const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
+    const size_t fixed = verify_ws_bytes(p, 0, shared) + (shared ? pad256(p.pk) : 0);
+    const size_t ws_lane = (verify_ws_bytes(p, 1024, shared) - (shared ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
+    const size_t io_lane = (shared ? 0 : p.pk) + p.sig + 1 + 8 + 4 + 2 * avg_msg + 2 * avg_ctx;
+    size_t chunk = pick_chunk(cx->arena_bytes, n, fixed, ws_lane + io_lane);
+    cudaStream_t st = cx->stream;
+    for (size_t lo = 0; lo < n;) {
+        size_t m = n - lo < chunk ? n - lo : chunk;
+        const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
+        const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
+        const size_t io = pad256(shared ? p.pk : m * p.pk) + pad256(m * p.sig) + pad256(m) + pad256((m + 1) * 8) +
+                          pad256((m + 1) * 4) + pad256(mbytes + 8) + pad256(cbytes + 8);
+        rc = cx->reserve(io + verify_ws_bytes(p, m, shared));
+        if (rc) return rc;
+        Carver c(cx->arena);
+        uint8_t* d_pk = c.take<uint8_t>(shared ? p.pk : m * p.pk);
+        uint8_t* d_sig = c.take<uint8_t>(m * p.sig);
+        uint8_t* d_ok = c.take<uint8_t>(m);
+        uint64_t* d_mo = c.take<uint64_t>(m + 1);
+        uint32_t* d_co = c.take<uint32_t>(m + 1);
+        uint8_t* d_m = c.take<uint8_t>(mbytes + 8);
+        uint8_t* d_c = c.take<uint8_t>(cbytes + 8);
+        CK(cudaMemcpyAsync(d_pk, pk + pk_stride * lo, shared ? p.pk : m * p.pk, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_sig, sig + p.sig * lo, m * p.sig, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (mbytes) CK(cudaMemcpyAsync(d_m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, st));
+        if (ctx_off) {
+            CK(cudaMemcpyAsync(d_co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, st));
+            if (cbytes) CK(cudaMemcpyAsync(d_c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, st));
+        }
+        rc = verify_core(*cx, st, ps, framing, m, d_pk, pk_stride, d_m - msg_off[lo], d_mo,
+                         ctx_off ? d_c - ctx_off[lo] : nullptr, ctx_off ? d_co : nullptr, d_sig, d_ok, c.off);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ok + lo, d_ok, m, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        lo += m;
+    }
+    return OK;
+}
+
+static int micro_host(int dev, size_t n, const void* in, size_t in_bytes, void* out, size_t out_bytes, int which)
+{
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    rc = cx->reserve(pad256(in_bytes) + pad256(out_bytes));
+    if (rc) return rc;
+    cudaStream_t st = cx->stream;
+    Carver c(cx->arena);
+    uint8_t* d_in = c.take<uint8_t>(in_bytes);
+    uint8_t* d_out = which == 2 ? c.take<uint8_t>(out_bytes) : d_in;
+    CK(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+    if (which == 0) CK(launch_ntt(st, reinterpret_cast<int32_t*>(d_in), n, false));
+    if (which == 1) CK(launch_ntt(st, reinterpret_cast<int32_t*>(d_in), n, true));
+    if (which == 2) CK(launch_expand_a_seed34(st, d_in, n, reinterpret_cast<int32_t*>(d_out)));
+    CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
+int mldsa_ntt_batch(int dev, size_t n, int32_t* polys)
+{
+    if (n && !polys) return E_PARAM;
+    return n ? micro_host(dev, n, polys, n * 1024, polys, n * 1024, 0) : OK;
+}
+int mldsa_intt_batch(int dev, size_t n, int32_t* polys)
+{
+    if (n && !polys) return E_PARAM;
+    return n ? micro_host(dev, n, polys, n * 1024, polys, n * 1024, 1) : OK;
+}
+int mldsa_expand_a_batch(int dev, size_t n, const uint8_t* seed34, int32_t* out)
+{
+    if (n && (!seed34 || !out)) return E_PARAM;
+    return n ? micro_host(dev, n, seed34, n * 34, out, n * 1024, 2) : OK;
+}
+
+int mldsa_shake_batch(int dev, int bits, size_t n, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len)
+{
+    if ((bits != 128 && bits != 256) || (n && (!out || (in_len && !in))) || out_len == 0 || out_len > (1u << 20))
+        return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    rc = cx->reserve(pad256(n * in_len + 8) + pad256(n * out_len));
+    if (rc) return rc;
+    cudaStream_t st = cx->stream;
+    Carver c(cx->arena);
+    uint8_t* d_in = c.take<uint8_t>(n * in_len + 8);
+    uint8_t* d_out = c.take<uint8_t>(n * out_len);
+    if (in_len) CK(cudaMemcpyAsync(d_in, in, n * in_len, cudaMemcpyHostToDevice, st));
+    if (bits == 256) CK(launch_shake256_rows(st, d_in, in_len, in_len, n, d_out, out_len, (int)out_len));
+    else CK(launch_shake128_rows(st, d_in, in_len, in_len, n, d_out, out_len, (int)out_len));
+    CK(cudaMemcpyAsync(out, d_out, n * out_len, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// engine.h -- internal interface between the kernel translation units and the host runtime.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace mldsa {
+
+// error codes of the C ABI (include/mldsa_b200.h)
+enum : int { OK = 0, E_PARAM = -1, E_CTX = -2, E_CUDA = -3, E_NOMEM = -4, E_UNSUPPORTED = -5 };
+
+constexpr int SIB_BYTES = 136;   // one SHAKE256 block of H(c~) for SampleInBall
+constexpr int MU_BYTES = 64;
+constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_run saw |ctx| > 255
+
+// launch telemetry (mldsa_kernel_launches)
+void count_launch(int n = 1);
+
+// ---- k_common.cu ----
+// Commitment hash.  Verify mode (ctilde_out == nullptr): ok[i] = pre_ok[i] && H(mu||w1')[0..CT) == sig_i[0..CT)
+// (src/ml_dsa.rs:427-436).  Sign mode: ctilde_out[i] = H(mu||w1)[0..CT) and sib_out[i] = first SHAKE256 block
+// of H(c~) (src/ml_dsa.rs:231-237).  act: optional list of lane ids (n entries), else lanes 0..n-1.
+cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
+                          const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
+                          uint8_t* sib_out);
+
+// A[key][r*L+s][256] = RejNTTPoly(rho_key || s || r)          (src/hashing.rs:225-239)
+cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,
+                            int32_t* A);
+// out[i][256] = RejNTTPoly(seed34[i])                          (src/hashing.rs:111-146)
+cudaError_t launch_expand_a_seed34(cudaStream_t st, const uint8_t* seeds, size_t n, int32_t* out);
+cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse);
+// generic thread-per-message SHAKE256(in_i) -> out_i[outlen<=136] (tr = H(pk), test hook for the sponge)
+cudaError_t launch_shake256_rows(cudaStream_t st, const uint8_t* in, size_t in_stride, size_t in_len, size_t n,
+                                 uint8_t* out, size_t out_stride, int out_len);
+cudaError_t launch_shake128_rows(cudaStream_t st, const uint8_t* in, size_t in_stride, size_t in_len, size_t n,
+                                 uint8_t* out, size_t out_stride, int out_len);
+
+// message framing for mu (src/ml_dsa.rs:185-196, :386-397)
+struct MsgDesc {
+    const uint8_t* msgs;      // concatenated messages
+    const uint64_t* msg_off;  // n + 1 offsets
+    const uint8_t* ctx;       // concatenated contexts or nullptr
+    const uint32_t* ctx_off;  // n + 1 offsets or nullptr (= empty ctx)
+    int framing;              // 0 external, 1 internal, 2 pre-hash (msgs already hold OID || PH(M))
+};
+
+// ---- k_keygen.cu ----
+struct KeygenWs {
+    uint8_t* seeds;   // [n][128]  rho || rho' || K
+    int8_t* s;        // [n][L+K][256]
+    int32_t* A;       // [n][K*L][256]
+    static size_t bytes_per_lane(int K, int L) { return 128 + (size_t)(K + L) * 256 + (size_t)K * L * 1024; }
+};
+cudaError_t keygen_run(int ps, cudaStream_t st, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk,
+                       const KeygenWs& ws);
+
+// ---- k_verify.cu ----
+struct VerifyWs {
+    int32_t* A;        // [nkeys][K*L][256]
+    int32_t* t1h;      // [nkeys][K][256]   NTT(t1 * 2^d)   (only materialised for a shared key)
+    uint8_t* tr;       // [nkeys][64]
+    uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1'
+    uint8_t* sib;      // [n][136]
+    uint8_t* pre_ok;   // [n]
+    static size_t bytes_per_lane(int K, int L, int w1len, bool shared)
+    {
+        return (shared ? 0 : (size_t)K * L * 1024 + 64) + 64 + w1len + SIB_BYTES + 8;
+    }
+};
+cudaError_t verify_run(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,
+                       const uint8_t* sig, uint8_t* ok, const VerifyWs& ws);
+
+// ---- k_sign.cu ----
+struct SignWs {
+    int32_t* A;        // [nkeys][K*L][256]
+    int32_t* s1h;      // [nkeys][L][256]
+    int32_t* s2h;      // [nkeys][K][256]
+    int32_t* t0h;      // [nkeys][K][256]
+    int32_t* w;        // [n][K][256]
+    uint8_t* yraw;     // [n][L][32*ZBITS]
+    uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1
+    uint8_t* rhopp;    // [n][64]
+    uint8_t* ctilde;   // [n][64]
+    uint8_t* sib;      // [n][136]
+    uint32_t* kappa;   // [n]
+    uint8_t* done;     // [n]
+    uint32_t* act[2];  // [n] active lane lists (ping-pong)
+    uint32_t* nact;    // [2] device counters
+    uint32_t* h_nact;  // pinned host mirror [2]: [0] active count / ctx flag, [1] CTX_ERR_MARK
+    static size_t bytes_per_lane(int K, int L, int zbits, int w1len, bool shared)
+    {
+        return (shared ? 0 : (size_t)(K * L + L + 2 * K) * 1024) + (size_t)K * 1024 + (size_t)L * 32 * zbits + 64 +
+               w1len + 64 + 64 + SIB_BYTES + 4 + 1 + 8 + 16;
+    }
+};
+// returns cudaSuccess; *rounds_out = number of rejection-loop rounds executed
+cudaError_t sign_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out);
+
+}  // namespace mldsa

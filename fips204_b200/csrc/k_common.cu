@@ -1,0 +1,285 @@
+// k_common.cu -- kernels shared by keygen / sign / verify and the microbench entry points:
+//   * expand_a       : thread-per-stream SHAKE128 + RejNTTPoly   (src/hashing.rs:111-146, :225-239)
+//   * ntt / inv_ntt  : warp-per-polynomial transforms on int32   (src/ntt.rs:14-161)
+//   * shake rows     : thread-per-message SHAKE128/256 (tr = H(pk); also the Keccak test hook)
+#include "engine.h"
+#include "keccak.cuh"
+#include "ntt.cuh"
+#include "pack.cuh"
+
+namespace mldsa {
+
+// ------------------------------------------------------------------------------------------------
+// expand_a.  One thread owns one SHAKE128 stream (one polynomial of A-hat).  Per squeeze block the
+// thread parses its 56 three-byte candidates straight out of the state registers
+// (CoeffFromThreeBytes, src/conversion.rs:40-61), appends the accepted ones to its row of a
+// shared-memory tile, and the warp then flushes the 32 rows with coalesced stores, so a stream's
+// coefficient j is its j-th accepted candidate.  The loop runs until every stream of the warp has
+// 256 coefficients: 5 blocks in practice, a 6th with p ~ 1e-39 -- handled exactly, not assumed away.
+// ------------------------------------------------------------------------------------------------
+constexpr int EA_THREADS = 128;
+constexpr int EA_ROW = 57;  // 56 candidates per block, odd stride -> conflict-free column writes
+
+template <bool SEED34>
+__global__ void __launch_bounds__(EA_THREADS, 4)
+expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstreams, int KL, int L,
+                int32_t* __restrict__ out)
+{
+    __shared__ int32_t tile_all[EA_THREADS / 32][32 * EA_ROW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t* tile = tile_all[warp];
+    const size_t q = (size_t)blockIdx.x * EA_THREADS + threadIdx.x;
+    const size_t qbase = q - lane;
+    const bool valid = q < nstreams;
+
+    uint64_t a[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = 0;
+    if (valid) {
+        const size_t key = SEED34 ? q : q / KL;
+        const int idx = SEED34 ? 0 : (int)(q % KL);
+        uint32_t w[9];
+        load_span<SEED34 ? 34 : 32>(rho + key * rho_stride, reinterpret_cast<uint32_t(&)[SEED34 ? 9 : 8]>(w));
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+        // rho || IntegerToBytes(s,1) || IntegerToBytes(r,1)   (hashing.rs:236), then SHAKE pad 0x1F
+        const uint32_t sr = SEED34 ? (w[8] & 0xFFFF) : (uint32_t)((idx % L) | ((idx / L) << 8));
+        a[4] = (uint64_t)(sr | (0x1Fu << 16));
+        a[20] = 0x8000000000000000ULL;  // byte 167 of the 168-byte rate
+    }
+
+    int j = valid ? 0 : 256;  // coefficients produced so far for this thread's stream
+    while (__any_sync(0xffffffffu, j < 256)) {
+        keccak_f1600(a);
+        int cnt = 0;
+        int32_t* row = tile + lane * EA_ROW;
+#pragma unroll
+        for (int g = 0; g < 14; g++) {  // 14 groups of 4 candidates = 3 words each
+            const uint64_t l0 = a[(3 * g) >> 1], l1 = a[((3 * g) >> 1) + 1];
+            uint32_t w0, w1, w2;
+            if ((g & 1) == 0) { w0 = (uint32_t)l0; w1 = (uint32_t)(l0 >> 32); w2 = (uint32_t)l1; }
+            else              { w0 = (uint32_t)(l0 >> 32); w1 = (uint32_t)l1; w2 = (uint32_t)(l1 >> 32); }
+            const uint32_t c0 = w0 & 0x7FFFFF;
+            const uint32_t c1 = __funnelshift_r(w0, w1, 24) & 0x7FFFFF;
+            const uint32_t c2 = __funnelshift_r(w1, w2, 16) & 0x7FFFFF;
+            const uint32_t c3 = (w2 >> 8) & 0x7FFFFF;
+            if (c0 < (uint32_t)Q) row[cnt++] = (int32_t)c0;
+            if (c1 < (uint32_t)Q) row[cnt++] = (int32_t)c1;
+            if (c2 < (uint32_t)Q) row[cnt++] = (int32_t)c2;
+            if (c3 < (uint32_t)Q) row[cnt++] = (int32_t)c3;
+        }
+        if (j >= 256) cnt = 0;
+        __syncwarp();
+        // flush: row s of the tile -> out[stream s][j_s ...], contiguous per stream
+        for (int s = 0; s < 32; s++) {
+            const int n_s = __shfl_sync(0xffffffffu, cnt, s);
+            const int j_s = __shfl_sync(0xffffffffu, j, s);
+            int32_t* dst = out + (qbase + s) * 256 + j_s;
+            const int lim = min(n_s, 256 - j_s);
+            for (int c = lane; c < lim; c += 32) dst[c] = tile[s * EA_ROW + c];
+        }
+        j += cnt;
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,
+                            int32_t* A)
+{
+    const size_t ns = nkeys * (size_t)(K * L);
+    if (ns == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((ns + EA_THREADS - 1) / EA_THREADS);
+    expand_a_kernel<false><<<grid, EA_THREADS, 0, st>>>(rho, rho_stride, ns, K * L, L, A);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_expand_a_seed34(cudaStream_t st, const uint8_t* seeds, size_t n, int32_t* out)
+{
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + EA_THREADS - 1) / EA_THREADS);
+    expand_a_kernel<true><<<grid, EA_THREADS, 0, st>>>(seeds, 34, n, 1, 1, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standalone NTT / inverse NTT over n polynomials in place (BASELINE config 2).  HBM-bound:
+// 1 KiB in + 1 KiB out per polynomial.  Forward loads rows (layout A, 128 B per warp request) and
+// stores 2 x 128-bit per lane (layout B); the inverse mirrors it.
+// ------------------------------------------------------------------------------------------------
+constexpr int NTT_WARPS = 8;
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict__ polys, size_t n)
+{
+    __shared__ __align__(16) int32_t tiles[NTT_WARPS][NTT_TILE_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t* tile = tiles[warp];
+    const size_t stride = (size_t)gridDim.x * NTT_WARPS;
+    for (size_t p = (size_t)blockIdx.x * NTT_WARPS + warp; p < n; p += stride) {
+        int32_t* g = polys + p * 256;
+        int32_t v[8];
+        if (!INVERSE) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = g[32 * i + lane];
+            ntt_fwd_A2B(v, tile, lane);
+            int4* o = reinterpret_cast<int4*>(g + 8 * lane);
+            o[0] = make_int4(v[0], v[1], v[2], v[3]);
+            o[1] = make_int4(v[4], v[5], v[6], v[7]);
+        } else {
+            const int4* in = reinterpret_cast<const int4*>(g + 8 * lane);
+            const int4 x = in[0], y = in[1];
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+            ntt_inv_B2A<F_MONT>(v, tile, lane);
+#pragma unroll
+            for (int i = 0; i < 8; i++) g[32 * i + lane] = v[i];
+        }
+    }
+}
+
+cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse)
+{
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t want = (n + NTT_WARPS - 1) / NTT_WARPS;
+    const unsigned grid = (unsigned)(want < (size_t)sms * 8 ? want : (size_t)sms * 8);
+    if (inverse) ntt_kernel<true><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);
+    else ntt_kernel<false><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thread-per-row SHAKE over fixed-length rows via the flexible sponge.
+// ------------------------------------------------------------------------------------------------
+template <int RATE>
+__global__ void __launch_bounds__(128) shake_rows_kernel(const uint8_t* __restrict__ in, size_t in_stride,
+                                                         size_t in_len, size_t n, uint8_t* __restrict__ out,
+                                                         size_t out_stride, int out_len)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sponge<RATE> sp;
+    sp.init();
+    sp.absorb(in + i * in_stride, in_len);
+    sp.finish();
+    uint8_t* o = out + i * out_stride;
+    int pos = 0;
+    for (int k = 0; k < out_len; k++) {
+        if (pos == RATE) {
+            sp.next_block();
+            pos = 0;
+        }
+        o[k] = (uint8_t)(sp.s[pos >> 3] >> (8 * (pos & 7)));
+        pos++;
+    }
+}
+
+cudaError_t launch_shake256_rows(cudaStream_t st, const uint8_t* in, size_t in_stride, size_t in_len, size_t n,
+                                 uint8_t* out, size_t out_stride, int out_len)
+{
+    if (n == 0) return cudaSuccess;
+    shake_rows_kernel<SHAKE256_RATE><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, in_stride, in_len, n, out,
+                                                                                out_stride, out_len);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_shake128_rows(cudaStream_t st, const uint8_t* in, size_t in_stride, size_t in_len, size_t n,
+                                 uint8_t* out, size_t out_stride, int out_len)
+{
+    if (n == 0) return cudaSuccess;
+    shake_rows_kernel<SHAKE128_RATE><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, in_stride, in_len, n, out,
+                                                                                out_stride, out_len);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Commitment hash c~ = H(mu || w1Encode(w1), lambda/4): one thread per lane, state in registers,
+// one permutation call site.  The input is 64 + W1_LEN bytes, always a whole number of 64-bit
+// words, read straight from the lane's mu||w1 row.
+// ------------------------------------------------------------------------------------------------
+template <class P, bool SIGN>
+__global__ void __launch_bounds__(128, 4)
+ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restrict__ mw1,
+              const uint8_t* __restrict__ sig, const uint8_t* __restrict__ pre_ok, uint8_t* __restrict__ ok,
+              uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ sib_out)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const size_t ln = act ? act[idx] : idx;
+    constexpr int NW = (MU_BYTES + P::W1_LEN) / 8;  // 104 or 136 words
+    constexpr int NBLK = NW / 17 + 1;               // 7 or 9 absorb blocks (the last holds the padding)
+    constexpr int CW = P::CTILDE / 8;               // c~ words
+    const uint64_t* in = reinterpret_cast<const uint64_t*>(mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN));
+    uint64_t a[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = 0;
+    uint64_t ct[CW];
+#pragma unroll 1
+    for (int b = 0; b < NBLK + (SIGN ? 1 : 0); b++) {
+        if (b < NBLK) {
+#pragma unroll
+            for (int k = 0; k < 17; k++)
+                if (b * 17 + k < NW) a[k] ^= in[b * 17 + k];
+            if (b == NBLK - 1) {
+                a[NW % 17] ^= 0x1F;
+                a[16] ^= 0x8000000000000000ULL;
+            }
+        } else {  // sign: start the second sponge H(c~) for SampleInBall
+#pragma unroll
+            for (int k = 0; k < CW; k++) ct[k] = a[k];
+#pragma unroll
+            for (int k = 0; k < 25; k++) a[k] = k < CW ? ct[k] : 0;
+            a[CW] = 0x1F;
+            a[16] ^= 0x8000000000000000ULL;
+        }
+        keccak_f1600(a);
+    }
+    if (SIGN) {
+        uint64_t* co = reinterpret_cast<uint64_t*>(ctilde_out + ln * 64);
+#pragma unroll
+        for (int k = 0; k < CW; k++) co[k] = ct[k];
+        uint64_t* so = reinterpret_cast<uint64_t*>(sib_out + ln * (size_t)SIB_BYTES);
+#pragma unroll
+        for (int k = 0; k < 17; k++) so[k] = a[k];
+    } else {
+        uint32_t w[P::CTILDE / 4];
+        load_span<P::CTILDE>(sig + ln * (size_t)P::SIG_LEN, w);
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < CW; k++) eq &= a[k] == ((uint64_t)w[2 * k] | ((uint64_t)w[2 * k + 1] << 32));
+        ok[ln] = (eq && pre_ok[ln]) ? 1 : 0;
+    }
+}
+
+template <class P>
+static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
+                                   const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
+                                   uint8_t* sib_out)
+{
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (ctilde_out)
+        ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    else
+        ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
+                          const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
+                          uint8_t* sib_out)
+{
+    if (n == 0) return cudaSuccess;
+    switch (ps) {
+    case 44: return launch_ctilde_t<Params<44>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 65: return launch_ctilde_t<Params<65>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 87: return launch_ctilde_t<Params<87>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace mldsa

@@ -1,0 +1,460 @@
+// k_sign.cu -- batched ML-DSA.Sign_internal with the rejection loop run as lock-step rounds over a
+// compacted list of still-active lanes.
+// Replaces src/ml_dsa.rs:153-337 (sign_internal) with expand_private (ml_dsa.rs:445-469) and
+// sk_decode / sig_encode (src/encodings.rs:168-224, :238-276) folded in.
+//
+// A lane (one (sk, message, rnd)) is owned by ONE WARP in the arithmetic kernels, so a rejection is a
+// warp-uniform branch: nothing diverges inside a warp.  After every round the rejected lanes are
+// re-queued into a dense list (compact_kernel) and only those are launched again; lanes finish in
+// any order, and a lane's bytes depend on its own inputs only, so scheduling never affects results.
+//
+//   once per chunk
+//     sign_prep     thread/lane  mu = H(tr || M'), rho'' = H(K || rnd || mu)        ml_dsa.rs:185-201
+//     sign_key      warp/key     s1-hat, s2-hat, t0-hat from the packed sk           ml_dsa.rs:447-453
+//     expand_a      thread/poly  A-hat                                               ml_dsa.rs:181
+//   per round, over the active list
+//     mask          thread/poly  y bytes = H(rho'' || LE16(kappa + r), 32c)          hashing.rs:281-313
+//     sign_w        warp/lane    w = INTT(A-hat o NTT(y)); w1 = HighBits(w); w1Encode ml_dsa.rs:215-232
+//     ctilde        thread/lane  c~ = H(mu || w1), first block of H(c~)              ml_dsa.rs:233-237
+//     sign_z        warp/lane    c, z, r0 / ct0 / hint checks, sigEncode on accept   ml_dsa.rs:237-336
+//     compact       thread/lane  rebuild the active list
+#include "engine.h"
+#include "keccak.cuh"
+#include "ntt.cuh"
+#include "pack.cuh"
+#include "sampling.cuh"
+
+namespace mldsa {
+
+template <class P>
+__global__ void __launch_bounds__(128)
+sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
+                 const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mw1, uint8_t* __restrict__ rhopp,
+                 uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
+                 int* __restrict__ ctx_err)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* key = sk + i * sk_stride;
+    Sponge<SHAKE256_RATE> sp;
+    if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
+    uint64_t mu[8];
+    sp.out_words(mu, 8);
+    uint64_t* mo = reinterpret_cast<uint64_t*>(mw1 + i * (size_t)(MU_BYTES + P::W1_LEN));
+#pragma unroll
+    for (int k = 0; k < 8; k++) mo[k] = mu[k];
+    sp.init();                                            // rho'' = H(K || rnd || mu, 64)  ml_dsa.rs:199-201
+    sp.absorb(key + 32, 32);
+    sp.absorb(rnd + 32 * i, 32);
+    sp.absorb(reinterpret_cast<const uint8_t*>(mu), 64);
+    sp.finish();
+    sp.out_words(reinterpret_cast<uint64_t*>(rhopp + 64 * i), 8);
+    kappa[i] = 0;
+    done[i] = 0;
+    act0[i] = (uint32_t)i;
+}
+
+constexpr int SG_WARPS = 4;
+
+// s1-hat, s2-hat, t0-hat (plain NTT domain) for every key.  warp per key.
+template <class P>
+__global__ void __launch_bounds__(SG_WARPS * 32)
+sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, int32_t* __restrict__ s1h,
+                int32_t* __restrict__ s2h, int32_t* __restrict__ t0h)
+{
+    using LO = Layout<P>;
+    constexpr int K = P::K, L = P::L;
+    __shared__ __align__(16) int32_t tiles[SG_WARPS][NTT_TILE_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t* tile = tiles[warp];
+    const size_t stride = (size_t)gridDim.x * SG_WARPS;
+    for (size_t kn = (size_t)blockIdx.x * SG_WARPS + warp; kn < nkeys; kn += stride) {
+        const uint8_t* key = sk + kn * sk_stride;
+#pragma unroll 1
+        for (int p = 0; p < L + 2 * K; p++) {
+            int32_t v[8];
+            int32_t* dst;
+            if (p < L + K) {  // BitUnpack(eta, eta): s = eta - field            (encodings.rs:185-198)
+                uint32_t w[(P::ETABITS + 3) / 4];
+                load_span<P::ETABITS>(key + LO::SK_S1 + p * 32 * P::ETABITS + P::ETABITS * lane, w);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = P::ETA - (int32_t)get_field<P::ETABITS>(w, i);
+                dst = p < L ? s1h + (kn * L + p) * 256 : s2h + (kn * K + (p - L)) * 256;
+            } else {          // BitUnpack(2^12 - 1, 2^12): t0 = 2^12 - field     (encodings.rs:203-210)
+                uint32_t w[4];
+                load_span<13>(key + LO::SK_T0 + (p - L - K) * 416 + 13 * lane, w);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = (1 << (D - 1)) - (int32_t)get_field<13>(w, i);
+                dst = t0h + (kn * K + (p - L - K)) * 256;
+            }
+            ntt_fwd_B2B(v, tile, lane);
+            int4* o = reinterpret_cast<int4*>(dst + 8 * lane);
+            o[0] = make_int4(v[0], v[1], v[2], v[3]);
+            o[1] = make_int4(v[4], v[5], v[6], v[7]);
+        }
+    }
+}
+
+// ExpandMask: one thread per (active lane, r) SHAKE256 stream; the squeezed bytes ARE the packed y.
+template <class P>
+__global__ void __launch_bounds__(128, 4)
+mask_kernel(size_t nstreams, const uint32_t* __restrict__ act, const uint8_t* __restrict__ rhopp,
+            const uint32_t* __restrict__ kappa, uint8_t* __restrict__ yraw)
+{
+    constexpr int L = P::L;
+    constexpr int YW = 32 * P::ZBITS / 8;  // 72 or 80 output words
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nstreams) return;
+    const size_t ln = act[q / L];
+    const uint32_t r = (uint32_t)(q % L);
+    const uint64_t* rp = reinterpret_cast<const uint64_t*>(rhopp + 64 * ln);
+    uint64_t a[25];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = rp[i];
+    const uint32_t nonce = (kappa[ln] + r) & 0xFFFF;  // u16 counter (ml_dsa.rs:204, hashing.rs:296)
+    a[8] = (uint64_t)(nonce | (0x1Fu << 16));
+#pragma unroll
+    for (int i = 9; i < 25; i++) a[i] = 0;
+    a[16] = 0x8000000000000000ULL;
+    uint64_t* out = reinterpret_cast<uint64_t*>(yraw + (ln * L + r) * (size_t)(YW * 8));
+#pragma unroll 1
+    for (int b = 0; b < (YW + 16) / 17; b++) {
+        keccak_f1600(a);
+#pragma unroll
+        for (int k = 0; k < 17; k++)
+            if (b * 17 + k < YW) out[b * 17 + k] = a[k];
+    }
+}
+
+// y (layout B regs) from the packed mask bytes: BitUnpack(gamma1 - 1, gamma1)
+template <class P>
+__device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (&y)[8])
+{
+    uint32_t w[(P::ZBITS + 3) / 4];
+    load_span<P::ZBITS>(ypoly + P::ZBITS * lane, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) y[i] = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(w, i);
+}
+
+template <class P, bool SHARED>
+__global__ void __launch_bounds__(SG_WARPS * 32)
+sign_w_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __restrict__ Aall,
+              const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, uint8_t* __restrict__ mw1)
+{
+    constexpr int K = P::K, L = P::L;
+    __shared__ __align__(16) int32_t tiles[SG_WARPS][NTT_TILE_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t* tile = tiles[warp];
+    const size_t stride = (size_t)gridDim.x * SG_WARPS;
+    for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
+        const size_t ln = act[ai];
+        const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
+        const uint8_t* yp = yraw + ln * (size_t)(L * 32 * P::ZBITS);
+        int32_t* wo = wall + ln * (size_t)K * 256;
+        uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
+        int32_t yh[L][8];
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+            load_y<P>(yp + l * 32 * P::ZBITS, lane, yh[l]);
+            ntt_fwd_B2B(yh[l], tile, lane);
+        }
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            int64_t acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = 0;
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
+                const int4 x = __ldg(ap), y = __ldg(ap + 1);
+                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * yh[l][i];
+            }
+            int32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
+            ntt_inv_B2B<F_MONT2>(t, tile, lane);  // w[k], canonical
+            int4* o = reinterpret_cast<int4*>(wo + 256 * k + 8 * lane);
+            o[0] = make_int4(t[0], t[1], t[2], t[3]);
+            o[1] = make_int4(t[4], t[5], t[6], t[7]);
+            uint32_t f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                int32_t r0;
+                f[i] = (uint32_t)decompose<P::GAMMA2>(t[i], r0);  // HighBits (ml_dsa.rs:225-226)
+            }
+            uint32_t w[(P::W1BITS + 3) / 4];
+            pack_fields<P::W1BITS>(f, w);
+            store_span<P::W1BITS>(w1o + k * 32 * P::W1BITS + P::W1BITS * lane, w);
+        }
+    }
+}
+
+template <class P>
+struct SignSmem {
+    int32_t tile[NTT_TILE_WORDS];
+    uint32_t stage[32 * P::ZBITS / 4 + 1];  // packed z polynomial (576/640 B) or the hint bytes
+    uint32_t sibs[SIB_BYTES / 4];
+};
+
+template <class P, bool SHARED>
+__global__ void __launch_bounds__(SG_WARPS * 32)
+sign_z_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __restrict__ s1h_all,
+              const int32_t* __restrict__ s2h_all, const int32_t* __restrict__ t0h_all,
+              const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, const uint8_t* __restrict__ ctilde,
+              const uint8_t* __restrict__ sib, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
+              uint8_t* __restrict__ sig, uint32_t* __restrict__ iters)
+{
+    using LO = Layout<P>;
+    constexpr int K = P::K, L = P::L;
+    __shared__ __align__(16) SignSmem<P> sm_all[SG_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SignSmem<P>& sm = sm_all[warp];
+    int32_t* tile = sm.tile;
+    const size_t stride = (size_t)gridDim.x * SG_WARPS;
+    for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
+        const size_t ln = act[ai];
+        const size_t kn = SHARED ? 0 : ln;
+        const int32_t* s1h = s1h_all + kn * (size_t)L * 256;
+        const int32_t* s2h = s2h_all + kn * (size_t)K * 256;
+        const int32_t* t0h = t0h_all + kn * (size_t)K * 256;
+        const uint8_t* yp = yraw + ln * (size_t)(L * 32 * P::ZBITS);
+        int32_t* wl = wall + ln * (size_t)K * 256;
+        const uint8_t* ct = ctilde + ln * 64;
+        uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
+
+        // c = SampleInBall(c~), c-hat = NTT(c)                                ml_dsa.rs:237-240
+        int32_t ch[8];
+        sample_in_ball_warp<P>(sib + ln * (size_t)SIB_BYTES, ct, sm.sibs, tile, lane, ch);
+        ntt_fwd_A2B(ch, tile, lane);
+#pragma unroll
+        for (int i = 0; i < 8; i++) ch[i] = reduce32(ch[i]);
+
+        bool rej = false;
+        // z = y + c*s1, ||z||inf < gamma1 - beta                              ml_dsa.rs:243-250, 263-265, 277-283
+#pragma unroll 1
+        for (int l = 0; l < L && !rej; l++) {
+            const int4* sp = reinterpret_cast<const int4*>(s1h + 256 * l + 8 * lane);
+            const int4 x = __ldg(sp), y4 = __ldg(sp + 1);
+            const int32_t sv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
+            int32_t t[8], y[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = mont_mul(ch[i], reduce32(sv[i]));
+            ntt_inv_B2B<F_MONT2>(t, tile, lane);
+            load_y<P>(yp + l * 32 * P::ZBITS, lane, y);
+            uint32_t f[8];
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int32_t z = center(freeze(y[i] + t[i]));                   // z mod+- q (ml_dsa.rs:334-335)
+                bad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;
+                f[i] = (uint32_t)(P::GAMMA1 - z);                                // BitPack(z, gamma1 - 1, gamma1)
+            }
+            rej = __any_sync(0xffffffffu, bad);
+            if (!rej) {  // speculative sigEncode of z[l]; overwritten if a later check rejects
+                uint32_t w[(P::ZBITS + 3) / 4];
+                pack_fields<P::ZBITS>(f, w);
+                __syncwarp();
+                store_span<P::ZBITS>(reinterpret_cast<uint8_t*>(sm.stage) + P::ZBITS * lane, w);
+                __syncwarp();
+                warp_copy_out(sg + LO::SIG_Z + l * 32 * P::ZBITS, sm.stage, 32 * P::ZBITS, lane);
+            }
+        }
+        // r0 = LowBits(w - c*s2), ||r0||inf < gamma2 - beta                   ml_dsa.rs:253-260, 268-272, 277-283
+#pragma unroll 1
+        for (int k = 0; k < K && !rej; k++) {
+            const int4* sp = reinterpret_cast<const int4*>(s2h + 256 * k + 8 * lane);
+            const int4 x = __ldg(sp), y4 = __ldg(sp + 1);
+            const int32_t sv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
+            int32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = mont_mul(ch[i], reduce32(sv[i]));
+            ntt_inv_B2B<F_MONT2>(t, tile, lane);
+            int4* wp = reinterpret_cast<int4*>(wl + 256 * k + 8 * lane);
+            const int4 wx = wp[0], wy = wp[1];
+            const int32_t wv[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
+            int32_t v[8];
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                v[i] = caddq(wv[i] - t[i]);  // w - cs2, canonical
+                int32_t r0;
+                decompose<P::GAMMA2>(v[i], r0);
+                bad |= (r0 < 0 ? -r0 : r0) >= P::GAMMA2 - P::BETA;
+            }
+            rej = __any_sync(0xffffffffu, bad);
+            wp[0] = make_int4(v[0], v[1], v[2], v[3]);  // w is only ever needed as w - cs2 from here on
+            wp[1] = make_int4(v[4], v[5], v[6], v[7]);
+        }
+        // ct0, hint                                                           ml_dsa.rs:288-319
+        uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
+        int hcount = 0;
+        if (!rej) {
+            __syncwarp();
+            for (int i = lane; i < P::OMEGA + K; i += 32) hb[i] = 0;
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (int k = 0; k < K && !rej; k++) {
+            const int4* tp = reinterpret_cast<const int4*>(t0h + 256 * k + 8 * lane);
+            const int4 x = __ldg(tp), y4 = __ldg(tp + 1);
+            const int32_t tv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
+            int32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = mont_mul(ch[i], reduce32(tv[i]));
+            ntt_inv_B2B<F_MONT2>(t, tile, lane);  // ct0, canonical
+            const int4* wp = reinterpret_cast<const int4*>(wl + 256 * k + 8 * lane);
+            const int4 wx = wp[0], wy = wp[1];
+            const int32_t v[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
+            uint32_t hbits = 0;
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int32_t c0 = center(t[i]);
+                bad |= (c0 < 0 ? -c0 : c0) >= P::GAMMA2;                         // ml_dsa.rs:314
+                int32_t r0;
+                int32_t u = v[i] + t[i];                                         // w - cs2 + ct0 in [0, 2q)
+                u -= (u >= Q) ? Q : 0;
+                const int32_t h1 = decompose<P::GAMMA2>(u, r0);
+                const int32_t h0 = decompose<P::GAMMA2>(v[i], r0);               // HighBits(r + z) = HighBits(w - cs2)
+                hbits |= (uint32_t)(h1 != h0) << i;                              // high_low.rs:134-144
+            }
+            // HintBitPack (conversion.rs:277-328): ordered compaction by warp prefix sum
+            const int cnt = __popc(hbits);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            int pos = hcount + incl - cnt;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if ((hbits >> i) & 1) {
+                    if (pos < P::OMEGA) hb[pos] = (uint8_t)(8 * lane + i);
+                    pos++;
+                }
+            hcount += total;
+            rej = __any_sync(0xffffffffu, bad) || hcount > P::OMEGA;             // ml_dsa.rs:312-319
+            if (!rej && lane == 0) hb[P::OMEGA + k] = (uint8_t)hcount;
+        }
+        if (rej) {
+            if (lane == 0) kappa[ln] += L;                                       // ml_dsa.rs:281, 317
+            continue;
+        }
+        // accept: c~ and hints complete the signature                          encodings.rs:254, 273
+        __syncwarp();
+        warp_copy_out(sg + LO::SIG_H, sm.stage, P::OMEGA + K, lane);
+        warp_copy_bytes(sg, ct, P::CTILDE, lane);
+        if (lane == 0) {
+            done[ln] = 1;
+            if (iters) iters[ln] = kappa[ln] / L + 1;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+compact_kernel(size_t nact, const uint32_t* __restrict__ act_in, const uint8_t* __restrict__ done,
+               uint32_t* __restrict__ act_out, uint32_t* __restrict__ nout)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool keep = i < nact && !done[act_in[i]];
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(nout, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) act_out[base + __popc(m & ((1u << lane) - 1))] = act_in[i];
+}
+
+template <class P>
+static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                              const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out)
+{
+    constexpr int K = P::K, L = P::L;
+    const bool shared = sk_stride == 0;
+    const size_t nkeys = shared ? 1 : n;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto warp_grid = [&](size_t items) {
+        const size_t want = (items + SG_WARPS - 1) / SG_WARPS;
+        return (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
+    };
+    cudaError_t e;
+    int* ctx_err = reinterpret_cast<int*>(ws.nact + 2);
+    e = cudaMemsetAsync(ws.nact, 0, 16, st);
+    if (e != cudaSuccess) return e;
+    sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
+                                                                    ws.kappa, ws.done, ws.act[0], ctx_err);
+    sign_key_kernel<P><<<warp_grid(nkeys), SG_WARPS * 32, 0, st>>>(nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
+    count_launch(2);
+    e = launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(ws.h_nact, ctx_err, 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    if (ws.h_nact[0] != 0) {  // ctx too long: the caller maps this marker to -2 (lib.rs:274)
+        ws.h_nact[1] = CTX_ERR_MARK;
+        return cudaErrorInvalidValue;
+    }
+
+    size_t nact = n;
+    int cur = 0, rounds = 0;
+    while (nact > 0) {
+        const size_t nstreams = nact * L;
+        mask_kernel<P><<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(nstreams, ws.act[cur], ws.rhopp, ws.kappa,
+                                                                         ws.yraw);
+        if (shared)
+            sign_w_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw, ws.w,
+                                                                            ws.mw1);
+        else
+            sign_w_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw, ws.w,
+                                                                             ws.mw1);
+        count_launch(2);
+        e = launch_ctilde(P::PS, st, nact, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.sib);
+        if (e != cudaSuccess) return e;
+        if (shared)
+            sign_z_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
+                nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done, sig,
+                iters);
+        else
+            sign_z_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
+                nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done, sig,
+                iters);
+        e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);
+        if (e != cudaSuccess) return e;
+        compact_kernel<<<(unsigned)((nact + 255) / 256), 256, 0, st>>>(nact, ws.act[cur], ws.done, ws.act[cur ^ 1],
+                                                                      ws.nact + (cur ^ 1));
+        count_launch(2);
+        e = cudaMemcpyAsync(ws.h_nact, ws.nact + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return e;
+        nact = ws.h_nact[0];
+        cur ^= 1;
+        rounds++;
+    }
+    if (rounds_out) *rounds_out = rounds;
+    return cudaGetLastError();
+}
+
+cudaError_t sign_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out)
+{
+    if (rounds_out) *rounds_out = 0;
+    if (n == 0) return cudaSuccess;
+    switch (ps) {
+    case 44: return sign_run_t<Params<44>>(st, n, sk, sk_stride, md, rnd, sig, iters, ws, rounds_out);
+    case 65: return sign_run_t<Params<65>>(st, n, sk, sk_stride, md, rnd, sig, iters, ws, rounds_out);
+    case 87: return sign_run_t<Params<87>>(st, n, sk, sk_stride, md, rnd, sig, iters, ws, rounds_out);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace mldsa

@@ -1,0 +1,256 @@
+// k_verify.cu -- batched ML-DSA.Verify_internal over packed bytes.
+// Replaces src/ml_dsa.rs:351-437 (verify_internal) with expand_public (ml_dsa.rs:477-498) and
+// sig_decode / pk_decode (src/encodings.rs:292-328, :55-80) folded in.
+//
+// Pipeline over a chunk of lanes (one lane = one (pk, message, signature)):
+//   [key prep]    expand_a per key; for a shared key also tr = H(pk) and NTT(t1 * 2^d), once
+//   verify_pre    thread/lane  tr (per-lane keys), mu = H(tr || M'), first SHAKE256 block of H(c~)
+//   verify_arith  warp/lane    hint decode + checks, z unpack + norm, SampleInBall, NTTs,
+//                              w' = INTT(A-hat o z-hat - c-hat o t1-hat), UseHint, w1Encode
+//   ctilde_check  thread/lane  c~' = H(mu || w1'), compare with c~, AND with the pre-checks
+#include "engine.h"
+#include "keccak.cuh"
+#include "ntt.cuh"
+#include "pack.cuh"
+#include "sampling.cuh"
+
+namespace mldsa {
+
+template <class P>
+__global__ void __launch_bounds__(128)
+verify_pre_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ tr_shared,
+                  MsgDesc md, const uint8_t* __restrict__ sig, uint8_t* __restrict__ mw1, uint8_t* __restrict__ sib,
+                  uint8_t* __restrict__ pre_ok)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sponge<SHAKE256_RATE> sp;
+    uint64_t tr[8];
+    if (tr_shared) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) tr[k] = reinterpret_cast<const uint64_t*>(tr_shared)[k];
+    } else {
+        sp.init();
+        sp.absorb(pk + i * pk_stride, P::PK_LEN);  // ml_dsa.rs:486-488
+        sp.finish();
+        sp.out_words(tr, 8);
+    }
+    uint8_t* mu = mw1 + i * (size_t)(MU_BYTES + P::W1_LEN);
+    const bool ctx_ok = absorb_mu(sp, reinterpret_cast<const uint8_t*>(tr), md, i);  // ml_dsa.rs:386-397
+    sp.out_words(reinterpret_cast<uint64_t*>(mu), 8);
+    pre_ok[i] = ctx_ok ? 1 : 0;  // ctx > 255 -> false (lib.rs:368-370)
+    // first block of H(c~) for SampleInBall (hashing.rs:50-55)
+    sp.init();
+    const uint8_t* ct = sig + i * (size_t)P::SIG_LEN;
+    for (int k = 0; k < P::CTILDE; k++) sp.absorb_byte(ct[k]);
+    sp.finish();
+    sp.out_words(reinterpret_cast<uint64_t*>(sib + i * (size_t)SIB_BYTES), SIB_BYTES / 8);
+}
+
+// NTT(t1 * 2^d) for one polynomial of a public key, from the 10-bit packed bytes (layout B regs)
+__device__ __forceinline__ void load_t1_hat(const uint8_t* pkpoly, int32_t (&v)[8], int32_t* tile, int lane)
+{
+    uint32_t w[3];
+    load_span<10>(pkpoly + 10 * lane, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = (int32_t)(get_field<10>(w, i) << D);  // pk_decode + ml_dsa.rs:490-495
+    ntt_fwd_B2B(v, tile, lane);
+}
+
+template <class P>
+__global__ void __launch_bounds__(128)
+t1hat_kernel(const uint8_t* __restrict__ pk, int32_t* __restrict__ t1h)
+{
+    __shared__ __align__(16) int32_t tiles[4][NTT_TILE_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < P::K; k += 4) {
+        int32_t v[8];
+        load_t1_hat(pk + 32 + 320 * k, v, tiles[warp], lane);
+        int4* o = reinterpret_cast<int4*>(t1h + 256 * k + 8 * lane);
+        o[0] = make_int4(v[0], v[1], v[2], v[3]);
+        o[1] = make_int4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+constexpr int VF_WARPS = 4;
+
+template <class P>
+struct VerifySmem {
+    int32_t tile[NTT_TILE_WORDS];
+    uint32_t hbits[P::K * 8];                       // hint bitmap, 256 bits per polynomial
+    uint32_t stage[(P::OMEGA + P::K + 3) / 4 + 1];  // hint bytes
+    uint32_t sibs[SIB_BYTES / 4];
+};
+
+template <class P, bool SHARED>
+__global__ void __launch_bounds__(VF_WARPS * 32)
+verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ sig,
+                    const int32_t* __restrict__ Aall, const int32_t* __restrict__ t1h_shared,
+                    const uint8_t* __restrict__ sib, uint8_t* __restrict__ mw1, uint8_t* __restrict__ pre_ok)
+{
+    using LO = Layout<P>;
+    constexpr int K = P::K, L = P::L;
+    __shared__ __align__(16) VerifySmem<P> sm_all[VF_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    VerifySmem<P>& sm = sm_all[warp];
+    int32_t* tile = sm.tile;
+    const size_t stride = (size_t)gridDim.x * VF_WARPS;
+    for (size_t ln = (size_t)blockIdx.x * VF_WARPS + warp; ln < n; ln += stride) {
+        const uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
+        const uint8_t* pkl = pk + (SHARED ? 0 : ln * pk_stride);
+        const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
+        uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
+        __syncwarp();
+
+        // ---- HintBitUnpack with its three malformed-input exits (conversion.rs:357, :373, :398) ----
+        uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
+        warp_copy_bytes(hb, sg + LO::SIG_H, P::OMEGA + K, lane);
+        if (lane < K * 8) sm.hbits[lane] = 0;
+        if (K * 8 > 32 && lane + 32 < K * 8) sm.hbits[lane + 32] = 0;
+        __syncwarp();
+        bool bad = false;
+        if (lane < K) {
+            const int cur = hb[P::OMEGA + lane], prev = lane ? hb[P::OMEGA + lane - 1] : 0;
+            bad = cur < prev || cur > P::OMEGA;
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (!bad) {
+            const int total = hb[P::OMEGA + K - 1];
+            for (int p = lane; p < P::OMEGA; p += 32) {
+                if (p >= total) {
+                    bad |= hb[p] != 0;
+                } else {
+                    int poly = 0, first = 0;
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const int c = hb[P::OMEGA + k];
+                        if (p >= c) { poly = k + 1; first = c; }
+                    }
+                    if (p > first) bad |= hb[p - 1] >= hb[p];
+                    atomicOr(&sm.hbits[poly * 8 + (hb[p] >> 5)], 1u << (hb[p] & 31));
+                }
+            }
+            bad = __any_sync(0xffffffffu, bad);
+        }
+        if (bad) {  // verify returns false (ml_dsa.rs:368-376); warp-uniform exit
+            if (lane == 0) pre_ok[ln] = 0;
+            continue;
+        }
+
+        // ---- c = SampleInBall(c~) from the precomputed SHAKE block, c-hat = NTT(c) ----
+        int32_t ch[8];
+        sample_in_ball_warp<P>(sib + ln * (size_t)SIB_BYTES, sg, sm.sibs, tile, lane, ch);
+        ntt_fwd_A2B(ch, tile, lane);
+#pragma unroll
+        for (int i = 0; i < 8; i++) ch[i] = reduce32(ch[i]);
+
+        // ---- z = BitUnpack(gamma1 - 1, gamma1), ||z||inf check, z-hat ----
+        int32_t zh[L][8];
+        bool zbad = false;
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+            uint32_t w[(P::ZBITS + 3) / 4];
+            load_span<P::ZBITS>(sg + LO::SIG_Z + l * 32 * P::ZBITS + P::ZBITS * lane, w);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int32_t z = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(w, i);  // conversion.rs:250
+                zbad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;                   // ml_dsa.rs:434
+                zh[l][i] = z;
+            }
+            ntt_fwd_B2B(zh[l], tile, lane);
+        }
+        zbad = __any_sync(0xffffffffu, zbad);
+        if (zbad) {
+            if (lane == 0) pre_ok[ln] = 0;
+            continue;
+        }
+
+        // ---- per row: w' = INTT(sum_l A[k][l] o z-hat[l] - c-hat o t1-hat[k]); UseHint; w1Encode ----
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            int32_t t1v[8];
+            if (SHARED) {
+                const int4* tp = reinterpret_cast<const int4*>(t1h_shared + 256 * k + 8 * lane);
+                const int4 x = __ldg(tp), y = __ldg(tp + 1);
+                t1v[0] = x.x; t1v[1] = x.y; t1v[2] = x.z; t1v[3] = x.w;
+                t1v[4] = y.x; t1v[5] = y.y; t1v[6] = y.z; t1v[7] = y.w;
+            } else {
+                load_t1_hat(pkl + 32 + 320 * k, t1v, tile, lane);
+            }
+            int64_t acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = -(int64_t)ch[i] * reduce32(t1v[i]);
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
+                const int4 x = __ldg(ap), y = __ldg(ap + 1);
+                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * zh[l][i];
+            }
+            int32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
+            ntt_inv_B2B<F_MONT2>(t, tile, lane);
+            const uint32_t hbyte = (sm.hbits[k * 8 + (lane >> 2)] >> (8 * (lane & 3))) & 0xFF;
+            uint32_t f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = (uint32_t)use_hint<P::GAMMA2>((hbyte >> i) & 1, t[i]);
+            uint32_t w[(P::W1BITS + 3) / 4];
+            pack_fields<P::W1BITS>(f, w);                                           // encodings.rs:338-360
+            store_span<P::W1BITS>(w1o + k * 32 * P::W1BITS + P::W1BITS * lane, w);
+        }
+    }
+}
+
+template <class P>
+static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,
+                                const uint8_t* sig, uint8_t* ok, const VerifyWs& ws)
+{
+    constexpr int K = P::K, L = P::L;
+    const bool shared = pk_stride == 0;
+    cudaError_t e;
+    if (shared) {
+        e = launch_expand_a(st, K, L, pk, 0, 1, ws.A);
+        if (e != cudaSuccess) return e;
+        e = launch_shake256_rows(st, pk, 0, P::PK_LEN, 1, ws.tr, 64, 64);
+        if (e != cudaSuccess) return e;
+        t1hat_kernel<P><<<1, 128, 0, st>>>(pk, ws.t1h);
+        count_launch();
+    } else {
+        e = launch_expand_a(st, K, L, pk, pk_stride, n, ws.A);
+        if (e != cudaSuccess) return e;
+    }
+    verify_pre_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, pk, pk_stride, shared ? ws.tr : nullptr, md,
+                                                                     sig, ws.mw1, ws.sib, ws.pre_ok);
+    count_launch();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t want = (n + VF_WARPS - 1) / VF_WARPS;
+    const unsigned grid = (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
+    if (shared)
+        verify_arith_kernel<P, true><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h, ws.sib,
+                                                                     ws.mw1, ws.pre_ok);
+    else
+        verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr, ws.sib,
+                                                                      ws.mw1, ws.pre_ok);
+    count_launch();
+    e = launch_ctilde(P::PS, st, n, nullptr, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t verify_run(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,
+                       const uint8_t* sig, uint8_t* ok, const VerifyWs& ws)
+{
+    if (n == 0) return cudaSuccess;
+    switch (ps) {
+    case 44: return verify_run_t<Params<44>>(st, n, pk, pk_stride, md, sig, ok, ws);
+    case 65: return verify_run_t<Params<65>>(st, n, pk, pk_stride, md, sig, ok, ws);
+    case 87: return verify_run_t<Params<87>>(st, n, pk, pk_stride, md, sig, ok, ws);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace mldsa

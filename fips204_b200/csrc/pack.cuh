@@ -1,0 +1,97 @@
+// pack.cuh -- lane-local bit (un)packing in register layout B (lane t owns coefficients 8t..8t+7)
+// plus warp-cooperative byte movers for byte-aligned regions of keys and signatures.
+//
+// Replaces src/conversion.rs:143-182 (bit_pack), :227-262 (bit_unpack), :277-328 (hint_bit_pack),
+// :340-414 (hint_bit_unpack) and the layouts of src/encodings.rs.  All packing is LSB-first,
+// little-endian, c bits per coefficient, so 8 coefficients are exactly c bytes: a lane's byte
+// window is [c*t, c*t + c) of the 32*c-byte polynomial and no cross-lane traffic is needed.
+#pragma once
+#include "field.cuh"
+
+namespace mldsa {
+
+// Read NB bytes at an arbitrarily aligned address into little-endian words.  Never touches an
+// aligned word that does not contain at least one requested byte.
+template <int NB>
+__device__ __forceinline__ void load_span(const uint8_t* p, uint32_t (&w)[(NB + 3) / 4])
+{
+    constexpr int NW = (NB + 3) / 4;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned off = (unsigned)(a & 3);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a - off);
+    uint32_t x[NW + 1];
+#pragma unroll
+    for (int k = 0; k < NW; k++) x[k] = __ldg(q + k);
+    x[NW] = (off + NB > 4 * NW) ? __ldg(q + NW) : 0u;
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = __funnelshift_r(x[k], x[k + 1], off * 8);
+}
+
+// field i (compile-time) of width BITS from a little-endian word string
+template <int BITS>
+__device__ __forceinline__ uint32_t get_field(const uint32_t* w, int i)
+{
+    const int bit = BITS * i, k = bit >> 5, s = bit & 31;
+    const uint32_t v = (s + BITS <= 32) ? (w[k] >> s) : __funnelshift_r(w[k], w[k + 1], s);
+    return v & ((1u << BITS) - 1);
+}
+// 8 fields of BITS bits -> BITS bytes = ceil(BITS/4) words (upper bytes of the last word are zero)
+template <int BITS>
+__device__ __forceinline__ void pack_fields(const uint32_t (&f)[8], uint32_t (&w)[(BITS + 3) / 4])
+{
+#pragma unroll
+    for (int k = 0; k < (BITS + 3) / 4; k++) w[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int bit = BITS * i, k = bit >> 5, s = bit & 31;
+        w[k] |= f[i] << s;
+        if (s + BITS > 32) w[k + 1] |= f[i] >> (32 - s);
+    }
+}
+
+// Store a lane's NB packed bytes (little-endian words w) at dst.  Picks the widest store the
+// alignment of dst and NB allows; the choice is resolved per call site, not per byte.
+template <int NB>
+__device__ __forceinline__ void store_span(uint8_t* dst, const uint32_t (&w)[(NB + 3) / 4])
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    if (NB % 4 == 0 && (a & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < NB / 4; k++) reinterpret_cast<uint32_t*>(dst)[k] = w[k];
+    } else if (NB % 2 == 0 && (a & 1) == 0) {
+#pragma unroll
+        for (int k = 0; k < NB / 2; k++)
+            reinterpret_cast<uint16_t*>(dst)[k] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB; k++) dst[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
+// Warp-cooperative byte copies (any alignment, n small: hint regions, c~, seeds)
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, int n, int lane)
+{
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// Warp-cooperative copy of n bytes from a word-aligned shared staging buffer to an arbitrarily
+// aligned global address: aligned interior goes out as 32-bit stores (funnel-shifted), the <= 3
+// head/tail bytes as byte stores.  The staging buffer must be readable one word past n.
+__device__ __forceinline__ void warp_copy_out(uint8_t* dst, const uint32_t* stage, int n, int lane)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    const int nh = (int)((4 - (a & 3)) & 3);          // head bytes until dst is word aligned
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage);
+    if (lane < nh && lane < n) dst[lane] = sb[lane];
+    if (n <= nh) return;
+    const int nw = (n - nh) >> 2;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + nh);
+    for (int j = lane; j < nw; j += 32) {
+        // source bytes nh + 4j .. nh + 4j + 3
+        dw[j] = __funnelshift_r(stage[j], stage[j + 1], nh * 8);
+    }
+    const int done = nh + 4 * nw;
+    if (lane < n - done) dst[done + lane] = sb[done + lane];
+}
+
+}  // namespace mldsa

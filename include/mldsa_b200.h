@@ -1,0 +1,111 @@
+/*
+ * mldsa_b200.h -- C ABI of the B200-native batched ML-DSA (FIPS 204) engine.
+ *
+ * This is the drop-in boundary for the hot path of integritychain/fips204 (pure Rust, v0.4.6).
+ * The reference has no FFI of its own; each entry point below names the reference interface it
+ * replaces (file:line into the reference tree).  A Rust host crate binds these with `extern "C"`
+ * (see INTEGRATION.md); the in-repo host mirrors are fips204_b200/host/fips204.hpp (C++) and
+ * fips204_b200/__init__.py (ctypes).
+ *
+ * Conventions
+ *   ps       parameter set: 44, 65 or 87            (ml_dsa_44/65/87, src/lib.rs:639,681,723)
+ *   dev      CUDA device ordinal the batch runs on
+ *   framing  0 = ML-DSA.Sign/Verify   mu = H(tr || 0x00 || |ctx| || ctx || M)   (src/ml_dsa.rs:190,391)
+ *            1 = *_internal (ACVP)    mu = H(tr || M)                           (src/ml_dsa.rs:187,388)
+ *   All keys / signatures are the canonical FIPS 204 byte strings the reference's SerDes produces
+ *   (src/lib.rs:417-494): pk PK_LEN, sk SK_LEN, sig SIG_LEN bytes, densely packed lane after lane.
+ *   Randomness never originates on the device: xi / rnd are drawn by the caller (exactly one
+ *   32-byte draw per keygen and per sign, src/ml_dsa.rs:40-41 and src/lib.rs:282-283), so results
+ *   are byte-exact with the reference for identical seeds.
+ *   Host entry points take host pointers (pageable or pinned) and return after the results are in
+ *   the output buffers.  *_dev entry points take device pointers on the CURRENT device plus a
+ *   cudaStream_t (as void*) and return after the work has completed on that stream.
+ *   The library keeps no caller pointer after return.  Device scratch that held secrets
+ *   (s1, s2, t0, y, rho'', K) is zeroed before it is released.
+ *
+ * Return codes: 0 ok, -1 bad parameter, -2 ctx longer than 255 bytes (sign only; verify yields
+ * ok[i] = 0, src/lib.rs:368-370), -3 CUDA error (see mldsa_last_cuda_error), -4 out of device memory,
+ * -5 not supported.  Malformed signatures are NOT errors: they verify as 0.
+ */
+#ifndef MLDSA_B200_H
+#define MLDSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLDSA_OK 0
+#define MLDSA_E_PARAM (-1)
+#define MLDSA_E_CTX (-2)
+#define MLDSA_E_CUDA (-3)
+#define MLDSA_E_NOMEM (-4)
+#define MLDSA_E_UNSUPPORTED (-5)
+
+/* ---- introspection ---------------------------------------------------------------------- */
+int mldsa_device_count(void);
+const char* mldsa_strerror(int code);
+const char* mldsa_last_cuda_error(void); /* thread-local text of the last -3 */
+/* PK_LEN / SK_LEN / SIG_LEN of a parameter set (src/lib.rs:649-653); 0 on success */
+int mldsa_sizes(int ps, size_t* pk_len, size_t* sk_len, size_t* sig_len);
+
+/* pinned host buffers for callers that want DMA straight from their own memory */
+void* mldsa_host_alloc(size_t bytes);
+void mldsa_host_free(void* p);
+
+/* ---- keygen: KG::keygen_from_seed / try_keygen_with_rng + SerDes::into_bytes ------------
+ * (src/lib.rs:230-251, src/ml_dsa.rs:57-134).  xi: n x 32 seed bytes; pk: n x PK_LEN; sk: n x SK_LEN. */
+int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk);
+int mldsa_keygen_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_xi, uint8_t* d_pk, uint8_t* d_sk);
+
+/* ---- sign: PrivateKey::try_sign_with_rng / try_sign_with_seed / _internal_sign ----------
+ * (src/lib.rs:268-296, :586-594, src/ml_dsa.rs:153-337).
+ * sk: n x SK_LEN with sk_stride = SK_LEN, or one key with sk_stride = 0 (shared key).
+ * msgs + msg_off[n+1]: concatenated messages.  ctx + ctx_off[n+1]: contexts, or NULL,NULL = empty.
+ * rnd: n x 32 (all-zero rows = deterministic variant).  sig: n x SIG_LEN.
+ * iters: optional n trip counts of the rejection loop (src/ml_dsa.rs:212-330), may be NULL. */
+int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, size_t sk_stride,
+                     const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters);
+int mldsa_sign_batch_dev(int ps, void* stream, int framing, size_t n, const uint8_t* d_sk, size_t sk_stride,
+                         const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
+                         const uint32_t* d_ctx_off, const uint8_t* d_rnd, uint8_t* d_sig, uint32_t* d_iters);
+
+/* ---- verify: PublicKey::verify / _internal_verify ----------------------------------------
+ * (src/lib.rs:364-380, :605-612, src/ml_dsa.rs:351-437).
+ * pk: n x PK_LEN with pk_stride = PK_LEN, or one key with pk_stride = 0 (A-hat, tr and
+ * NTT(t1*2^d) are then expanded once and cached for the whole batch).  ok: n bytes, 1 = valid. */
+int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk, size_t pk_stride,
+                       const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                       const uint8_t* sig, uint8_t* ok);
+int mldsa_verify_batch_dev(int ps, void* stream, int framing, size_t n, const uint8_t* d_pk, size_t pk_stride,
+                           const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
+                           const uint32_t* d_ctx_off, const uint8_t* d_sig, uint8_t* d_ok);
+
+/* ---- microbench / leaf entry points (BASELINE config 2) ----------------------------------
+ * ntt: src/ntt.rs:14-76, raw-bit-exact representatives; intt: src/ntt.rs:85-161, canonical [0,q).
+ * expand_a: out[i] = RejNTTPoly(seed34[i]), src/hashing.rs:111-146.  In place on n x 256 int32. */
+int mldsa_ntt_batch(int dev, size_t n, int32_t* polys);
+int mldsa_intt_batch(int dev, size_t n, int32_t* polys);
+int mldsa_expand_a_batch(int dev, size_t n, const uint8_t* seed34, int32_t* out);
+int mldsa_ntt_batch_dev(void* stream, size_t n, int32_t* d_polys);
+int mldsa_intt_batch_dev(void* stream, size_t n, int32_t* d_polys);
+int mldsa_expand_a_batch_dev(void* stream, size_t n, const uint8_t* d_seed34, int32_t* d_out);
+/* SHAKE128 / SHAKE256 of n fixed-length rows (h256_xof / g128_xof, src/hashing.rs:13-27) */
+int mldsa_shake_batch(int dev, int bits /*128|256*/, size_t n, const uint8_t* in, size_t in_len, uint8_t* out,
+                      size_t out_len);
+
+/* ---- tuning / telemetry ------------------------------------------------------------------ */
+/* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 64 GiB) */
+void mldsa_set_workspace_limit(size_t bytes);
+/* kernels launched by this library since process start (all devices) */
+uint64_t mldsa_kernel_launches(void);
+/* rejection-loop rounds executed by the most recent sign call on this thread */
+int mldsa_last_sign_rounds(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

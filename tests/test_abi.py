@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/mldsa_b200.h declares, and the host mirror fails loudly (no CPU fallback) without a GPU."""
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def built():
+    from fips204_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(built):
+    import ctypes
+    hdr = (ROOT / "include" / "mldsa_b200.h").read_text()
+    names = sorted(set(re.findall(r"\b(mldsa_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(str(built))
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    from fips204_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_sizes_and_errors(built):
+    import ctypes as C
+    from fips204_b200 import _lib
+    l = _lib.lib()
+    for ps, want in ((44, (1312, 2560, 2420)), (65, (1952, 4032, 3309)), (87, (2592, 4896, 4627))):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        assert l.mldsa_sizes(ps, C.byref(a), C.byref(b), C.byref(c)) == 0
+        assert (a.value, b.value, c.value) == want  # src/lib.rs:649-653, 691-695, 733-737
+    assert l.mldsa_sizes(99, None, None, None) == -1
+    assert l.mldsa_strerror(-2) == b"ML-DSA.Sign: ctx too long"  # src/lib.rs:274
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import fips204_b200 as F
+    with pytest.raises(F.MldsaError):
+        F.ml_dsa_44.keygen_batch(bytes(32))
+    with pytest.raises(F.MldsaError):
+        F.micro.ntt([[0] * 256])
+
+
+def test_host_mirror_argument_rules(built):
+    import fips204_b200 as F
+    m = F.ml_dsa_44
+    sk = m.PrivateKey.try_from_bytes(bytes(m.SK_LEN))
+    with pytest.raises(ValueError, match="ctx too long"):  # src/lib.rs:274
+        sk.try_sign_with_seed(bytes(32), b"m", b"\0" * 256)
+    with pytest.raises(ValueError):
+        m.PrivateKey.try_from_bytes(bytes(10))
+    pk = m.PublicKey.try_from_bytes(bytes(m.PK_LEN))
+    assert pk.verify(b"m", bytes(m.SIG_LEN), b"\0" * 256) is False  # src/lib.rs:368-370
+    assert pk.into_bytes() == bytes(m.PK_LEN)
+
+    class BadRng:
+        def try_fill_bytes(self, n):
+            raise OSError("entropy source failed")
+
+    with pytest.raises(ValueError, match="KeyGen: Random number generator failed"):  # src/ml_dsa.rs:41
+        m.try_keygen_with_rng(BadRng())
+    with pytest.raises(ValueError, match="random number generator failed"):  # src/lib.rs:283
+        sk.try_sign_with_rng(BadRng(), b"m", b"")

@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle and the
+reference's golden vectors.  Bit-exact everywhere (integer / byte work)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import PS_OF
+from synth import synth, synth_block, synth_rows
+
+pytestmark = pytest.mark.gpu
+Q = 8380417
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fips204_b200 as F
+    assert F.device_count() >= 1, "no CUDA device: GPU tests need the B200 box"
+    return F
+
+
+# ---------------------------------------------------------------- leaves
+def test_shake_rows_vs_hashlib(F):
+    for bits, fn in ((128, hashlib.shake_128), (256, hashlib.shake_256)):
+        for in_len in (1, 7, 8, 33, 34, 66, 135, 136, 137, 167, 168, 169, 272, 1312, 1952):
+            rows = synth_block(f"shake{bits}-{in_len}", 37, in_len)
+            for out_len in (32, 64, 136, 200, 840):
+                got = F.micro.shake(bits, rows, out_len)
+                for i in range(rows.shape[0]):
+                    assert got[i].tobytes() == fn(rows[i].tobytes()).digest(out_len), (bits, in_len, out_len, i)
+
+
+def test_ntt_raw_bit_exact(F):
+    n = 4096
+    raw = synth_block("ntt", n, 1024).view(np.uint32).astype(np.int64) % Q
+    polys = raw.astype(np.int32).reshape(n, 256)
+    got = F.micro.ntt(polys)
+    want = O.ntt_batch(polys)
+    assert (got == want).all(), f"{(got != want).sum()} coefficient mismatches"
+    # extreme inputs: q-1 everywhere and alternating signs near the reference's documented growth bound
+    edge = np.stack([np.full(256, Q - 1), np.zeros(256), np.arange(256), -np.arange(256),
+                     np.where(np.arange(256) % 2 == 0, Q - 1, -(Q - 1))]).astype(np.int32)
+    assert (F.micro.ntt(edge) == O.ntt_batch(edge)).all()
+
+
+def test_intt_canonical(F):
+    n = 4096
+    raw = synth_block("intt", n, 1024).view(np.uint32).astype(np.int64) % Q
+    polys = raw.astype(np.int32).reshape(n, 256)
+    got = F.micro.inv_ntt(polys)
+    want = O.inv_ntt_batch(polys)
+    assert (got == want).all()
+    assert got.min() >= 0 and got.max() < Q
+    # round trip through both device transforms
+    back = F.micro.inv_ntt((F.micro.ntt(polys).astype(np.int64) % Q).astype(np.int32))
+    assert (back == polys).all()
+
+
+def test_expand_a_exact(F):
+    n = 2048 + 5  # ragged tail: not a multiple of the block size
+    seeds = synth_block("rho34", n, 34)
+    got = F.micro.expand_a(seeds)
+    want = O.expand_a_batch(seeds)
+    assert (got == want).all()
+
+
+# ---------------------------------------------------------------- keygen
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_keygen_acvp(F, acvp_keygen, ps):
+    m = F.PARAM_SETS[ps]
+    vec = [t for t in acvp_keygen if PS_OF[t["ps"]] == ps]
+    assert len(vec) == 25
+    xi = b"".join(bytes.fromhex(t["seed"]) for t in vec)
+    pk, sk = m.keygen_batch(xi)
+    for i, t in enumerate(vec):
+        assert pk[i].tobytes().hex().upper() == t["pk"].upper(), ("pk", t["tc"])
+        assert sk[i].tobytes().hex().upper() == t["sk"].upper(), ("sk", t["tc"])
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_keygen_vs_oracle(F, ps):
+    m = F.PARAM_SETS[ps]
+    n = 1000 + 3
+    xi = synth_block(f"xi{ps}", n, 32)
+    pk, sk = m.keygen_batch(xi)
+    opk, osk = O.keygen_batch(ps, xi)
+    assert (pk == opk).all()
+    assert (sk == osk).all()
+
+
+def test_keygen_pk0_pins(F):
+    # src/lib.rs:536-545
+    for ps, want in ((44, 197), (65, 177), (87, 16)):
+        pk, sk = F.PARAM_SETS[ps].KG.keygen_from_seed(b"\x11" * 32)
+        assert pk.into_bytes()[0] == want
+
+
+# ---------------------------------------------------------------- verify
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_verify_acvp(F, acvp_sigver, ps):
+    m = F.PARAM_SETS[ps]
+    vec = [t for t in acvp_sigver if PS_OF[t["ps"]] == ps]
+    assert len(vec) == 15
+    pk = bytes.fromhex(vec[0]["pk"])
+    msgs = [bytes.fromhex(t["message"]) for t in vec]
+    sigs = [bytes.fromhex(t["signature"]) for t in vec]
+    want = [t["passed"] for t in vec]
+    shared = m.verify_batch(pk, msgs, sigs, shared_key=True, framing=1)
+    assert [bool(x) for x in shared] == want, [t["reason"] for t in vec]
+    distinct = m.verify_batch(pk * len(vec), msgs, sigs, framing=1)
+    assert [bool(x) for x in distinct] == want
+
+
+def test_verify_bad_sig(F, reference_kats):
+    # tests/integration.rs:60-74
+    b = reference_kats["bad_sig"]
+    m = F.ml_dsa_44
+    pk = m.PublicKey.try_from_bytes(bytes.fromhex(b["pk"]))
+    assert m._internal_verify(pk, bytes.fromhex(b["msg"]), bytes.fromhex(b["good_sig"])) is True
+    assert m._internal_verify(pk, bytes.fromhex(b["msg"]), bytes.fromhex(b["bad_sig"])) is False
+
+
+def _mutate(ps, sig, cls, p):
+    """The 8 corruption classes of SURVEY.md section 8d config 3."""
+    s = bytearray(sig)
+    zoff, hoff = p.lambda_div4, p.lambda_div4 + p.l * 32 * p.z_bits
+    if cls == 0:
+        s[3] ^= 0x10                      # c~
+    elif cls == 1:
+        s[zoff + 77] ^= 0x04              # z
+    elif cls == 2:
+        s[hoff + 1] ^= 0x01               # hint index
+    elif cls == 3:
+        s[hoff + p.omega + p.k - 1] = p.omega + 1   # hint count > omega
+    elif cls == 4:
+        s[hoff], s[hoff + 1] = 9, 9
+        s[hoff + p.omega] = max(s[hoff + p.omega], 2)  # non-increasing hint index
+    elif cls == 5:
+        s[hoff + p.omega - 1] = 1 if s[hoff + p.omega - 1] == 0 else s[hoff + p.omega - 1]  # padding
+    elif cls == 6:
+        # force z[0][0] = gamma1 - beta exactly (the smallest rejected magnitude): field = gamma1 - z
+        field = p.gamma1 - (p.gamma1 - p.beta)
+        v = int.from_bytes(s[zoff:zoff + 4], "little")
+        v = (v & ~((1 << p.z_bits) - 1)) | field
+        s[zoff:zoff + 4] = v.to_bytes(4, "little")
+    return bytes(s)
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_verify_mutations_vs_oracle(F, ps):
+    m = F.PARAM_SETS[ps]
+    p = O.params(ps)
+    n = 256
+    pk, sk = O.keygen(ps, synth("xi", ps, 32))
+    msgs = [synth("msg", i, 32 + (i % 5)) for i in range(n)]
+    ctxs = [synth("ctx", i, i % 7) for i in range(n)]
+    rnds = synth_rows("rnd", n, 32)
+    sigs, _ = O.sign_batch(ps, np.frombuffer(sk, dtype=np.uint8), msgs, rnds, ctxs=ctxs, shared_key=True)
+    sigs = [s.tobytes() for s in sigs]
+    for i in range(0, n, 2):
+        cls = (i // 2) % 8
+        if cls == 7:
+            msgs[i] = msgs[i] + b"!"       # wrong message
+        else:
+            sigs[i] = _mutate(ps, sigs[i], cls, p)
+    want = O.verify_batch(ps, np.frombuffer(pk, dtype=np.uint8), msgs, np.frombuffer(b"".join(sigs), dtype=np.uint8),
+                          ctxs=ctxs, shared_key=True)
+    assert want[1::2].all() and not want[0::2].all()
+    got_s = m.verify_batch(pk, msgs, sigs, ctxs=ctxs, shared_key=True)
+    assert (got_s == want).all(), np.nonzero(got_s != want)
+    got_d = m.verify_batch(pk * n, msgs, sigs, ctxs=ctxs)
+    assert (got_d == want).all(), np.nonzero(got_d != want)
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_verify_distinct_keys(F, ps):
+    m = F.PARAM_SETS[ps]
+    n = 96
+    xi = synth_block(f"vk{ps}", n, 32)
+    pks, sks = O.keygen_batch(ps, xi)
+    msgs = [synth("vm", i, 1 + 3 * i) for i in range(n)]   # ragged, up to ~290 B: multi-block mu
+    rnds = synth_rows("vr", n, 32)
+    sigs, _ = O.sign_batch(ps, sks, msgs, rnds)
+    ok = m.verify_batch(pks, msgs, sigs)
+    assert ok.all()
+    # swapping two public keys must break exactly those two lanes
+    pks2 = pks.copy()
+    pks2[[3, 4]] = pks2[[4, 3]]
+    ok = m.verify_batch(pks2, msgs, sigs)
+    assert list(np.nonzero(ok == 0)[0]) == [3, 4]
+
+
+# ---------------------------------------------------------------- sign
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_sign_acvp(F, acvp_siggen, ps):
+    m = F.PARAM_SETS[ps]
+    vec = [t for t in acvp_siggen if PS_OF[t["ps"]] == ps]
+    assert len(vec) == 20
+    sks = np.frombuffer(b"".join(bytes.fromhex(t["sk"]) for t in vec), dtype=np.uint8)
+    msgs = [bytes.fromhex(t["message"]) for t in vec]
+    rnds = b"".join(bytes.fromhex(t["rnd"]) if t["rnd"] else bytes(32) for t in vec)  # mod.rs:107-112
+    sig, iters = m.sign_batch(sks, msgs, rnds, framing=1, want_iters=True)
+    for i, t in enumerate(vec):
+        assert sig[i].tobytes().hex().upper() == t["signature"].upper(), (t["tc"], int(iters[i]))
+
+
+def test_sign_messages_rs_kat(F, reference_kats):
+    # tests/messages.rs:9-21 through the single-op mirror API (external framing, ctx = [])
+    k = reference_kats["messages_rs"]
+    m = F.ml_dsa_44
+
+    class Replay:
+        def __init__(self, *chunks):
+            self.q = list(chunks)
+
+        def try_fill_bytes(self, n):
+            return self.q.pop(0)
+
+    rng = Replay(bytes.fromhex(k["xi"]), bytes.fromhex(k["rnd"]))
+    pk, sk = m.KG.try_keygen_with_rng(rng)
+    sig = sk.try_sign_with_rng(rng, bytes.fromhex(k["msg"]), b"")
+    assert pk.verify(bytes.fromhex(k["msg"]), sig, b"")
+    assert sk.into_bytes().hex() == k["sk"]
+    assert sig.hex() == k["sig"]
+    assert pk.into_bytes().hex() == k["pk"]
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_sign_vs_oracle_distinct_keys(F, ps):
+    m = F.PARAM_SETS[ps]
+    n = 700 + 1
+    xi = synth_block(f"sk{ps}", n, 32)
+    pks, sks = O.keygen_batch(ps, xi)
+    msgs = [synth("sm", i, (i * 13) % 300) for i in range(n)]   # includes the empty message
+    ctxs = [synth("sc", i, (i * 5) % 256) for i in range(n)]    # includes |ctx| = 255
+    rnds = synth_rows("sr", n, 32)
+    sig, iters = m.sign_batch(sks, msgs, rnds, ctxs=ctxs, want_iters=True)
+    osig, oiters = O.sign_batch(ps, sks, msgs, rnds, ctxs=ctxs)
+    bad = np.nonzero((sig != osig).any(axis=1))[0]
+    assert bad.size == 0, (bad[:10], iters[bad[:10]], oiters[bad[:10]])
+    assert (iters == oiters).all()
+    assert m.verify_batch(pks, msgs, sig, ctxs=ctxs).all()
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_sign_shared_key_and_deterministic(F, ps):
+    m = F.PARAM_SETS[ps]
+    n = 300
+    pk, sk = O.keygen(ps, synth("shk", ps, 32))
+    msgs = [synth("shm", i, 32) for i in range(n)]
+    rnds = np.zeros((n, 32), dtype=np.uint8)                    # deterministic variant
+    sig = m.sign_batch(sk, msgs, rnds, shared_key=True)
+    osig, _ = O.sign_batch(ps, np.frombuffer(sk, dtype=np.uint8), msgs, rnds, shared_key=True)
+    assert (sig == osig).all()
+    assert m.verify_batch(pk, msgs, sig, shared_key=True).all()
+
+
+def test_sign_rejects_long_ctx(F):
+    m = F.ml_dsa_44
+    pk, sk = m.KG.keygen_from_seed(bytes(32))
+    with pytest.raises(ValueError, match="ctx too long"):
+        sk.try_sign_with_seed(bytes(32), b"m", b"\1" * 256)
+    sig = sk.try_sign_with_seed(bytes(32), b"m", b"\1" * 255)
+    assert pk.verify(b"m", sig, b"\1" * 255)
+    assert not pk.verify(b"m", sig, b"\1" * 256)
+    assert not pk.verify(b"m", sig, b"\1" * 254)
+
+
+def test_sign_out_of_range_secret_key(F):
+    # SURVEY 8a note T: sk_decode never fails; fuzz_all signs with arbitrary sk bytes.  Same mod-q result.
+    for ps in (44, 65, 87):
+        m = F.PARAM_SETS[ps]
+        n = 24
+        sks = synth_block(f"fuzzsk{ps}", n, m.SK_LEN)
+        msgs = [synth("fm", i, 16) for i in range(n)]
+        rnds = synth_rows("fr", n, 32)
+        sig, iters = m.sign_batch(sks, msgs, rnds, want_iters=True)
+        osig, oiters = O.sign_batch(ps, sks, msgs, rnds)
+        assert (sig == osig).all() and (iters == oiters).all()
