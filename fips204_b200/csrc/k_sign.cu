@@ -192,7 +192,7 @@ sign_w_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __re
 }
 
 template <class P>
-struct SignSmem {
+struct alignas(16) SignSmem {
     int32_t tile[NTT_TILE_WORDS];
     uint32_t stage[32 * P::ZBITS / 4 + 1];  // packed z polynomial (576/640 B) or the hint bytes
     uint32_t sibs[SIB_BYTES / 4];

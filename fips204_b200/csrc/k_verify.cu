@@ -75,7 +75,7 @@ t1hat_kernel(const uint8_t* __restrict__ pk, int32_t* __restrict__ t1h)
 constexpr int VF_WARPS = 4;
 
 template <class P>
-struct VerifySmem {
+struct alignas(16) VerifySmem {
     int32_t tile[NTT_TILE_WORDS];
     uint32_t hbits[P::K * 8];                       // hint bitmap, 256 bits per polynomial
     uint32_t stage[(P::OMEGA + P::K + 3) / 4 + 1];  // hint bytes
