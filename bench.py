@@ -1,0 +1,419 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's headline metric on its configuration.
+
+Metric   : ML-DSA-65 signs/sec (primary `value`) and verifies/sec (`verify` object), host-core
+           reference beside it (`cpu_baseline`, and the `--impl reference` arm).
+Workload : BASELINE.json configs[3] -- ML-DSA-65 batched sign, 2^20 distinct keys/messages per GPU
+           (32-byte messages, empty ctx, external framing, hedged rnd), sharded over the ranks with
+           no collective ("scaling": "weak": per-GPU lanes fixed).
+A "step" : one pass of the sign hot path over the whole batch.
+  value  : device-resident -- sk / msg / rnd already in HBM, signatures left in HBM; CUDA events on
+           the launching stream around mldsa_sign_batch_dev.
+  e2e    : the same batch through the host-pointer C-ABI call mldsa_sign_batch with PINNED host
+           buffers; H2D of sk+msg+rnd and D2H of sig+iters are inside the timed region.
+Inputs are ~4.3 GB per step and >> L2 (126 MB), so no explicit L2 flush is needed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--lanes LANES_PER_GPU]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+PS = 65
+MSG_LEN = 32
+# SURVEY.md 8(d) conversion constants (algorithmic int32 ops)
+KECCAK_F, NTT_OPS, INTT_OPS, MAC_OPS = 4320, 6144, 7168, 5
+PARAMS = {44: dict(K=4, L=4, ct_blocks=7, zbytes=576, w1=768, pk=1312, sk=2560, sig=2420, tr_blocks=10),
+          65: dict(K=6, L=5, ct_blocks=7, zbytes=640, w1=768, pk=1952, sk=4032, sig=3309, tr_blocks=15),
+          87: dict(K=8, L=7, ct_blocks=9, zbytes=640, w1=1024, pk=2592, sk=4896, sig=4627, tr_blocks=20)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lanes", type=int, default=1 << 20, help="lanes per GPU (weak scaling)")
+    ap.add_argument("--ps", type=int, default=PS, choices=[44, 65, 87])
+    ap.add_argument("--ref-sample", type=int, default=0, help="lanes per step of the reference arm (0 = auto)")
+    ap.add_argument("--no-verify-leg", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per kernel class (int32 ops and HBM bytes), SURVEY.md 8(d)
+# ------------------------------------------------------------------------------------------------
+def kernel_work(ps, n, total_iters, accepted):
+    p = PARAMS[ps]
+    K, L = p["K"], p["L"]
+    it = float(total_iters)
+    return {
+        # name: (int32 ops, algorithmic bytes) per step
+        "expand_a": (n * K * L * 5 * KECCAK_F, n * (32 + K * L * 1024)),
+        "sign_key": (n * (L + 2 * K) * NTT_OPS, n * (p["sk"] - 128 + (L + 2 * K) * 1024)),
+        "sign_prep": (n * 2 * KECCAK_F, n * (128 + MSG_LEN + 32 + 128)),
+        "mask": (it * L * 5 * KECCAK_F, it * L * (66 + p["zbytes"])),
+        "sign_w": (it * (L * NTT_OPS + K * INTT_OPS + K * L * 256 * MAC_OPS),
+                   it * (L * p["zbytes"] + K * L * 1024 + K * 1024 + p["w1"])),
+        "ctilde": (it * (p["ct_blocks"] + 1) * KECCAK_F, it * (64 + p["w1"] + 64 + 136)),
+        "sign_z": (it * (NTT_OPS + (L + K) * (INTT_OPS + 256 * MAC_OPS)) + accepted * K * (INTT_OPS + 256 * MAC_OPS),
+                   it * ((L + K) * 1024 + L * p["zbytes"] + 2 * K * 1024 + 200) + accepted * (K * 1024 + p["sig"])),
+        "compact": (0.0, it * 9),
+    }
+
+
+def verify_work(ps, n, shared):
+    p = PARAMS[ps]
+    K, L = p["K"], p["L"]
+    kec = (1 + 1 + p["ct_blocks"]) + (0 if shared else K * L * 5 + p["tr_blocks"])
+    ntt = (L + 1) + (0 if shared else K)
+    return n * (kec * KECCAK_F + ntt * NTT_OPS + K * INTT_OPS + (K * L + K) * 256 * MAC_OPS)
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path, timed on the host cores.  The crate is Rust
+    and cannot be built in this image (no rustc/cargo), so this is the CPU oracle port (kind 'port'),
+    one scalar instance per host core, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    from synth import synth_block
+    cores = O.ncores()
+    sample = args.ref_sample or max(256, min(args.lanes, cores * 96))
+    xi = synth_block("bench-xi", sample, 32)
+    pk, sk = O.keygen_batch(args.ps, xi)
+    msgs = [bytes(m) for m in synth_block("bench-msg", sample, MSG_LEN)]
+    rnd = synth_block("bench-rnd", sample, 32)
+    for _ in range(args.warmup):
+        O.sign_batch(args.ps, sk, msgs, rnd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sig, iters = O.sign_batch(args.ps, sk, msgs, rnd)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    tv0 = time.perf_counter()
+    ok = O.verify_batch(args.ps, pk, msgs, sig)
+    tv = time.perf_counter() - tv0
+    assert ok.all()
+    line = {
+        "impl": "reference", "metric": f"ML-DSA-{args.ps} signs/sec", "value": value, "unit": "signs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {"value": value, "unit": "signs/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} lanes/step of the same workload (distinct keys, 32-B msgs), "
+                                   f"all {cores} host threads, C oracle (reference crate needs rustc: absent)"},
+        "e2e": {"value": value, "unit": "signs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "verify": {"value": sample / tv, "unit": "verifies/s", "keys": "distinct"},
+        "gpu_launches": 0, "mean_iters": float(iters.mean()),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, lanes):
+    return {"workload": f"BASELINE configs[3]: ML-DSA-{args.ps} batched sign, distinct keys/messages, "
+                        f"{MSG_LEN}-byte messages, empty ctx, external framing",
+            "lanes_per_gpu": lanes, "param_set": args.ps, "msg_len": MSG_LEN, "keys": "distinct",
+            "l2": "inputs (>= 4 GB/step) exceed the 126 MB L2; no flush needed", "parallelism": f"batch-shard x{args.gpus}"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fips204_b200 as F
+    from fips204_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    m = F.PARAM_SETS[args.ps]
+    p = PARAMS[args.ps]
+    n = args.lanes
+    stream = torch.cuda.current_stream()
+    sh = C.c_void_p(stream.cuda_stream)
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    # ---- synthetic inputs, generated on the device: xi, msg, rnd from torch's Philox, keys by our keygen
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x204 + rank)
+    d_xi = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    d_msg = torch.randint(0, 256, (n, MSG_LEN), dtype=torch.uint8, device=dev, generator=g)
+    d_rnd = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    d_moff = (torch.arange(n + 1, dtype=torch.int64, device=dev) * MSG_LEN)
+    d_pk = torch.empty((n, m.PK_LEN), dtype=torch.uint8, device=dev)
+    d_sk = torch.empty((n, m.SK_LEN), dtype=torch.uint8, device=dev)
+    d_sig = torch.empty((n, m.SIG_LEN), dtype=torch.uint8, device=dev)
+    d_iters = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+    _lib.check(L.mldsa_keygen_batch_dev(args.ps, sh, n, ptr(d_xi), ptr(d_pk), ptr(d_sk)))
+
+    def sign_dev():
+        _lib.check(L.mldsa_sign_batch_dev(args.ps, sh, 0, n, ptr(d_sk), m.SK_LEN, ptr(d_msg), ptr(d_moff), None, None,
+                                          ptr(d_rnd), ptr(d_sig), ptr(d_iters)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- integer issue peak of this device (roofline denominator for an int32-issue-bound path)
+    peaks = {}
+    for mode, name in ((0, "alu_lop3_shf"), (1, "fma_imad"), (2, "both")):
+        v = C.c_double()
+        _lib.check(L.mldsa_int32_peak_probe(mode, C.byref(v)))
+        peaks[name] = v.value
+
+    # ---- warm-up, then K timed steps between barriers; CUDA events on the launching stream
+    for _ in range(max(args.warmup, 3)):
+        sign_dev()
+    L.mldsa_profile_reset()
+    L.mldsa_profile_enable(1)
+    launches0 = L.mldsa_kernel_launches()
+    clocks = Clocks(local)
+    clocks.start()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    rounds = 0
+    for a, b in ev:
+        a.record(stream)
+        sign_dev()
+        b.record(stream)
+        rounds += L.mldsa_last_sign_rounds()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    clk = clocks.stop()
+    L.mldsa_profile_enable(0)
+    launches = L.mldsa_kernel_launches() - launches0
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # per-kernel device time over the timed region
+    prof = {}
+    for i in range(L.mldsa_profile_count()):
+        ms, cnt = C.c_double(), C.c_uint64()
+        L.mldsa_profile_get(i, C.byref(ms), C.byref(cnt))
+        if cnt.value:
+            prof[L.mldsa_profile_name(i).decode()] = (ms.value, cnt.value)
+    iters_total = int(d_iters.to(torch.int64).sum().item())
+    work = kernel_work(args.ps, n, iters_total, n)
+    kernels = {}
+    for name, (ms, cnt) in prof.items():
+        ops, byts = work.get(name, (0.0, 0.0))
+        kernels[name] = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
+                         "share": ms / (sum(v[0] for v in prof.values()) or 1.0),
+                         "int32_tops": ops / (ms / args.steps * 1e-3) / 1e12 if ms else None,
+                         "hbm_gbs": byts / (ms / args.steps * 1e-3) / 1e9 if ms else None}
+    top = max(prof, key=lambda k: prof[k][0]) if prof else None
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if peaks_file.exists():
+        hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    roofline = None
+    if top:
+        tk = kernels[top]
+        launches_top = prof[top][1] / args.steps
+        ops, byts = work.get(top, (0.0, 0.0))
+        pipe = "alu_lop3_shf" if top in ("mask", "ctilde", "expand_a", "sign_prep") else "both"
+        roofline = {
+            "kernel": top, "bound": "int32",
+            "achieved": tk["int32_tops"], "peak": peaks[pipe] / 1e12, "unit": "Tops/s (algorithmic int32 ops)",
+            "frac": (tk["int32_tops"] or 0) / (peaks[pipe] / 1e12), "peak_source": f"measured live: {pipe} issue probe",
+            "avg_launch_ms": tk["ms_per_step"] / launches_top, "launches_per_step": launches_top,
+            "algorithmic_ops_per_launch": ops / launches_top, "algorithmic_bytes_per_launch": byts / launches_top,
+            "hbm": {"bound": "hbm", "achieved": tk["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (tk["hbm_gbs"] or 0) / hbm_peak, "peak_source": hbm_src},
+            "traffic": None,
+        }
+    whole_ops = sum(v[0] for v in work.values())
+
+    # ---- correctness guards outside the timed region: all signatures verify on the GPU, and a sample is
+    # byte-identical to the CPU oracle
+    _lib.check(L.mldsa_verify_batch_dev(args.ps, sh, 0, n, ptr(d_pk), m.PK_LEN, ptr(d_msg), ptr(d_moff), None, None,
+                                        ptr(d_sig), ptr(d_ok)))
+    all_verify = bool(d_ok.all().item())
+    check = {"all_signatures_verify": all_verify}
+    verify_obj = None
+    if not args.no_verify_leg:
+        vev = []
+        for shared in (False, True):
+            if shared:
+                # one key, n messages: sign with the shared key first (untimed)
+                _lib.check(L.mldsa_sign_batch_dev(args.ps, sh, 0, n, ptr(d_sk), 0, ptr(d_msg), ptr(d_moff), None, None,
+                                                  ptr(d_rnd), ptr(d_sig), None))
+            stride = 0 if shared else m.PK_LEN
+            for _ in range(3):
+                _lib.check(L.mldsa_verify_batch_dev(args.ps, sh, 0, n, ptr(d_pk), stride, ptr(d_msg), ptr(d_moff),
+                                                    None, None, ptr(d_sig), ptr(d_ok)))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record(stream)
+            for _ in range(args.steps):
+                _lib.check(L.mldsa_verify_batch_dev(args.ps, sh, 0, n, ptr(d_pk), stride, ptr(d_msg), ptr(d_moff),
+                                                    None, None, ptr(d_sig), ptr(d_ok)))
+            b.record(stream)
+            barrier()
+            ms = a.elapsed_time(b) / args.steps
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            assert bool(d_ok.all().item())
+            vops = verify_work(args.ps, n, shared)
+            vev.append({"keys": "shared" if shared else "distinct", "value": world * n / (ms * 1e-3),
+                        "unit": "verifies/s", "ms_per_step": ms,
+                        "int32_tops": vops / (ms * 1e-3) / 1e12, "frac_of_int32_peak": vops / (ms * 1e-3) / peaks["both"]})
+        verify_obj = {"value": vev[0]["value"], "unit": "verifies/s", "legs": vev}
+        # restore the distinct-key signatures for the e2e / oracle checks
+        sign_dev()
+
+    # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region
+    h_sk = d_sk.cpu().pin_memory()
+    h_msg = d_msg.cpu().pin_memory()
+    h_rnd = d_rnd.cpu().pin_memory()
+    h_moff = d_moff.cpu().to(torch.int64).pin_memory()
+    h_sig = torch.empty((n, m.SIG_LEN), dtype=torch.uint8).pin_memory()
+    h_iters = torch.zeros(n, dtype=torch.int32).pin_memory()
+
+    def sign_host():
+        _lib.check(L.mldsa_sign_batch(args.ps, local, 0, n, ptr(h_sk), m.SK_LEN, ptr(h_msg), ptr(h_moff), None, None,
+                                      ptr(h_rnd), ptr(h_sig), ptr(h_iters)))
+
+    del d_ok
+    sign_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        sign_host()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    check["e2e_equals_device_resident"] = bool(torch.equal(h_sig, d_sig.cpu()))
+    e2e = {"value": world * n / e2e_s, "unit": "signs/s",
+           "h2d_bytes_per_step": int(h_sk.numel() + h_msg.numel() + h_rnd.numel() + h_moff.numel() * 8),
+           "d2h_bytes_per_step": int(h_sig.numel() + h_iters.numel() * 4), "ms_per_step": e2e_s * 1e3,
+           "host_buffers": "pinned", "api": "mldsa_sign_batch (host pointers)"}
+
+    cpu_baseline = None
+    if rank == 0:
+        import oracle_lib as O
+        ns = 256
+        idx = np.linspace(0, n - 1, ns).astype(np.int64)
+        osig, oit = O.sign_batch(args.ps, h_sk.numpy()[idx], [bytes(x) for x in h_msg.numpy()[idx]], h_rnd.numpy()[idx])
+        check["oracle_sample"] = ns
+        check["oracle_sample_bit_exact"] = bool((osig == h_sig.numpy()[idx]).all() and
+                                                (oit == h_iters.numpy()[idx].astype(np.uint32)).all())
+        if world == 1 and not args.no_cpu_baseline:
+            cores = O.ncores()
+            sample = max(256, cores * 64)
+            sidx = np.arange(sample) % n
+            sks, msgs, rnds = h_sk.numpy()[sidx], [bytes(x) for x in h_msg.numpy()[sidx]], h_rnd.numpy()[sidx]
+            O.sign_batch(args.ps, sks[:cores], msgs[:cores], rnds[:cores])
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 10.0:
+                O.sign_batch(args.ps, sks, msgs, rnds)
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+            cpu_baseline = {"value": sample / dt, "unit": "signs/s", "cores": cores, "kind": "port",
+                            "sample": f"{sample} lanes of this workload x {reps} passes (~10 s), C oracle, "
+                                      f"one scalar instance per host thread"}
+
+    if rank == 0:
+        line = {
+            "metric": f"ML-DSA-{args.ps} signs/sec", "value": value, "unit": "signs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, n),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk, "verify": verify_obj,
+            "sign": {"mean_iters": iters_total / n, "rounds_per_step": rounds / args.steps,
+                     "algorithmic_int32_ops_per_sign": whole_ops / n,
+                     "whole_step_int32_tops": whole_ops / (ms_per_step * 1e-3) / 1e12 * 1.0,
+                     "whole_step_frac_of_int32_peak": whole_ops / (ms_per_step * 1e-3) / peaks["both"]},
+            "int32_peaks_tops": {k: v / 1e12 for k, v in peaks.items()},
+            "kernels": kernels, "check": check,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

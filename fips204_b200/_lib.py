@@ -37,6 +37,12 @@ SIGNATURES = {
     "mldsa_set_workspace_limit": (None, [sz]),
     "mldsa_kernel_launches": (C.c_uint64, []),
     "mldsa_last_sign_rounds": (C.c_int, []),
+    "mldsa_profile_enable": (None, [C.c_int]),
+    "mldsa_profile_reset": (None, []),
+    "mldsa_profile_count": (C.c_int, []),
+    "mldsa_profile_name": (C.c_char_p, [C.c_int]),
+    "mldsa_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "mldsa_int32_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/mldsa_b200.h"
 #include "params.h"
@@ -19,7 +20,64 @@
 namespace mldsa {
 
 static std::atomic<uint64_t> g_launches{0};
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+static std::atomic<int> g_profiling{0};
+static std::mutex g_prof_mu;
+static double g_prof_ms[KID_COUNT];
+static uint64_t g_prof_n[KID_COUNT];
+static const char* const KERNEL_NAMES[KID_COUNT] = {
+    "expand_a", "ntt", "intt", "shake_rows", "ctilde", "kg_seed", "rej_bounded", "kg_arith", "verify_pre",
+    "t1hat", "verify_arith", "sign_prep", "sign_key", "mask", "sign_w", "sign_z", "compact", "int_probe"};
+
+struct EvPair {
+    int id;
+    cudaEvent_t a, b;
+};
+static thread_local std::vector<EvPair> t_events;      // launched, not yet collected
+static thread_local std::vector<cudaEvent_t> t_evpool;  // recycled events
+
+static cudaEvent_t ev_get()
+{
+    if (!t_evpool.empty()) {
+        cudaEvent_t e = t_evpool.back();
+        t_evpool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+KLaunch::KLaunch(int id_, cudaStream_t st_) : id(id_), st(st_)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_profiling.load(std::memory_order_relaxed)) {
+        EvPair p{id, ev_get(), ev_get()};
+        cudaEventRecord(p.a, st);
+        t_events.push_back(p);
+    }
+}
+KLaunch::~KLaunch()
+{
+    if (g_profiling.load(std::memory_order_relaxed) && !t_events.empty() && t_events.back().id == id)
+        cudaEventRecord(t_events.back().b, st);
+}
+void prof_collect()
+{
+    if (t_events.empty()) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& p : t_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_prof_ms[p.id] += ms;
+            g_prof_n[p.id] += 1;
+        } else {
+            cudaGetLastError();
+        }
+        t_evpool.push_back(p.a);
+        t_evpool.push_back(p.b);
+    }
+    t_events.clear();
+}
 
 static thread_local std::string t_cuda_err;
 static thread_local int t_last_rounds = 0;
@@ -224,6 +282,7 @@ static int keygen_core(DeviceCtx& cx, cudaStream_t st, int ps, size_t n, const u
         CK(cudaMemsetAsync(ws.s, 0, m * (size_t)(p.K + p.L) * 256, st));
     }
     CK(cudaStreamSynchronize(st));
+    prof_collect();
     return OK;
 }
 
@@ -246,6 +305,7 @@ static int verify_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size
         CK(verify_run(ps, st, m, d_pk + pk_stride * lo, pk_stride, md, d_sig + p.sig * lo, d_ok + lo, ws));
     }
     CK(cudaStreamSynchronize(st));
+    prof_collect();
     return OK;
 }
 
@@ -282,6 +342,7 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
         }
     }
     CK(cudaStreamSynchronize(st));
+    prof_collect();
     return OK;
 }
 
@@ -371,6 +432,59 @@ void mldsa_host_free(void* p)
 }
 void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
 uint64_t mldsa_kernel_launches(void) { return g_launches.load(); }
+
+void mldsa_profile_enable(int on) { g_profiling.store(on ? 1 : 0); }
+void mldsa_profile_reset(void)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < KID_COUNT; i++) {
+        g_prof_ms[i] = 0;
+        g_prof_n[i] = 0;
+    }
+}
+int mldsa_profile_count(void) { return KID_COUNT; }
+const char* mldsa_profile_name(int id) { return id >= 0 && id < KID_COUNT ? KERNEL_NAMES[id] : ""; }
+int mldsa_profile_get(int id, double* ms, uint64_t* launches)
+{
+    if (id < 0 || id >= KID_COUNT) return E_PARAM;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (ms) *ms = g_prof_ms[id];
+    if (launches) *launches = g_prof_n[id];
+    return OK;
+}
+
+// Integer issue-rate probe on the current device: mode 0 = LOP3+SHF (ALU pipe), 1 = IMAD+IMAD.HI (FMA
+// pipe), 2 = both interleaved.  Returns thread-level integer instructions per second.
+int mldsa_int32_peak_probe(int mode, double* ops_per_sec)
+{
+    if (mode < 0 || mode > 2 || !ops_per_sec) return E_PARAM;
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t* scratch = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&scratch), 256));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double ops = 0, best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a, 0);
+        cudaError_t e = launch_int_probe(0, mode, sms * 8, 2048, scratch, &ops);
+        cudaEventRecord(b, 0);
+        if (e != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) {
+            cudaFree(scratch);
+            return cuda_fail(e != cudaSuccess ? e : cudaGetLastError(), "int probe");
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(scratch);
+    *ops_per_sec = best;
+    return OK;
+}
 int mldsa_last_sign_rounds(void) { return t_last_rounds; }
 
 // ---------------------------------------------------------------- device-pointer entry points
@@ -425,6 +539,7 @@ int mldsa_ntt_batch_dev(void* stream, size_t n, int32_t* d_polys)
     if (n && !d_polys) return E_PARAM;
     CK(launch_ntt((cudaStream_t)stream, d_polys, n, false));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    prof_collect();
     return OK;
 }
 int mldsa_intt_batch_dev(void* stream, size_t n, int32_t* d_polys)
@@ -432,6 +547,7 @@ int mldsa_intt_batch_dev(void* stream, size_t n, int32_t* d_polys)
     if (n && !d_polys) return E_PARAM;
     CK(launch_ntt((cudaStream_t)stream, d_polys, n, true));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    prof_collect();
     return OK;
 }
 int mldsa_expand_a_batch_dev(void* stream, size_t n, const uint8_t* d_seed34, int32_t* d_out)
@@ -439,6 +555,7 @@ int mldsa_expand_a_batch_dev(void* stream, size_t n, const uint8_t* d_seed34, in
     if (n && (!d_seed34 || !d_out)) return E_PARAM;
     CK(launch_expand_a_seed34((cudaStream_t)stream, d_seed34, n, d_out));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    prof_collect();
     return OK;
 }
 
@@ -623,6 +740,7 @@ static int micro_host(int dev, size_t n, const void* in, size_t in_bytes, void* 
     if (which == 2) CK(launch_expand_a_seed34(st, d_in, n, reinterpret_cast<int32_t*>(d_out)));
     CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    prof_collect();
     return OK;
 }
 

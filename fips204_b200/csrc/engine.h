@@ -14,8 +14,20 @@ constexpr int SIB_BYTES = 136;   // one SHAKE256 block of H(c~) for SampleInBall
 constexpr int MU_BYTES = 64;
 constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_run saw |ctx| > 255
 
-// launch telemetry (mldsa_kernel_launches)
-void count_launch(int n = 1);
+// Kernel classes for launch telemetry (mldsa_kernel_launches) and the optional per-kernel device
+// timing (mldsa_profile_*): CUDA events recorded around every launch on the launching stream.
+enum KernelId : int {
+    KID_EXPAND_A = 0, KID_NTT, KID_INTT, KID_SHAKE_ROWS, KID_CTILDE, KID_KG_SEED, KID_REJ_BOUNDED, KID_KG_ARITH,
+    KID_VERIFY_PRE, KID_T1HAT, KID_VERIFY_ARITH, KID_SIGN_PREP, KID_SIGN_KEY, KID_MASK, KID_SIGN_W, KID_SIGN_Z,
+    KID_COMPACT, KID_PROBE, KID_COUNT
+};
+struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<...>>>(...); }`
+    int id;
+    cudaStream_t st;
+    KLaunch(int id, cudaStream_t st);
+    ~KLaunch();
+};
+void prof_collect();  // fold finished event pairs into the per-kernel totals (call after a stream sync)
 
 // ---- k_common.cu ----
 // Commitment hash.  Verify mode (ctilde_out == nullptr): ok[i] = pre_ok[i] && H(mu||w1')[0..CT) == sig_i[0..CT)
@@ -25,6 +37,7 @@ cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act
                           const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
                           uint8_t* sib_out);
 
+cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops);
 // A[key][r*L+s][256] = RejNTTPoly(rho_key || s || r)          (src/hashing.rs:225-239)
 cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,
                             int32_t* A);

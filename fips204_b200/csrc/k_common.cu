@@ -89,16 +89,20 @@ cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, s
     const size_t ns = nkeys * (size_t)(K * L);
     if (ns == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((ns + EA_THREADS - 1) / EA_THREADS);
-    expand_a_kernel<false><<<grid, EA_THREADS, 0, st>>>(rho, rho_stride, ns, K * L, L, A);
-    count_launch();
+    {
+        KLaunch kl(KID_EXPAND_A, st);
+        expand_a_kernel<false><<<grid, EA_THREADS, 0, st>>>(rho, rho_stride, ns, K * L, L, A);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_expand_a_seed34(cudaStream_t st, const uint8_t* seeds, size_t n, int32_t* out)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + EA_THREADS - 1) / EA_THREADS);
-    expand_a_kernel<true><<<grid, EA_THREADS, 0, st>>>(seeds, 34, n, 1, 1, out);
-    count_launch();
+    {
+        KLaunch kl(KID_EXPAND_A, st);
+        expand_a_kernel<true><<<grid, EA_THREADS, 0, st>>>(seeds, 34, n, 1, 1, out);
+    }
     return cudaGetLastError();
 }
 
@@ -145,9 +149,11 @@ cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t want = (n + NTT_WARPS - 1) / NTT_WARPS;
     const unsigned grid = (unsigned)(want < (size_t)sms * 8 ? want : (size_t)sms * 8);
-    if (inverse) ntt_kernel<true><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);
-    else ntt_kernel<false><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);
-    count_launch();
+    {
+        KLaunch kl(inverse ? KID_INTT : KID_NTT, st);
+        if (inverse) ntt_kernel<true><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);
+        else ntt_kernel<false><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);
+    }
     return cudaGetLastError();
 }
 
@@ -181,18 +187,22 @@ cudaError_t launch_shake256_rows(cudaStream_t st, const uint8_t* in, size_t in_s
                                  uint8_t* out, size_t out_stride, int out_len)
 {
     if (n == 0) return cudaSuccess;
-    shake_rows_kernel<SHAKE256_RATE><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, in_stride, in_len, n, out,
-                                                                                out_stride, out_len);
-    count_launch();
+    {
+        KLaunch kl(KID_SHAKE_ROWS, st);
+        shake_rows_kernel<SHAKE256_RATE><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, in_stride, in_len, n, out,
+                                                                                    out_stride, out_len);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_shake128_rows(cudaStream_t st, const uint8_t* in, size_t in_stride, size_t in_len, size_t n,
                                  uint8_t* out, size_t out_stride, int out_len)
 {
     if (n == 0) return cudaSuccess;
-    shake_rows_kernel<SHAKE128_RATE><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, in_stride, in_len, n, out,
-                                                                                out_stride, out_len);
-    count_launch();
+    {
+        KLaunch kl(KID_SHAKE_ROWS, st);
+        shake_rows_kernel<SHAKE128_RATE><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, in_stride, in_len, n, out,
+                                                                                    out_stride, out_len);
+    }
     return cudaGetLastError();
 }
 
@@ -261,11 +271,13 @@ static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* ac
                                    uint8_t* sib_out)
 {
     const unsigned grid = (unsigned)((n + 127) / 128);
-    if (ctilde_out)
-        ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    else
-        ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    count_launch();
+    {
+        KLaunch kl(KID_CTILDE, st);
+        if (ctilde_out)
+            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+        else
+            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    }
     return cudaGetLastError();
 }
 
@@ -280,6 +292,53 @@ cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act
     case 87: return launch_ctilde_t<Params<87>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
     }
     return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer issue-rate probe: the roofline denominator for this path ("measure it").
+// mode 0: LOP3 + SHF streams (ALU pipe, what Keccak runs on); mode 1: IMAD + IMAD.HI streams (FMA
+// pipe, the Montgomery multiplies); mode 2: both interleaved.  16 independent chains per thread.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters, uint32_t seed)
+{
+    uint32_t x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u + blockIdx.x;
+    const uint32_t m = seed | 1u;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (MODE == 0 || MODE == 2) {
+                    x[i] = x[i] ^ (~x[(i + 1) & 15] & m);                 // LOP3
+                    x[i] = __funnelshift_l(x[i], x[(i + 5) & 15], 7);     // SHF
+                }
+                if (MODE == 1 || MODE == 2) {
+                    x[i] = x[i] * m + (uint32_t)i;                        // IMAD
+                    x[i] = (uint32_t)__mulhi((int32_t)x[i], (int32_t)m) + x[i];  // IMAD.HI
+                }
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= x[i];
+    if (acc == 0x12345678u) out[0] = acc;  // keep the chains alive
+}
+
+// returns thread-level integer instructions issued (ops) for the launched grid
+cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops)
+{
+    const double per_thread = (double)iters * 4 * 16 * (mode == 2 ? 4 : 2);
+    *ops = per_thread * 256.0 * blocks;
+    KLaunch kl(KID_PROBE, st);
+    if (mode == 0) int_probe_kernel<0><<<blocks, 256, 0, st>>>(scratch, iters, 12345u);
+    else if (mode == 1) int_probe_kernel<1><<<blocks, 256, 0, st>>>(scratch, iters, 12345u);
+    else int_probe_kernel<2><<<blocks, 256, 0, st>>>(scratch, iters, 12345u);
+    return cudaGetLastError();
 }
 
 }  // namespace mldsa

@@ -178,11 +178,16 @@ static cudaError_t keygen_run_t(cudaStream_t st, size_t n, const uint8_t* xi, ui
                                 const KeygenWs& ws)
 {
     constexpr int K = P::K, L = P::L;
-    kg_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(xi, n, K, L, ws.seeds);
+    {
+        KLaunch kl(KID_KG_SEED, st);
+        kg_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(xi, n, K, L, ws.seeds);
+    }
     const size_t ns = n * (size_t)(K + L);
-    rej_bounded_kernel<P::ETA><<<(unsigned)((ns + RB_THREADS - 1) / RB_THREADS), RB_THREADS, 0, st>>>(
-        ws.seeds, ns, K + L, ws.s);
-    count_launch(2);
+    {
+        KLaunch kl(KID_REJ_BOUNDED, st);
+        rej_bounded_kernel<P::ETA><<<(unsigned)((ns + RB_THREADS - 1) / RB_THREADS), RB_THREADS, 0, st>>>(
+            ws.seeds, ns, K + L, ws.s);
+    }
     cudaError_t e = launch_expand_a(st, K, L, ws.seeds, 128, n, ws.A);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
@@ -190,8 +195,10 @@ static cudaError_t keygen_run_t(cudaStream_t st, size_t n, const uint8_t* xi, ui
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t want = (n + KG_WARPS - 1) / KG_WARPS;
     const unsigned grid = (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
-    kg_arith_kernel<P><<<grid, KG_WARPS * 32, 0, st>>>(n, ws.seeds, ws.s, ws.A, pk, sk);
-    count_launch();
+    {
+        KLaunch kl(KID_KG_ARITH, st);
+        kg_arith_kernel<P><<<grid, KG_WARPS * 32, 0, st>>>(n, ws.seeds, ws.s, ws.A, pk, sk);
+    }
     e = launch_shake256_rows(st, pk, P::PK_LEN, P::PK_LEN, n, sk + 64, P::SK_LEN, 64);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();

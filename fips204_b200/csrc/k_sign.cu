@@ -389,10 +389,15 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     int* ctx_err = reinterpret_cast<int*>(ws.nact + 2);
     e = cudaMemsetAsync(ws.nact, 0, 16, st);
     if (e != cudaSuccess) return e;
-    sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
-                                                                    ws.kappa, ws.done, ws.act[0], ctx_err);
-    sign_key_kernel<P><<<warp_grid(nkeys), SG_WARPS * 32, 0, st>>>(nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
-    count_launch(2);
+    {
+        KLaunch kl(KID_SIGN_PREP, st);
+        sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
+                                                                        ws.kappa, ws.done, ws.act[0], ctx_err);
+    }
+    {
+        KLaunch kl(KID_SIGN_KEY, st);
+        sign_key_kernel<P><<<warp_grid(nkeys), SG_WARPS * 32, 0, st>>>(nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
+    }
     e = launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(ws.h_nact, ctx_err, 4, cudaMemcpyDeviceToHost, st);
@@ -408,30 +413,40 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     int cur = 0, rounds = 0;
     while (nact > 0) {
         const size_t nstreams = nact * L;
-        mask_kernel<P><<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(nstreams, ws.act[cur], ws.rhopp, ws.kappa,
-                                                                         ws.yraw);
-        if (shared)
-            sign_w_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw, ws.w,
-                                                                            ws.mw1);
-        else
-            sign_w_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw, ws.w,
-                                                                             ws.mw1);
-        count_launch(2);
+        {
+            KLaunch kl(KID_MASK, st);
+            mask_kernel<P><<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(nstreams, ws.act[cur], ws.rhopp,
+                                                                             ws.kappa, ws.yraw);
+        }
+        {
+            KLaunch kl(KID_SIGN_W, st);
+            if (shared)
+                sign_w_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw,
+                                                                                ws.w, ws.mw1);
+            else
+                sign_w_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw,
+                                                                                 ws.w, ws.mw1);
+        }
         e = launch_ctilde(P::PS, st, nact, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.sib);
         if (e != cudaSuccess) return e;
-        if (shared)
-            sign_z_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
-                nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done, sig,
-                iters);
-        else
-            sign_z_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
-                nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done, sig,
-                iters);
+        {
+            KLaunch kl(KID_SIGN_Z, st);
+            if (shared)
+                sign_z_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
+                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done,
+                    sig, iters);
+            else
+                sign_z_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
+                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done,
+                    sig, iters);
+        }
         e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);
         if (e != cudaSuccess) return e;
-        compact_kernel<<<(unsigned)((nact + 255) / 256), 256, 0, st>>>(nact, ws.act[cur], ws.done, ws.act[cur ^ 1],
-                                                                      ws.nact + (cur ^ 1));
-        count_launch(2);
+        {
+            KLaunch kl(KID_COMPACT, st);
+            compact_kernel<<<(unsigned)((nact + 255) / 256), 256, 0, st>>>(nact, ws.act[cur], ws.done,
+                                                                          ws.act[cur ^ 1], ws.nact + (cur ^ 1));
+        }
         e = cudaMemcpyAsync(ws.h_nact, ws.nact + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;
         e = cudaStreamSynchronize(st);

@@ -215,27 +215,33 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
         if (e != cudaSuccess) return e;
         e = launch_shake256_rows(st, pk, 0, P::PK_LEN, 1, ws.tr, 64, 64);
         if (e != cudaSuccess) return e;
-        t1hat_kernel<P><<<1, 128, 0, st>>>(pk, ws.t1h);
-        count_launch();
+        {
+            KLaunch kl(KID_T1HAT, st);
+            t1hat_kernel<P><<<1, 128, 0, st>>>(pk, ws.t1h);
+        }
     } else {
         e = launch_expand_a(st, K, L, pk, pk_stride, n, ws.A);
         if (e != cudaSuccess) return e;
     }
-    verify_pre_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, pk, pk_stride, shared ? ws.tr : nullptr, md,
-                                                                     sig, ws.mw1, ws.sib, ws.pre_ok);
-    count_launch();
+    {
+        KLaunch kl(KID_VERIFY_PRE, st);
+        verify_pre_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, pk, pk_stride, shared ? ws.tr : nullptr,
+                                                                         md, sig, ws.mw1, ws.sib, ws.pre_ok);
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t want = (n + VF_WARPS - 1) / VF_WARPS;
     const unsigned grid = (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
-    if (shared)
-        verify_arith_kernel<P, true><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h, ws.sib,
-                                                                     ws.mw1, ws.pre_ok);
-    else
-        verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr, ws.sib,
-                                                                      ws.mw1, ws.pre_ok);
-    count_launch();
+    {
+        KLaunch kl(KID_VERIFY_ARITH, st);
+        if (shared)
+            verify_arith_kernel<P, true><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h, ws.sib,
+                                                                         ws.mw1, ws.pre_ok);
+        else
+            verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr, ws.sib,
+                                                                          ws.mw1, ws.pre_ok);
+    }
     e = launch_ctilde(P::PS, st, n, nullptr, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();

@@ -104,6 +104,16 @@ void mldsa_set_workspace_limit(size_t bytes);
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */
 int mldsa_last_sign_rounds(void);
+/* optional per-kernel device timing: CUDA events around every launch on the launching stream,
+ * accumulated per kernel class.  Off by default (two event records per launch when on). */
+void mldsa_profile_enable(int on);
+void mldsa_profile_reset(void);
+int mldsa_profile_count(void);
+const char* mldsa_profile_name(int id);
+int mldsa_profile_get(int id, double* ms, uint64_t* launches);
+/* measured integer issue rate of the current device, thread-level instructions / s:
+ * mode 0 LOP3+SHF (ALU pipe), 1 IMAD+IMAD.HI (FMA pipe), 2 both interleaved */
+int mldsa_int32_peak_probe(int mode, double* ops_per_sec);
 
 #ifdef __cplusplus
 }
