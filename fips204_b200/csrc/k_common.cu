@@ -300,12 +300,11 @@ cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act
 // pipe, the Montgomery multiplies); mode 2: both interleaved.  16 independent chains per thread.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters, uint32_t seed)
+__global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters, uint32_t seed, uint32_t m)
 {
     uint32_t x[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u + blockIdx.x;
-    const uint32_t m = seed | 1u;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
@@ -313,12 +312,12 @@ __global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 if (MODE == 0 || MODE == 2) {
-                    x[i] = x[i] ^ (~x[(i + 1) & 15] & m);                 // LOP3
-                    x[i] = __funnelshift_l(x[i], x[(i + 5) & 15], 7);     // SHF
+                    x[i] = x[i] ^ (x[(i + 1) & 15] & m);                  // one LOP3 (3 register inputs)
+                    x[i] = __funnelshift_l(x[i], x[(i + 5) & 15], 7);     // one SHF
                 }
                 if (MODE == 1 || MODE == 2) {
-                    x[i] = x[i] * m + (uint32_t)i;                        // IMAD
-                    x[i] = (uint32_t)__mulhi((int32_t)x[i], (int32_t)m) + x[i];  // IMAD.HI
+                    x[i] = x[i] * m + x[(i + 3) & 15];                    // one IMAD
+                    x[i] = (uint32_t)__mulhi((int32_t)x[i], (int32_t)m) + x[(i + 7) & 15];  // one IMAD.HI
                 }
             }
         }
@@ -335,9 +334,9 @@ cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, u
     const double per_thread = (double)iters * 4 * 16 * (mode == 2 ? 4 : 2);
     *ops = per_thread * 256.0 * blocks;
     KLaunch kl(KID_PROBE, st);
-    if (mode == 0) int_probe_kernel<0><<<blocks, 256, 0, st>>>(scratch, iters, 12345u);
-    else if (mode == 1) int_probe_kernel<1><<<blocks, 256, 0, st>>>(scratch, iters, 12345u);
-    else int_probe_kernel<2><<<blocks, 256, 0, st>>>(scratch, iters, 12345u);
+    if (mode == 0) int_probe_kernel<0><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u);
+    else if (mode == 1) int_probe_kernel<1><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u);
+    else int_probe_kernel<2><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u);
     return cudaGetLastError();
 }
 
