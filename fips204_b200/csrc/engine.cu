@@ -457,7 +457,7 @@ int mldsa_profile_get(int id, double* ms, uint64_t* launches)
 // pipe), 2 = both interleaved.  Returns thread-level integer instructions per second.
 int mldsa_int32_peak_probe(int mode, double* ops_per_sec)
 {
-    if (mode < 0 || mode > 2 || !ops_per_sec) return E_PARAM;
+    if (mode < 0 || mode > 8 || !ops_per_sec) return E_PARAM;
     int dev = 0, sms = 148;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

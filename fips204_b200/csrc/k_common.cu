@@ -297,7 +297,8 @@ cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act
 // ------------------------------------------------------------------------------------------------
 // Integer issue-rate probe: the roofline denominator for this path ("measure it").
 // mode 0: LOP3 + SHF streams (ALU pipe, what Keccak runs on); mode 1: IMAD + IMAD.HI streams (FMA
-// pipe, the Montgomery multiplies); mode 2: both interleaved.  16 independent chains per thread.
+// pipe, the Montgomery multiplies); mode 2: both interleaved; modes 3..8: IMAD, IMAD.HI, IMAD.WIDE(+LOP3),
+// SHF, LOP3, IADD3 alone.  16 independent chains per thread.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters, uint32_t seed, uint32_t m)
@@ -311,14 +312,17 @@ __global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                if (MODE == 0 || MODE == 2) {
-                    x[i] = x[i] ^ (x[(i + 1) & 15] & m);                  // one LOP3 (3 register inputs)
-                    x[i] = __funnelshift_l(x[i], x[(i + 5) & 15], 7);     // one SHF
+                const uint32_t y = x[(i + 5) & 15];
+                if (MODE == 0 || MODE == 2 || MODE == 7) x[i] = x[i] ^ (x[(i + 1) & 15] & m);   // LOP3
+                if (MODE == 0 || MODE == 2 || MODE == 6) x[i] = __funnelshift_l(x[i], y, 7);    // SHF
+                if (MODE == 1 || MODE == 2 || MODE == 3) x[i] = x[i] * m + x[(i + 3) & 15];     // IMAD
+                if (MODE == 1 || MODE == 2 || MODE == 4)                                        // IMAD.HI
+                    x[i] = (uint32_t)__mulhi((int32_t)x[i], (int32_t)m) + x[(i + 7) & 15];
+                if (MODE == 5) {                                                                // IMAD.WIDE
+                    const uint64_t w = (uint64_t)x[i] * m + (((uint64_t)y << 32) | x[(i + 9) & 15]);
+                    x[i] = (uint32_t)w ^ (uint32_t)(w >> 32);                                   // (+1 LOP3)
                 }
-                if (MODE == 1 || MODE == 2) {
-                    x[i] = x[i] * m + x[(i + 3) & 15];                    // one IMAD
-                    x[i] = (uint32_t)__mulhi((int32_t)x[i], (int32_t)m) + x[(i + 7) & 15];  // one IMAD.HI
-                }
+                if (MODE == 8) x[i] = x[i] + y + m;                                             // IADD3
             }
         }
     }
@@ -328,15 +332,26 @@ __global__ void __launch_bounds__(256) int_probe_kernel(uint32_t* out, int iters
     if (acc == 0x12345678u) out[0] = acc;  // keep the chains alive
 }
 
+static const int PROBE_OPS_PER_ELEM[9] = {2, 2, 4, 1, 1, 2, 1, 1, 1};
+
 // returns thread-level integer instructions issued (ops) for the launched grid
 cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops)
 {
-    const double per_thread = (double)iters * 4 * 16 * (mode == 2 ? 4 : 2);
+    if (mode < 0 || mode > 8) return cudaErrorInvalidValue;
+    const double per_thread = (double)iters * 4 * 16 * PROBE_OPS_PER_ELEM[mode];
     *ops = per_thread * 256.0 * blocks;
     KLaunch kl(KID_PROBE, st);
-    if (mode == 0) int_probe_kernel<0><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u);
-    else if (mode == 1) int_probe_kernel<1><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u);
-    else int_probe_kernel<2><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u);
+    switch (mode) {
+    case 0: int_probe_kernel<0><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 1: int_probe_kernel<1><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 2: int_probe_kernel<2><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 3: int_probe_kernel<3><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 4: int_probe_kernel<4><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 5: int_probe_kernel<5><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 6: int_probe_kernel<6><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 7: int_probe_kernel<7><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    case 8: int_probe_kernel<8><<<blocks, 256, 0, st>>>(scratch, iters, 12345u, 0x9E3779B1u); break;
+    }
     return cudaGetLastError();
 }
 

@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Summarise gpurun_out ncu artefacts into profiles/ (tracked).
+
+    python tools/summarize_ncu.py <tag> [--launches gpurun_out/launches_X.csv] [--rep gpurun_out/prof_X.ncu-rep]
+"""
+import argparse
+import collections
+import csv
+import io
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+METRICS = [
+    ("gpu__time_duration.sum", "time"),
+    ("launch__registers_per_thread", "regs"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active%"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active%"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "pipe_alu%"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "pipe_fma%"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "pipe_lsu%"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+    ("dram__bytes_read.sum", "dram_rd"),
+    ("dram__bytes_write.sum", "dram_wr"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
+    ("smsp__inst_executed.sum", "warp_inst"),
+]
+
+
+def short(name):
+    n = name.replace("void ", "").replace("mldsa::", "")
+    return n.split("(")[0][:44]
+
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows:
+        if r is hdr or r[0] == "ID" or len(r) <= vi:
+            continue
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        scale = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "ms": 1.0, "msecond": 1.0, "second": 1e3}.get(r[ui], 1e-6)
+        k = short(r[ki])
+        if k.startswith(("int_probe", "at::", "<unnamed>")):
+            continue  # roofline probe and torch's input generators are not part of the step
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v * scale
+    tot = sum(a[1] for a in agg.values())
+    out.write(f"## Launch list ({Path(path).name}: `ncu --metrics gpu__time_duration.sum --clock-control none`)\n\n")
+    out.write("Per-launch times are cold-cache and serialised; compare SHARES, not absolutes.\n\n")
+    out.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+    for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.write(f"| `{k}` | {c} | {ms:.3f} | {100 * ms / tot:.1f}% |\n")
+    out.write(f"| **total** | {sum(a[0] for a in agg.values())} | {tot:.3f} | 100% |\n\n")
+
+
+def full(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    out.write(f"## Full captures ({Path(rep).name}: `ncu --set full --clock-control none --import-source on`)\n\n")
+    out.write("| kernel | " + " | ".join(n for _, n in METRICS) + " |\n|---|" + "---:|" * len(METRICS) + "\n")
+    for r in data:
+        cells = []
+        for m, _ in METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                try:
+                    v = float(r[i].replace(",", ""))
+                    cells.append(f"{v:.4g} {units[i]}".replace(" %", "").replace("register/thread", "").strip())
+                except ValueError:
+                    cells.append(r[i])
+            else:
+                cells.append("-")
+        out.write(f"| `{short(r[hdr.index('Kernel Name')])}` | " + " | ".join(cells) + " |\n")
+    stall = [i for i, c in enumerate(hdr) if "pcsamp_warps_issue_stalled" in c and "not_issued" not in c]
+    if stall:
+        out.write("\nTop warp-stall reasons (share of PC samples):\n\n")
+        for r in data:
+            tot = sum(float(r[i] or 0) for i in stall) or 1.0
+            top = sorted(((float(r[i] or 0) / tot, hdr[i].replace("smsp__pcsamp_warps_issue_stalled_", "")) for i in stall), reverse=True)[:5]
+            out.write(f"- `{short(r[hdr.index('Kernel Name')])}`: " + ", ".join(f"{n} {100 * v:.0f}%" for v, n in top) + "\n")
+    out.write("\n")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("tag")
+    ap.add_argument("--launches")
+    ap.add_argument("--rep")
+    ap.add_argument("--note", default="")
+    a = ap.parse_args()
+    dst = ROOT / "profiles" / f"{a.tag}.md"
+    with open(dst, "w") as out:
+        out.write(f"# ncu summary {a.tag}\n\n{a.note}\n\n")
+        if a.launches:
+            launches(a.launches, out)
+        if a.rep:
+            full(a.rep, out)
+    print(dst)
