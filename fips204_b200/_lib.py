@@ -27,6 +27,9 @@ SIGNATURES = {
     "mldsa_sign_batch_dev": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
     "mldsa_verify_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
     "mldsa_verify_batch_dev": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
+    "mldsa_keygen_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, vp, vp]),
+    "mldsa_sign_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
+    "mldsa_verify_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
     "mldsa_ntt_batch": (C.c_int, [C.c_int, sz, vp]),
     "mldsa_intt_batch": (C.c_int, [C.c_int, sz, vp]),
     "mldsa_expand_a_batch": (C.c_int, [C.c_int, sz, vp, vp]),

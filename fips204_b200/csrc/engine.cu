@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mldsa_b200.h"
@@ -349,7 +350,13 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
 static DeviceCtx* lock_ctx(int dev, std::unique_lock<std::mutex>& lk, int& rc)
 {
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || dev < 0 || dev >= ndev || dev >= MAX_DEV) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        t_cuda_err = "no CUDA device available (this library has no CPU fallback)";
+        rc = E_CUDA;
+        return nullptr;
+    }
+    if (dev < 0 || dev >= ndev || dev >= MAX_DEV) {
         rc = E_PARAM;
         return nullptr;
     }
@@ -720,6 +727,58 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
         lo += m;
     }
     return OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU host entry points
+}  // extern "C"
+template <class Fn>
+static int run_sharded(const int* devs, int ndev, size_t n, Fn&& fn)
+{
+    if (!devs || ndev <= 0) return E_PARAM;
+    if (ndev == 1) return fn(devs[0], (size_t)0, n);
+    std::vector<std::thread> th;
+    std::vector<int> rcs((size_t)ndev, OK);
+    for (int g = 0; g < ndev; g++) {
+        const size_t lo = n * (size_t)g / (size_t)ndev, hi = n * (size_t)(g + 1) / (size_t)ndev;
+        th.emplace_back([&, g, lo, hi] { rcs[(size_t)g] = hi > lo ? fn(devs[g], lo, hi - lo) : OK; });
+    }
+    for (auto& t : th) t.join();
+    for (int rc : rcs)
+        if (rc) return rc;
+    return OK;
+}
+extern "C" {
+
+int mldsa_keygen_batch_multi(int ps, const int* devs, int ndev, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk)
+{
+    PSInfo p;
+    if (!ps_info(ps, p)) return E_PARAM;
+    return run_sharded(devs, ndev, n, [&](int dev, size_t lo, size_t m) {
+        return mldsa_keygen_batch(ps, dev, m, xi + 32 * lo, pk + p.pk * lo, sk + p.sk * lo);
+    });
+}
+int mldsa_sign_batch_multi(int ps, const int* devs, int ndev, int framing, size_t n, const uint8_t* sk,
+                           size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx,
+                           const uint32_t* ctx_off, const uint8_t* rnd, uint8_t* sig, uint32_t* iters)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || !msg_off) return E_PARAM;
+    return run_sharded(devs, ndev, n, [&](int dev, size_t lo, size_t m) {
+        return mldsa_sign_batch(ps, dev, framing, m, sk + sk_stride * lo, sk_stride, msgs, msg_off + lo, ctx,
+                                ctx_off ? ctx_off + lo : nullptr, rnd + 32 * lo, sig + p.sig * lo,
+                                iters ? iters + lo : nullptr);
+    });
+}
+int mldsa_verify_batch_multi(int ps, const int* devs, int ndev, int framing, size_t n, const uint8_t* pk,
+                             size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx,
+                             const uint32_t* ctx_off, const uint8_t* sig, uint8_t* ok)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || !msg_off) return E_PARAM;
+    return run_sharded(devs, ndev, n, [&](int dev, size_t lo, size_t m) {
+        return mldsa_verify_batch(ps, dev, framing, m, pk + pk_stride * lo, pk_stride, msgs, msg_off + lo, ctx,
+                                  ctx_off ? ctx_off + lo : nullptr, sig + p.sig * lo, ok + lo);
+    });
 }
 
 static int micro_host(int dev, size_t n, const void* in, size_t in_bytes, void* out, size_t out_bytes, int which)

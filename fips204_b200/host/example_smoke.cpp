@@ -1,0 +1,38 @@
+// Mirrors the reference's in-crate smoke test (src/lib.rs:503-551) through the C++ host mirror.
+//   g++ -std=c++17 -O2 example_smoke.cpp -L.. -lmldsa_b200 -Wl,-rpath,'$ORIGIN/..' -o example_smoke
+#include <cstdio>
+
+#include "fips204.hpp"
+
+template <class M> static int run(const char* name, int want_pk0)
+{
+    using namespace fips204;
+    std::array<uint8_t, 32> xi;
+    xi.fill(0x11);
+    auto [pk, sk] = M::KG::keygen_from_seed(xi);  // lib.rs:535
+    std::vector<uint8_t> m1{0, 1, 2, 3, 4, 5, 6, 7}, m2{7, 7, 7, 7, 7, 7, 7, 7};
+    std::array<uint8_t, 32> seed;
+    seed.fill(12);
+    auto sig = sk.try_sign_with_seed(seed, m1, {});
+    bool ok = pk.verify(m1, sig, {}) && !pk.verify(m2, sig, {}) && !pk.verify(m1, sig, std::vector<uint8_t>(257, 0));
+    bool threw = false;
+    try {
+        sk.try_sign_with_seed(seed, m1, std::vector<uint8_t>(257, 0));
+    } catch (const Error& e) {
+        threw = std::string(e.what()) == "ML-DSA.Sign: ctx too long";
+    }
+    ok = ok && threw && pk.into_bytes()[0] == want_pk0;  // lib.rs:543-545
+    std::printf("%s: %s\n", name, ok ? "ok" : "FAILED");
+    return ok ? 0 : 1;
+}
+
+int main()
+{
+    try {
+        return run<fips204::ml_dsa_44>("ml_dsa_44", 197) | run<fips204::ml_dsa_65>("ml_dsa_65", 177) |
+               run<fips204::ml_dsa_87>("ml_dsa_87", 16);
+    } catch (const fips204::Error& e) {
+        std::printf("error %d: %s\n", e.code, e.what());
+        return 2;
+    }
+}

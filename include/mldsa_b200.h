@@ -84,6 +84,18 @@ int mldsa_verify_batch_dev(int ps, void* stream, int framing, size_t n, const ui
                            const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
                            const uint32_t* d_ctx_off, const uint8_t* d_sig, uint8_t* d_ok);
 
+/* ---- multi-GPU: one host batch split contiguously over a device list -----------------------
+ * Lanes are independent, so there is no collective: device g of ndev gets lanes
+ * [n*g/ndev, n*(g+1)/ndev), runs on its own host thread, and writes its disjoint output slice.
+ * Arguments as in the single-device host entry points. */
+int mldsa_keygen_batch_multi(int ps, const int* devs, int ndev, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk);
+int mldsa_sign_batch_multi(int ps, const int* devs, int ndev, int framing, size_t n, const uint8_t* sk,
+                           size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx,
+                           const uint32_t* ctx_off, const uint8_t* rnd, uint8_t* sig, uint32_t* iters);
+int mldsa_verify_batch_multi(int ps, const int* devs, int ndev, int framing, size_t n, const uint8_t* pk,
+                             size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx,
+                             const uint32_t* ctx_off, const uint8_t* sig, uint8_t* ok);
+
 /* ---- microbench / leaf entry points (BASELINE config 2) ----------------------------------
  * ntt: src/ntt.rs:14-76, raw-bit-exact representatives; intt: src/ntt.rs:85-161, canonical [0,q).
  * expand_a: out[i] = RejNTTPoly(seed34[i]), src/hashing.rs:111-146.  In place on n x 256 int32. */
