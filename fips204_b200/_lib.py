@@ -38,6 +38,7 @@ SIGNATURES = {
     "mldsa_expand_a_batch_dev": (C.c_int, [vp, sz, vp, vp]),
     "mldsa_shake_batch": (C.c_int, [C.c_int, C.c_int, sz, vp, sz, vp, sz]),
     "mldsa_set_workspace_limit": (None, [sz]),
+    "mldsa_set_tuning": (None, [C.c_int, C.c_int, C.c_int]),
     "mldsa_kernel_launches": (C.c_uint64, []),
     "mldsa_last_sign_rounds": (C.c_int, []),
     "mldsa_profile_enable": (None, [C.c_int]),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "mldsa_profile_name": (C.c_char_p, [C.c_int]),
     "mldsa_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mldsa_int32_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "mldsa_keccak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]),
 }
 
 _lib = None

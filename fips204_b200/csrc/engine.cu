@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -80,6 +81,37 @@ void prof_collect()
     t_events.clear();
 }
 
+static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1};
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+Tuning tuning()
+{
+    int w = g_ways.load(), k = g_kcap.load(), a = g_acap.load();
+    if (w < 0) g_ways.store(w = env_int("MLDSA_WAYS", 1));
+    if (k < 0) g_kcap.store(k = env_int("MLDSA_KCAP", 0));
+    if (a < 0) g_acap.store(a = env_int("MLDSA_ACAP", 0));
+    if (w < 1) w = 1;
+    if (w > 8) w = 8;
+    return Tuning{w, k, a};
+}
+unsigned capped_grid(size_t want_ctas, int cap_per_sm)
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms = n;
+    }
+    if (want_ctas < 1) want_ctas = 1;
+    if (cap_per_sm > 0 && want_ctas > (size_t)sms * cap_per_sm) want_ctas = (size_t)sms * cap_per_sm;
+    if (want_ctas > 0x7fffffffu) want_ctas = 0x7fffffffu;
+    return (unsigned)want_ctas;
+}
+
 static thread_local std::string t_cuda_err;
 static thread_local int t_last_rounds = 0;
 static std::atomic<size_t> g_ws_limit{0};
@@ -116,16 +148,26 @@ struct DeviceCtx {
     std::mutex mu;
     int dev = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t way_stream[8] = {};  // extra streams for the concurrent ways of a sign chunk
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // H2D / D2H streams of the chunk pipeline
+    cudaEvent_t ev_in[2] = {}, ev_out[2] = {};
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
-    uint32_t* mailbox = nullptr;  // pinned, 16 words
+    uint32_t* mailbox = nullptr;  // pinned, 4 words per way
 
     int init(int d)
     {
         if (dev == d) return OK;
         CK(cudaSetDevice(d));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 64, cudaHostAllocDefault));
+        for (auto& ws : way_stream) CK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 256, cudaHostAllocDefault));
         dev = d;
         return OK;
     }
@@ -216,7 +258,7 @@ static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n, bool shared)
     w.t1h = c.take<int32_t>((size_t)p.K * 256);
     w.tr = c.take<uint8_t>(64);
     w.mw1 = c.take<uint8_t>(n * (size_t)(64 + p.w1len));
-    w.sib = c.take<uint8_t>(n * (size_t)SIB_BYTES);
+    w.cmask = c.take<uint8_t>(n * (size_t)SIB_BYTES);
     w.pre_ok = c.take<uint8_t>(n);
     return w;
 }
@@ -241,7 +283,7 @@ static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint
     w.mw1 = c.take<uint8_t>(n * (size_t)(64 + p.w1len));
     w.rhopp = c.take<uint8_t>(n * 64);
     w.ctilde = c.take<uint8_t>(n * 64);
-    w.sib = c.take<uint8_t>(n * (size_t)SIB_BYTES);
+    w.cmask = c.take<uint8_t>(n * (size_t)SIB_BYTES);
     w.kappa = c.take<uint32_t>(n);
     w.done = c.take<uint8_t>(n);
     w.act[0] = c.take<uint32_t>(n);
@@ -320,28 +362,71 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
     const bool shared = sk_stride == 0;
     const size_t fixed = sign_ws_bytes(p, 0, shared);
     const size_t per_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? fixed : 0)) / 1024 + 1;
-    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + fixed, per_lane);
-    int rc = cx.reserve(arena_skip + sign_ws_bytes(p, chunk, shared), arena_skip);
+    int ways = tuning().ways;
+    if (n < (size_t)ways * 4096) ways = 1;  // small batches: concurrency only adds latency
+    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + (size_t)ways * (fixed + 4096), per_lane);
+    // worst-case carve: every way carries its own fixed part; lanes are split evenly
+    const size_t way_lanes = (chunk + ways - 1) / ways;
+    int rc = cx.reserve(arena_skip + (size_t)ways * sign_ws_bytes(p, way_lanes, shared), arena_skip);
     if (rc) return rc;
     t_last_rounds = 0;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    cudaEvent_t ready = nullptr;
+    if (ways > 1) {
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(ready, st));  // inputs staged on `st` must be visible to the other ways' streams
+    }
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
-        Carver c(cx.arena + arena_skip);
-        SignWs ws = sign_carve(c, p, m, shared, cx.mailbox);
-        ws.h_nact[1] = 0;
-        MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
-        int rounds = 0;
-        cudaError_t e = sign_run(ps, st, m, d_sk + sk_stride * lo, sk_stride, md, d_rnd + 32 * lo, d_sig + p.sig * lo,
-                                 d_iters ? d_iters + lo : nullptr, ws, &rounds);
-        t_last_rounds += rounds;
-        // zero everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop)
-        cudaMemsetAsync(cx.arena + arena_skip, 0, c.off, st);
-        if (e != cudaSuccess) {
-            cudaStreamSynchronize(st);
-            if (ws.h_nact[1] == CTX_ERR_MARK) return E_CTX;
-            return cuda_fail(e, "sign_run");
+        std::vector<int> rcs((size_t)ways, OK), rounds((size_t)ways, 0);
+        std::vector<std::string> errs((size_t)ways);
+        auto run_way = [&](int w) {
+            const size_t wlo = lo + m * (size_t)w / (size_t)ways, whi = lo + m * (size_t)(w + 1) / (size_t)ways;
+            const size_t wm = whi - wlo;
+            if (wm == 0) return;
+            cudaSetDevice(dev);
+            cudaStream_t ws_stream = w == 0 ? st : cx.way_stream[w];
+            if (w != 0) cudaStreamWaitEvent(ws_stream, ready, 0);
+            Carver c(cx.arena + arena_skip + (size_t)w * sign_ws_bytes(p, way_lanes, shared));
+            SignWs ws = sign_carve(c, p, wm, shared, cx.mailbox + 4 * w);
+            ws.h_nact[1] = 0;
+            MsgDesc md{d_msgs, d_msg_off + wlo, d_ctx, d_ctx_off ? d_ctx_off + wlo : nullptr, framing};
+            cudaError_t e = sign_run(ps, ws_stream, wm, d_sk + sk_stride * wlo, sk_stride, md, d_rnd + 32 * wlo,
+                                     d_sig + p.sig * wlo, d_iters ? d_iters + wlo : nullptr, ws, &rounds[(size_t)w]);
+            // zero everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop)
+            cudaMemsetAsync(c.base, 0, c.off, ws_stream);
+            cudaStreamSynchronize(ws_stream);
+            prof_collect();
+            if (e != cudaSuccess) {
+                if (ws.h_nact[1] == CTX_ERR_MARK) {
+                    rcs[(size_t)w] = E_CTX;
+                } else {
+                    rcs[(size_t)w] = cuda_fail(e, "sign_run");
+                    errs[(size_t)w] = t_cuda_err;
+                }
+            }
+        };
+        if (ways == 1) {
+            run_way(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int w = 1; w < ways; w++) th.emplace_back(run_way, w);
+            run_way(0);
+            for (auto& t : th) t.join();
         }
+        int worst = 0;
+        for (int w = 0; w < ways; w++) {
+            if (rounds[(size_t)w] > worst) worst = rounds[(size_t)w];
+            if (rcs[(size_t)w]) {
+                if (!errs[(size_t)w].empty()) t_cuda_err = errs[(size_t)w];
+                if (ready) cudaEventDestroy(ready);
+                return rcs[(size_t)w];
+            }
+        }
+        t_last_rounds += worst;
     }
+    if (ready) cudaEventDestroy(ready);
     CK(cudaStreamSynchronize(st));
     prof_collect();
     return OK;
@@ -438,6 +523,12 @@ void mldsa_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
+void mldsa_set_tuning(int ways, int kcap, int acap)
+{
+    g_ways.store(ways < 1 ? 1 : ways);
+    g_kcap.store(kcap < 0 ? 0 : kcap);
+    g_acap.store(acap < 0 ? 0 : acap);
+}
 uint64_t mldsa_kernel_launches(void) { return g_launches.load(); }
 
 void mldsa_profile_enable(int on) { g_profiling.store(on ? 1 : 0); }
@@ -457,6 +548,43 @@ int mldsa_profile_get(int id, double* ms, uint64_t* launches)
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (ms) *ms = g_prof_ms[id];
     if (launches) *launches = g_prof_n[id];
+    return OK;
+}
+
+// Keccak-f[1600] permutations per second for rotation-split variant `variant` (see k_probe.cu); *mask
+// receives the variant's KECCAK_FMA_SITES value.  Returns -1 when variant is out of range.
+int mldsa_keccak_probe(int variant, double* perms_per_sec, uint32_t* mask)
+{
+    if (variant < 0 || variant >= keccak_probe_variants() || !perms_per_sec) return E_PARAM;
+    if (mask) *mask = keccak_probe_mask(variant);
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 4 * 4, reps = 64;
+    uint64_t* state = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&state), (size_t)blocks * 128 * 25 * 8));
+    CK(cudaMemset(state, 0x5a, (size_t)blocks * 128 * 25 * 8));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a, 0);
+        cudaError_t e = launch_keccak_probe(0, variant, blocks, reps, state);
+        cudaEventRecord(b, 0);
+        if (e != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) {
+            cudaFree(state);
+            return cuda_fail(e != cudaSuccess ? e : cudaGetLastError(), "keccak probe");
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double rate = (double)blocks * 128 * reps / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(state);
+    *perms_per_sec = best;
     return OK;
 }
 
@@ -603,14 +731,35 @@ int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk
     return OK;
 }
 
-// stage the ragged message / ctx slices of lanes [lo, lo+m) and build a MsgDesc whose offsets are
-// the caller's absolute ones (the base pointers are rebased instead)
-struct StagedMsgs {
-    const uint8_t* d_msgs;
-    const uint64_t* d_msg_off;
-    const uint8_t* d_ctx;
-    const uint32_t* d_ctx_off;
+// ---- chunk pipeline of the host-pointer entry points ---------------------------------------------
+// A batch is cut into chunks; chunk i+1's inputs are copied in (stream s_in) and chunk i-1's results are
+// copied out (stream s_out) while chunk i computes, with two sets of staging buffers.  With pinned caller
+// buffers the copies are true async DMA in both directions, so a step costs ~max(compute, H2D, D2H) instead
+// of their sum.  Per-chunk inputs are the packed bytes only (SURVEY.md section 7 "PCIe can beat compute").
+struct ChunkPlan {
+    size_t chunk = 0, nchunks = 0, max_mbytes = 0, max_cbytes = 0;
 };
+static ChunkPlan plan_chunks(size_t arena_bytes, size_t n, size_t fixed, size_t per_lane, const uint64_t* msg_off,
+                             const uint32_t* ctx_off)
+{
+    ChunkPlan pl;
+    size_t chunk = pick_chunk(arena_bytes, n, fixed, per_lane);
+    // at least 4 chunks once the batch is big enough for the copies to matter, so the pipeline has stages
+    if (n >= (size_t(1) << 17)) {
+        const size_t quarter = (n + 3) / 4;
+        if (chunk > quarter) chunk = quarter;
+    }
+    pl.chunk = chunk;
+    pl.nchunks = (n + chunk - 1) / chunk;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        const size_t mb = (size_t)(msg_off[lo + m] - msg_off[lo]);
+        const size_t cb = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
+        if (mb > pl.max_mbytes) pl.max_mbytes = mb;
+        if (cb > pl.max_cbytes) pl.max_cbytes = cb;
+    }
+    return pl;
+}
 
 int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
                      const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
@@ -629,48 +778,83 @@ int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, 
     DeviceCtx* cx = lock_ctx(dev, lk, rc);
     if (!cx) return rc;
     const bool shared = sk_stride == 0;
+    const int ways = tuning().ways;
     const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
     const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
-    const size_t fixed = sign_ws_bytes(p, 0, shared) + (shared ? pad256(p.sk) : 0);
+    const size_t fixed = (size_t)ways * (sign_ws_bytes(p, 0, shared) + 4096) + (shared ? 2 * pad256(p.sk) : 0) + 65536;
     const size_t ws_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? sign_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
-    const size_t io_lane = (shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + 2 * avg_msg + 2 * avg_ctx;
-    size_t chunk = pick_chunk(cx->arena_bytes, n, fixed, ws_lane + io_lane);
+    const size_t io_lane = 2 * ((shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + avg_msg + avg_ctx);
+    const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
+    const size_t C = pl.chunk;
+    struct Set {
+        uint8_t *sk, *rnd, *sig, *m, *c;
+        uint32_t *it, *co;
+        uint64_t* mo;
+    } set[2];
+    const size_t set_bytes = pad256(shared ? p.sk : C * p.sk) + pad256(C * 32) + pad256(C * p.sig) + pad256(C * 4) +
+                             pad256((C + 1) * 8) + pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) +
+                             pad256(pl.max_cbytes + 8);
+    const size_t way_lanes = (C + ways - 1) / ways;
+    rc = cx->reserve(2 * set_bytes + (size_t)ways * sign_ws_bytes(p, way_lanes, shared) + 4096);
+    if (rc) return rc;
+    Carver c(cx->arena);
+    for (auto& s : set) {
+        s.sk = c.take<uint8_t>(shared ? p.sk : C * p.sk);
+        s.rnd = c.take<uint8_t>(C * 32);
+        s.sig = c.take<uint8_t>(C * p.sig);
+        s.it = c.take<uint32_t>(C);
+        s.mo = c.take<uint64_t>(C + 1);
+        s.co = c.take<uint32_t>(C + 1);
+        s.m = c.take<uint8_t>(pl.max_mbytes + 8);
+        s.c = c.take<uint8_t>(pl.max_cbytes + 8);
+    }
+    const size_t io = c.off;
     cudaStream_t st = cx->stream;
-    for (size_t lo = 0; lo < n;) {
-        size_t m = n - lo < chunk ? n - lo : chunk;
+    auto copy_in = [&](size_t i) -> int {
+        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        Set& s = set[i & 1];
         const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
-        const size_t io = pad256(shared ? p.sk : m * p.sk) + pad256(m * 32) + pad256(m * p.sig) + pad256(m * 4) +
-                          pad256((m + 1) * 8) + pad256((m + 1) * 4) + pad256(mbytes + 8) + pad256(cbytes + 8);
-        rc = cx->reserve(io + sign_ws_bytes(p, m, shared));
-        if (rc) return rc;
-        Carver c(cx->arena);
-        uint8_t* d_sk = c.take<uint8_t>(shared ? p.sk : m * p.sk);
-        uint8_t* d_rnd = c.take<uint8_t>(m * 32);
-        uint8_t* d_sig = c.take<uint8_t>(m * p.sig);
-        uint32_t* d_it = c.take<uint32_t>(m);
-        uint64_t* d_mo = c.take<uint64_t>(m + 1);
-        uint32_t* d_co = c.take<uint32_t>(m + 1);
-        uint8_t* d_m = c.take<uint8_t>(mbytes + 8);
-        uint8_t* d_c = c.take<uint8_t>(cbytes + 8);
-        CK(cudaMemcpyAsync(d_sk, sk + sk_stride * lo, shared ? p.sk : m * p.sk, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_rnd, rnd + 32 * lo, m * 32, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (mbytes) CK(cudaMemcpyAsync(d_m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.sk, sk + sk_stride * lo, shared ? p.sk : m * p.sk, cudaMemcpyHostToDevice, cx->s_in));
+        CK(cudaMemcpyAsync(s.rnd, rnd + 32 * lo, m * 32, cudaMemcpyHostToDevice, cx->s_in));
+        CK(cudaMemcpyAsync(s.mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, cx->s_in));
+        if (mbytes) CK(cudaMemcpyAsync(s.m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, cx->s_in));
         if (ctx_off) {
-            CK(cudaMemcpyAsync(d_co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, st));
-            if (cbytes) CK(cudaMemcpyAsync(d_c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s.co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, cx->s_in));
+            if (cbytes) CK(cudaMemcpyAsync(s.c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, cx->s_in));
         }
-        rc = sign_core(*cx, st, ps, framing, m, d_sk, sk_stride, d_m - msg_off[lo], d_mo, ctx_off ? d_c - ctx_off[lo] : nullptr,
-                       ctx_off ? d_co : nullptr, d_rnd, d_sig, d_it, c.off);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(sig + p.sig * lo, d_sig, m * p.sig, cudaMemcpyDeviceToHost, st));
-        if (iters) CK(cudaMemcpyAsync(iters + lo, d_it, m * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemsetAsync(d_sk, 0, shared ? p.sk : m * p.sk, st));
-        CK(cudaMemsetAsync(d_rnd, 0, m * 32, st));
+        CK(cudaEventRecord(cx->ev_in[i & 1], cx->s_in));
+        return OK;
+    };
+    // make sure nothing of a previous call is still in flight on the copy streams
+    CK(cudaStreamSynchronize(cx->s_in));
+    CK(cudaStreamSynchronize(cx->s_out));
+    rc = copy_in(0);
+    if (rc) return rc;
+    for (size_t i = 0; i < pl.nchunks; i++) {
+        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        Set& s = set[i & 1];
+        if (i + 1 < pl.nchunks) {
+            rc = copy_in(i + 1);  // overlaps with this chunk's compute
+            if (rc) return rc;
+        }
+        CK(cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0));
+        if (i >= 2) CK(cudaStreamWaitEvent(st, cx->ev_out[i & 1], 0));  // D2H(i-2) has drained this set's outputs
+        rc = sign_core(*cx, st, ps, framing, m, s.sk, sk_stride, s.m - msg_off[lo], s.mo,
+                       ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, s.rnd, s.sig, s.it, io);
+        if (rc) {
+            cudaStreamSynchronize(cx->s_in);
+            cudaStreamSynchronize(cx->s_out);
+            return rc;
+        }
+        CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, st));  // secrets do not linger in the staging set
+        CK(cudaMemsetAsync(s.rnd, 0, m * 32, st));
         CK(cudaStreamSynchronize(st));
-        lo += m;
+        CK(cudaMemcpyAsync(sig + p.sig * lo, s.sig, m * p.sig, cudaMemcpyDeviceToHost, cx->s_out));
+        if (iters) CK(cudaMemcpyAsync(iters + lo, s.it, m * 4, cudaMemcpyDeviceToHost, cx->s_out));
+        CK(cudaEventRecord(cx->ev_out[i & 1], cx->s_out));
     }
+    CK(cudaStreamSynchronize(cx->s_out));
     return OK;
 }
 
@@ -690,42 +874,72 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
     const bool shared = pk_stride == 0;
     const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
     const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
-    const size_t fixed = verify_ws_bytes(p, 0, shared) + (shared ? pad256(p.pk) : 0);
+    const size_t fixed = verify_ws_bytes(p, 0, shared) + (shared ? 2 * pad256(p.pk) : 0) + 65536;
     const size_t ws_lane = (verify_ws_bytes(p, 1024, shared) - (shared ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
-    const size_t io_lane = (shared ? 0 : p.pk) + p.sig + 1 + 8 + 4 + 2 * avg_msg + 2 * avg_ctx;
-    size_t chunk = pick_chunk(cx->arena_bytes, n, fixed, ws_lane + io_lane);
+    const size_t io_lane = 2 * ((shared ? 0 : p.pk) + p.sig + 1 + 8 + 4 + avg_msg + avg_ctx);
+    const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
+    const size_t C = pl.chunk;
+    struct Set {
+        uint8_t *pk, *sig, *ok, *m, *c;
+        uint32_t* co;
+        uint64_t* mo;
+    } set[2];
+    const size_t set_bytes = pad256(shared ? p.pk : C * p.pk) + pad256(C * p.sig) + pad256(C) + pad256((C + 1) * 8) +
+                             pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) + pad256(pl.max_cbytes + 8);
+    rc = cx->reserve(2 * set_bytes + verify_ws_bytes(p, C, shared) + 4096);
+    if (rc) return rc;
+    Carver c(cx->arena);
+    for (auto& s : set) {
+        s.pk = c.take<uint8_t>(shared ? p.pk : C * p.pk);
+        s.sig = c.take<uint8_t>(C * p.sig);
+        s.ok = c.take<uint8_t>(C);
+        s.mo = c.take<uint64_t>(C + 1);
+        s.co = c.take<uint32_t>(C + 1);
+        s.m = c.take<uint8_t>(pl.max_mbytes + 8);
+        s.c = c.take<uint8_t>(pl.max_cbytes + 8);
+    }
+    const size_t io = c.off;
     cudaStream_t st = cx->stream;
-    for (size_t lo = 0; lo < n;) {
-        size_t m = n - lo < chunk ? n - lo : chunk;
+    auto copy_in = [&](size_t i) -> int {
+        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        Set& s = set[i & 1];
         const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
-        const size_t io = pad256(shared ? p.pk : m * p.pk) + pad256(m * p.sig) + pad256(m) + pad256((m + 1) * 8) +
-                          pad256((m + 1) * 4) + pad256(mbytes + 8) + pad256(cbytes + 8);
-        rc = cx->reserve(io + verify_ws_bytes(p, m, shared));
-        if (rc) return rc;
-        Carver c(cx->arena);
-        uint8_t* d_pk = c.take<uint8_t>(shared ? p.pk : m * p.pk);
-        uint8_t* d_sig = c.take<uint8_t>(m * p.sig);
-        uint8_t* d_ok = c.take<uint8_t>(m);
-        uint64_t* d_mo = c.take<uint64_t>(m + 1);
-        uint32_t* d_co = c.take<uint32_t>(m + 1);
-        uint8_t* d_m = c.take<uint8_t>(mbytes + 8);
-        uint8_t* d_c = c.take<uint8_t>(cbytes + 8);
-        CK(cudaMemcpyAsync(d_pk, pk + pk_stride * lo, shared ? p.pk : m * p.pk, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_sig, sig + p.sig * lo, m * p.sig, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (mbytes) CK(cudaMemcpyAsync(d_m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.pk, pk + pk_stride * lo, shared ? p.pk : m * p.pk, cudaMemcpyHostToDevice, cx->s_in));
+        CK(cudaMemcpyAsync(s.sig, sig + p.sig * lo, m * p.sig, cudaMemcpyHostToDevice, cx->s_in));
+        CK(cudaMemcpyAsync(s.mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, cx->s_in));
+        if (mbytes) CK(cudaMemcpyAsync(s.m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, cx->s_in));
         if (ctx_off) {
-            CK(cudaMemcpyAsync(d_co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, st));
-            if (cbytes) CK(cudaMemcpyAsync(d_c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s.co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, cx->s_in));
+            if (cbytes) CK(cudaMemcpyAsync(s.c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, cx->s_in));
         }
-        rc = verify_core(*cx, st, ps, framing, m, d_pk, pk_stride, d_m - msg_off[lo], d_mo,
-                         ctx_off ? d_c - ctx_off[lo] : nullptr, ctx_off ? d_co : nullptr, d_sig, d_ok, c.off);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(ok + lo, d_ok, m, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        lo += m;
+        CK(cudaEventRecord(cx->ev_in[i & 1], cx->s_in));
+        return OK;
+    };
+    CK(cudaStreamSynchronize(cx->s_in));
+    CK(cudaStreamSynchronize(cx->s_out));
+    rc = copy_in(0);
+    if (rc) return rc;
+    for (size_t i = 0; i < pl.nchunks; i++) {
+        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        Set& s = set[i & 1];
+        if (i + 1 < pl.nchunks) {
+            rc = copy_in(i + 1);
+            if (rc) return rc;
+        }
+        CK(cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0));
+        if (i >= 2) CK(cudaStreamWaitEvent(st, cx->ev_out[i & 1], 0));
+        rc = verify_core(*cx, st, ps, framing, m, s.pk, pk_stride, s.m - msg_off[lo], s.mo,
+                         ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, s.sig, s.ok, io);
+        if (rc) {
+            cudaStreamSynchronize(cx->s_in);
+            cudaStreamSynchronize(cx->s_out);
+            return rc;
+        }
+        CK(cudaMemcpyAsync(ok + lo, s.ok, m, cudaMemcpyDeviceToHost, cx->s_out));
+        CK(cudaEventRecord(cx->ev_out[i & 1], cx->s_out));
     }
+    CK(cudaStreamSynchronize(cx->s_out));
     return OK;
 }
 

@@ -11,6 +11,7 @@ namespace mldsa {
 enum : int { OK = 0, E_PARAM = -1, E_CTX = -2, E_CUDA = -3, E_NOMEM = -4, E_UNSUPPORTED = -5 };
 
 constexpr int SIB_BYTES = 136;   // one SHAKE256 block of H(c~) for SampleInBall
+constexpr int CMASK_STRIDE = 64;  // bytes per lane of the challenge masks
 constexpr int MU_BYTES = 64;
 constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_run saw |ctx| > 255
 
@@ -27,16 +28,30 @@ struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<
     KLaunch(int id, cudaStream_t st);
     ~KLaunch();
 };
-void prof_collect();  // fold finished event pairs into the per-kernel totals (call after a stream sync)
+void prof_collect();
+
+// Launch tunables (mldsa_set_tuning / MLDSA_WAYS, MLDSA_KCAP, MLDSA_ACAP).  A sign chunk is split into
+// `ways` independent sub-batches that run concurrently on separate streams, so the ALU-pipe-bound Keccak
+// kernels of one way overlap the FMA/DRAM-bound arithmetic kernels of another.  kcap / acap cap the
+// CTAs per SM of the (grid-stride) Keccak / arithmetic kernels so that kernels of different ways can be
+// co-resident on an SM (0 = no cap).
+struct Tuning {
+    int ways, kcap, acap;
+};
+Tuning tuning();
+unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event pairs into the per-kernel totals (call after a stream sync)
 
 // ---- k_common.cu ----
 // Commitment hash.  Verify mode (ctilde_out == nullptr): ok[i] = pre_ok[i] && H(mu||w1')[0..CT) == sig_i[0..CT)
-// (src/ml_dsa.rs:427-436).  Sign mode: ctilde_out[i] = H(mu||w1)[0..CT) and sib_out[i] = first SHAKE256 block
-// of H(c~) (src/ml_dsa.rs:231-237).  act: optional list of lane ids (n entries), else lanes 0..n-1.
+// (src/ml_dsa.rs:427-436).  Sign mode: ctilde_out[i] = H(mu||w1)[0..CT) and cmask_out[i] = SampleInBall(c~) as
+// two 256-bit masks (src/ml_dsa.rs:231-237, src/hashing.rs:43-100).  act: optional list of lane ids (n entries), else lanes 0..n-1.
 cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
                           const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
-                          uint8_t* sib_out);
+                          uint8_t* cmask_out);
 
+int keccak_probe_variants();
+uint32_t keccak_probe_mask(int v);
+cudaError_t launch_keccak_probe(cudaStream_t st, int variant, int blocks, int reps, uint64_t* state);
 cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops);
 // A[key][r*L+s][256] = RejNTTPoly(rho_key || s || r)          (src/hashing.rs:225-239)
 cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,
@@ -75,7 +90,7 @@ struct VerifyWs {
     int32_t* t1h;      // [nkeys][K][256]   NTT(t1 * 2^d)   (only materialised for a shared key)
     uint8_t* tr;       // [nkeys][64]
     uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1'
-    uint8_t* sib;      // [n][136]
+    uint8_t* cmask;    // [n][64]   c = SampleInBall(c~) as nonzero / negative bit masks
     uint8_t* pre_ok;   // [n]
     static size_t bytes_per_lane(int K, int L, int w1len, bool shared)
     {
@@ -96,7 +111,7 @@ struct SignWs {
     uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1
     uint8_t* rhopp;    // [n][64]
     uint8_t* ctilde;   // [n][64]
-    uint8_t* sib;      // [n][136]
+    uint8_t* cmask;    // [n][64]
     uint32_t* kappa;   // [n]
     uint8_t* done;     // [n]
     uint32_t* act[2];  // [n] active lane lists (ping-pong)

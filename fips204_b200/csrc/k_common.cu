@@ -6,6 +6,7 @@
 #include "keccak.cuh"
 #include "ntt.cuh"
 #include "pack.cuh"
+#include "sampling.cuh"
 
 namespace mldsa {
 
@@ -28,9 +29,12 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
     __shared__ int32_t tile_all[EA_THREADS / 32][32 * EA_ROW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t* tile = tile_all[warp];
-    const size_t q = (size_t)blockIdx.x * EA_THREADS + threadIdx.x;
+    // grid-stride over groups of EA_THREADS streams (a warp always owns 32 consecutive streams)
+    for (size_t q0 = (size_t)blockIdx.x * EA_THREADS; q0 < nstreams; q0 += (size_t)gridDim.x * EA_THREADS) {
+    const size_t q = q0 + threadIdx.x;
     const size_t qbase = q - lane;
     const bool valid = q < nstreams;
+    __syncwarp();
 
     uint64_t a[25];
 #pragma unroll
@@ -81,6 +85,7 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
         j += cnt;
         __syncwarp();
     }
+    }
 }
 
 cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,
@@ -88,7 +93,7 @@ cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, s
 {
     const size_t ns = nkeys * (size_t)(K * L);
     if (ns == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((ns + EA_THREADS - 1) / EA_THREADS);
+    const unsigned grid = capped_grid((ns + EA_THREADS - 1) / EA_THREADS, tuning().kcap);
     {
         KLaunch kl(KID_EXPAND_A, st);
         expand_a_kernel<false><<<grid, EA_THREADS, 0, st>>>(rho, rho_stride, ns, K * L, L, A);
@@ -215,10 +220,9 @@ template <class P, bool SIGN>
 __global__ void __launch_bounds__(128, 4)
 ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restrict__ mw1,
               const uint8_t* __restrict__ sig, const uint8_t* __restrict__ pre_ok, uint8_t* __restrict__ ok,
-              uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ sib_out)
+              uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ cmask_out)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t ln = act ? act[idx] : idx;
     constexpr int NW = (MU_BYTES + P::W1_LEN) / 8;  // 104 or 136 words
     constexpr int NBLK = NW / 17 + 1;               // 7 or 9 absorb blocks (the last holds the padding)
@@ -227,9 +231,13 @@ ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restr
     uint64_t a[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) a[i] = 0;
-    uint64_t ct[CW];
+    SibWalk walk;
+    uint64_t blk[17];  // squeeze block of H(c~) in local memory: the walk indexes it by byte
+    if (SIGN) walk.init(P::TAU);
+    // One permutation call site for: the NBLK absorb blocks of H(mu || w1), and (sign) every squeeze
+    // block of the second sponge H(c~) that SampleInBall consumes (one, except with negligible probability).
 #pragma unroll 1
-    for (int b = 0; b < NBLK + (SIGN ? 1 : 0); b++) {
+    for (int b = 0;; b++) {
         if (b < NBLK) {
 #pragma unroll
             for (int k = 0; k < 17; k++)
@@ -238,23 +246,26 @@ ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restr
                 a[NW % 17] ^= 0x1F;
                 a[16] ^= 0x8000000000000000ULL;
             }
-        } else {  // sign: start the second sponge H(c~) for SampleInBall
+        } else if (b == NBLK) {  // sign: c~ is out; start the second sponge H(c~)
+            uint64_t* co = reinterpret_cast<uint64_t*>(ctilde_out + ln * 64);
 #pragma unroll
-            for (int k = 0; k < CW; k++) ct[k] = a[k];
+            for (int k = 0; k < CW; k++) co[k] = a[k];
 #pragma unroll
-            for (int k = 0; k < 25; k++) a[k] = k < CW ? ct[k] : 0;
+            for (int k = CW; k < 25; k++) a[k] = 0;
             a[CW] = 0x1F;
             a[16] ^= 0x8000000000000000ULL;
         }
         keccak_f1600(a);
+        if (!SIGN) {
+            if (b == NBLK - 1) break;
+        } else if (b >= NBLK) {
+#pragma unroll
+            for (int k = 0; k < 17; k++) blk[k] = a[k];
+            if (walk.consume(blk, P::TAU)) break;
+        }
     }
     if (SIGN) {
-        uint64_t* co = reinterpret_cast<uint64_t*>(ctilde_out + ln * 64);
-#pragma unroll
-        for (int k = 0; k < CW; k++) co[k] = ct[k];
-        uint64_t* so = reinterpret_cast<uint64_t*>(sib_out + ln * (size_t)SIB_BYTES);
-#pragma unroll
-        for (int k = 0; k < 17; k++) so[k] = a[k];
+        walk.store(cmask_out + ln * (size_t)CMASK_STRIDE);
     } else {
         uint32_t w[P::CTILDE / 4];
         load_span<P::CTILDE>(sig + ln * (size_t)P::SIG_LEN, w);
@@ -263,6 +274,7 @@ ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restr
         for (int k = 0; k < CW; k++) eq &= a[k] == ((uint64_t)w[2 * k] | ((uint64_t)w[2 * k + 1] << 32));
         ok[ln] = (eq && pre_ok[ln]) ? 1 : 0;
     }
+    }
 }
 
 template <class P>
@@ -270,7 +282,7 @@ static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* ac
                                    const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
                                    uint8_t* sib_out)
 {
-    const unsigned grid = (unsigned)((n + 127) / 128);
+    const unsigned grid = capped_grid((n + 127) / 128, tuning().kcap);
     {
         KLaunch kl(KID_CTILDE, st);
         if (ctilde_out)

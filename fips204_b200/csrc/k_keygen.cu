@@ -116,6 +116,7 @@ kg_arith_kernel(size_t n, const uint8_t* __restrict__ seeds, const int8_t* __res
         sko[lane] = sd[lane];
         sko[32 + lane] = sd[96 + lane];
 
+        warp_prefetch_l2(A, 2 * L * 1024, lane);
         int32_t s1h[L][8];
 #pragma unroll
         for (int l = 0; l < L; l++) {
@@ -134,6 +135,7 @@ kg_arith_kernel(size_t n, const uint8_t* __restrict__ seeds, const int8_t* __res
         }
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
+            if (k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
             int64_t acc[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = 0;

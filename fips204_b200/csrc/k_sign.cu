@@ -15,8 +15,8 @@
 //   per round, over the active list
 //     mask          thread/poly  y bytes = H(rho'' || LE16(kappa + r), 32c)          hashing.rs:281-313
 //     sign_w        warp/lane    w = INTT(A-hat o NTT(y)); w1 = HighBits(w); w1Encode ml_dsa.rs:215-232
-//     ctilde        thread/lane  c~ = H(mu || w1), first block of H(c~)              ml_dsa.rs:233-237
-//     sign_z        warp/lane    c, z, r0 / ct0 / hint checks, sigEncode on accept   ml_dsa.rs:237-336
+//     ctilde        thread/lane  c~ = H(mu || w1), c = SampleInBall(c~) as bit masks   ml_dsa.rs:233-237
+//     sign_z        warp/lane    c-hat, r0 / z / ct0 / hint checks, sigEncode          ml_dsa.rs:240-336
 //     compact       thread/lane  rebuild the active list
 #include "engine.h"
 #include "keccak.cuh"
@@ -103,8 +103,7 @@ mask_kernel(size_t nstreams, const uint32_t* __restrict__ act, const uint8_t* __
 {
     constexpr int L = P::L;
     constexpr int YW = 32 * P::ZBITS / 8;  // 72 or 80 output words
-    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nstreams) return;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nstreams; q += (size_t)gridDim.x * blockDim.x) {
     const size_t ln = act[q / L];
     const uint32_t r = (uint32_t)(q % L);
     const uint64_t* rp = reinterpret_cast<const uint64_t*>(rhopp + 64 * ln);
@@ -124,6 +123,7 @@ mask_kernel(size_t nstreams, const uint32_t* __restrict__ act, const uint8_t* __
         for (int k = 0; k < 17; k++)
             if (b * 17 + k < YW) out[b * 17 + k] = a[k];
     }
+    }
 }
 
 // y (layout B regs) from the packed mask bytes: BitUnpack(gamma1 - 1, gamma1)
@@ -136,15 +136,22 @@ __device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (
     for (int i = 0; i < 8; i++) y[i] = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(w, i);
 }
 
+template <class P>
+struct alignas(16) SignWSmem {
+    int32_t tile[NTT_TILE_WORDS];
+    alignas(16) int32_t yh[P::L][256];  // y-hat, NTT domain, natural order (lane t owns words 8t..8t+7 of each row)
+};
+
 template <class P, bool SHARED>
-__global__ void __launch_bounds__(SG_WARPS * 32)
+__global__ void __launch_bounds__(SG_WARPS * 32, 5)
 sign_w_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __restrict__ Aall,
               const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, uint8_t* __restrict__ mw1)
 {
     constexpr int K = P::K, L = P::L;
-    __shared__ __align__(16) int32_t tiles[SG_WARPS][NTT_TILE_WORDS];
+    __shared__ __align__(16) SignWSmem<P> sm_all[SG_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* tile = tiles[warp];
+    SignWSmem<P>& sm = sm_all[warp];
+    int32_t* tile = sm.tile;
     const size_t stride = (size_t)gridDim.x * SG_WARPS;
     for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
         const size_t ln = act[ai];
@@ -152,14 +159,18 @@ sign_w_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __re
         const uint8_t* yp = yraw + ln * (size_t)(L * 32 * P::ZBITS);
         int32_t* wo = wall + ln * (size_t)K * 256;
         uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
-        int32_t yh[L][8];
-#pragma unroll
+        __syncwarp();
+        warp_prefetch_l2(A, 2 * L * 1024, lane);  // rows 0 and 1 of A-hat stream in during the forward NTTs
+#pragma unroll 1
         for (int l = 0; l < L; l++) {
-            load_y<P>(yp + l * 32 * P::ZBITS, lane, yh[l]);
-            ntt_fwd_B2B(yh[l], tile, lane);
+            int32_t y[8];
+            load_y<P>(yp + l * 32 * P::ZBITS, lane, y);
+            ntt_fwd_B2B(y, tile, lane);
+            row_store(sm.yh[l], lane, y);  // only this lane reads these words back
         }
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
+            if (k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
             int64_t acc[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = 0;
@@ -168,8 +179,10 @@ sign_w_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __re
                 const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
                 const int4 x = __ldg(ap), y = __ldg(ap + 1);
                 const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                int32_t yv[8];
+                row_load(sm.yh[l], lane, yv);
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * yh[l][i];
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * yv[i];
             }
             int32_t t[8];
 #pragma unroll
@@ -195,15 +208,18 @@ template <class P>
 struct alignas(16) SignSmem {
     int32_t tile[NTT_TILE_WORDS];
     uint32_t stage[32 * P::ZBITS / 4 + 1];  // packed z polynomial (576/640 B) or the hint bytes
-    uint32_t sibs[SIB_BYTES / 4];
 };
 
+// One pass of the second half of a rejection-loop iteration for one lane.  The three vector products
+// c*s2, c*s1, c*t0 share ONE instance of the inverse-NTT code (a single loop over 2K+L polynomials); the
+// checks run most-selective-first (r0, then z, then ct0/hints) so a rejected iteration stops early.  The
+// order of the checks does not affect the outcome: the reference rejects if ANY fails (ml_dsa.rs:277-319).
 template <class P, bool SHARED>
-__global__ void __launch_bounds__(SG_WARPS * 32)
+__global__ void __launch_bounds__(SG_WARPS * 32, 5)
 sign_z_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __restrict__ s1h_all,
               const int32_t* __restrict__ s2h_all, const int32_t* __restrict__ t0h_all,
               const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, const uint8_t* __restrict__ ctilde,
-              const uint8_t* __restrict__ sib, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
+              const uint8_t* __restrict__ cmask, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
               uint8_t* __restrict__ sig, uint32_t* __restrict__ iters)
 {
     using LO = Layout<P>;
@@ -212,142 +228,143 @@ sign_z_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __re
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SignSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
+    uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
     const size_t stride = (size_t)gridDim.x * SG_WARPS;
     for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
         const size_t ln = act[ai];
         const size_t kn = SHARED ? 0 : ln;
-        const int32_t* s1h = s1h_all + kn * (size_t)L * 256;
-        const int32_t* s2h = s2h_all + kn * (size_t)K * 256;
-        const int32_t* t0h = t0h_all + kn * (size_t)K * 256;
         const uint8_t* yp = yraw + ln * (size_t)(L * 32 * P::ZBITS);
         int32_t* wl = wall + ln * (size_t)K * 256;
-        const uint8_t* ct = ctilde + ln * 64;
         uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
 
-        // c = SampleInBall(c~), c-hat = NTT(c)                                ml_dsa.rs:237-240
-        int32_t ch[8];
-        sample_in_ball_warp<P>(sib + ln * (size_t)SIB_BYTES, ct, sm.sibs, tile, lane, ch);
+        // first operands of the r0 phase stream in while c-hat is computed
+        if (lane < 16) {
+            const char* nxt = lane < 8 ? reinterpret_cast<const char*>(s2h_all + kn * (size_t)K * 256) + 128 * lane
+                                       : reinterpret_cast<const char*>(wl) + 128 * (lane - 8);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+        }
+        // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240), with c-hat * QINV for mont_mul_pre
+        int32_t ch[8], chq[8];
+        load_c_layoutA(cmask + ln * (size_t)CMASK_STRIDE, lane, ch);
         ntt_fwd_A2B(ch, tile, lane);
 #pragma unroll
-        for (int i = 0; i < 8; i++) ch[i] = reduce32(ch[i]);
+        for (int i = 0; i < 8; i++) {
+            ch[i] = reduce32(ch[i]);
+            chq[i] = (int32_t)((uint32_t)ch[i] * (uint32_t)QINV);
+        }
 
         bool rej = false;
-        // z = y + c*s1, ||z||inf < gamma1 - beta                              ml_dsa.rs:243-250, 263-265, 277-283
-#pragma unroll 1
-        for (int l = 0; l < L && !rej; l++) {
-            const int4* sp = reinterpret_cast<const int4*>(s1h + 256 * l + 8 * lane);
-            const int4 x = __ldg(sp), y4 = __ldg(sp + 1);
-            const int32_t sv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
-            int32_t t[8], y[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_mul(ch[i], reduce32(sv[i]));
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);
-            load_y<P>(yp + l * 32 * P::ZBITS, lane, y);
-            uint32_t f[8];
-            bool bad = false;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int32_t z = center(freeze(y[i] + t[i]));                   // z mod+- q (ml_dsa.rs:334-335)
-                bad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;
-                f[i] = (uint32_t)(P::GAMMA1 - z);                                // BitPack(z, gamma1 - 1, gamma1)
-            }
-            rej = __any_sync(0xffffffffu, bad);
-            if (!rej) {  // speculative sigEncode of z[l]; overwritten if a later check rejects
-                uint32_t w[(P::ZBITS + 3) / 4];
-                pack_fields<P::ZBITS>(f, w);
-                __syncwarp();
-                store_span<P::ZBITS>(reinterpret_cast<uint8_t*>(sm.stage) + P::ZBITS * lane, w);
-                __syncwarp();
-                warp_copy_out(sg + LO::SIG_Z + l * 32 * P::ZBITS, sm.stage, 32 * P::ZBITS, lane);
-            }
-        }
-        // r0 = LowBits(w - c*s2), ||r0||inf < gamma2 - beta                   ml_dsa.rs:253-260, 268-272, 277-283
-#pragma unroll 1
-        for (int k = 0; k < K && !rej; k++) {
-            const int4* sp = reinterpret_cast<const int4*>(s2h + 256 * k + 8 * lane);
-            const int4 x = __ldg(sp), y4 = __ldg(sp + 1);
-            const int32_t sv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
-            int32_t t[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_mul(ch[i], reduce32(sv[i]));
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);
-            int4* wp = reinterpret_cast<int4*>(wl + 256 * k + 8 * lane);
-            const int4 wx = wp[0], wy = wp[1];
-            const int32_t wv[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
-            int32_t v[8];
-            bool bad = false;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                v[i] = caddq(wv[i] - t[i]);  // w - cs2, canonical
-                int32_t r0;
-                decompose<P::GAMMA2>(v[i], r0);
-                bad |= (r0 < 0 ? -r0 : r0) >= P::GAMMA2 - P::BETA;
-            }
-            rej = __any_sync(0xffffffffu, bad);
-            wp[0] = make_int4(v[0], v[1], v[2], v[3]);  // w is only ever needed as w - cs2 from here on
-            wp[1] = make_int4(v[4], v[5], v[6], v[7]);
-        }
-        // ct0, hint                                                           ml_dsa.rs:288-319
-        uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
         int hcount = 0;
-        if (!rej) {
-            __syncwarp();
-            for (int i = lane; i < P::OMEGA + K; i += 32) hb[i] = 0;
-            __syncwarp();
-        }
 #pragma unroll 1
-        for (int k = 0; k < K && !rej; k++) {
-            const int4* tp = reinterpret_cast<const int4*>(t0h + 256 * k + 8 * lane);
-            const int4 x = __ldg(tp), y4 = __ldg(tp + 1);
-            const int32_t tv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
+        for (int p = 0; p < 2 * K + L && !rej; p++) {
+            const int phase = p < K ? 0 : (p < K + L ? 1 : 2);
+            const int idx = phase == 0 ? p : (phase == 1 ? p - K : p - K - L);
+            const int32_t* src = phase == 0 ? s2h_all + (kn * K + idx) * 256
+                                            : (phase == 1 ? s1h_all + (kn * L + idx) * 256 : t0h_all + (kn * K + idx) * 256);
+            const int4* sp = reinterpret_cast<const int4*>(src + 8 * lane);
+            const int4 x = __ldg(sp), y4 = __ldg(sp + 1);
+            const int32_t sv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
+            // the s2-hat rows and w rows of one key / lane are contiguous: pull the next ones into L2
+            if (phase == 0 && lane < 16) {
+                const char* nxt = lane < 8 ? reinterpret_cast<const char*>(src + 256) + 128 * lane
+                                           : reinterpret_cast<const char*>(wl + 256 * (idx + 1)) + 128 * (lane - 8);
+                if (idx + 1 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            }
             int32_t t[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_mul(ch[i], reduce32(tv[i]));
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);  // ct0, canonical
-            const int4* wp = reinterpret_cast<const int4*>(wl + 256 * k + 8 * lane);
-            const int4 wx = wp[0], wy = wp[1];
-            const int32_t v[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
-            uint32_t hbits = 0;
+            for (int i = 0; i < 8; i++) t[i] = mont_mul_pre(sv[i], ch[i], chq[i]);
+            ntt_inv_B2B<F_MONT2>(t, tile, lane);  // c*s2[idx] / c*s1[idx] / c*t0[idx], canonical
+
             bool bad = false;
+            if (phase == 0) {
+                // r0 = LowBits(w - c*s2), ||r0||inf < gamma2 - beta              ml_dsa.rs:253-260, 268-272
+                int4* wp = reinterpret_cast<int4*>(wl + 256 * idx + 8 * lane);
+                const int4 wx = wp[0], wy = wp[1];
+                const int32_t wv[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
+                int32_t v[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int32_t c0 = center(t[i]);
-                bad |= (c0 < 0 ? -c0 : c0) >= P::GAMMA2;                         // ml_dsa.rs:314
-                int32_t r0;
-                int32_t u = v[i] + t[i];                                         // w - cs2 + ct0 in [0, 2q)
-                u -= (u >= Q) ? Q : 0;
-                const int32_t h1 = decompose<P::GAMMA2>(u, r0);
-                const int32_t h0 = decompose<P::GAMMA2>(v[i], r0);               // HighBits(r + z) = HighBits(w - cs2)
-                hbits |= (uint32_t)(h1 != h0) << i;                              // high_low.rs:134-144
-            }
-            // HintBitPack (conversion.rs:277-328): ordered compaction by warp prefix sum
-            const int cnt = __popc(hbits);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
-            }
-            int pos = hcount + incl - cnt;
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if ((hbits >> i) & 1) {
-                    if (pos < P::OMEGA) hb[pos] = (uint8_t)(8 * lane + i);
-                    pos++;
+                for (int i = 0; i < 8; i++) {
+                    v[i] = caddq(wv[i] - t[i]);  // w - cs2, canonical
+                    int32_t r0;
+                    decompose<P::GAMMA2>(v[i], r0);
+                    bad |= (r0 < 0 ? -r0 : r0) >= P::GAMMA2 - P::BETA;
                 }
-            hcount += total;
-            rej = __any_sync(0xffffffffu, bad) || hcount > P::OMEGA;             // ml_dsa.rs:312-319
-            if (!rej && lane == 0) hb[P::OMEGA + k] = (uint8_t)hcount;
+                rej = __any_sync(0xffffffffu, bad);
+                if (!rej) {  // w is only ever needed as w - cs2 from here on
+                    wp[0] = make_int4(v[0], v[1], v[2], v[3]);
+                    wp[1] = make_int4(v[4], v[5], v[6], v[7]);
+                }
+            } else if (phase == 1) {
+                // z = y + c*s1, ||z||inf < gamma1 - beta                          ml_dsa.rs:243-250, 263-265
+                int32_t y[8];
+                load_y<P>(yp + idx * 32 * P::ZBITS, lane, y);
+                uint32_t f[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int32_t z = center(freeze(y[i] + t[i]));                 // z mod+- q (ml_dsa.rs:334-335)
+                    bad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;
+                    f[i] = (uint32_t)(P::GAMMA1 - z);                              // BitPack(z, gamma1 - 1, gamma1)
+                }
+                rej = __any_sync(0xffffffffu, bad);
+                if (!rej) {  // sigEncode z[idx] into the output; a later rejection just overwrites it
+                    uint32_t w[(P::ZBITS + 3) / 4];
+                    pack_fields<P::ZBITS>(f, w);
+                    __syncwarp();
+                    store_span<P::ZBITS>(reinterpret_cast<uint8_t*>(sm.stage) + P::ZBITS * lane, w);
+                    __syncwarp();
+                    warp_copy_out(sg + LO::SIG_Z + idx * 32 * P::ZBITS, sm.stage, 32 * P::ZBITS, lane);
+                    if (idx == L - 1) {  // entering the hint phase: clear the hint staging area
+                        __syncwarp();
+                        for (int i = lane; i < P::OMEGA + K; i += 32) hb[i] = 0;
+                        __syncwarp();
+                    }
+                }
+            } else {
+                // ||c*t0||inf < gamma2; h = MakeHint(-ct0, w - cs2 + ct0)          ml_dsa.rs:288-319
+                const int4* wp = reinterpret_cast<const int4*>(wl + 256 * idx + 8 * lane);
+                const int4 wx = wp[0], wy = wp[1];
+                const int32_t v[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
+                uint32_t hbits = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int32_t c0 = center(t[i]);
+                    bad |= (c0 < 0 ? -c0 : c0) >= P::GAMMA2;                       // ml_dsa.rs:314
+                    int32_t r0;
+                    int32_t u = v[i] + t[i];                                       // w - cs2 + ct0 in [0, 2q)
+                    u -= (u >= Q) ? Q : 0;
+                    const int32_t h1 = decompose<P::GAMMA2>(u, r0);
+                    const int32_t h0 = decompose<P::GAMMA2>(v[i], r0);             // HighBits(r + z) = HighBits(w - cs2)
+                    hbits |= (uint32_t)(h1 != h0) << i;                            // high_low.rs:134-144
+                }
+                // HintBitPack (conversion.rs:277-328): ordered compaction by warp prefix sum
+                const int cnt = __popc(hbits);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                int pos = hcount + incl - cnt;
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if ((hbits >> i) & 1) {
+                        if (pos < P::OMEGA) hb[pos] = (uint8_t)(8 * lane + i);
+                        pos++;
+                    }
+                hcount += total;
+                rej = __any_sync(0xffffffffu, bad) || hcount > P::OMEGA;           // ml_dsa.rs:312-319
+                if (!rej && lane == 0) hb[P::OMEGA + idx] = (uint8_t)hcount;
+            }
         }
         if (rej) {
-            if (lane == 0) kappa[ln] += L;                                       // ml_dsa.rs:281, 317
+            if (lane == 0) kappa[ln] += L;                                         // ml_dsa.rs:281, 317
             continue;
         }
-        // accept: c~ and hints complete the signature                          encodings.rs:254, 273
+        // accept: c~ and hints complete the signature                            encodings.rs:254, 273
         __syncwarp();
         warp_copy_out(sg + LO::SIG_H, sm.stage, P::OMEGA + K, lane);
-        warp_copy_bytes(sg, ct, P::CTILDE, lane);
+        warp_copy_bytes(sg, ctilde + ln * 64, P::CTILDE, lane);
         if (lane == 0) {
             done[ln] = 1;
             if (iters) iters[ln] = kappa[ln] / L + 1;
@@ -378,12 +395,9 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     constexpr int K = P::K, L = P::L;
     const bool shared = sk_stride == 0;
     const size_t nkeys = shared ? 1 : n;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const Tuning tn = tuning();
     auto warp_grid = [&](size_t items) {
-        const size_t want = (items + SG_WARPS - 1) / SG_WARPS;
-        return (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
+        return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16);
     };
     cudaError_t e;
     int* ctx_err = reinterpret_cast<int*>(ws.nact + 2);
@@ -415,7 +429,7 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
         const size_t nstreams = nact * L;
         {
             KLaunch kl(KID_MASK, st);
-            mask_kernel<P><<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(nstreams, ws.act[cur], ws.rhopp,
+            mask_kernel<P><<<capped_grid((nstreams + 127) / 128, tn.kcap), 128, 0, st>>>(nstreams, ws.act[cur], ws.rhopp,
                                                                              ws.kappa, ws.yraw);
         }
         {
@@ -427,17 +441,17 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
                 sign_w_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw,
                                                                                  ws.w, ws.mw1);
         }
-        e = launch_ctilde(P::PS, st, nact, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.sib);
+        e = launch_ctilde(P::PS, st, nact, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.cmask);
         if (e != cudaSuccess) return e;
         {
             KLaunch kl(KID_SIGN_Z, st);
             if (shared)
                 sign_z_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
-                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done,
+                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done,
                     sig, iters);
             else
                 sign_z_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
-                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.sib, ws.kappa, ws.done,
+                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done,
                     sig, iters);
         }
         e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);

@@ -4,8 +4,8 @@
 //
 // Pipeline over a chunk of lanes (one lane = one (pk, message, signature)):
 //   [key prep]    expand_a per key; for a shared key also tr = H(pk) and NTT(t1 * 2^d), once
-//   verify_pre    thread/lane  tr (per-lane keys), mu = H(tr || M'), first SHAKE256 block of H(c~)
-//   verify_arith  warp/lane    hint decode + checks, z unpack + norm, SampleInBall, NTTs,
+//   verify_pre    thread/lane  tr (per-lane keys), mu = H(tr || M'), c = SampleInBall(c~) as bit masks
+//   verify_arith  warp/lane    hint decode + checks, z unpack + norm, NTTs,
 //                              w' = INTT(A-hat o z-hat - c-hat o t1-hat), UseHint, w1Encode
 //   ctilde_check  thread/lane  c~' = H(mu || w1'), compare with c~, AND with the pre-checks
 #include "engine.h"
@@ -19,7 +19,7 @@ namespace mldsa {
 template <class P>
 __global__ void __launch_bounds__(128)
 verify_pre_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ tr_shared,
-                  MsgDesc md, const uint8_t* __restrict__ sig, uint8_t* __restrict__ mw1, uint8_t* __restrict__ sib,
+                  MsgDesc md, const uint8_t* __restrict__ sig, uint8_t* __restrict__ mw1, uint8_t* __restrict__ cmask,
                   uint8_t* __restrict__ pre_ok)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,12 +39,15 @@ verify_pre_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, co
     const bool ctx_ok = absorb_mu(sp, reinterpret_cast<const uint8_t*>(tr), md, i);  // ml_dsa.rs:386-397
     sp.out_words(reinterpret_cast<uint64_t*>(mu), 8);
     pre_ok[i] = ctx_ok ? 1 : 0;  // ctx > 255 -> false (lib.rs:368-370)
-    // first block of H(c~) for SampleInBall (hashing.rs:50-55)
+    // c = SampleInBall(c~) (ml_dsa.rs:400, hashing.rs:43-100), stored as nonzero / negative masks
     sp.init();
     const uint8_t* ct = sig + i * (size_t)P::SIG_LEN;
     for (int k = 0; k < P::CTILDE; k++) sp.absorb_byte(ct[k]);
     sp.finish();
-    sp.out_words(reinterpret_cast<uint64_t*>(sib + i * (size_t)SIB_BYTES), SIB_BYTES / 8);
+    SibWalk walk;
+    walk.init(P::TAU);
+    while (!walk.consume(sp.s, P::TAU)) sp.next_block();
+    walk.store(cmask + i * (size_t)CMASK_STRIDE);
 }
 
 // NTT(t1 * 2^d) for one polynomial of a public key, from the 10-bit packed bytes (layout B regs)
@@ -79,14 +82,14 @@ struct alignas(16) VerifySmem {
     int32_t tile[NTT_TILE_WORDS];
     uint32_t hbits[P::K * 8];                       // hint bitmap, 256 bits per polynomial
     uint32_t stage[(P::OMEGA + P::K + 3) / 4 + 1];  // hint bytes
-    uint32_t sibs[SIB_BYTES / 4];
+    alignas(16) int32_t zh[P::L][256];              // z-hat, NTT domain, natural order
 };
 
 template <class P, bool SHARED>
 __global__ void __launch_bounds__(VF_WARPS * 32)
 verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ sig,
                     const int32_t* __restrict__ Aall, const int32_t* __restrict__ t1h_shared,
-                    const uint8_t* __restrict__ sib, uint8_t* __restrict__ mw1, uint8_t* __restrict__ pre_ok)
+                    const uint8_t* __restrict__ cmask, uint8_t* __restrict__ mw1, uint8_t* __restrict__ pre_ok)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
@@ -137,27 +140,21 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
             continue;
         }
 
-        // ---- c = SampleInBall(c~) from the precomputed SHAKE block, c-hat = NTT(c) ----
-        int32_t ch[8];
-        sample_in_ball_warp<P>(sib + ln * (size_t)SIB_BYTES, sg, sm.sibs, tile, lane, ch);
-        ntt_fwd_A2B(ch, tile, lane);
-#pragma unroll
-        for (int i = 0; i < 8; i++) ch[i] = reduce32(ch[i]);
-
-        // ---- z = BitUnpack(gamma1 - 1, gamma1), ||z||inf check, z-hat ----
-        int32_t zh[L][8];
+        // ---- z = BitUnpack(gamma1 - 1, gamma1), ||z||inf check, z-hat (kept in shared memory) ----
         bool zbad = false;
-#pragma unroll
+#pragma unroll 1
         for (int l = 0; l < L; l++) {
             uint32_t w[(P::ZBITS + 3) / 4];
             load_span<P::ZBITS>(sg + LO::SIG_Z + l * 32 * P::ZBITS + P::ZBITS * lane, w);
+            int32_t zv[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int32_t z = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(w, i);  // conversion.rs:250
                 zbad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;                   // ml_dsa.rs:434
-                zh[l][i] = z;
+                zv[i] = z;
             }
-            ntt_fwd_B2B(zh[l], tile, lane);
+            ntt_fwd_B2B(zv, tile, lane);
+            row_store(sm.zh[l], lane, zv);
         }
         zbad = __any_sync(0xffffffffu, zbad);
         if (zbad) {
@@ -165,9 +162,18 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
             continue;
         }
 
+        // ---- c from the challenge masks, c-hat = NTT(c) ----
+        int32_t ch[8];
+        load_c_layoutA(cmask + ln * (size_t)CMASK_STRIDE, lane, ch);
+        ntt_fwd_A2B(ch, tile, lane);
+#pragma unroll
+        for (int i = 0; i < 8; i++) ch[i] = reduce32(ch[i]);
+
         // ---- per row: w' = INTT(sum_l A[k][l] o z-hat[l] - c-hat o t1-hat[k]); UseHint; w1Encode ----
+        if (!SHARED) warp_prefetch_l2(A, 2 * L * 1024, lane);
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
+            if (!SHARED && k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
             int32_t t1v[8];
             if (SHARED) {
                 const int4* tp = reinterpret_cast<const int4*>(t1h_shared + 256 * k + 8 * lane);
@@ -185,8 +191,10 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
                 const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
                 const int4 x = __ldg(ap), y = __ldg(ap + 1);
                 const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                int32_t zz[8];
+                row_load(sm.zh[l], lane, zz);
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * zh[l][i];
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * zz[i];
             }
             int32_t t[8];
 #pragma unroll
@@ -226,7 +234,7 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
     {
         KLaunch kl(KID_VERIFY_PRE, st);
         verify_pre_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, pk, pk_stride, shared ? ws.tr : nullptr,
-                                                                         md, sig, ws.mw1, ws.sib, ws.pre_ok);
+                                                                         md, sig, ws.mw1, ws.cmask, ws.pre_ok);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -236,11 +244,11 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
     {
         KLaunch kl(KID_VERIFY_ARITH, st);
         if (shared)
-            verify_arith_kernel<P, true><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h, ws.sib,
-                                                                         ws.mw1, ws.pre_ok);
+            verify_arith_kernel<P, true><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h,
+                                                                         ws.cmask, ws.mw1, ws.pre_ok);
         else
-            verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr, ws.sib,
-                                                                          ws.mw1, ws.pre_ok);
+            verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr,
+                                                                          ws.cmask, ws.mw1, ws.pre_ok);
     }
     e = launch_ctilde(P::PS, st, n, nullptr, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
     if (e != cudaSuccess) return e;

@@ -161,6 +161,23 @@ __device__ __forceinline__ void ntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int 
     __syncwarp();
 }
 
+// A polynomial row parked in shared memory by its owning warp (y-hat / z-hat between the NTT and the
+// matrix-vector product).  Lane t's coefficients 8t..8t+3 go to words [4t, 4t+4) and 8t+4..8t+7 to
+// words [128 + 4t, 128 + 4t + 4): every 128-bit access of a quarter-warp is one contiguous 128 B line,
+// so both halves are bank-conflict free (a plain 8t layout would be 2-way conflicted).
+__device__ __forceinline__ void row_store(int32_t* row, int lane, const int32_t (&v)[8])
+{
+    int4* p = reinterpret_cast<int4*>(row);
+    p[lane] = make_int4(v[0], v[1], v[2], v[3]);
+    p[32 + lane] = make_int4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void row_load(const int32_t* row, int lane, int32_t (&v)[8])
+{
+    const int4* p = reinterpret_cast<const int4*>(row);
+    const int4 x = p[lane], y = p[32 + lane];
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+}
+
 // Convenience wrappers used by the fused kernels: coefficient-domain data lives in layout B
 // (lane-local bit packing), NTT-domain data too.
 __device__ __forceinline__ void ntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int lane)

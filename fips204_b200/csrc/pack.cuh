@@ -68,6 +68,16 @@ __device__ __forceinline__ void store_span(uint8_t* dst, const uint32_t (&w)[(NB
     }
 }
 
+// Warp-cooperative L2 prefetch of `bytes` starting at p (128-byte lines): the streamed per-lane operands
+// (rows of A-hat, s-hat, w) are pulled from HBM into L2 while the warp is busy with an NTT, so the
+// demand loads that follow see L2 latency instead of DRAM latency.
+__device__ __forceinline__ void warp_prefetch_l2(const void* p, int bytes, int lane)
+{
+    const char* c = reinterpret_cast<const char*>(p);
+    for (int off = lane * 128; off < bytes; off += 32 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+}
+
 // Warp-cooperative byte copies (any alignment, n small: hint regions, c~, seeds)
 __device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, int n, int lane)
 {

@@ -30,54 +30,75 @@ __device__ __forceinline__ bool absorb_mu(Sponge<SHAKE256_RATE>& sp, const uint8
     return ok;
 }
 
-// Slow path of SampleInBall: block `blk` (>= 1) of SHAKE256(c~).  One SHAKE256 block covers the 8 sign
-// bytes plus 128 index draws; tau <= 60 draws with acceptance >= 0.77 practically never needs more,
-// but the reference's reader is unbounded (hashing.rs:68-77), so this exists for exactness.
-static __device__ __noinline__ void sib_refill(const uint8_t* ctilde, int ctlen, int blk, uint32_t* sibs)
-{
-    Sponge<SHAKE256_RATE> sp;
-    sp.init();
-    for (int k = 0; k < ctlen; k++) sp.absorb_byte(ctilde[k]);
-    sp.finish();
-    for (int b = 0; b < blk; b++) sp.next_block();
-    for (int k = 0; k < SIB_BYTES / 8; k++) {
-        sibs[2 * k] = (uint32_t)sp.s[k];
-        sibs[2 * k + 1] = (uint32_t)(sp.s[k] >> 32);
-    }
-}
+// SampleInBall (src/hashing.rs:43-100) as a per-THREAD walk over the SHAKE256(c~) stream.  It runs
+// inside the thread-per-lane hash kernels (32 lanes of a warp walk 32 different challenges at once);
+// the result is c as two 256-bit masks (nonzero, negative) = CMASK_BYTES, which the warp-per-lane
+// arithmetic kernels expand straight into registers.  The Fisher-Yates walk is on public data.
+// The reader is unbounded like the reference's (hashing.rs:68-77): consume() is fed one 136-byte
+// block at a time and reports whether it needs another one (practically never: tau <= 60 draws with
+// acceptance >= 0.77 fit 128 bytes with overwhelming probability).
+constexpr int CMASK_BYTES = 64;
 
-// SampleInBall (src/hashing.rs:43-100).  The Fisher-Yates walk is inherently sequential (tau dependent
-// swaps on public data), so lane 0 performs it on the warp's tile; the other lanes only help to stage
-// the hash block and clear the tile.  Result: c in register layout A, ready for ntt_fwd_A2B.
-template <class P>
-__device__ __forceinline__ void sample_in_ball_warp(const uint8_t* sib_block, const uint8_t* ctilde, uint32_t* sibs,
-                                                    int32_t* tile, int lane, int32_t (&c)[8])
-{
-    __syncwarp();
-    for (int w = lane; w < SIB_BYTES / 4; w += 32) sibs[w] = reinterpret_cast<const uint32_t*>(sib_block)[w];
+struct SibWalk {
+    uint32_t nz[8], sg[8];
+    uint64_t signs;
+    int i;
+    bool have_signs;
+    __device__ __forceinline__ void init(int tau)
+    {
 #pragma unroll
-    for (int i = 0; i < 8; i++) tile[NTT_ROW * i + lane] = 0;
-    __syncwarp();
-    if (lane == 0) {
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(sibs);
-        const uint64_t signs = (uint64_t)sibs[0] | ((uint64_t)sibs[1] << 32);  // hashing.rs:53-55
-        int pos = 8, blk = 0;
-        for (int i = 256 - P::TAU; i < 256; i++) {
-            int j;
-            do {
-                if (pos == SIB_BYTES) {
-                    sib_refill(ctilde, P::CTILDE, ++blk, sibs);
-                    pos = 0;
-                }
-                j = sb[pos++];
-            } while (j > i);                                                     // hashing.rs:68-77
-            const int ai = (i >> 5) * NTT_ROW + (i & 31), aj = (j >> 5) * NTT_ROW + (j & 31);
-            tile[ai] = tile[aj];                                                 // hashing.rs:80
-            tile[aj] = 1 - 2 * (int32_t)((signs >> (i + P::TAU - 256)) & 1);     // hashing.rs:83-86
+        for (int k = 0; k < 8; k++) nz[k] = sg[k] = 0;
+        i = 256 - tau;
+        have_signs = false;
+        signs = 0;
+    }
+    // blk: 17 little-endian 64-bit words of one squeeze block (in local/shared memory)
+    __device__ __forceinline__ bool consume(const uint64_t* blk, int tau)
+    {
+        int pos = 0;
+        if (!have_signs) {
+            signs = blk[0];  // hashing.rs:53-55
+            have_signs = true;
+            pos = 8;
+        }
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(blk);
+        while (i < 256) {
+            if (pos == SIB_BYTES) return false;
+            const int j = b[pos++];
+            if (j > i) continue;                                            // hashing.rs:68-77
+            const uint32_t nzj = (nz[j >> 5] >> (j & 31)) & 1u, sgj = (sg[j >> 5] >> (j & 31)) & 1u;
+            nz[i >> 5] |= nzj << (i & 31);                                  // c_i <- c_j (bit i was still 0)
+            sg[i >> 5] |= sgj << (i & 31);
+            const uint32_t neg = (uint32_t)(signs >> (i + tau - 256)) & 1u; // hashing.rs:83-86
+            nz[j >> 5] |= 1u << (j & 31);
+            sg[j >> 5] = (sg[j >> 5] & ~(1u << (j & 31))) | (neg << (j & 31));
+            i++;
+        }
+        return true;
+    }
+    __device__ __forceinline__ void store(uint8_t* cmask) const
+    {
+        uint32_t* o = reinterpret_cast<uint32_t*>(cmask);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            o[k] = nz[k];
+            o[8 + k] = sg[k];
         }
     }
-    __syncwarp();
-    tile_load_A(tile, lane, c);
+};
+
+// c in register layout A (idx = 32*i + lane) from the challenge masks
+__device__ __forceinline__ void load_c_layoutA(const uint8_t* cmask, int lane, int32_t (&c)[8])
+{
+    const uint4* p = reinterpret_cast<const uint4*>(cmask);
+    const uint4 n0 = __ldg(p), n1 = __ldg(p + 1), s0 = __ldg(p + 2), s1 = __ldg(p + 3);
+    const uint32_t nz[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+    const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int32_t on = (int32_t)((nz[i] >> lane) & 1u), neg = (int32_t)((sg[i] >> lane) & 1u);
+        c[i] = on - 2 * (on & neg);
+    }
 }
 
 }  // namespace mldsa

@@ -112,6 +112,10 @@ int mldsa_shake_batch(int dev, int bits /*128|256*/, size_t n, const uint8_t* in
 /* ---- tuning / telemetry ------------------------------------------------------------------ */
 /* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 64 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);
+/* launch tuning: a sign chunk runs as `ways` concurrent sub-batches on separate streams; kcap / acap cap
+ * the CTAs per SM of the Keccak / arithmetic kernels so kernels of different ways share an SM
+ * (0 = uncapped).  Defaults come from MLDSA_WAYS / MLDSA_KCAP / MLDSA_ACAP, else 1 / 0 / 0. */
+void mldsa_set_tuning(int ways, int kcap, int acap);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */
@@ -126,6 +130,9 @@ int mldsa_profile_get(int id, double* ms, uint64_t* launches);
 /* measured integer issue rate of the current device, thread-level instructions / s:
  * mode 0 LOP3+SHF (ALU pipe), 1 IMAD+IMAD.HI (FMA pipe), 2 both interleaved */
 int mldsa_int32_peak_probe(int mode, double* ops_per_sec);
+/* Keccak-f[1600] permutations/s (thread-per-state) for variant v of the ALU/FMA rotation split;
+ * *mask = that variant's KECCAK_FMA_SITES.  -1 when v is out of range. */
+int mldsa_keccak_probe(int variant, double* perms_per_sec, uint32_t* mask);
 
 #ifdef __cplusplus
 }

@@ -278,3 +278,36 @@ def test_sign_out_of_range_secret_key(F):
         sig, iters = m.sign_batch(sks, msgs, rnds, want_iters=True)
         osig, oiters = O.sign_batch(ps, sks, msgs, rnds)
         assert (sig == osig).all() and (iters == oiters).all()
+
+
+def test_host_chunk_pipeline_many_chunks(F):
+    """Force the host entry points to cut a batch into many chunks (tiny workspace limit) so the
+    double-buffered H2D / compute / D2H pipeline is exercised; bytes must not depend on the chunking."""
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    ps, n = 65, 2500
+    m = F.PARAM_SETS[ps]
+    xi = synth_block("chunk-xi", n, 32)
+    pks, sks = O.keygen_batch(ps, xi)
+    msgs = [synth("chunk-m", i, i % 97) for i in range(n)]
+    ctxs = [synth("chunk-c", i, i % 11) for i in range(n)]
+    rnds = synth_rows("chunk-r", n, 32)
+    want, wit = O.sign_batch(ps, sks, msgs, rnds, ctxs=ctxs)
+    try:
+        L.mldsa_set_workspace_limit(64 << 20)   # -> chunks of a few hundred lanes
+        for ways in (1, 2):
+            L.mldsa_set_tuning(ways, 0, 0)
+            sig, it = m.sign_batch(sks, msgs, rnds, ctxs=ctxs, want_iters=True)
+            assert (sig == want).all() and (it == wit).all()
+        bad = sig.copy()
+        bad[[5, 700, 2499], 100] ^= 0x40
+        ok = m.verify_batch(pks, msgs, bad, ctxs=ctxs)
+        assert list(np.nonzero(ok == 0)[0]) == [5, 700, 2499]
+        ok = m.verify_batch(pks[7].tobytes(), [msgs[7]] * n, np.repeat(sig[7:8], n, axis=0), ctxs=[ctxs[7]] * n,
+                            shared_key=True)
+        assert ok.all()
+        pk2, sk2 = m.keygen_batch(xi)
+        assert (pk2 == pks).all() and (sk2 == sks).all()
+    finally:
+        L.mldsa_set_workspace_limit(0)
+        L.mldsa_set_tuning(1, 0, 0)

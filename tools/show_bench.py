@@ -1,0 +1,15 @@
+#!/usr/bin/env python3
+"""Pretty-print the last JSON line of a bench.py output file."""
+import json
+import sys
+
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(f"{d['metric']}: {d['value']:.0f} {d['unit']}  ({d['ms_per_step']:.1f} ms/step)  e2e {d['e2e']['value']:.0f}")
+if d.get("verify"):
+    print("verify:", [(l["keys"], round(l["value"])) for l in d["verify"]["legs"]])
+for k, v in sorted(d.get("kernels", {}).items(), key=lambda kv: -kv[1]["ms_per_step"]):
+    print(f"  {k:12s} {v['ms_per_step']:8.2f} ms {v['share'] * 100:5.1f}%  {v['int32_tops'] or 0:6.2f} Tops  {v['hbm_gbs'] or 0:7.0f} GB/s")
+print("roofline:", {k: d["roofline"][k] for k in ("kernel", "achieved", "peak", "frac")} if d.get("roofline") else None)
+print("sign:", d.get("sign"))
+print("peaks:", d.get("int32_peaks_tops"), "cpu:", d.get("cpu_baseline", {}) and d["cpu_baseline"].get("value"))
+print("check:", d.get("check"), "clocks:", d.get("clocks"), "launches:", d.get("gpu_launches"))
