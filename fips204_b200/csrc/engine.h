@@ -45,9 +45,10 @@ unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event 
 // Commitment hash.  Verify mode (ctilde_out == nullptr): ok[i] = pre_ok[i] && H(mu||w1')[0..CT) == sig_i[0..CT)
 // (src/ml_dsa.rs:427-436).  Sign mode: ctilde_out[i] = H(mu||w1)[0..CT) and cmask_out[i] = SampleInBall(c~) as
 // two 256-bit masks (src/ml_dsa.rs:231-237, src/hashing.rs:43-100).  act: optional list of lane ids (n entries), else lanes 0..n-1.
-cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
-                          const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
-                          uint8_t* cmask_out);
+// n_dev: optional device-side lane count that overrides n inside the kernel (n then only sizes the grid).
+cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act,
+                          const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
+                          uint8_t* ctilde_out, uint8_t* cmask_out);
 
 int keccak_probe_variants();
 uint32_t keccak_probe_mask(int v);

@@ -218,10 +218,11 @@ cudaError_t launch_shake128_rows(cudaStream_t st, const uint8_t* in, size_t in_s
 // ------------------------------------------------------------------------------------------------
 template <class P, bool SIGN>
 __global__ void __launch_bounds__(128, 4)
-ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restrict__ mw1,
-              const uint8_t* __restrict__ sig, const uint8_t* __restrict__ pre_ok, uint8_t* __restrict__ ok,
-              uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ cmask_out)
+ctilde_kernel(size_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ act,
+              const uint8_t* __restrict__ mw1, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ pre_ok,
+              uint8_t* __restrict__ ok, uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ cmask_out)
 {
+    if (n_dev) n = *n_dev;  // sign rounds: the live active-lane count (n is only the launch bound)
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t ln = act ? act[idx] : idx;
     constexpr int NW = (MU_BYTES + P::W1_LEN) / 8;  // 104 or 136 words
@@ -278,30 +279,30 @@ ctilde_kernel(size_t n, const uint32_t* __restrict__ act, const uint8_t* __restr
 }
 
 template <class P>
-static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
-                                   const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
-                                   uint8_t* sib_out)
+static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act,
+                                   const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
+                                   uint8_t* ctilde_out, uint8_t* sib_out)
 {
     const unsigned grid = capped_grid((n + 127) / 128, tuning().kcap);
     {
         KLaunch kl(KID_CTILDE, st);
         if (ctilde_out)
-            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
         else
-            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* act, const uint8_t* mw1,
-                          const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok, uint8_t* ctilde_out,
-                          uint8_t* sib_out)
+cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act,
+                          const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
+                          uint8_t* ctilde_out, uint8_t* sib_out)
 {
     if (n == 0) return cudaSuccess;
     switch (ps) {
-    case 44: return launch_ctilde_t<Params<44>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    case 65: return launch_ctilde_t<Params<65>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    case 87: return launch_ctilde_t<Params<87>>(st, n, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 44: return launch_ctilde_t<Params<44>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 65: return launch_ctilde_t<Params<65>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 87: return launch_ctilde_t<Params<87>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
     }
     return cudaErrorInvalidValue;
 }

@@ -31,10 +31,11 @@ __global__ void __launch_bounds__(128)
 sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
                  const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mw1, uint8_t* __restrict__ rhopp,
                  uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
-                 int* __restrict__ ctx_err)
+                 uint32_t* __restrict__ nact0, int* __restrict__ ctx_err)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i == 0) *nact0 = (uint32_t)n;
     const uint8_t* key = sk + i * sk_stride;
     Sponge<SHAKE256_RATE> sp;
     if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
@@ -98,11 +99,12 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
 // ExpandMask: one thread per (active lane, r) SHAKE256 stream; the squeezed bytes ARE the packed y.
 template <class P>
 __global__ void __launch_bounds__(128, 4)
-mask_kernel(size_t nstreams, const uint32_t* __restrict__ act, const uint8_t* __restrict__ rhopp,
-            const uint32_t* __restrict__ kappa, uint8_t* __restrict__ yraw)
+mask_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
+            const uint8_t* __restrict__ rhopp, const uint32_t* __restrict__ kappa, uint8_t* __restrict__ yraw)
 {
     constexpr int L = P::L;
     constexpr int YW = 32 * P::ZBITS / 8;  // 72 or 80 output words
+    const size_t nstreams = (size_t)*nact_dev * L;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nstreams; q += (size_t)gridDim.x * blockDim.x) {
     const size_t ln = act[q / L];
     const uint32_t r = (uint32_t)(q % L);
@@ -144,10 +146,12 @@ struct alignas(16) SignWSmem {
 
 template <class P, bool SHARED>
 __global__ void __launch_bounds__(SG_WARPS * 32, 5)
-sign_w_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __restrict__ Aall,
-              const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, uint8_t* __restrict__ mw1)
+sign_w_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
+              const int32_t* __restrict__ Aall, const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall,
+              uint8_t* __restrict__ mw1)
 {
     constexpr int K = P::K, L = P::L;
+    const size_t nact = *nact_dev;
     __shared__ __align__(16) SignWSmem<P> sm_all[SG_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SignWSmem<P>& sm = sm_all[warp];
@@ -216,7 +220,8 @@ struct alignas(16) SignSmem {
 // order of the checks does not affect the outcome: the reference rejects if ANY fails (ml_dsa.rs:277-319).
 template <class P, bool SHARED>
 __global__ void __launch_bounds__(SG_WARPS * 32, 5)
-sign_z_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __restrict__ s1h_all,
+sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
+              const int32_t* __restrict__ s1h_all,
               const int32_t* __restrict__ s2h_all, const int32_t* __restrict__ t0h_all,
               const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, const uint8_t* __restrict__ ctilde,
               const uint8_t* __restrict__ cmask, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
@@ -224,6 +229,7 @@ sign_z_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __re
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
+    const size_t nact = *nact_dev;
     __shared__ __align__(16) SignSmem<P> sm_all[SG_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SignSmem<P>& sm = sm_all[warp];
@@ -374,9 +380,10 @@ sign_z_kernel(size_t nact, const uint32_t* __restrict__ act, const int32_t* __re
 }
 
 __global__ void __launch_bounds__(256)
-compact_kernel(size_t nact, const uint32_t* __restrict__ act_in, const uint8_t* __restrict__ done,
-               uint32_t* __restrict__ act_out, uint32_t* __restrict__ nout)
+compact_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act_in,
+               const uint8_t* __restrict__ done, uint32_t* __restrict__ act_out, uint32_t* __restrict__ nout)
 {
+    const size_t nact = *nact_dev;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool keep = i < nact && !done[act_in[i]];
     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -406,7 +413,7 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     {
         KLaunch kl(KID_SIGN_PREP, st);
         sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
-                                                                        ws.kappa, ws.done, ws.act[0], ctx_err);
+                                                                        ws.kappa, ws.done, ws.act[0], ws.nact, ctx_err);
     }
     {
         KLaunch kl(KID_SIGN_KEY, st);
@@ -423,51 +430,58 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
         return cudaErrorInvalidValue;
     }
 
-    size_t nact = n;
-    int cur = 0, rounds = 0;
-    while (nact > 0) {
-        const size_t nstreams = nact * L;
+    // Round loop.  The kernels read the live active-lane count from device memory (nact[cur]); the host
+    // only needs an upper bound to size the grids, so once the active set is small it re-reads the count
+    // every few rounds instead of stalling the stream after each one.
+    size_t bound = n;
+    int cur = 0, rounds = 0, since_sync = 0;
+    while (bound > 0) {
         {
             KLaunch kl(KID_MASK, st);
-            mask_kernel<P><<<capped_grid((nstreams + 127) / 128, tn.kcap), 128, 0, st>>>(nstreams, ws.act[cur], ws.rhopp,
-                                                                             ws.kappa, ws.yraw);
+            mask_kernel<P><<<capped_grid((bound * L + 127) / 128, tn.kcap), 128, 0, st>>>(ws.nact + cur, ws.act[cur],
+                                                                                       ws.rhopp, ws.kappa, ws.yraw);
         }
         {
             KLaunch kl(KID_SIGN_W, st);
             if (shared)
-                sign_w_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw,
-                                                                                ws.w, ws.mw1);
+                sign_w_kernel<P, true><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
+                                                                                 ws.yraw, ws.w, ws.mw1);
             else
-                sign_w_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(nact, ws.act[cur], ws.A, ws.yraw,
-                                                                                 ws.w, ws.mw1);
+                sign_w_kernel<P, false><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
+                                                                                  ws.yraw, ws.w, ws.mw1);
         }
-        e = launch_ctilde(P::PS, st, nact, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.cmask);
+        e = launch_ctilde(P::PS, st, bound, ws.nact + cur, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde,
+                          ws.cmask);
         if (e != cudaSuccess) return e;
         {
             KLaunch kl(KID_SIGN_Z, st);
             if (shared)
-                sign_z_kernel<P, true><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
-                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done,
-                    sig, iters);
+                sign_z_kernel<P, true><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
+                    ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
+                    ws.done, sig, iters);
             else
-                sign_z_kernel<P, false><<<warp_grid(nact), SG_WARPS * 32, 0, st>>>(
-                    nact, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done,
-                    sig, iters);
+                sign_z_kernel<P, false><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
+                    ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
+                    ws.done, sig, iters);
         }
         e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);
         if (e != cudaSuccess) return e;
         {
             KLaunch kl(KID_COMPACT, st);
-            compact_kernel<<<(unsigned)((nact + 255) / 256), 256, 0, st>>>(nact, ws.act[cur], ws.done,
-                                                                          ws.act[cur ^ 1], ws.nact + (cur ^ 1));
+            compact_kernel<<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(ws.nact + cur, ws.act[cur], ws.done,
+                                                                           ws.act[cur ^ 1], ws.nact + (cur ^ 1));
         }
-        e = cudaMemcpyAsync(ws.h_nact, ws.nact + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return e;
-        nact = ws.h_nact[0];
         cur ^= 1;
         rounds++;
+        const int every = bound > 65536 ? 1 : (bound > 4096 ? 3 : 6);
+        if (++since_sync >= every) {
+            e = cudaMemcpyAsync(ws.h_nact, ws.nact + cur, 4, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            bound = ws.h_nact[0];
+            since_sync = 0;
+        }
     }
     if (rounds_out) *rounds_out = rounds;
     return cudaGetLastError();
