@@ -118,6 +118,28 @@ cudaError_t launch_expand_a_seed34(cudaStream_t st, const uint8_t* seeds, size_t
 // ------------------------------------------------------------------------------------------------
 constexpr int NTT_WARPS = 8;
 
+// streaming accesses: every polynomial is touched exactly once, keep it out of L1 and mark it evict-first
+__device__ __forceinline__ int32_t ldg_stream(const int32_t* p)
+{
+    int32_t v;
+    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ldg_stream4(const int4* p)
+{
+    int4 v;
+    asm volatile("ld.global.cs.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(int32_t* p, int32_t v)
+{
+    asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(v));
+}
+__device__ __forceinline__ void stg_stream4(int4* p, int4 v)
+{
+    asm volatile("st.global.cs.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict__ polys, size_t n)
 {
@@ -125,23 +147,28 @@ __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t* tile = tiles[warp];
     const size_t stride = (size_t)gridDim.x * NTT_WARPS;
-    for (size_t p = (size_t)blockIdx.x * NTT_WARPS + warp; p < n; p += stride) {
+    const size_t first = (size_t)blockIdx.x * NTT_WARPS + warp;
+    // the warp's next two polynomials are pulled into L2 while it transforms the current one
+    if (lane < 8 && first + stride < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(polys + (first + stride) * 256 + 32 * lane));
+    for (size_t p = first; p < n; p += stride) {
         int32_t* g = polys + p * 256;
+        if (lane < 8 && p + 2 * stride < n)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(polys + (p + 2 * stride) * 256 + 32 * lane));
         int32_t v[8];
         if (!INVERSE) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = g[32 * i + lane];
+            for (int i = 0; i < 8; i++) v[i] = ldg_stream(g + 32 * i + lane);
             ntt_fwd_A2B(v, tile, lane);
             int4* o = reinterpret_cast<int4*>(g + 8 * lane);
-            o[0] = make_int4(v[0], v[1], v[2], v[3]);
-            o[1] = make_int4(v[4], v[5], v[6], v[7]);
+            stg_stream4(o, make_int4(v[0], v[1], v[2], v[3]));
+            stg_stream4(o + 1, make_int4(v[4], v[5], v[6], v[7]));
         } else {
             const int4* in = reinterpret_cast<const int4*>(g + 8 * lane);
-            const int4 x = in[0], y = in[1];
+            const int4 x = ldg_stream4(in), y = ldg_stream4(in + 1);
             v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
             ntt_inv_B2A<F_MONT>(v, tile, lane);
 #pragma unroll
-            for (int i = 0; i < 8; i++) g[32 * i + lane] = v[i];
+            for (int i = 0; i < 8; i++) stg_stream(g + 32 * i + lane, v[i]);
         }
     }
 }
