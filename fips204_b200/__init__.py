@@ -28,7 +28,12 @@ import numpy as np
 from . import _lib
 from ._lib import MldsaError
 
-__all__ = ["ml_dsa_44", "ml_dsa_65", "ml_dsa_87", "MldsaError", "micro", "device_count", "kernel_launches"]
+__all__ = ["ml_dsa_44", "ml_dsa_65", "ml_dsa_87", "Ph", "MldsaError", "micro", "device_count", "kernel_launches"]
+
+
+class Ph:
+    """Pre-hash function selector of HashML-DSA (`pub enum Ph`, src/types.rs:5-12)."""
+    SHA256, SHA512, SHAKE128 = 0, 1, 2
 
 
 def device_count():
@@ -105,6 +110,11 @@ class _ParamSet:
                     return False
                 return bool(mod.verify_batch(self._b, [message], [sig], ctxs=[ctx], shared_key=True)[0])
 
+            def hash_verify(self, message, sig, ctx, ph):  # lib.rs:391-411
+                if len(ctx) > 255 or len(sig) != mod.SIG_LEN:
+                    return False
+                return bool(mod.hash_verify_batch(self._b, [message], [sig], ph, ctxs=[ctx], shared_key=True)[0])
+
             def __eq__(self, o):
                 return isinstance(o, PublicKey) and o._b == self._b
 
@@ -136,6 +146,23 @@ class _ParamSet:
                 if len(ctx) > 255:
                     raise ValueError("ML-DSA.Sign: ctx too long")
                 return mod.sign_batch(self._b, [message], seed, ctxs=[ctx], shared_key=True)[0].tobytes()
+
+            def try_hash_sign(self, message, ctx, ph):  # traits.rs:247
+                return self.try_hash_sign_with_rng(OsRng(), message, ctx, ph)
+
+            def try_hash_sign_with_rng(self, rng, message, ctx, ph):  # lib.rs:310-342
+                if len(ctx) > 255:
+                    raise ValueError("HashML-DSA.Sign: ctx too long")
+                rnd = _draw(rng, 32, "HashML-DSA.Sign: random number generator failed")
+                return self.try_hash_sign_with_seed(rnd, message, ctx, ph)
+
+            def try_hash_sign_with_seed(self, seed, message, ctx, ph):  # traits.rs:280-284
+                if len(ctx) > 255:
+                    raise ValueError("HashML-DSA.Sign: ctx too long")
+                return mod.hash_sign_batch(self._b, [message], seed, ph, ctxs=[ctx], shared_key=True)[0].tobytes()
+
+            def get_public_key(self):  # lib.rs:344-346 -> ml_dsa.rs:502-563
+                return PublicKey(mod.sk_to_pk_batch(self._b)[0].tobytes())
 
         class KG:
             @staticmethod
@@ -187,8 +214,9 @@ class _ParamSet:
         xi = b"".join(_draw(rng, 32, "KeyGen: Random number generator failed") for _ in range(n))
         return self.keygen_batch(xi, dev)
 
-    def sign_batch(self, sks, msgs, rnds, ctxs=None, shared_key=False, framing=0, dev=0, want_iters=False):
-        """sks: n x SK_LEN (or one key with shared_key), msgs: list of bytes, rnds: n x 32."""
+    def sign_batch(self, sks, msgs, rnds, ctxs=None, shared_key=False, framing=0, dev=0, want_iters=False, ph=None):
+        """sks: n x SK_LEN (or one key with shared_key), msgs: list of bytes, rnds: n x 32.
+        ph = Ph.* selects HashML-DSA (pre-hash on the device, lib.rs:310-342)."""
         n = len(msgs)
         sk = _u8(sks)
         if sk.size != (1 if shared_key else n) * self.SK_LEN:
@@ -202,14 +230,15 @@ class _ParamSet:
             if len(ctxs) != n:
                 raise ValueError("ctxs must have n entries")
             if any(len(c) > 255 for c in ctxs):
-                raise ValueError("ML-DSA.Sign: ctx too long")
+                raise ValueError(("ML-DSA" if ph is None else "HashML-DSA") + ".Sign: ctx too long")
             cb, co = _ragged(ctxs, np.uint32)
         sig = np.empty((n, self.SIG_LEN), dtype=np.uint8)
         iters = np.zeros(n, dtype=np.uint32)
-        rc = _lib.lib().mldsa_sign_batch(self.PS, dev, framing, n, _ptr(sk), 0 if shared_key else self.SK_LEN,
-                                         _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(rnd), _ptr(sig), _ptr(iters))
+        fn = _lib.lib().mldsa_sign_batch if ph is None else _lib.lib().mldsa_hash_sign_batch
+        rc = fn(self.PS, dev, framing if ph is None else int(ph), n, _ptr(sk), 0 if shared_key else self.SK_LEN,
+                _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(rnd), _ptr(sig), _ptr(iters))
         if rc == -2:
-            raise ValueError("ML-DSA.Sign: ctx too long")
+            raise ValueError(("ML-DSA" if ph is None else "HashML-DSA") + ".Sign: ctx too long")
         _lib.check(rc)
         return (sig, iters) if want_iters else sig
 
@@ -217,7 +246,20 @@ class _ParamSet:
         rnd = b"".join(_draw(rng, 32, "ML-DSA.Sign: random number generator failed") for _ in range(len(msgs)))
         return self.sign_batch(sks, msgs, rnd, ctxs, **kw)
 
-    def verify_batch(self, pks, msgs, sigs, ctxs=None, shared_key=False, framing=0, dev=0):
+    def hash_sign_batch(self, sks, msgs, rnds, ph, **kw):
+        return self.sign_batch(sks, msgs, rnds, ph=ph, **kw)
+
+    def hash_verify_batch(self, pks, msgs, sigs, ph, **kw):
+        return self.verify_batch(pks, msgs, sigs, ph=ph, **kw)
+
+    def sk_to_pk_batch(self, sks, dev=0):
+        """Signer::get_public_key over a batch: n x SK_LEN -> pk[n, PK_LEN] (ml_dsa.rs:502-563)."""
+        sk = _u8(sks).reshape(-1, self.SK_LEN)
+        pk = np.empty((sk.shape[0], self.PK_LEN), dtype=np.uint8)
+        _lib.check(_lib.lib().mldsa_sk_to_pk_batch(self.PS, dev, sk.shape[0], _ptr(sk), _ptr(pk)))
+        return pk
+
+    def verify_batch(self, pks, msgs, sigs, ctxs=None, shared_key=False, framing=0, dev=0, ph=None):
         """-> uint8[n], 1 = valid.  Never raises for malformed signatures (lib.rs:368-370)."""
         n = len(msgs)
         pk = _u8(pks)
@@ -234,8 +276,9 @@ class _ParamSet:
         if ctxs is not None:
             cb, co = _ragged(ctxs, np.uint32)
         ok = np.zeros(n, dtype=np.uint8)
-        _lib.check(_lib.lib().mldsa_verify_batch(self.PS, dev, framing, n, _ptr(pk), 0 if shared_key else self.PK_LEN,
-                                                 _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(sg), _ptr(ok)))
+        fn = _lib.lib().mldsa_verify_batch if ph is None else _lib.lib().mldsa_hash_verify_batch
+        _lib.check(fn(self.PS, dev, framing if ph is None else int(ph), n, _ptr(pk), 0 if shared_key else self.PK_LEN,
+                      _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(sg), _ptr(ok)))
         return ok
 
 

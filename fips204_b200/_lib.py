@@ -27,6 +27,10 @@ SIGNATURES = {
     "mldsa_sign_batch_dev": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
     "mldsa_verify_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
     "mldsa_verify_batch_dev": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
+    "mldsa_hash_sign_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
+    "mldsa_hash_verify_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
+    "mldsa_sk_to_pk_batch": (C.c_int, [C.c_int, C.c_int, sz, vp, vp]),
+    "mldsa_sk_to_pk_batch_dev": (C.c_int, [C.c_int, vp, sz, vp, vp]),
     "mldsa_keygen_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, sz, vp, vp, vp]),
     "mldsa_sign_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp, vp]),
     "mldsa_verify_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, sz, vp, sz, vp, vp, vp, vp, vp, vp]),

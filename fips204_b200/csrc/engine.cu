@@ -28,7 +28,8 @@ static double g_prof_ms[KID_COUNT];
 static uint64_t g_prof_n[KID_COUNT];
 static const char* const KERNEL_NAMES[KID_COUNT] = {
     "expand_a", "ntt", "intt", "shake_rows", "ctilde", "kg_seed", "rej_bounded", "kg_arith", "verify_pre",
-    "t1hat", "verify_arith", "sign_prep", "sign_key", "mask", "sign_w", "sign_z", "compact", "int_probe"};
+    "t1hat", "verify_arith", "sign_prep", "sign_key", "mask", "sign_w", "sign_z", "compact", "int_probe", "prehash",
+    "sk_to_pk"};
 
 struct EvPair {
     int id;
@@ -739,36 +740,49 @@ int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk
 // buffers the copies are true async DMA in both directions, so a step costs ~max(compute, H2D, D2H) instead
 // of their sum.  Per-chunk inputs are the packed bytes only (SURVEY.md section 7 "PCIe can beat compute").
 struct ChunkPlan {
-    size_t chunk = 0, nchunks = 0, max_mbytes = 0, max_cbytes = 0;
+    std::vector<size_t> lo;  // chunk i covers lanes [lo[i], lo[i+1])
+    size_t max_lanes = 0, max_mbytes = 0, max_cbytes = 0;
+    size_t nchunks() const { return lo.size() - 1; }
 };
 static ChunkPlan plan_chunks(size_t arena_bytes, size_t n, size_t fixed, size_t per_lane, const uint64_t* msg_off,
                              const uint32_t* ctx_off)
 {
     ChunkPlan pl;
-    size_t chunk = pick_chunk(arena_bytes, n, fixed, per_lane);
-    // at least 4 chunks once the batch is big enough for the copies to matter, so the pipeline has stages
-    if (n >= (size_t(1) << 17)) {
-        const size_t quarter = (n + 3) / 4;
-        if (chunk > quarter) chunk = quarter;
+    const size_t cap = pick_chunk(arena_bytes, n, fixed, per_lane);
+    pl.lo.push_back(0);
+    if (n >= (size_t(1) << 17) && cap >= (n + 3) / 4) {
+        // Big batch that would fit in <= 4 chunks: use 1-3-4-4-3-1 sixteenths, so the exposed pipeline fill
+        // (first copy-in) and drain (last copy-out) are 1/16 of the traffic instead of 1/4.
+        static const int frac[6] = {1, 3, 4, 4, 3, 1};
+        size_t acc = 0;
+        for (int f : frac) {
+            acc += f;
+            pl.lo.push_back(n * acc / 16);
+        }
+    } else {
+        for (size_t lo = cap; lo < n; lo += cap) pl.lo.push_back(lo);
+        pl.lo.push_back(n);
     }
-    pl.chunk = chunk;
-    pl.nchunks = (n + chunk - 1) / chunk;
-    for (size_t lo = 0; lo < n; lo += chunk) {
-        const size_t m = n - lo < chunk ? n - lo : chunk;
+    for (size_t i = 0; i + 1 < pl.lo.size(); i++) {
+        const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
         const size_t mb = (size_t)(msg_off[lo + m] - msg_off[lo]);
         const size_t cb = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
+        if (m > pl.max_lanes) pl.max_lanes = m;
         if (mb > pl.max_mbytes) pl.max_mbytes = mb;
         if (cb > pl.max_cbytes) pl.max_cbytes = cb;
     }
     return pl;
 }
 
-int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
-                     const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
-                     uint8_t* sig, uint32_t* iters)
+}  // extern "C"
+// ph < 0: plain ML-DSA with `framing`; ph = 0/1/2: HashML-DSA with SHA-256 / SHA-512 / SHAKE128 pre-hash
+static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8_t* sk, size_t sk_stride,
+                     const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters)
 {
     PSInfo p;
-    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return framing == 2 ? E_UNSUPPORTED : E_PARAM;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1) || ph > 2) return E_PARAM;
+    if (ph >= 0) framing = 2;
     if (sk_stride != 0 && sk_stride != p.sk) return E_PARAM;
     if (n && (!sk || !rnd || !sig || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
     if (n == 0) return OK;
@@ -787,15 +801,15 @@ int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, 
     const size_t ws_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? sign_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
     const size_t io_lane = 2 * ((shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + avg_msg + avg_ctx);
     const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
-    const size_t C = pl.chunk;
+    const size_t C = pl.max_lanes;
     struct Set {
-        uint8_t *sk, *rnd, *sig, *m, *c;
+        uint8_t *sk, *rnd, *sig, *m, *c, *pm;
         uint32_t *it, *co;
-        uint64_t* mo;
+        uint64_t *mo, *po;
     } set[2];
     const size_t set_bytes = pad256(shared ? p.sk : C * p.sk) + pad256(C * 32) + pad256(C * p.sig) + pad256(C * 4) +
                              pad256((C + 1) * 8) + pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) +
-                             pad256(pl.max_cbytes + 8);
+                             pad256(pl.max_cbytes + 8) + pad256(C * PREHASH_STRIDE) + pad256((C + 1) * 8);
     const size_t way_lanes = (C + ways - 1) / ways;
     rc = cx->reserve(2 * set_bytes + (size_t)ways * sign_ws_bytes(p, way_lanes, shared) + 4096);
     if (rc) return rc;
@@ -809,11 +823,13 @@ int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, 
         s.co = c.take<uint32_t>(C + 1);
         s.m = c.take<uint8_t>(pl.max_mbytes + 8);
         s.c = c.take<uint8_t>(pl.max_cbytes + 8);
+        s.pm = c.take<uint8_t>(C * PREHASH_STRIDE);
+        s.po = c.take<uint64_t>(C + 1);
     }
     const size_t io = c.off;
     cudaStream_t st = cx->stream;
     auto copy_in = [&](size_t i) -> int {
-        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
         Set& s = set[i & 1];
         const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
@@ -833,17 +849,24 @@ int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, 
     CK(cudaStreamSynchronize(cx->s_out));
     rc = copy_in(0);
     if (rc) return rc;
-    for (size_t i = 0; i < pl.nchunks; i++) {
-        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+    for (size_t i = 0; i < pl.nchunks(); i++) {
+        const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
         Set& s = set[i & 1];
-        if (i + 1 < pl.nchunks) {
+        if (i + 1 < pl.nchunks()) {
             rc = copy_in(i + 1);  // overlaps with this chunk's compute
             if (rc) return rc;
         }
         CK(cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0));
         if (i >= 2) CK(cudaStreamWaitEvent(st, cx->ev_out[i & 1], 0));  // D2H(i-2) has drained this set's outputs
-        rc = sign_core(*cx, st, ps, framing, m, s.sk, sk_stride, s.m - msg_off[lo], s.mo,
-                       ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, s.rnd, s.sig, s.it, io);
+        const uint8_t* cm = s.m - msg_off[lo];
+        const uint64_t* cmo = s.mo;
+        if (ph >= 0) {  // HashML-DSA: M' carries OID || PH(M) (src/lib.rs:310-342)
+            CK(launch_prehash(st, ph, m, cm, cmo, s.pm, s.po));
+            cm = s.pm;
+            cmo = s.po;
+        }
+        rc = sign_core(*cx, st, ps, framing, m, s.sk, sk_stride, cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr,
+                       ctx_off ? s.co : nullptr, s.rnd, s.sig, s.it, io);
         if (rc) {
             cudaStreamSynchronize(cx->s_in);
             cudaStreamSynchronize(cx->s_out);
@@ -860,12 +883,13 @@ int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, 
     return OK;
 }
 
-int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk, size_t pk_stride,
+static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uint8_t* pk, size_t pk_stride,
                        const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
                        const uint8_t* sig, uint8_t* ok)
 {
     PSInfo p;
-    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return framing == 2 ? E_UNSUPPORTED : E_PARAM;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1) || ph > 2) return E_PARAM;
+    if (ph >= 0) framing = 2;
     if (pk_stride != 0 && pk_stride != p.pk) return E_PARAM;
     if (n && (!pk || !sig || !ok || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
     if (n == 0) return OK;
@@ -880,14 +904,15 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
     const size_t ws_lane = (verify_ws_bytes(p, 1024, shared) - (shared ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
     const size_t io_lane = 2 * ((shared ? 0 : p.pk) + p.sig + 1 + 8 + 4 + avg_msg + avg_ctx);
     const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
-    const size_t C = pl.chunk;
+    const size_t C = pl.max_lanes;
     struct Set {
-        uint8_t *pk, *sig, *ok, *m, *c;
+        uint8_t *pk, *sig, *ok, *m, *c, *pm;
         uint32_t* co;
-        uint64_t* mo;
+        uint64_t *mo, *po;
     } set[2];
     const size_t set_bytes = pad256(shared ? p.pk : C * p.pk) + pad256(C * p.sig) + pad256(C) + pad256((C + 1) * 8) +
-                             pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) + pad256(pl.max_cbytes + 8);
+                             pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) + pad256(pl.max_cbytes + 8) +
+                             pad256(C * PREHASH_STRIDE) + pad256((C + 1) * 8);
     rc = cx->reserve(2 * set_bytes + verify_ws_bytes(p, C, shared) + 4096);
     if (rc) return rc;
     Carver c(cx->arena);
@@ -899,11 +924,13 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
         s.co = c.take<uint32_t>(C + 1);
         s.m = c.take<uint8_t>(pl.max_mbytes + 8);
         s.c = c.take<uint8_t>(pl.max_cbytes + 8);
+        s.pm = c.take<uint8_t>(C * PREHASH_STRIDE);
+        s.po = c.take<uint64_t>(C + 1);
     }
     const size_t io = c.off;
     cudaStream_t st = cx->stream;
     auto copy_in = [&](size_t i) -> int {
-        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
         Set& s = set[i & 1];
         const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
@@ -922,17 +949,24 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
     CK(cudaStreamSynchronize(cx->s_out));
     rc = copy_in(0);
     if (rc) return rc;
-    for (size_t i = 0; i < pl.nchunks; i++) {
-        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+    for (size_t i = 0; i < pl.nchunks(); i++) {
+        const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
         Set& s = set[i & 1];
-        if (i + 1 < pl.nchunks) {
+        if (i + 1 < pl.nchunks()) {
             rc = copy_in(i + 1);
             if (rc) return rc;
         }
         CK(cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0));
         if (i >= 2) CK(cudaStreamWaitEvent(st, cx->ev_out[i & 1], 0));
-        rc = verify_core(*cx, st, ps, framing, m, s.pk, pk_stride, s.m - msg_off[lo], s.mo,
-                         ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, s.sig, s.ok, io);
+        const uint8_t* cm = s.m - msg_off[lo];
+        const uint64_t* cmo = s.mo;
+        if (ph >= 0) {  // HashML-DSA (src/lib.rs:391-411)
+            CK(launch_prehash(st, ph, m, cm, cmo, s.pm, s.po));
+            cm = s.pm;
+            cmo = s.po;
+        }
+        rc = verify_core(*cx, st, ps, framing, m, s.pk, pk_stride, cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr,
+                         ctx_off ? s.co : nullptr, s.sig, s.ok, io);
         if (rc) {
             cudaStreamSynchronize(cx->s_in);
             cudaStreamSynchronize(cx->s_out);
@@ -942,6 +976,91 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
         CK(cudaEventRecord(cx->ev_out[i & 1], cx->s_out));
     }
     CK(cudaStreamSynchronize(cx->s_out));
+    return OK;
+}
+
+extern "C" {
+
+int mldsa_sign_batch(int ps, int dev, int framing, size_t n, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
+                     const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                     uint8_t* sig, uint32_t* iters)
+{
+    return sign_host(ps, dev, framing, -1, n, sk, sk_stride, msgs, msg_off, ctx, ctx_off, rnd, sig, iters);
+}
+int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk, size_t pk_stride,
+                       const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                       const uint8_t* sig, uint8_t* ok)
+{
+    return verify_host(ps, dev, framing, -1, n, pk, pk_stride, msgs, msg_off, ctx, ctx_off, sig, ok);
+}
+int mldsa_hash_sign_batch(int ps, int dev, int ph, size_t n, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
+                          const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                          uint8_t* sig, uint32_t* iters)
+{
+    if (ph < 0 || ph > 2) return E_PARAM;
+    return sign_host(ps, dev, 0, ph, n, sk, sk_stride, msgs, msg_off, ctx, ctx_off, rnd, sig, iters);
+}
+int mldsa_hash_verify_batch(int ps, int dev, int ph, size_t n, const uint8_t* pk, size_t pk_stride,
+                            const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                            const uint8_t* sig, uint8_t* ok)
+{
+    if (ph < 0 || ph > 2) return E_PARAM;
+    return verify_host(ps, dev, 0, ph, n, pk, pk_stride, msgs, msg_off, ctx, ctx_off, sig, ok);
+}
+
+// Signer::get_public_key (src/lib.rs:344-346 -> src/ml_dsa.rs:502-563): pk bytes from sk bytes
+int mldsa_sk_to_pk_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_sk, uint8_t* d_pk)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (n && (!d_sk || !d_pk))) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_current(lk, rc);
+    if (!cx) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : cx->stream;
+    const size_t per_lane = (size_t)p.K * p.L * 1024 + 64;
+    const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, per_lane);
+    rc = cx->reserve(pad256(chunk * per_lane));
+    if (rc) return rc;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        KeygenWs ws{};
+        ws.A = reinterpret_cast<int32_t*>(cx->arena);
+        CK(sk_to_pk_run(ps, st, m, d_sk + p.sk * lo, d_pk + p.pk * lo, ws));
+    }
+    CK(cudaStreamSynchronize(st));
+    prof_collect();
+    return OK;
+}
+int mldsa_sk_to_pk_batch(int ps, int dev, size_t n, const uint8_t* sk, uint8_t* pk)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (n && (!sk || !pk))) return E_PARAM;
+    if (n == 0) return OK;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    cudaStream_t st = cx->stream;
+    const size_t per_lane = (size_t)p.K * p.L * 1024 + p.sk + p.pk + 64;
+    const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, per_lane);
+    rc = cx->reserve(pad256(chunk * p.sk) + pad256(chunk * p.pk) + pad256(chunk * (size_t)p.K * p.L * 1024));
+    if (rc) return rc;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        Carver c(cx->arena);
+        uint8_t* d_sk = c.take<uint8_t>(chunk * p.sk);
+        uint8_t* d_pk = c.take<uint8_t>(chunk * p.pk);
+        KeygenWs ws{};
+        ws.A = c.take<int32_t>(chunk * (size_t)p.K * p.L * 256);
+        CK(cudaMemcpyAsync(d_sk, sk + p.sk * lo, m * p.sk, cudaMemcpyHostToDevice, st));
+        CK(sk_to_pk_run(ps, st, m, d_sk, d_pk, ws));
+        CK(cudaMemcpyAsync(pk + p.pk * lo, d_pk, m * p.pk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(d_sk, 0, m * p.sk, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    prof_collect();
     return OK;
 }
 

@@ -13,6 +13,7 @@ enum : int { OK = 0, E_PARAM = -1, E_CTX = -2, E_CUDA = -3, E_NOMEM = -4, E_UNSU
 constexpr int SIB_BYTES = 136;   // one SHAKE256 block of H(c~) for SampleInBall
 constexpr int CMASK_STRIDE = 64;  // bytes per lane of the challenge masks
 constexpr int MU_BYTES = 64;
+constexpr int PREHASH_STRIDE = 80;  // OID (11) || PH(M) (<= 64), padded
 constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_run saw |ctx| > 255
 
 // Kernel classes for launch telemetry (mldsa_kernel_launches) and the optional per-kernel device
@@ -20,7 +21,7 @@ constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_r
 enum KernelId : int {
     KID_EXPAND_A = 0, KID_NTT, KID_INTT, KID_SHAKE_ROWS, KID_CTILDE, KID_KG_SEED, KID_REJ_BOUNDED, KID_KG_ARITH,
     KID_VERIFY_PRE, KID_T1HAT, KID_VERIFY_ARITH, KID_SIGN_PREP, KID_SIGN_KEY, KID_MASK, KID_SIGN_W, KID_SIGN_Z,
-    KID_COMPACT, KID_PROBE, KID_COUNT
+    KID_COMPACT, KID_PROBE, KID_PREHASH, KID_SK2PK, KID_COUNT
 };
 struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<...>>>(...); }`
     int id;
@@ -53,6 +54,9 @@ cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_d
 int keccak_probe_variants();
 uint32_t keccak_probe_mask(int v);
 cudaError_t launch_keccak_probe(cudaStream_t st, int variant, int blocks, int reps, uint64_t* state);
+// HashML-DSA: out rows = OID || PH(M_i) with out_off[i] = i * PREHASH_STRIDE .. (message framing 2)
+cudaError_t launch_prehash(cudaStream_t st, int ph, size_t n, const uint8_t* msgs, const uint64_t* msg_off,
+                           uint8_t* out, uint64_t* out_off);
 cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops);
 // A[key][r*L+s][256] = RejNTTPoly(rho_key || s || r)          (src/hashing.rs:225-239)
 cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,
@@ -84,6 +88,8 @@ struct KeygenWs {
 };
 cudaError_t keygen_run(int ps, cudaStream_t st, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk,
                        const KeygenWs& ws);
+// pk from sk (Signer::get_public_key, src/ml_dsa.rs:502-563): only ws.A is used
+cudaError_t sk_to_pk_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, uint8_t* pk, const KeygenWs& ws);
 
 // ---- k_verify.cu ----
 struct VerifyWs {

@@ -7,6 +7,7 @@
 #include "ntt.cuh"
 #include "pack.cuh"
 #include "sampling.cuh"
+#include "sha2.cuh"
 
 namespace mldsa {
 
@@ -332,6 +333,48 @@ cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_d
     case 87: return launch_ctilde_t<Params<87>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
     }
     return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// HashML-DSA pre-hash (src/hashing.rs:317-354): out[i] = OID(11 bytes) || PH(M_i), rows packed back to back; ph 0 = SHA-256 (32 B), 1 = SHA-512 (64 B), 2 = SHAKE128 (32 B).  One thread per message.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+prehash_kernel(int ph, size_t n, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
+               uint8_t* __restrict__ out, uint64_t* __restrict__ out_off)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const uint32_t rowlen = 11 + (ph == 1 ? 64 : 32);  // rows are packed back to back (<= PREHASH_STRIDE each)
+    out_off[i] = (uint64_t)i * rowlen;                 // n + 1 offsets
+    if (i == n) return;
+    uint8_t* o = out + i * rowlen;
+    const uint8_t oid[11] = {0x06, 0x09, 0x60, 0x86, 0x48, 0x01, 0x65, 0x03, 0x04, 0x02,
+                             (uint8_t)(ph == 0 ? 0x01 : (ph == 1 ? 0x03 : 0x0B))};  // hashing.rs:321, 332, 343
+    for (int k = 0; k < 11; k++) o[k] = oid[k];
+    const uint8_t* m = msgs + msg_off[i];
+    const size_t len = (size_t)(msg_off[i + 1] - msg_off[i]);
+    uint8_t dg[64];
+    if (ph == 0) {
+        sha256_msg(m, len, dg);
+    } else if (ph == 1) {
+        sha512_msg(m, len, dg);
+    } else {
+        Sponge<SHAKE128_RATE> sp;
+        sp.init();
+        sp.absorb(m, len);
+        sp.finish();
+        for (int k = 0; k < 32; k++) dg[k] = (uint8_t)(sp.s[k >> 3] >> (8 * (k & 7)));
+    }
+    const int dl = ph == 1 ? 64 : 32;
+    for (int k = 0; k < dl; k++) o[11 + k] = dg[k];
+}
+
+cudaError_t launch_prehash(cudaStream_t st, int ph, size_t n, const uint8_t* msgs, const uint64_t* msg_off,
+                           uint8_t* out, uint64_t* out_off)
+{
+    KLaunch kl(KID_PREHASH, st);
+    prehash_kernel<<<(unsigned)((n + 1 + 127) / 128), 128, 0, st>>>(ph, n, msgs, msg_off, out, out_off);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
  *   dev      CUDA device ordinal the batch runs on
  *   framing  0 = ML-DSA.Sign/Verify   mu = H(tr || 0x00 || |ctx| || ctx || M)   (src/ml_dsa.rs:190,391)
  *            1 = *_internal (ACVP)    mu = H(tr || M)                           (src/ml_dsa.rs:187,388)
+ *            (HashML-DSA, mu = H(tr || 0x01 || |ctx| || ctx || OID || PH(M)), has its own entry points)
  *   All keys / signatures are the canonical FIPS 204 byte strings the reference's SerDes produces
  *   (src/lib.rs:417-494): pk PK_LEN, sk SK_LEN, sig SIG_LEN bytes, densely packed lane after lane.
  *   Randomness never originates on the device: xi / rnd are drawn by the caller (exactly one
@@ -83,6 +84,21 @@ int mldsa_verify_batch(int ps, int dev, int framing, size_t n, const uint8_t* pk
 int mldsa_verify_batch_dev(int ps, void* stream, int framing, size_t n, const uint8_t* d_pk, size_t pk_stride,
                            const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
                            const uint32_t* d_ctx_off, const uint8_t* d_sig, uint8_t* d_ok);
+
+/* ---- HashML-DSA: Signer::try_hash_sign_with_rng / Verifier::hash_verify -------------------
+ * (src/lib.rs:310-342, :391-411; pre-hash + OID src/hashing.rs:317-354).  ph: 0 = SHA-256, 1 = SHA-512,
+ * 2 = SHAKE128 (types::Ph).  The pre-hash runs on the device; mu = H(tr || 0x01 || |ctx| || ctx || OID || PH(M)).
+ * Other arguments as mldsa_sign_batch / mldsa_verify_batch. */
+int mldsa_hash_sign_batch(int ps, int dev, int ph, size_t n, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
+                          const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                          uint8_t* sig, uint32_t* iters);
+int mldsa_hash_verify_batch(int ps, int dev, int ph, size_t n, const uint8_t* pk, size_t pk_stride,
+                            const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                            const uint8_t* sig, uint8_t* ok);
+
+/* ---- Signer::get_public_key (src/lib.rs:344-346, src/ml_dsa.rs:502-563): pk bytes from sk bytes ---- */
+int mldsa_sk_to_pk_batch(int ps, int dev, size_t n, const uint8_t* sk, uint8_t* pk);
+int mldsa_sk_to_pk_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_sk, uint8_t* d_pk);
 
 /* ---- multi-GPU: one host batch split contiguously over a device list -----------------------
  * Lanes are independent, so there is no collective: device g of ndev gets lanes

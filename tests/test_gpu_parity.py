@@ -311,3 +311,68 @@ def test_host_chunk_pipeline_many_chunks(F):
     finally:
         L.mldsa_set_workspace_limit(0)
         L.mldsa_set_tuning(1, 0, 0)
+
+
+# ---------------------------------------------------------------- HashML-DSA and get_public_key (8f-3)
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_hash_sign_verify_vs_oracle(F, ps):
+    """try_hash_sign* / hash_verify (src/lib.rs:310-342, :391-411): device pre-hash (SHA-256 / SHA-512 /
+    SHAKE128) + OID framing.  The reference has no KAT for these (sha2 is 'parity unpinned' there); the
+    oracle's SHA-2 is pinned against hashlib (test_oracle_leaves) and the GPU must match it byte for byte."""
+    m = F.PARAM_SETS[ps]
+    n = 90
+    pk, sk = O.keygen(ps, synth("hxi", ps, 32))
+    # ragged messages straddling the SHA-256 (55/56/64) and SHA-512 (111/112/128) padding boundaries
+    lens = [0, 1, 54, 55, 56, 63, 64, 65, 110, 111, 112, 119, 120, 127, 128, 129, 135, 136, 137, 167, 168, 169, 300, 1000]
+    msgs = [synth("hm", i, lens[i % len(lens)] + (i // len(lens))) for i in range(n)]
+    ctxs = [synth("hc", i, (i * 37) % 256) for i in range(n)]
+    rnds = synth_rows("hr", n, 32)
+    for ph in (F.Ph.SHA256, F.Ph.SHA512, F.Ph.SHAKE128):
+        sig = m.hash_sign_batch(sk, msgs, rnds, ph, ctxs=ctxs, shared_key=True)
+        for i in range(n):
+            want = O.sign(ps, sk, msgs[i], rnds[i].tobytes(), ctx=ctxs[i], framing=2, ph=ph)
+            assert sig[i].tobytes() == want, (ph, i, len(msgs[i]))
+        assert m.hash_verify_batch(pk, msgs, sig, ph, ctxs=ctxs, shared_key=True).all()
+        # a HashML-DSA signature is not a pure ML-DSA signature, nor valid under another pre-hash
+        assert not m.verify_batch(pk, msgs, sig, ctxs=ctxs, shared_key=True).any()
+        other = (ph + 1) % 3
+        assert not m.hash_verify_batch(pk, msgs, sig, other, ctxs=ctxs, shared_key=True).any()
+        for i in (0, 7, 33):
+            assert O.verify(ps, pk, msgs[i], sig[i].tobytes(), ctx=ctxs[i], framing=2, ph=ph)
+
+
+def test_hash_sign_single_op_api(F):
+    # the self-consistency flow of src/lib.rs:514-533 through the mirrored Signer / Verifier methods
+    for m in (F.ml_dsa_44, F.ml_dsa_65, F.ml_dsa_87):
+        pk, sk = m.KG.keygen_from_seed(bytes(range(32)))
+        msg, ctx = b"message to pre-hash", b"context"
+        for ph in (F.Ph.SHA256, F.Ph.SHA512, F.Ph.SHAKE128):
+            sig = sk.try_hash_sign_with_seed(bytes(32), msg, ctx, ph)
+            assert pk.hash_verify(msg, sig, ctx, ph)
+            assert not pk.hash_verify(msg + b"x", sig, ctx, ph)
+            assert not pk.hash_verify(msg, sig, b"other", ph)
+            assert not pk.verify(msg, sig, ctx)
+        with pytest.raises(ValueError, match="HashML-DSA.Sign: ctx too long"):
+            sk.try_hash_sign_with_seed(bytes(32), msg, bytes(256), F.Ph.SHA256)
+        assert pk.hash_verify(msg, sig, bytes(256), F.Ph.SHA256) is False
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_get_public_key(F, ps, acvp_keygen):
+    """Signer::get_public_key (src/lib.rs:344-346, ml_dsa.rs:502-563): pk bytes recomputed from sk bytes."""
+    m = F.PARAM_SETS[ps]
+    vec = [t for t in acvp_keygen if PS_OF[t["ps"]] == ps]
+    sks = np.frombuffer(b"".join(bytes.fromhex(t["sk"]) for t in vec), dtype=np.uint8)
+    pk = m.sk_to_pk_batch(sks)
+    for i, t in enumerate(vec):
+        assert pk[i].tobytes().hex().upper() == t["pk"].upper(), t["tc"]
+    n = 500 + 7
+    pks, sks = O.keygen_batch(ps, synth_block(f"gpk{ps}", n, 32))
+    assert (m.sk_to_pk_batch(sks) == pks).all()
+    sk0 = m.PrivateKey.try_from_bytes(sks[0].tobytes())
+    assert sk0.get_public_key().into_bytes() == pks[0].tobytes()
+    # arbitrary (out-of-range) sk bytes: same mod-q computation as the oracle's private_to_public_key
+    fz = synth_block(f"gpkfuzz{ps}", 16, m.SK_LEN)
+    got = m.sk_to_pk_batch(fz)
+    for i in range(16):
+        assert got[i].tobytes() == O.sk_to_pk(ps, fz[i].tobytes())
