@@ -81,7 +81,14 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
             const int j_s = __shfl_sync(0xffffffffu, j, s);
             int32_t* dst = out + (qbase + s) * 256 + j_s;
             const int lim = min(n_s, 256 - j_s);
-            for (int c = lane; c < lim; c += 32) dst[c] = tile[s * EA_ROW + c];
+            // The A-hat that feeds the fused kernels is stored prescaled by 2^32 / 256 mod q (the Montgomery factor of
+            // the matrix-vector accumulator and the 1/256 of the un-scaled inverse NTT; see ntt.cuh).  These multiplies
+            // sit on the FMA pipe, which this ALU-bound kernel leaves idle.  The microbench entry point (SEED34)
+            // returns the plain RejNTTPoly output.
+            for (int c = lane; c < lim; c += 32) {
+                const int32_t x = tile[s * EA_ROW + c];
+                dst[c] = SEED34 ? x : shoup_mul(x, SC_MONT_INV256, SC_MONT_INV256S);
+            }
         }
         j += cnt;
         __syncwarp();

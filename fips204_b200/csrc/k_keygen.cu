@@ -131,7 +131,7 @@ kg_arith_kernel(size_t n, const uint8_t* __restrict__ seeds, const int8_t* __res
             uint32_t w[(P::ETABITS + 3) / 4];
             pack_fields<P::ETABITS>(f, w);
             store_span<P::ETABITS>(sko + LO::SK_S1 + l * 32 * P::ETABITS + P::ETABITS * lane, w);
-            ntt_fwd_B2B(s1h[l], tile, lane);
+            sntt_fwd_B2B(s1h[l], tile, lane);
         }
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
@@ -149,8 +149,8 @@ kg_arith_kernel(size_t n, const uint8_t* __restrict__ seeds, const int8_t* __res
             }
             int32_t t[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);  // carries 2^-32, undone by F_MONT2
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);
+            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);  // A-hat is prescaled by 2^32 / 256
+            sntt_inv_B2B(t, tile, lane);
 
             const uint2 raw = *reinterpret_cast<const uint2*>(sp + (L + k) * 256 + 8 * lane);
             uint32_t fs[8], f1[8], f0[8];
@@ -199,7 +199,7 @@ sk_to_pk_kernel(size_t n, const uint8_t* __restrict__ sk, const int32_t* __restr
             load_span<P::ETABITS>(key + LO::SK_S1 + l * 32 * P::ETABITS + P::ETABITS * lane, w);
 #pragma unroll
             for (int i = 0; i < 8; i++) s1h[l][i] = P::ETA - (int32_t)get_field<P::ETABITS>(w, i);
-            ntt_fwd_B2B(s1h[l], tile, lane);
+            sntt_fwd_B2B(s1h[l], tile, lane);
         }
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
@@ -217,7 +217,7 @@ sk_to_pk_kernel(size_t n, const uint8_t* __restrict__ sk, const int32_t* __restr
             int32_t t[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);
+            sntt_inv_B2B(t, tile, lane);
             uint32_t w2[(P::ETABITS + 3) / 4], f1[8];
             load_span<P::ETABITS>(key + LO::SK_S2 + k * 32 * P::ETABITS + P::ETABITS * lane, w2);
 #pragma unroll

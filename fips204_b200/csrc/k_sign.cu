@@ -88,7 +88,10 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
                 for (int i = 0; i < 8; i++) v[i] = (1 << (D - 1)) - (int32_t)get_field<13>(w, i);
                 dst = t0h + (kn * K + (p - L - K)) * 256;
             }
-            ntt_fwd_B2B(v, tile, lane);
+            sntt_fwd_B2B(v, tile, lane);
+            // prescaled by 1/256: the inverse transforms of c*s1, c*s2, c*t0 in sign_z do not scale
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = shoup_mul(v[i], SC_INV256, SC_INV256S);
             int4* o = reinterpret_cast<int4*>(dst + 8 * lane);
             o[0] = make_int4(v[0], v[1], v[2], v[3]);
             o[1] = make_int4(v[4], v[5], v[6], v[7]);
@@ -169,7 +172,7 @@ sign_w_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
         for (int l = 0; l < L; l++) {
             int32_t y[8];
             load_y<P>(yp + l * 32 * P::ZBITS, lane, y);
-            ntt_fwd_B2B(y, tile, lane);
+            sntt_fwd_B2B(y, tile, lane);
             row_store(sm.yh[l], lane, y);  // only this lane reads these words back
         }
 #pragma unroll 1
@@ -191,7 +194,7 @@ sign_w_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
             int32_t t[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);  // w[k], canonical
+            sntt_inv_B2B(t, tile, lane);  // w[k], canonical (A-hat is prescaled by 2^32 / 256)
             int4* o = reinterpret_cast<int4*>(wo + 256 * k + 8 * lane);
             o[0] = make_int4(t[0], t[1], t[2], t[3]);
             o[1] = make_int4(t[4], t[5], t[6], t[7]);
@@ -249,14 +252,14 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
                                        : reinterpret_cast<const char*>(wl) + 128 * (lane - 8);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
         }
-        // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240), with c-hat * QINV for mont_mul_pre
-        int32_t ch[8], chq[8];
+        // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240) centred, with its Shoup companion
+        int32_t ch[8], chs[8];
         load_c_layoutA(cmask + ln * (size_t)CMASK_STRIDE, lane, ch);
-        ntt_fwd_A2B(ch, tile, lane);
+        sntt_fwd_A2B(ch, tile, lane);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            ch[i] = reduce32(ch[i]);
-            chq[i] = (int32_t)((uint32_t)ch[i] * (uint32_t)QINV);
+            ch[i] = center(freeze(ch[i]));
+            chs[i] = shoup_companion(ch[i]);
         }
 
         bool rej = false;
@@ -278,8 +281,8 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
             }
             int32_t t[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_mul_pre(sv[i], ch[i], chq[i]);
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);  // c*s2[idx] / c*s1[idx] / c*t0[idx], canonical
+            for (int i = 0; i < 8; i++) t[i] = shoup_mul(sv[i], ch[i], chs[i]);  // s-hat rows are prescaled by 1/256
+            sntt_inv_B2B(t, tile, lane);  // c*s2[idx] / c*s1[idx] / c*t0[idx], canonical
 
             bool bad = false;
             if (phase == 0) {

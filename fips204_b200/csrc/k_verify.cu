@@ -57,7 +57,11 @@ __device__ __forceinline__ void load_t1_hat(const uint8_t* pkpoly, int32_t (&v)[
     load_span<10>(pkpoly + 10 * lane, w);
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = (int32_t)(get_field<10>(w, i) << D);  // pk_decode + ml_dsa.rs:490-495
-    ntt_fwd_B2B(v, tile, lane);
+    sntt_fwd_B2B(v, tile, lane);
+    // carries the same 2^32 / 256 as the prescaled A-hat: both terms of A z - c t1 then share one mont_reduce and an
+    // un-scaled inverse transform
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = shoup_mul(v[i], SC_MONT_INV256, SC_MONT_INV256S);
 }
 
 template <class P>
@@ -153,7 +157,7 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
                 zbad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;                   // ml_dsa.rs:434
                 zv[i] = z;
             }
-            ntt_fwd_B2B(zv, tile, lane);
+            sntt_fwd_B2B(zv, tile, lane);
             row_store(sm.zh[l], lane, zv);
         }
         zbad = __any_sync(0xffffffffu, zbad);
@@ -165,7 +169,7 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
         // ---- c from the challenge masks, c-hat = NTT(c) ----
         int32_t ch[8];
         load_c_layoutA(cmask + ln * (size_t)CMASK_STRIDE, lane, ch);
-        ntt_fwd_A2B(ch, tile, lane);
+        sntt_fwd_A2B(ch, tile, lane);
 #pragma unroll
         for (int i = 0; i < 8; i++) ch[i] = reduce32(ch[i]);
 
@@ -185,7 +189,7 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
             }
             int64_t acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = -(int64_t)ch[i] * reduce32(t1v[i]);
+            for (int i = 0; i < 8; i++) acc[i] = -(int64_t)ch[i] * t1v[i];
 #pragma unroll
             for (int l = 0; l < L; l++) {
                 const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
@@ -199,7 +203,7 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
             int32_t t[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
-            ntt_inv_B2B<F_MONT2>(t, tile, lane);
+            sntt_inv_B2B(t, tile, lane);
             const uint32_t hbyte = (sm.hbits[k * 8 + (lane >> 2)] >> (8 * (lane & 3))) & 0xFF;
             uint32_t f[8];
 #pragma unroll

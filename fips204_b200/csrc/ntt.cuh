@@ -178,6 +178,156 @@ __device__ __forceinline__ void row_load(const int32_t* row, int lane, int32_t (
     v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
 }
 
+// =================================================================================================
+// Shoup-multiplication transforms for the FUSED kernels (keygen / sign / verify), which need results
+// mod q only.  Measured on B200 (tools/pipe_probe.cu): IMAD 2.1 cycles per warp instruction, IMAD.HI
+// without an addend 4.0 (and the ALU pipe keeps issuing beside it), IMAD.HI WITH a register addend 5.1
+// and it stalls ALU issue -- which is what nvcc makes of the second high product of a Montgomery
+// multiplication.  A product with a precomputed quotient z' = round(z 2^32 / q) needs ONE high product:
+//     t = w z - mulhi(w, z') q          (IMAD.HI + 2 x IMAD = 8.2 cycles instead of 11.2 + stalls)
+// With |z| <= q/2 and any int32 w the result is in (-q/4, 5q/4): mulhi(w, z') = floor(w z / q + e),
+// |e| < 1/4.  Ranges: a forward transform adds < 1.25 q per level (< 11 q after 8 levels from |in| < q);
+// the inverse doubles its sum path per level, so it reduces once after five levels and its output is
+// canonical.  The inverse does NOT scale by 1/256: its callers fold that constant into one operand of the
+// preceding pointwise product (A-hat, s-hat, t-hat are prescaled when they are built).
+// =================================================================================================
+__device__ __forceinline__ int32_t mulhi_noadd(int32_t a, int32_t b)
+{
+    int32_t r;
+    asm("mul.hi.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));  // inline PTX: keeps the addend-free IMAD.HI form
+    return r;
+}
+__device__ __forceinline__ int32_t shoup_mul(int32_t w, int32_t z, int32_t zs)
+{
+    const int32_t qh = mulhi_noadd(w, zs);
+    return (int32_t)((uint32_t)w * (uint32_t)z - (uint32_t)qh * (uint32_t)Q);
+}
+// z' for a run-time multiplicand z in (-q/2, q/2] (c-hat, a fresh operand every signing iteration):
+// 2^32 / q = 513 - g with g = 0.49957...; z' = 513 z - floor(z g) is good to +-1, which costs |w| 2^-32 q of
+// extra range.  The intermediate 513 z may wrap; the result fits (|z'| <= 2^31 - 255).
+__device__ __forceinline__ int32_t shoup_companion(int32_t z)
+{
+    constexpr int64_t F32 = (((int64_t)1 << 32) % Q) * ((int64_t)1 << 32) / Q;  // frac(2^32 / q) * 2^32
+    constexpr int32_t G = (int32_t)(((int64_t)1 << 32) - F32);                  // (1 - frac) * 2^32 < 2^31
+    return (int32_t)((uint32_t)z * 513u - (uint32_t)mulhi_noadd(z, G));
+}
+__device__ __forceinline__ void ct_bfly_s(int32_t& a, int32_t& b, int32_t z, int32_t zs)
+{
+    const int32_t t = shoup_mul(b, z, zs);
+    b = a - t;
+    a = a + t;
+}
+__device__ __forceinline__ void gs_bfly_s(int32_t& a, int32_t& b, int32_t z, int32_t zs)
+{
+    const int32_t t = a;
+    a = t + b;
+    b = shoup_mul(t - b, z, zs);
+}
+
+// Forward NTT, layout A -> layout B, output = NTT(v) mod q as representatives in (-|in| - 10 q, |in| + 10 q).
+__device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int lane)
+{
+    ct_bfly_s(v[0], v[4], ZSF1, ZSF1S); ct_bfly_s(v[1], v[5], ZSF1, ZSF1S);
+    ct_bfly_s(v[2], v[6], ZSF1, ZSF1S); ct_bfly_s(v[3], v[7], ZSF1, ZSF1S);
+    ct_bfly_s(v[0], v[2], ZSF2, ZSF2S); ct_bfly_s(v[1], v[3], ZSF2, ZSF2S);
+    ct_bfly_s(v[4], v[6], ZSF3, ZSF3S); ct_bfly_s(v[5], v[7], ZSF3, ZSF3S);
+    ct_bfly_s(v[0], v[1], ZSF4, ZSF4S); ct_bfly_s(v[2], v[3], ZSF5, ZSF5S);
+    ct_bfly_s(v[4], v[5], ZSF6, ZSF6S); ct_bfly_s(v[6], v[7], ZSF7, ZSF7S);
+    __syncwarp();
+    tile_store_A(tile, lane, v);
+    __syncwarp();
+    tile_load_M(tile, lane, v);
+    {
+        const int r = lane >> 2;
+        const int2 z8 = __ldg(&ZS_FWD[8 + r]);
+        ct_bfly_s(v[0], v[4], z8.x, z8.y); ct_bfly_s(v[1], v[5], z8.x, z8.y);
+        ct_bfly_s(v[2], v[6], z8.x, z8.y); ct_bfly_s(v[3], v[7], z8.x, z8.y);
+        const int2 za = __ldg(&ZS_FWD[16 + 2 * r]), zb = __ldg(&ZS_FWD[17 + 2 * r]);
+        ct_bfly_s(v[0], v[2], za.x, za.y); ct_bfly_s(v[1], v[3], za.x, za.y);
+        ct_bfly_s(v[4], v[6], zb.x, zb.y); ct_bfly_s(v[5], v[7], zb.x, zb.y);
+        const int2 y0 = __ldg(&ZS_FWD[32 + 4 * r]), y1 = __ldg(&ZS_FWD[33 + 4 * r]);
+        const int2 y2 = __ldg(&ZS_FWD[34 + 4 * r]), y3 = __ldg(&ZS_FWD[35 + 4 * r]);
+        ct_bfly_s(v[0], v[1], y0.x, y0.y); ct_bfly_s(v[2], v[3], y1.x, y1.y);
+        ct_bfly_s(v[4], v[5], y2.x, y2.y); ct_bfly_s(v[6], v[7], y3.x, y3.y);
+    }
+    tile_store_M(tile, lane, v);
+    __syncwarp();
+    tile_load_B(tile, lane, v);
+    {
+        const int2 za = __ldg(&ZS_FWD[64 + 2 * lane]), zb = __ldg(&ZS_FWD[65 + 2 * lane]);
+        ct_bfly_s(v[0], v[2], za.x, za.y); ct_bfly_s(v[1], v[3], za.x, za.y);
+        ct_bfly_s(v[4], v[6], zb.x, zb.y); ct_bfly_s(v[5], v[7], zb.x, zb.y);
+        const int2 y0 = __ldg(&ZS_FWD[128 + 4 * lane]), y1 = __ldg(&ZS_FWD[129 + 4 * lane]);
+        const int2 y2 = __ldg(&ZS_FWD[130 + 4 * lane]), y3 = __ldg(&ZS_FWD[131 + 4 * lane]);
+        ct_bfly_s(v[0], v[1], y0.x, y0.y); ct_bfly_s(v[2], v[3], y1.x, y1.y);
+        ct_bfly_s(v[4], v[5], y2.x, y2.y); ct_bfly_s(v[6], v[7], y3.x, y3.y);
+    }
+    __syncwarp();
+}
+
+// Inverse NTT WITHOUT the 1/256 scaling.  In: layout B, |v| < 2 q.  Out: layout A, canonical [0, q),
+// = 256 * INTT(v) mod q.
+__device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane)
+{
+    {
+        const int2 y0 = __ldg(&ZS_INV[255 - 4 * lane]), y1 = __ldg(&ZS_INV[254 - 4 * lane]);
+        const int2 y2 = __ldg(&ZS_INV[253 - 4 * lane]), y3 = __ldg(&ZS_INV[252 - 4 * lane]);
+        gs_bfly_s(v[0], v[1], y0.x, y0.y); gs_bfly_s(v[2], v[3], y1.x, y1.y);
+        gs_bfly_s(v[4], v[5], y2.x, y2.y); gs_bfly_s(v[6], v[7], y3.x, y3.y);
+        const int2 za = __ldg(&ZS_INV[127 - 2 * lane]), zb = __ldg(&ZS_INV[126 - 2 * lane]);
+        gs_bfly_s(v[0], v[2], za.x, za.y); gs_bfly_s(v[1], v[3], za.x, za.y);
+        gs_bfly_s(v[4], v[6], zb.x, zb.y); gs_bfly_s(v[5], v[7], zb.x, zb.y);
+    }
+    __syncwarp();
+    tile_store_B(tile, lane, v);
+    __syncwarp();
+    tile_load_M(tile, lane, v);
+    {
+        const int r = lane >> 2;
+        const int2 y0 = __ldg(&ZS_INV[63 - 4 * r]), y1 = __ldg(&ZS_INV[62 - 4 * r]);
+        const int2 y2 = __ldg(&ZS_INV[61 - 4 * r]), y3 = __ldg(&ZS_INV[60 - 4 * r]);
+        gs_bfly_s(v[0], v[1], y0.x, y0.y); gs_bfly_s(v[2], v[3], y1.x, y1.y);
+        gs_bfly_s(v[4], v[5], y2.x, y2.y); gs_bfly_s(v[6], v[7], y3.x, y3.y);
+        const int2 za = __ldg(&ZS_INV[31 - 2 * r]), zb = __ldg(&ZS_INV[30 - 2 * r]);
+        gs_bfly_s(v[0], v[2], za.x, za.y); gs_bfly_s(v[1], v[3], za.x, za.y);
+        gs_bfly_s(v[4], v[6], zb.x, zb.y); gs_bfly_s(v[5], v[7], zb.x, zb.y);
+        const int2 z8 = __ldg(&ZS_INV[15 - r]);
+        gs_bfly_s(v[0], v[4], z8.x, z8.y); gs_bfly_s(v[1], v[5], z8.x, z8.y);
+        gs_bfly_s(v[2], v[6], z8.x, z8.y); gs_bfly_s(v[3], v[7], z8.x, z8.y);
+    }
+    // five doubling levels done: |v| < 64 q.  Back under q so that the last three stay inside int32.
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = reduce32(v[i]);
+    tile_store_M(tile, lane, v);
+    __syncwarp();
+    tile_load_A(tile, lane, v);
+    gs_bfly_s(v[0], v[1], ZSI7, ZSI7S); gs_bfly_s(v[2], v[3], ZSI6, ZSI6S);
+    gs_bfly_s(v[4], v[5], ZSI5, ZSI5S); gs_bfly_s(v[6], v[7], ZSI4, ZSI4S);
+    gs_bfly_s(v[0], v[2], ZSI3, ZSI3S); gs_bfly_s(v[1], v[3], ZSI3, ZSI3S);
+    gs_bfly_s(v[4], v[6], ZSI2, ZSI2S); gs_bfly_s(v[5], v[7], ZSI2, ZSI2S);
+    gs_bfly_s(v[0], v[4], ZSI1, ZSI1S); gs_bfly_s(v[1], v[5], ZSI1, ZSI1S);
+    gs_bfly_s(v[2], v[6], ZSI1, ZSI1S); gs_bfly_s(v[3], v[7], ZSI1, ZSI1S);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = freeze(v[i]);
+    __syncwarp();
+}
+__device__ __forceinline__ void sntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int lane)
+{
+    __syncwarp();
+    tile_store_B(tile, lane, v);
+    __syncwarp();
+    tile_load_A(tile, lane, v);
+    sntt_fwd_A2B(v, tile, lane);
+}
+__device__ __forceinline__ void sntt_inv_B2B(int32_t (&v)[8], int32_t* tile, int lane)
+{
+    sntt_inv_B2A(v, tile, lane);
+    tile_store_A(tile, lane, v);
+    __syncwarp();
+    tile_load_B(tile, lane, v);
+    __syncwarp();
+}
+
 // Convenience wrappers used by the fused kernels: coefficient-domain data lives in layout B
 // (lane-local bit packing), NTT-domain data too.
 __device__ __forceinline__ void ntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int lane)
