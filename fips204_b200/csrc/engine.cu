@@ -395,10 +395,16 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
             MsgDesc md{d_msgs, d_msg_off + wlo, d_ctx, d_ctx_off ? d_ctx_off + wlo : nullptr, framing};
             cudaError_t e = sign_run(ps, ws_stream, wm, d_sk + sk_stride * wlo, sk_stride, md, d_rnd + 32 * wlo,
                                      d_sig + p.sig * wlo, d_iters ? d_iters + wlo : nullptr, ws, &rounds[(size_t)w]);
-            // zero everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop):
-            // s1-hat .. yraw are contiguous in the carve; A-hat, mu||w1, c~ and the challenge are public
-            cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.mw1 - (uint8_t*)ws.s1h), ws_stream);
-            cudaMemsetAsync(ws.rhopp, 0, wm * 64, ws_stream);
+            // Everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop) is zeroed by
+            // sign_z as each lane finishes; A-hat, mu||w1, c~ and the challenge are public.  What is left for
+            // the host: the shared key's s-hat rows, and everything if the run stopped early.
+            // (s1-hat .. yraw are contiguous in the carve.)
+            if (e != cudaSuccess) {
+                cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.mw1 - (uint8_t*)ws.s1h), ws_stream);
+                cudaMemsetAsync(ws.rhopp, 0, wm * 64, ws_stream);
+            } else if (shared) {
+                cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.w - (uint8_t*)ws.s1h), ws_stream);
+            }
             cudaStreamSynchronize(ws_stream);
             prof_collect();
             if (e != cudaSuccess) {

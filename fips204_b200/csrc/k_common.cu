@@ -14,28 +14,25 @@ namespace mldsa {
 // ------------------------------------------------------------------------------------------------
 // expand_a.  One thread owns one SHAKE128 stream (one polynomial of A-hat).  Per squeeze block the
 // thread parses its 56 three-byte candidates straight out of the state registers
-// (CoeffFromThreeBytes, src/conversion.rs:40-61), appends the accepted ones to its row of a
-// shared-memory tile, and the warp then flushes the 32 rows with coalesced stores, so a stream's
-// coefficient j is its j-th accepted candidate.  The loop runs until every stream of the warp has
-// 256 coefficients: 5 blocks in practice, a 6th with p ~ 1e-39 -- handled exactly, not assumed away.
+// (CoeffFromThreeBytes, src/conversion.rs:40-61) and stores each accepted one directly at its final
+// position, so a stream's coefficient j is its j-th accepted candidate.  A thread's stores walk its own
+// 1 KiB row, 8 to a 32-byte sector, so the sectors are complete in L2 long before they are written back;
+// an earlier version staged rows in shared memory and flushed them coalesced, which cost 15 % more
+// ALU-pipe instructions (shuffles, addressing, loop control) in a kernel that is ALU-pipe bound.
+// The loop runs until every stream of the warp has 256 coefficients: 5 blocks in practice, a 6th with
+// p ~ 1e-39 -- handled exactly, not assumed away.
 // ------------------------------------------------------------------------------------------------
 constexpr int EA_THREADS = 128;
-constexpr int EA_ROW = 57;  // 56 candidates per block, odd stride -> conflict-free column writes
 
 template <bool SEED34>
 __global__ void __launch_bounds__(EA_THREADS, 4)
 expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstreams, int KL, int L,
                 int32_t* __restrict__ out)
 {
-    __shared__ int32_t tile_all[EA_THREADS / 32][32 * EA_ROW];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* tile = tile_all[warp];
-    // grid-stride over groups of EA_THREADS streams (a warp always owns 32 consecutive streams)
+    // grid-stride over groups of EA_THREADS streams
     for (size_t q0 = (size_t)blockIdx.x * EA_THREADS; q0 < nstreams; q0 += (size_t)gridDim.x * EA_THREADS) {
     const size_t q = q0 + threadIdx.x;
-    const size_t qbase = q - lane;
     const bool valid = q < nstreams;
-    __syncwarp();
 
     uint64_t a[25];
 #pragma unroll
@@ -53,11 +50,18 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
         a[20] = 0x8000000000000000ULL;  // byte 167 of the 168-byte rate
     }
 
+    int32_t* row = out + (valid ? q : 0) * 256;
     int j = valid ? 0 : 256;  // coefficients produced so far for this thread's stream
     while (__any_sync(0xffffffffu, j < 256)) {
         keccak_f1600(a);
-        int cnt = 0;
-        int32_t* row = tile + lane * EA_ROW;
+        // The A-hat that feeds the fused kernels is stored prescaled by 2^32 / 256 mod q (the Montgomery factor of
+        // the matrix-vector accumulator and the 1/256 of the un-scaled inverse NTT; see ntt.cuh).  These multiplies
+        // sit on the FMA pipe, which this ALU-bound kernel leaves idle.  The microbench entry point (SEED34)
+        // returns the plain RejNTTPoly output.
+#define EA_TAKE(c)                                                                                   \
+        if ((c) < (uint32_t)Q && j < 256) {                                                          \
+            row[j++] = SEED34 ? (int32_t)(c) : shoup_mul((int32_t)(c), SC_MONT_INV256, SC_MONT_INV256S); \
+        }
 #pragma unroll
         for (int g = 0; g < 14; g++) {  // 14 groups of 4 candidates = 3 words each
             const uint64_t l0 = a[(3 * g) >> 1], l1 = a[((3 * g) >> 1) + 1];
@@ -68,30 +72,9 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
             const uint32_t c1 = __funnelshift_r(w0, w1, 24) & 0x7FFFFF;
             const uint32_t c2 = __funnelshift_r(w1, w2, 16) & 0x7FFFFF;
             const uint32_t c3 = (w2 >> 8) & 0x7FFFFF;
-            if (c0 < (uint32_t)Q) row[cnt++] = (int32_t)c0;
-            if (c1 < (uint32_t)Q) row[cnt++] = (int32_t)c1;
-            if (c2 < (uint32_t)Q) row[cnt++] = (int32_t)c2;
-            if (c3 < (uint32_t)Q) row[cnt++] = (int32_t)c3;
+            EA_TAKE(c0) EA_TAKE(c1) EA_TAKE(c2) EA_TAKE(c3)
         }
-        if (j >= 256) cnt = 0;
-        __syncwarp();
-        // flush: row s of the tile -> out[stream s][j_s ...], contiguous per stream
-        for (int s = 0; s < 32; s++) {
-            const int n_s = __shfl_sync(0xffffffffu, cnt, s);
-            const int j_s = __shfl_sync(0xffffffffu, j, s);
-            int32_t* dst = out + (qbase + s) * 256 + j_s;
-            const int lim = min(n_s, 256 - j_s);
-            // The A-hat that feeds the fused kernels is stored prescaled by 2^32 / 256 mod q (the Montgomery factor of
-            // the matrix-vector accumulator and the 1/256 of the un-scaled inverse NTT; see ntt.cuh).  These multiplies
-            // sit on the FMA pipe, which this ALU-bound kernel leaves idle.  The microbench entry point (SEED34)
-            // returns the plain RejNTTPoly output.
-            for (int c = lane; c < lim; c += 32) {
-                const int32_t x = tile[s * EA_ROW + c];
-                dst[c] = SEED34 ? x : shoup_mul(x, SC_MONT_INV256, SC_MONT_INV256S);
-            }
-        }
-        j += cnt;
-        __syncwarp();
+#undef EA_TAKE
     }
     }
 }

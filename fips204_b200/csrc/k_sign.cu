@@ -228,7 +228,7 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
               const int32_t* __restrict__ s2h_all, const int32_t* __restrict__ t0h_all,
               const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, const uint8_t* __restrict__ ctilde,
               const uint8_t* __restrict__ cmask, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
-              uint8_t* __restrict__ sig, uint32_t* __restrict__ iters)
+              uint8_t* __restrict__ rhopp, uint8_t* __restrict__ sig, uint32_t* __restrict__ iters)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
@@ -378,6 +378,17 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
             done[ln] = 1;
             if (iters) iters[ln] = kappa[ln] / L + 1;
         }
+        // The lane is finished: zero everything it derived from the secret key and the mask (y, w - c*s2, rho'',
+        // and its own s1-hat / s2-hat / t0-hat) right here, where the stores hide behind other warps' arithmetic,
+        // instead of a 27 GB cudaMemset after the last round (src/types.rs:19 ZeroizeOnDrop analogue).
+        warp_zero16(wl, K * 1024, lane);
+        warp_zero16(const_cast<uint8_t*>(yp), L * 32 * P::ZBITS, lane);
+        warp_zero16(rhopp + ln * 64, 64, lane);
+        if (!SHARED) {
+            warp_zero16(const_cast<int32_t*>(s1h_all) + ln * (size_t)L * 256, L * 1024, lane);
+            warp_zero16(const_cast<int32_t*>(s2h_all) + ln * (size_t)K * 256, K * 1024, lane);
+            warp_zero16(const_cast<int32_t*>(t0h_all) + ln * (size_t)K * 256, K * 1024, lane);
+        }
         __syncwarp();
     }
 }
@@ -461,11 +472,11 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
             if (shared)
                 sign_z_kernel<P, true><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
                     ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
-                    ws.done, sig, iters);
+                    ws.done, ws.rhopp, sig, iters);
             else
                 sign_z_kernel<P, false><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
                     ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
-                    ws.done, sig, iters);
+                    ws.done, ws.rhopp, sig, iters);
         }
         e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);
         if (e != cudaSuccess) return e;

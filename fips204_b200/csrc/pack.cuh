@@ -78,6 +78,13 @@ __device__ __forceinline__ void warp_prefetch_l2(const void* p, int bytes, int l
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
+// Warp-cooperative zero fill of a 16-byte aligned region whose size is a multiple of 16 bytes
+__device__ __forceinline__ void warp_zero16(void* p, int bytes, int lane)
+{
+    int4* q = reinterpret_cast<int4*>(p);
+    for (int i = lane; i < bytes / 16; i += 32) q[i] = make_int4(0, 0, 0, 0);
+}
+
 // Warp-cooperative byte copies (any alignment, n small: hint regions, c~, seeds)
 __device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, int n, int lane)
 {
