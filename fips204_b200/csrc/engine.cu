@@ -82,7 +82,7 @@ void prof_collect()
     t_events.clear();
 }
 
-static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1};
+static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1};
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -96,7 +96,11 @@ Tuning tuning()
     if (a < 0) g_acap.store(a = env_int("MLDSA_ACAP", 0));
     if (w < 1) w = 1;
     if (w > 8) w = 8;
-    return Tuning{w, k, a};
+    int d = g_depth.load();
+    if (d < 0) g_depth.store(d = env_int("MLDSA_DEPTH", 2));
+    if (d < 1) d = 1;
+    if (d > 8) d = 8;
+    return Tuning{w, k, a, d};
 }
 unsigned capped_grid(size_t want_ctas, int cap_per_sm)
 {
@@ -225,7 +229,7 @@ static size_t workspace_budget(size_t arena_bytes)
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
     free_b += arena_bytes;  // the cached arena is ours to reuse
     size_t def = free_b / 10 * 6;
-    const size_t cap = size_t(64) << 30;
+    const size_t cap = size_t(96) << 30;
     if (def > cap) def = cap;
     if (lim == 0 || lim > free_b / 10 * 9) lim = lim == 0 ? def : free_b / 10 * 9;
     if (lim < (size_t(64) << 20)) lim = size_t(64) << 20;
@@ -265,26 +269,26 @@ static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n, bool shared)
 }
 static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared)
 {
-    const size_t nk = shared ? 1 : n;
+    const size_t nk = shared ? 1 : n, D = (size_t)tuning().depth;
     return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
-           pad256(n * (size_t)p.K * 1024) + pad256(n * (size_t)p.L * 32 * p.zbits) + pad256(n * (size_t)(64 + p.w1len)) +
-           2 * pad256(n * 64) + pad256(n * (size_t)SIB_BYTES) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) +
-           pad256(16);
+           pad256(n * D * p.K * 1024) + pad256(n * D * p.L * 32 * p.zbits) + pad256(n * D * (64 + p.w1len)) +
+           pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(16);
 }
 static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox)
 {
-    const size_t nk = shared ? 1 : n;
+    const size_t nk = shared ? 1 : n, D = (size_t)tuning().depth;
     SignWs w;
+    w.depth = (int)D;
     w.A = c.take<int32_t>(nk * (size_t)p.K * p.L * 256);
     w.s1h = c.take<int32_t>(nk * (size_t)p.L * 256);
     w.s2h = c.take<int32_t>(nk * (size_t)p.K * 256);
     w.t0h = c.take<int32_t>(nk * (size_t)p.K * 256);
-    w.w = c.take<int32_t>(n * (size_t)p.K * 256);
-    w.yraw = c.take<uint8_t>(n * (size_t)p.L * 32 * p.zbits);
-    w.mw1 = c.take<uint8_t>(n * (size_t)(64 + p.w1len));
+    w.w = c.take<int32_t>(n * D * p.K * 256);
+    w.yraw = c.take<uint8_t>(n * D * p.L * 32 * p.zbits);
+    w.mw1 = c.take<uint8_t>(n * D * (64 + p.w1len));
     w.rhopp = c.take<uint8_t>(n * 64);
-    w.ctilde = c.take<uint8_t>(n * 64);
-    w.cmask = c.take<uint8_t>(n * (size_t)SIB_BYTES);
+    w.ctilde = c.take<uint8_t>(n * D * 64);
+    w.cmask = c.take<uint8_t>(n * D * 64);
     w.kappa = c.take<uint32_t>(n);
     w.done = c.take<uint8_t>(n);
     w.act[0] = c.take<uint32_t>(n);
@@ -532,6 +536,7 @@ void mldsa_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
+void mldsa_set_depth(int depth) { g_depth.store(depth < 1 ? 1 : (depth > 8 ? 8 : depth)); }
 void mldsa_set_tuning(int ways, int kcap, int acap)
 {
     g_ways.store(ways < 1 ? 1 : ways);

@@ -38,6 +38,7 @@ void prof_collect();
 // co-resident on an SM (0 = no cap).
 struct Tuning {
     int ways, kcap, acap;
+    int depth;  // candidates tried per active lane and round of the sign loop (MLDSA_DEPTH, default 2)
 };
 Tuning tuning();
 unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event pairs into the per-kernel totals (call after a stream sync)
@@ -47,7 +48,8 @@ unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event 
 // (src/ml_dsa.rs:427-436).  Sign mode: ctilde_out[i] = H(mu||w1)[0..CT) and cmask_out[i] = SampleInBall(c~) as
 // two 256-bit masks (src/ml_dsa.rs:231-237, src/hashing.rs:43-100).  act: optional list of lane ids (n entries), else lanes 0..n-1.
 // n_dev: optional device-side lane count that overrides n inside the kernel (n then only sizes the grid).
-cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act,
+// depth: rows per lane (sign: candidates per round; row = act[i / depth] * depth + i % depth), 1 for verify.
+cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act, int depth,
                           const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
                           uint8_t* ctilde_out, uint8_t* cmask_out);
 
@@ -113,12 +115,13 @@ struct SignWs {
     int32_t* s1h;      // [nkeys][L][256]
     int32_t* s2h;      // [nkeys][K][256]
     int32_t* t0h;      // [nkeys][K][256]
-    int32_t* w;        // [n][K][256]
-    uint8_t* yraw;     // [n][L][32*ZBITS]
-    uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1
+    int depth;         // D = candidates per lane and round
+    int32_t* w;        // [n][D][K][256]
+    uint8_t* yraw;     // [n][D][L][32*ZBITS]
+    uint8_t* mw1;      // [n][D][64 + W1_LEN]  mu || w1
     uint8_t* rhopp;    // [n][64]
-    uint8_t* ctilde;   // [n][64]
-    uint8_t* cmask;    // [n][64]
+    uint8_t* ctilde;   // [n][D][64]
+    uint8_t* cmask;    // [n][D][64]
     uint32_t* kappa;   // [n]
     uint8_t* done;     // [n]
     uint32_t* act[2];  // [n] active lane lists (ping-pong)

@@ -14,21 +14,26 @@ namespace mldsa {
 // ------------------------------------------------------------------------------------------------
 // expand_a.  One thread owns one SHAKE128 stream (one polynomial of A-hat).  Per squeeze block the
 // thread parses its 56 three-byte candidates straight out of the state registers
-// (CoeffFromThreeBytes, src/conversion.rs:40-61) and stores each accepted one directly at its final
-// position, so a stream's coefficient j is its j-th accepted candidate.  A thread's stores walk its own
-// 1 KiB row, 8 to a 32-byte sector, so the sectors are complete in L2 long before they are written back;
-// an earlier version staged rows in shared memory and flushed them coalesced, which cost 15 % more
-// ALU-pipe instructions (shuffles, addressing, loop control) in a kernel that is ALU-pipe bound.
+// (CoeffFromThreeBytes, src/conversion.rs:40-61) and appends the accepted ones to its own row of a
+// shared-memory tile; after the block it moves the complete groups of four to their final position
+// with 128-bit stores and keeps the 0..3 left-over coefficients at the head of the row for the next
+// block, so a stream's coefficient j is its j-th accepted candidate.  The kernel is ALU-pipe bound
+// (Keccak); the staging costs that pipe ~1 predicate per candidate and per store, everything else
+// runs on the LSU / FMA pipes.  (Tried and measured worse: a warp-cooperative coalesced flush -- 15 %
+// more ALU instructions -- and 32-bit stores straight from registers -- LSU bound, ncu long_scoreboard 54 %.)
 // The loop runs until every stream of the warp has 256 coefficients: 5 blocks in practice, a 6th with
 // p ~ 1e-39 -- handled exactly, not assumed away.
 // ------------------------------------------------------------------------------------------------
 constexpr int EA_THREADS = 128;
+constexpr int EA_ROW = 64;  // words per thread: 3 carried + 56 candidates, rounded up to whole int4s
 
 template <bool SEED34>
 __global__ void __launch_bounds__(EA_THREADS, 4)
 expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstreams, int KL, int L,
                 int32_t* __restrict__ out)
 {
+    __shared__ __align__(16) int32_t tile_all[EA_THREADS * EA_ROW];
+    int32_t* row = tile_all + threadIdx.x * EA_ROW;  // private to this thread: no barriers needed
     // grid-stride over groups of EA_THREADS streams
     for (size_t q0 = (size_t)blockIdx.x * EA_THREADS; q0 < nstreams; q0 += (size_t)gridDim.x * EA_THREADS) {
     const size_t q = q0 + threadIdx.x;
@@ -50,18 +55,18 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
         a[20] = 0x8000000000000000ULL;  // byte 167 of the 168-byte rate
     }
 
-    int32_t* row = out + (valid ? q : 0) * 256;
-    int j = valid ? 0 : 256;  // coefficients produced so far for this thread's stream
-    while (__any_sync(0xffffffffu, j < 256)) {
+    int4* dst = reinterpret_cast<int4*>(out + (valid ? q : 0) * 256);  // next group of four to write
+    int quads_left = valid ? 64 : 0;
+    int have = 0;  // coefficients waiting at the head of the row (0..3 between blocks)
+    while (__any_sync(0xffffffffu, quads_left > 0)) {
         keccak_f1600(a);
         // The A-hat that feeds the fused kernels is stored prescaled by 2^32 / 256 mod q (the Montgomery factor of
         // the matrix-vector accumulator and the 1/256 of the un-scaled inverse NTT; see ntt.cuh).  These multiplies
         // sit on the FMA pipe, which this ALU-bound kernel leaves idle.  The microbench entry point (SEED34)
         // returns the plain RejNTTPoly output.
-#define EA_TAKE(c)                                                                                   \
-        if ((c) < (uint32_t)Q && j < 256) {                                                          \
-            row[j++] = SEED34 ? (int32_t)(c) : shoup_mul((int32_t)(c), SC_MONT_INV256, SC_MONT_INV256S); \
-        }
+#define EA_TAKE(c)                                                                                        \
+        if ((c) < (uint32_t)Q)                                                                            \
+            row[have++] = SEED34 ? (int32_t)(c) : shoup_mul((int32_t)(c), SC_MONT_INV256, SC_MONT_INV256S);
 #pragma unroll
         for (int g = 0; g < 14; g++) {  // 14 groups of 4 candidates = 3 words each
             const uint64_t l0 = a[(3 * g) >> 1], l1 = a[((3 * g) >> 1) + 1];
@@ -75,6 +80,17 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
             EA_TAKE(c0) EA_TAKE(c1) EA_TAKE(c2) EA_TAKE(c3)
         }
 #undef EA_TAKE
+        const int nq = min(have >> 2, quads_left);
+        const int4* src = reinterpret_cast<const int4*>(row);
+#pragma unroll
+        for (int k = 0; k < (3 + 56) / 4; k++)
+            if (k < nq) dst[k] = src[k];
+        // carry the incomplete group to the head of the row (a finished stream just parks garbage there)
+        const int4 tail = src[have >> 2];
+        dst += nq;
+        quads_left -= nq;
+        have &= 3;
+        *reinterpret_cast<int4*>(row) = tail;
     }
     }
 }
@@ -236,13 +252,13 @@ cudaError_t launch_shake128_rows(cudaStream_t st, const uint8_t* in, size_t in_s
 // ------------------------------------------------------------------------------------------------
 template <class P, bool SIGN>
 __global__ void __launch_bounds__(128, 4)
-ctilde_kernel(size_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ act,
+ctilde_kernel(size_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ act, int depth,
               const uint8_t* __restrict__ mw1, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ pre_ok,
               uint8_t* __restrict__ ok, uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ cmask_out)
 {
-    if (n_dev) n = *n_dev;  // sign rounds: the live active-lane count (n is only the launch bound)
+    if (n_dev) n = (size_t)*n_dev * depth;  // sign rounds: live (active lane, candidate) count; n only bounds the launch
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    const size_t ln = act ? act[idx] : idx;
+    const size_t ln = act ? (size_t)act[idx / depth] * depth + idx % depth : idx;  // row = lane * depth + candidate
     constexpr int NW = (MU_BYTES + P::W1_LEN) / 8;  // 104 or 136 words
     constexpr int NBLK = NW / 17 + 1;               // 7 or 9 absorb blocks (the last holds the padding)
     constexpr int CW = P::CTILDE / 8;               // c~ words
@@ -297,7 +313,7 @@ ctilde_kernel(size_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __re
 }
 
 template <class P>
-static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act,
+static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act, int depth,
                                    const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
                                    uint8_t* ctilde_out, uint8_t* sib_out)
 {
@@ -305,22 +321,22 @@ static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* n_
     {
         KLaunch kl(KID_CTILDE, st);
         if (ctilde_out)
-            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
         else
-            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act,
+cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act, int depth,
                           const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
                           uint8_t* ctilde_out, uint8_t* sib_out)
 {
     if (n == 0) return cudaSuccess;
     switch (ps) {
-    case 44: return launch_ctilde_t<Params<44>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    case 65: return launch_ctilde_t<Params<65>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    case 87: return launch_ctilde_t<Params<87>>(st, n, n_dev, act, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 44: return launch_ctilde_t<Params<44>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 65: return launch_ctilde_t<Params<65>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 87: return launch_ctilde_t<Params<87>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
     }
     return cudaErrorInvalidValue;
 }

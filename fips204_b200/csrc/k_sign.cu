@@ -12,7 +12,10 @@
 //     sign_prep     thread/lane  mu = H(tr || M'), rho'' = H(K || rnd || mu)        ml_dsa.rs:185-201
 //     sign_key      warp/key     s1-hat, s2-hat, t0-hat from the packed sk           ml_dsa.rs:447-453
 //     expand_a      thread/poly  A-hat                                               ml_dsa.rs:181
-//   per round, over the active list
+//   per round, over the active list; every active lane tries D consecutive candidates (kappa, kappa + L, ...)
+//   in one round ("depth", speculative: candidate j only counts if candidates 0..j-1 were rejected, exactly the
+//   reference's sequential order).  The D candidates of a lane run on neighbouring warps and share the lane's
+//   A-hat through L2, which halves (D = 2) the HBM traffic of the matrix-vector product and the round count.
 //     mask          thread/poly  y bytes = H(rho'' || LE16(kappa + r), 32c)          hashing.rs:281-313
 //     sign_w        warp/lane    w = INTT(A-hat o NTT(y)); w1 = HighBits(w); w1Encode ml_dsa.rs:215-232
 //     ctilde        thread/lane  c~ = H(mu || w1), c = SampleInBall(c~) as bit masks   ml_dsa.rs:233-237
@@ -31,7 +34,7 @@ __global__ void __launch_bounds__(128)
 sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
                  const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mw1, uint8_t* __restrict__ rhopp,
                  uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
-                 uint32_t* __restrict__ nact0, int* __restrict__ ctx_err)
+                 uint32_t* __restrict__ nact0, int* __restrict__ ctx_err, int depth)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -41,9 +44,11 @@ sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, Msg
     if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
     uint64_t mu[8];
     sp.out_words(mu, 8);
-    uint64_t* mo = reinterpret_cast<uint64_t*>(mw1 + i * (size_t)(MU_BYTES + P::W1_LEN));
+    for (int j = 0; j < depth; j++) {  // every candidate row starts with mu (the input row of the c~ hash)
+        uint64_t* mo = reinterpret_cast<uint64_t*>(mw1 + (i * depth + j) * (size_t)(MU_BYTES + P::W1_LEN));
 #pragma unroll
-    for (int k = 0; k < 8; k++) mo[k] = mu[k];
+        for (int k = 0; k < 8; k++) mo[k] = mu[k];
+    }
     sp.init();                                            // rho'' = H(K || rnd || mu, 64)  ml_dsa.rs:199-201
     sp.absorb(key + 32, 32);
     sp.absorb(rnd + 32 * i, 32);
@@ -103,10 +108,10 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
 template <class P>
 __global__ void __launch_bounds__(128, 4)
 mask_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
-            const uint8_t* __restrict__ rhopp, const uint32_t* __restrict__ kappa, uint8_t* __restrict__ yraw)
+            const uint8_t* __restrict__ rhopp, const uint32_t* __restrict__ kappa, uint8_t* __restrict__ yraw, int depth)
 {
-    constexpr int L = P::L;
     constexpr int YW = 32 * P::ZBITS / 8;  // 72 or 80 output words
+    const int L = P::L * depth;            // polynomial r of a lane belongs to candidate r / P::L: nonce kappa + r
     const size_t nstreams = (size_t)*nact_dev * L;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nstreams; q += (size_t)gridDim.x * blockDim.x) {
     const size_t ln = act[q / L];
@@ -151,27 +156,32 @@ template <class P, bool SHARED>
 __global__ void __launch_bounds__(SG_WARPS * 32, 5)
 sign_w_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
               const int32_t* __restrict__ Aall, const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall,
-              uint8_t* __restrict__ mw1)
+              uint8_t* __restrict__ mw1, int depth)
 {
     constexpr int K = P::K, L = P::L;
-    const size_t nact = *nact_dev;
+    const size_t nact = (size_t)*nact_dev * depth;  // work items: (active lane, candidate)
     __shared__ __align__(16) SignWSmem<P> sm_all[SG_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SignWSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
     const size_t stride = (size_t)gridDim.x * SG_WARPS;
     for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
-        const size_t ln = act[ai];
+        const size_t ln = act[ai / depth];
+        const size_t slot = ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
         const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
-        const uint8_t* yp = yraw + ln * (size_t)(L * 32 * P::ZBITS);
-        int32_t* wo = wall + ln * (size_t)K * 256;
-        uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
+        const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
+        int32_t* wo = wall + slot * (size_t)K * 256;
+        uint8_t* w1o = mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
         __syncwarp();
         warp_prefetch_l2(A, 2 * L * 1024, lane);  // rows 0 and 1 of A-hat stream in during the forward NTTs
-#pragma unroll 1
+        uint32_t yw[2][(P::ZBITS + 3) / 4];       // packed y of the next polynomial is in flight during an NTT
+        load_span<P::ZBITS>(yp + P::ZBITS * lane, yw[0]);
+#pragma unroll
         for (int l = 0; l < L; l++) {
+            if (l + 1 < L) load_span<P::ZBITS>(yp + (l + 1) * 32 * P::ZBITS + P::ZBITS * lane, yw[(l + 1) & 1]);
             int32_t y[8];
-            load_y<P>(yp + l * 32 * P::ZBITS, lane, y);
+#pragma unroll
+            for (int i = 0; i < 8; i++) y[i] = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(yw[l & 1], i);
             sntt_fwd_B2B(y, tile, lane);
             row_store(sm.yh[l], lane, y);  // only this lane reads these words back
         }
@@ -228,7 +238,7 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
               const int32_t* __restrict__ s2h_all, const int32_t* __restrict__ t0h_all,
               const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, const uint8_t* __restrict__ ctilde,
               const uint8_t* __restrict__ cmask, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
-              uint8_t* __restrict__ rhopp, uint8_t* __restrict__ sig, uint32_t* __restrict__ iters)
+              uint8_t* __restrict__ rhopp, uint8_t* __restrict__ sig, uint32_t* __restrict__ iters, int depth)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
@@ -242,9 +252,15 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
     for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
         const size_t ln = act[ai];
         const size_t kn = SHARED ? 0 : ln;
-        const uint8_t* yp = yraw + ln * (size_t)(L * 32 * P::ZBITS);
-        int32_t* wl = wall + ln * (size_t)K * 256;
         uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
+        bool rej = true;
+        int cand = 0;
+        // the lane's candidates in the reference's order: the first one that passes every check is the signature
+#pragma unroll 1
+        for (; cand < depth && rej; cand++) {
+        const size_t slot = ln * depth + cand;
+        const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
+        int32_t* wl = wall + slot * (size_t)K * 256;
 
         // first operands of the r0 phase stream in while c-hat is computed
         if (lane < 16) {
@@ -254,7 +270,7 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
         }
         // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240) centred, with its Shoup companion
         int32_t ch[8], chs[8];
-        load_c_layoutA(cmask + ln * (size_t)CMASK_STRIDE, lane, ch);
+        load_c_layoutA(cmask + slot * (size_t)CMASK_STRIDE, lane, ch);
         sntt_fwd_A2B(ch, tile, lane);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -262,7 +278,7 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
             chs[i] = shoup_companion(ch[i]);
         }
 
-        bool rej = false;
+        rej = false;
         int hcount = 0;
 #pragma unroll 1
         for (int p = 0; p < 2 * K + L && !rej; p++) {
@@ -366,23 +382,26 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
                 if (!rej && lane == 0) hb[P::OMEGA + idx] = (uint8_t)hcount;
             }
         }
+        __syncwarp();
+        }  // candidates
         if (rej) {
-            if (lane == 0) kappa[ln] += L;                                         // ml_dsa.rs:281, 317
+            if (lane == 0) kappa[ln] += L * depth;                                 // ml_dsa.rs:281, 317
             continue;
         }
+        cand--;  // the accepted candidate
         // accept: c~ and hints complete the signature                            encodings.rs:254, 273
         __syncwarp();
         warp_copy_out(sg + LO::SIG_H, sm.stage, P::OMEGA + K, lane);
-        warp_copy_bytes(sg, ctilde + ln * 64, P::CTILDE, lane);
+        warp_copy_bytes(sg, ctilde + (ln * depth + cand) * 64, P::CTILDE, lane);
         if (lane == 0) {
             done[ln] = 1;
-            if (iters) iters[ln] = kappa[ln] / L + 1;
+            if (iters) iters[ln] = kappa[ln] / L + cand + 1;
         }
         // The lane is finished: zero everything it derived from the secret key and the mask (y, w - c*s2, rho'',
         // and its own s1-hat / s2-hat / t0-hat) right here, where the stores hide behind other warps' arithmetic,
         // instead of a 27 GB cudaMemset after the last round (src/types.rs:19 ZeroizeOnDrop analogue).
-        warp_zero16(wl, K * 1024, lane);
-        warp_zero16(const_cast<uint8_t*>(yp), L * 32 * P::ZBITS, lane);
+        warp_zero16(wall + ln * (size_t)depth * K * 256, depth * K * 1024, lane);
+        warp_zero16(const_cast<uint8_t*>(yraw) + ln * (size_t)depth * (L * 32 * P::ZBITS), depth * L * 32 * P::ZBITS, lane);
         warp_zero16(rhopp + ln * 64, 64, lane);
         if (!SHARED) {
             warp_zero16(const_cast<int32_t*>(s1h_all) + ln * (size_t)L * 256, L * 1024, lane);
@@ -417,6 +436,7 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     const bool shared = sk_stride == 0;
     const size_t nkeys = shared ? 1 : n;
     const Tuning tn = tuning();
+    const int D = ws.depth;
     auto warp_grid = [&](size_t items) {
         return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16);
     };
@@ -427,7 +447,7 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     {
         KLaunch kl(KID_SIGN_PREP, st);
         sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
-                                                                        ws.kappa, ws.done, ws.act[0], ws.nact, ctx_err);
+                                                                        ws.kappa, ws.done, ws.act[0], ws.nact, ctx_err, D);
     }
     {
         KLaunch kl(KID_SIGN_KEY, st);
@@ -452,31 +472,31 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     while (bound > 0) {
         {
             KLaunch kl(KID_MASK, st);
-            mask_kernel<P><<<capped_grid((bound * L + 127) / 128, tn.kcap), 128, 0, st>>>(ws.nact + cur, ws.act[cur],
-                                                                                       ws.rhopp, ws.kappa, ws.yraw);
+            mask_kernel<P><<<capped_grid((bound * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(
+                ws.nact + cur, ws.act[cur], ws.rhopp, ws.kappa, ws.yraw, D);
         }
         {
             KLaunch kl(KID_SIGN_W, st);
             if (shared)
-                sign_w_kernel<P, true><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
-                                                                                 ws.yraw, ws.w, ws.mw1);
+                sign_w_kernel<P, true><<<warp_grid(bound * D), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
+                                                                                     ws.yraw, ws.w, ws.mw1, D);
             else
-                sign_w_kernel<P, false><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
-                                                                                  ws.yraw, ws.w, ws.mw1);
+                sign_w_kernel<P, false><<<warp_grid(bound * D), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
+                                                                                      ws.yraw, ws.w, ws.mw1, D);
         }
-        e = launch_ctilde(P::PS, st, bound, ws.nact + cur, ws.act[cur], ws.mw1, nullptr, nullptr, nullptr, ws.ctilde,
-                          ws.cmask);
+        e = launch_ctilde(P::PS, st, bound * D, ws.nact + cur, ws.act[cur], D, ws.mw1, nullptr, nullptr, nullptr,
+                          ws.ctilde, ws.cmask);
         if (e != cudaSuccess) return e;
         {
             KLaunch kl(KID_SIGN_Z, st);
             if (shared)
                 sign_z_kernel<P, true><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
                     ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
-                    ws.done, ws.rhopp, sig, iters);
+                    ws.done, ws.rhopp, sig, iters, D);
             else
                 sign_z_kernel<P, false><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
                     ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
-                    ws.done, ws.rhopp, sig, iters);
+                    ws.done, ws.rhopp, sig, iters, D);
         }
         e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);
         if (e != cudaSuccess) return e;

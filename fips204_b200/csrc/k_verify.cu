@@ -254,7 +254,7 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
             verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr,
                                                                           ws.cmask, ws.mw1, ws.pre_ok);
     }
-    e = launch_ctilde(P::PS, st, n, nullptr, nullptr, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
+    e = launch_ctilde(P::PS, st, n, nullptr, nullptr, 1, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

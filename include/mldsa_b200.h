@@ -126,12 +126,16 @@ int mldsa_shake_batch(int dev, int bits /*128|256*/, size_t n, const uint8_t* in
                       size_t out_len);
 
 /* ---- tuning / telemetry ------------------------------------------------------------------ */
-/* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 64 GiB) */
+/* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 96 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);
 /* launch tuning: a sign chunk runs as `ways` concurrent sub-batches on separate streams; kcap / acap cap
  * the CTAs per SM of the Keccak / arithmetic kernels so kernels of different ways share an SM
  * (0 = uncapped).  Defaults come from MLDSA_WAYS / MLDSA_KCAP / MLDSA_ACAP, else 1 / 0 / 0. */
 void mldsa_set_tuning(int ways, int kcap, int acap);
+/* candidates (kappa, kappa + L, ...) every still-active lane tries per round of the sign rejection loop, 1..8
+ * (default MLDSA_DEPTH, else 2).  Results never depend on it: candidates count in the reference's order
+ * (src/ml_dsa.rs:212-330); a larger depth trades a little speculative work for fewer rounds and less A-hat traffic. */
+void mldsa_set_depth(int depth);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */

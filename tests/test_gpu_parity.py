@@ -376,3 +376,28 @@ def test_get_public_key(F, ps, acvp_keygen):
     got = m.sk_to_pk_batch(fz)
     for i in range(16):
         assert got[i].tobytes() == O.sk_to_pk(ps, fz[i].tobytes())
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 8])
+def test_sign_speculation_depth_does_not_change_bytes(F, depth):
+    """The sign loop tries `depth` candidates per lane and round (mldsa_set_depth); a candidate only counts
+    if all earlier ones were rejected, so signatures AND iteration counts are those of the reference's
+    sequential loop (src/ml_dsa.rs:212-330) for every depth."""
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    try:
+        L.mldsa_set_depth(depth)
+        for ps in (44, 65, 87):
+            m = F.PARAM_SETS[ps]
+            n = 257
+            pks, sks = O.keygen_batch(ps, synth_block(f"dk{ps}", n, 32))
+            msgs = [synth("dm", i, i % 50) for i in range(n)]
+            rnds = synth_rows("dr", n, 32)
+            sig, it = m.sign_batch(sks, msgs, rnds, want_iters=True)
+            osig, oit = O.sign_batch(ps, sks, msgs, rnds)
+            assert (sig == osig).all() and (it == oit).all(), (ps, depth)
+            one = m.sign_batch(sks[5].tobytes(), msgs, rnds, shared_key=True)
+            oone, _ = O.sign_batch(ps, sks[5], msgs, rnds, shared_key=True)
+            assert (one == oone).all()
+    finally:
+        L.mldsa_set_depth(2)
