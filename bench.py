@@ -100,6 +100,15 @@ def kernel_work(ps, n, total_iters, accepted):
     p = PARAMS[ps]
     K, L = p["K"], p["L"]
     it = float(total_iters)
+    w = _kernel_work(ps, n, it, accepted)
+    # paired round launches: one Keccak stage (mask / ctilde) beside one arithmetic stage (sign_w / sign_z)
+    w["round_pair"] = tuple(sum(w[k][i] for k in ("mask", "sign_w", "ctilde", "sign_z")) for i in (0, 1))
+    return w
+
+
+def _kernel_work(ps, n, it, accepted):
+    p = PARAMS[ps]
+    K, L = p["K"], p["L"]
     return {
         # name: (int32 ops, algorithmic bytes) per step
         "expand_a": (n * K * L * 5 * KECCAK_F, n * (32 + K * L * 1024)),
@@ -297,7 +306,7 @@ def main():
                     "frac": (tk["hbm_gbs"] or 0) / hbm_peak, "peak_source": hbm_src},
             "traffic": None,
         }
-    whole_ops = sum(v[0] for v in work.values())
+    whole_ops = sum(v[0] for k, v in work.items() if k != "round_pair")
 
     # ---- correctness guards outside the timed region: all signatures verify on the GPU, and a sample is
     # byte-identical to the CPU oracle

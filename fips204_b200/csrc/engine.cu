@@ -29,7 +29,7 @@ static uint64_t g_prof_n[KID_COUNT];
 static const char* const KERNEL_NAMES[KID_COUNT] = {
     "expand_a", "ntt", "intt", "shake_rows", "ctilde", "kg_seed", "rej_bounded", "kg_arith", "verify_pre",
     "t1hat", "verify_arith", "sign_prep", "sign_key", "mask", "sign_w", "sign_z", "compact", "int_probe", "prehash",
-    "sk_to_pk"};
+    "sk_to_pk", "round_pair"};
 
 struct EvPair {
     int id;
@@ -82,7 +82,7 @@ void prof_collect()
     t_events.clear();
 }
 
-static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1};
+static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1}, g_pair{-1}, g_kshare{-1}, g_stage{-1};
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -100,7 +100,12 @@ Tuning tuning()
     if (d < 0) g_depth.store(d = env_int("MLDSA_DEPTH", 2));
     if (d < 1) d = 1;
     if (d > 8) d = 8;
-    return Tuning{w, k, a, d};
+    int pr = g_pair.load(), ks = g_kshare.load();
+    if (pr < 0) g_pair.store(pr = env_int("MLDSA_PAIR", 0));
+    if (ks < 0) g_kshare.store(ks = env_int("MLDSA_KSHARE", 2));
+    int sg = g_stage.load();
+    if (sg < 0) g_stage.store(sg = env_int("MLDSA_STAGE", 2));
+    return Tuning{w, k, a, d, pr, sg, ks};
 }
 unsigned capped_grid(size_t want_ctas, int cap_per_sm)
 {
@@ -172,7 +177,7 @@ struct DeviceCtx {
             CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
         }
-        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 256, cudaHostAllocDefault));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 512, cudaHostAllocDefault));
         dev = d;
         return OK;
     }
@@ -272,7 +277,7 @@ static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared)
     const size_t nk = shared ? 1 : n, D = (size_t)tuning().depth;
     return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
            pad256(n * D * p.K * 1024) + pad256(n * D * p.L * 32 * p.zbits) + pad256(n * D * (64 + p.w1len)) +
-           pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(16);
+           pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64) + pad256(2 * 2048 * 4);
 }
 static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox)
 {
@@ -293,7 +298,8 @@ static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint
     w.done = c.take<uint8_t>(n);
     w.act[0] = c.take<uint32_t>(n);
     w.act[1] = c.take<uint32_t>(n);
-    w.nact = c.take<uint32_t>(4);
+    w.nact = c.take<uint32_t>(16);
+    w.queue = c.take<uint32_t>(2 * 2048);
     w.h_nact = mailbox;
     return w;
 }
@@ -394,7 +400,7 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
             cudaStream_t ws_stream = w == 0 ? st : cx.way_stream[w];
             if (w != 0) cudaStreamWaitEvent(ws_stream, ready, 0);
             Carver c(cx.arena + arena_skip + (size_t)w * sign_ws_bytes(p, way_lanes, shared));
-            SignWs ws = sign_carve(c, p, wm, shared, cx.mailbox + 4 * w);
+            SignWs ws = sign_carve(c, p, wm, shared, cx.mailbox + 8 * w);
             ws.h_nact[1] = 0;
             MsgDesc md{d_msgs, d_msg_off + wlo, d_ctx, d_ctx_off ? d_ctx_off + wlo : nullptr, framing};
             cudaError_t e = sign_run(ps, ws_stream, wm, d_sk + sk_stride * wlo, sk_stride, md, d_rnd + 32 * wlo,
@@ -537,6 +543,11 @@ void mldsa_host_free(void* p)
 }
 void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
 void mldsa_set_depth(int depth) { g_depth.store(depth < 1 ? 1 : (depth > 8 ? 8 : depth)); }
+void mldsa_set_pairing(int pair, int kshare)
+{
+    g_pair.store(pair ? 1 : 0);
+    g_kshare.store(kshare < 1 ? 2 : (kshare > 4 ? 4 : kshare));
+}
 void mldsa_set_tuning(int ways, int kcap, int acap)
 {
     g_ways.store(ways < 1 ? 1 : ways);

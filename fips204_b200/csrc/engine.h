@@ -21,7 +21,7 @@ constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_r
 enum KernelId : int {
     KID_EXPAND_A = 0, KID_NTT, KID_INTT, KID_SHAKE_ROWS, KID_CTILDE, KID_KG_SEED, KID_REJ_BOUNDED, KID_KG_ARITH,
     KID_VERIFY_PRE, KID_T1HAT, KID_VERIFY_ARITH, KID_SIGN_PREP, KID_SIGN_KEY, KID_MASK, KID_SIGN_W, KID_SIGN_Z,
-    KID_COMPACT, KID_PROBE, KID_PREHASH, KID_SK2PK, KID_COUNT
+    KID_COMPACT, KID_PROBE, KID_PREHASH, KID_SK2PK, KID_ROUND_PAIR, KID_COUNT
 };
 struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<...>>>(...); }`
     int id;
@@ -39,6 +39,10 @@ void prof_collect();
 struct Tuning {
     int ways, kcap, acap;
     int depth;  // candidates tried per active lane and round of the sign loop (MLDSA_DEPTH, default 2)
+    int pair;   // 1: run a Keccak stage of one half-chunk beside an arithmetic stage of the other (MLDSA_PAIR, default 1)
+    int stage;  // sign_w: 0 = A-hat rows straight from global memory, 1 = TMA-staged per warp, 2 = staged and shared by
+                // the two candidate warps of a lane when the depth is even (MLDSA_STAGE, default 2)
+    int kshare; // paired kernel: CTAs out of 5 per SM that prefer the Keccak queue (MLDSA_KSHARE, default 2)
 };
 Tuning tuning();
 unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event pairs into the per-kernel totals (call after a stream sync)
@@ -125,7 +129,8 @@ struct SignWs {
     uint32_t* kappa;   // [n]
     uint8_t* done;     // [n]
     uint32_t* act[2];  // [n] active lane lists (ping-pong)
-    uint32_t* nact;    // [2] device counters
+    uint32_t* nact;    // [16] device control words: [4 * way + buffer] active counts, [8] ctx error flag
+    uint32_t* queue;   // [2 * 2048] work-unit counters of the paired round launches
     uint32_t* h_nact;  // pinned host mirror [2]: [0] active count / ctx flag, [1] CTX_ERR_MARK
     static size_t bytes_per_lane(int K, int L, int zbits, int w1len, bool shared)
     {

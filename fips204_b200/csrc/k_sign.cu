@@ -26,6 +26,7 @@
 #include "ntt.cuh"
 #include "pack.cuh"
 #include "sampling.cuh"
+#include "ctilde.cuh"
 
 namespace mldsa {
 
@@ -34,11 +35,14 @@ __global__ void __launch_bounds__(128)
 sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
                  const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mw1, uint8_t* __restrict__ rhopp,
                  uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
-                 uint32_t* __restrict__ nact0, int* __restrict__ ctx_err, int depth)
+                 uint32_t* __restrict__ ctl, size_t n_way_a, int* __restrict__ ctx_err, int depth)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (i == 0) *nact0 = (uint32_t)n;
+    if (i == 0) {  // active counts of the two ways: lanes [0, n_way_a) and [n_way_a, n)
+        ctl[0] = (uint32_t)n_way_a;
+        ctl[4] = (uint32_t)(n - n_way_a);
+    }
     const uint8_t* key = sk + i * sk_stride;
     Sponge<SHAKE256_RATE> sp;
     if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
@@ -61,6 +65,9 @@ sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, Msg
 }
 
 constexpr int SG_WARPS = 4;
+#ifndef SG_MINB
+#define SG_MINB 6
+#endif
 
 // s1-hat, s2-hat, t0-hat (plain NTT domain) for every key.  warp per key.
 template <class P>
@@ -104,28 +111,47 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
     }
 }
 
+// ---- per-stage jobs.  Every stage is written as a function of a WORK UNIT (what one 128-thread CTA does in one
+// step: 128 Keccak streams, or one item per warp), so that the same body runs in the stand-alone kernels
+// (grid-stride over units) and in the paired round kernel (units handed out from two queues).
+struct MaskJob {
+    const uint32_t* nact; const uint32_t* act; const uint8_t* rhopp; const uint32_t* kappa; uint8_t* yraw; int depth;
+};
+struct CtildeJob {
+    const uint32_t* nact; const uint32_t* act; const uint8_t* mw1; uint8_t* ctilde; uint8_t* cmask; int depth;
+};
+struct SignWJob {
+    const uint32_t* nact; const uint32_t* act; const int32_t* A; const uint8_t* yraw; int32_t* w; uint8_t* mw1; int depth;
+};
+struct SignZJob {
+    const uint32_t* nact; const uint32_t* act; const int32_t* s1h; const int32_t* s2h; const int32_t* t0h;
+    const uint8_t* yraw; int32_t* w; const uint8_t* ctilde; const uint8_t* cmask; uint32_t* kappa; uint8_t* done;
+    uint8_t* rhopp; uint8_t* sig; uint32_t* iters; int depth;
+};
+
 // ExpandMask: one thread per (active lane, r) SHAKE256 stream; the squeezed bytes ARE the packed y.
 template <class P>
-__global__ void __launch_bounds__(128, 4)
-mask_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
-            const uint8_t* __restrict__ rhopp, const uint32_t* __restrict__ kappa, uint8_t* __restrict__ yraw, int depth)
+__device__ __forceinline__ size_t mask_units(const MaskJob& j) { return ((size_t)*j.nact * P::L * j.depth + 127) / 128; }
+template <class P>
+__device__ __forceinline__ void mask_unit(const MaskJob& j, size_t unit)
 {
     constexpr int YW = 32 * P::ZBITS / 8;  // 72 or 80 output words
-    const int L = P::L * depth;            // polynomial r of a lane belongs to candidate r / P::L: nonce kappa + r
-    const size_t nstreams = (size_t)*nact_dev * L;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nstreams; q += (size_t)gridDim.x * blockDim.x) {
-    const size_t ln = act[q / L];
+    const int L = P::L * j.depth;          // polynomial r of a lane belongs to candidate r / P::L: nonce kappa + r
+    const size_t nstreams = (size_t)*j.nact * L;
+    const size_t q = unit * 128 + threadIdx.x;
+    if (q >= nstreams) return;
+    const size_t ln = j.act[q / L];
     const uint32_t r = (uint32_t)(q % L);
-    const uint64_t* rp = reinterpret_cast<const uint64_t*>(rhopp + 64 * ln);
+    const uint64_t* rp = reinterpret_cast<const uint64_t*>(j.rhopp + 64 * ln);
     uint64_t a[25];
 #pragma unroll
     for (int i = 0; i < 8; i++) a[i] = rp[i];
-    const uint32_t nonce = (kappa[ln] + r) & 0xFFFF;  // u16 counter (ml_dsa.rs:204, hashing.rs:296)
+    const uint32_t nonce = (j.kappa[ln] + r) & 0xFFFF;  // u16 counter (ml_dsa.rs:204, hashing.rs:296)
     a[8] = (uint64_t)(nonce | (0x1Fu << 16));
 #pragma unroll
     for (int i = 9; i < 25; i++) a[i] = 0;
     a[16] = 0x8000000000000000ULL;
-    uint64_t* out = reinterpret_cast<uint64_t*>(yraw + (ln * L + r) * (size_t)(YW * 8));
+    uint64_t* out = reinterpret_cast<uint64_t*>(j.yraw + (ln * L + r) * (size_t)(YW * 8));
 #pragma unroll 1
     for (int b = 0; b < (YW + 16) / 17; b++) {
         keccak_f1600(a);
@@ -133,7 +159,23 @@ mask_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ 
         for (int k = 0; k < 17; k++)
             if (b * 17 + k < YW) out[b * 17 + k] = a[k];
     }
-    }
+}
+template <class P>
+__global__ void __launch_bounds__(128, 4) mask_kernel(MaskJob j)
+{
+    const size_t nu = mask_units<P>(j);
+    for (size_t u = blockIdx.x; u < nu; u += gridDim.x) mask_unit<P>(j, u);
+}
+
+template <class P>
+__device__ __forceinline__ size_t ctilde_units(const CtildeJob& j) { return ((size_t)*j.nact * j.depth + 127) / 128; }
+template <class P>
+__device__ __forceinline__ void ctilde_unit(const CtildeJob& j, size_t unit)
+{
+    const size_t idx = unit * 128 + threadIdx.x;
+    if (idx >= (size_t)*j.nact * j.depth) return;
+    const size_t row = (size_t)j.act[idx / j.depth] * j.depth + idx % j.depth;
+    ctilde_row<P, true>(row, j.mw1, nullptr, nullptr, nullptr, j.ctilde, j.cmask);
 }
 
 // y (layout B regs) from the packed mask bytes: BitUnpack(gamma1 - 1, gamma1)
@@ -152,20 +194,24 @@ struct alignas(16) SignWSmem {
     alignas(16) int32_t yh[P::L][256];  // y-hat, NTT domain, natural order (lane t owns words 8t..8t+7 of each row)
 };
 
+template <class P>
+__device__ __forceinline__ size_t sign_w_units(const SignWJob& j) { return ((size_t)*j.nact * j.depth + SG_WARPS - 1) / SG_WARPS; }
 template <class P, bool SHARED>
-__global__ void __launch_bounds__(SG_WARPS * 32, 5)
-sign_w_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
-              const int32_t* __restrict__ Aall, const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall,
-              uint8_t* __restrict__ mw1, int depth)
+__device__ __forceinline__ void sign_w_unit(const SignWJob& j, size_t unit, SignWSmem<P>* sm_all)
 {
     constexpr int K = P::K, L = P::L;
-    const size_t nact = (size_t)*nact_dev * depth;  // work items: (active lane, candidate)
-    __shared__ __align__(16) SignWSmem<P> sm_all[SG_WARPS];
+    const uint32_t* __restrict__ act = j.act;
+    const int32_t* __restrict__ Aall = j.A;
+    const uint8_t* __restrict__ yraw = j.yraw;
+    int32_t* __restrict__ wall = j.w;
+    uint8_t* __restrict__ mw1 = j.mw1;
+    const int depth = j.depth;
+    const size_t nact = (size_t)*j.nact * depth;  // work items: (active lane, candidate)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SignWSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
-    const size_t stride = (size_t)gridDim.x * SG_WARPS;
-    for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
+    const size_t ai = unit * SG_WARPS + warp;
+    if (ai < nact) {
         const size_t ln = act[ai / depth];
         const size_t slot = ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
         const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
@@ -221,6 +267,183 @@ sign_w_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
     }
 }
 
+template <class P, bool SHARED>
+__global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_kernel(SignWJob j)
+{
+    __shared__ __align__(16) SignWSmem<P> sm_all[SG_WARPS];
+    const size_t nu = sign_w_units<P>(j);
+    for (size_t u = blockIdx.x; u < nu; u += gridDim.x) sign_w_unit<P, SHARED>(j, u, sm_all);
+}
+
+// ---- sign_w with A-hat rows staged through shared memory by the TMA unit --------------------------------
+// One bulk copy (cp.async.bulk, completion on an mbarrier) brings row k + 1 of A-hat (L KiB, contiguous) into
+// shared memory while the warp runs the inverse NTT of row k, so the matrix-vector product never waits on
+// HBM / L2 (ncu: 40 % of the un-staged kernel's stall samples were long-scoreboard waits on these loads).
+// With an even speculation depth the two candidates of a lane sit on neighbouring warps and SHARE the staged
+// row (G = 2): the row is fetched once for both, and whichever warp finishes its products last issues the next copy.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+template <class P, int G>
+struct alignas(128) SignWStage {
+    alignas(128) int32_t arow[SG_WARPS / G][P::L * 256];  // one staged row of A-hat per group of G warps
+    alignas(16) int32_t yh[SG_WARPS][P::L][256];
+    alignas(16) int32_t tile[SG_WARPS][NTT_TILE_WORDS];
+    alignas(8) uint64_t full[SG_WARPS / G];
+    uint32_t cnt[SG_WARPS / G];
+};
+
+template <class P, bool SHARED, int G>
+__global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(SignWJob j)
+{
+    constexpr int K = P::K, L = P::L;
+    constexpr uint32_t ROW_BYTES = L * 1024;
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    SignWStage<P, G>& sm = *reinterpret_cast<SignWStage<P, G>*>(sm_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = warp / G;
+    if (threadIdx.x < SG_WARPS / G) {
+        mbar_init(&sm.full[threadIdx.x], 1);
+        sm.cnt[threadIdx.x] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phase = 0;
+    int32_t* tile = sm.tile[warp];
+    // The staged row is in natural order, so lane t's coefficients 8t..8t+7 are the int4 slots 2t and 2t+1 -- a
+    // 2-way bank conflict for 128-bit loads.  Lanes with bit 2 set read their two slots in the opposite order
+    // (slot numbers of a quarter-warp are then distinct mod 8), keep their y-hat rows swapped the same way, and
+    // swap the two halves of the accumulator back before the inverse transform.
+    const int swz = (lane >> 2) & 1;
+    const int depth = j.depth;
+    const size_t nitems = (size_t)*j.nact * depth;
+    const size_t nu = (nitems + SG_WARPS - 1) / SG_WARPS;
+    for (size_t u = blockIdx.x; u < nu; u += gridDim.x) {
+        const size_t ai = u * SG_WARPS + warp;
+        if (ai >= nitems) continue;  // G = 2 needs an even depth, so both warps of a group skip together
+        const size_t ln = j.act[ai / depth];
+        const size_t slot = ln * depth + ai % depth;
+        const int32_t* A = j.A + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
+        const uint8_t* yp = j.yraw + slot * (size_t)(L * 32 * P::ZBITS);
+        int32_t* wo = j.w + slot * (size_t)K * 256;
+        uint8_t* w1o = j.mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
+        // Every warp of the group reports "done reading the staged row"; the last one to report starts the next copy.
+        auto release_and_fetch = [&](int row) {
+            __syncwarp();
+            if (lane == 0) {
+                bool last = true;
+                if (G > 1) last = atomicAdd(&sm.cnt[grp], 1u) == (uint32_t)(G - 1);
+                if (last) {
+                    if (G > 1) atomicExch(&sm.cnt[grp], 0u);
+                    mbar_expect_tx(&sm.full[grp], ROW_BYTES);
+                    bulk_g2s(sm.arow[grp], A + (size_t)row * L * 256, ROW_BYTES, &sm.full[grp]);
+                }
+            }
+        };
+        release_and_fetch(0);
+        uint32_t yw[2][(P::ZBITS + 3) / 4];  // packed y of the next polynomial is in flight during an NTT
+        load_span<P::ZBITS>(yp + P::ZBITS * lane, yw[0]);
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+            if (l + 1 < L) load_span<P::ZBITS>(yp + (l + 1) * 32 * P::ZBITS + P::ZBITS * lane, yw[(l + 1) & 1]);
+            int32_t y[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) y[i] = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(yw[l & 1], i);
+            sntt_fwd_B2B(y, tile, lane);
+            if (swz) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int32_t x = y[i];
+                    y[i] = y[i + 4];
+                    y[i + 4] = x;
+                }
+            }
+            row_store(sm.yh[warp][l], lane, y);  // only this lane reads these words back
+        }
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            mbar_wait(&sm.full[grp], phase);
+            phase ^= 1;
+            int64_t acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = 0;
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                const int4* ap = reinterpret_cast<const int4*>(sm.arow[grp] + l * 256 + 8 * lane);
+                const int4 x = ap[swz], y = ap[1 - swz];
+                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                int32_t yv[8];
+                row_load(sm.yh[warp][l], lane, yv);
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * yv[i];
+            }
+            if (k + 1 < K) release_and_fetch(k + 1);
+            int32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
+            if (swz) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int32_t x = t[i];
+                    t[i] = t[i + 4];
+                    t[i + 4] = x;
+                }
+            }
+            sntt_inv_B2B(t, tile, lane);  // w[k], canonical (A-hat is prescaled by 2^32 / 256)
+            int4* o = reinterpret_cast<int4*>(wo + 256 * k + 8 * lane);
+            o[0] = make_int4(t[0], t[1], t[2], t[3]);
+            o[1] = make_int4(t[4], t[5], t[6], t[7]);
+            uint32_t f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                int32_t r0;
+                f[i] = (uint32_t)decompose<P::GAMMA2>(t[i], r0);  // HighBits (ml_dsa.rs:225-226)
+            }
+            uint32_t w[(P::W1BITS + 3) / 4];
+            pack_fields<P::W1BITS>(f, w);
+            store_span<P::W1BITS>(w1o + k * 32 * P::W1BITS + P::W1BITS * lane, w);
+        }
+    }
+}
+
+template <class P, bool SHARED, int G>
+static cudaError_t launch_sign_w_staged(cudaStream_t st, const SignWJob& j, size_t items, int cap_per_sm)
+{
+    static bool configured = false;  // one attribute call per instantiation (idempotent; a benign race at worst)
+    constexpr size_t SMEM = sizeof(SignWStage<P, G>);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sign_w_staged_kernel<P, SHARED, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    KLaunch kl(KID_SIGN_W, st);
+    sign_w_staged_kernel<P, SHARED, G><<<capped_grid((items + SG_WARPS - 1) / SG_WARPS, cap_per_sm), SG_WARPS * 32, SMEM, st>>>(j);
+    return cudaGetLastError();
+}
+
 template <class P>
 struct alignas(16) SignSmem {
     int32_t tile[NTT_TILE_WORDS];
@@ -231,25 +454,34 @@ struct alignas(16) SignSmem {
 // c*s2, c*s1, c*t0 share ONE instance of the inverse-NTT code (a single loop over 2K+L polynomials); the
 // checks run most-selective-first (r0, then z, then ct0/hints) so a rejected iteration stops early.  The
 // order of the checks does not affect the outcome: the reference rejects if ANY fails (ml_dsa.rs:277-319).
+template <class P>
+__device__ __forceinline__ size_t sign_z_units(const SignZJob& j) { return ((size_t)*j.nact + SG_WARPS - 1) / SG_WARPS; }
 template <class P, bool SHARED>
-__global__ void __launch_bounds__(SG_WARPS * 32, 5)
-sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act,
-              const int32_t* __restrict__ s1h_all,
-              const int32_t* __restrict__ s2h_all, const int32_t* __restrict__ t0h_all,
-              const uint8_t* __restrict__ yraw, int32_t* __restrict__ wall, const uint8_t* __restrict__ ctilde,
-              const uint8_t* __restrict__ cmask, uint32_t* __restrict__ kappa, uint8_t* __restrict__ done,
-              uint8_t* __restrict__ rhopp, uint8_t* __restrict__ sig, uint32_t* __restrict__ iters, int depth)
+__device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, SignSmem<P>* sm_all)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
-    const size_t nact = *nact_dev;
-    __shared__ __align__(16) SignSmem<P> sm_all[SG_WARPS];
+    const uint32_t* __restrict__ act = j.act;
+    const int32_t* __restrict__ s1h_all = j.s1h;
+    const int32_t* __restrict__ s2h_all = j.s2h;
+    const int32_t* __restrict__ t0h_all = j.t0h;
+    const uint8_t* __restrict__ yraw = j.yraw;
+    int32_t* __restrict__ wall = j.w;
+    const uint8_t* __restrict__ ctilde = j.ctilde;
+    const uint8_t* __restrict__ cmask = j.cmask;
+    uint32_t* __restrict__ kappa = j.kappa;
+    uint8_t* __restrict__ done = j.done;
+    uint8_t* __restrict__ rhopp = j.rhopp;
+    uint8_t* __restrict__ sig = j.sig;
+    uint32_t* __restrict__ iters = j.iters;
+    const int depth = j.depth;
+    const size_t nact = *j.nact;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SignSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
     uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
-    const size_t stride = (size_t)gridDim.x * SG_WARPS;
-    for (size_t ai = (size_t)blockIdx.x * SG_WARPS + warp; ai < nact; ai += stride) {
+    const size_t ai = unit * SG_WARPS + warp;
+    if (ai < nact) {
         const size_t ln = act[ai];
         const size_t kn = SHARED ? 0 : ln;
         uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
@@ -386,7 +618,7 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
         }  // candidates
         if (rej) {
             if (lane == 0) kappa[ln] += L * depth;                                 // ml_dsa.rs:281, 317
-            continue;
+            return;
         }
         cand--;  // the accepted candidate
         // accept: c~ and hints complete the signature                            encodings.rs:254, 273
@@ -412,6 +644,17 @@ sign_z_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict_
     }
 }
 
+template <class P, bool SHARED>
+__global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_z_kernel(SignZJob j)
+{
+    __shared__ __align__(16) SignSmem<P> sm_all[SG_WARPS];
+    const size_t nu = sign_z_units<P>(j);
+    for (size_t u = blockIdx.x; u < nu; u += gridDim.x) {
+        sign_z_unit<P, SHARED>(j, u, sm_all);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 compact_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act_in,
                const uint8_t* __restrict__ done, uint32_t* __restrict__ act_out, uint32_t* __restrict__ nout)
@@ -428,6 +671,71 @@ compact_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict
     if (keep) act_out[base + __popc(m & ((1u << lane) - 1))] = act_in[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Paired round kernel.  The Keccak stages (mask, ctilde) saturate the ALU pipe and touch almost no memory;
+// the arithmetic stages (sign_w, sign_z) live on the FMA pipe and on HBM latency and leave half the issue
+// slots idle.  Run back to back each wastes what the other needs, so a chunk is split into two WAYS whose
+// round loops are staggered by one stage, and every launch runs one Keccak stage of one way next to one
+// arithmetic stage of the other on the SAME SMs:
+//        launch 0: mask(A)   || sign_z(B)      launch 2: ctilde(A) || sign_w(B)
+//        launch 1: mask(B)   || sign_w(A)      launch 3: ctilde(B) || sign_z(A)
+// The kernel is persistent (5 CTAs per SM); its CTAs pull work units from two queues (one atomic per unit),
+// `kshare` of every 5 CTAs prefer the Keccak queue, the others the arithmetic queue, and a CTA whose queue has
+// run dry takes from the other one, so no SM idles while either stage has work left.
+// ------------------------------------------------------------------------------------------------
+struct PairJob {
+    int kstage;  // 0 none, 1 mask, 2 ctilde
+    int astage;  // 0 none, 1 sign_w, 2 sign_z
+    MaskJob mask;
+    CtildeJob ct;
+    SignWJob w;
+    SignZJob z;
+    uint32_t* queue;  // [2] zeroed unit counters: Keccak, arithmetic
+    int kshare;
+};
+constexpr int PAIR_CTAS_PER_SM = 5;
+
+template <class P, bool SHARED>
+__global__ void __launch_bounds__(SG_WARPS * 32, PAIR_CTAS_PER_SM) round_pair_kernel(PairJob pj)
+{
+    __shared__ __align__(16) unsigned char sm_raw[sizeof(SignWSmem<P>) * SG_WARPS > sizeof(SignSmem<P>) * SG_WARPS
+                                                      ? sizeof(SignWSmem<P>) * SG_WARPS
+                                                      : sizeof(SignSmem<P>) * SG_WARPS];
+    __shared__ uint32_t s_unit;
+    const size_t nk = pj.kstage == 1 ? mask_units<P>(pj.mask) : (pj.kstage == 2 ? ctilde_units<P>(pj.ct) : 0);
+    const size_t na = pj.astage == 1 ? sign_w_units<P>(pj.w) : (pj.astage == 2 ? sign_z_units<P>(pj.z) : 0);
+    const int prefer = (int)(blockIdx.x % PAIR_CTAS_PER_SM) < pj.kshare ? 0 : 1;
+    bool kdone = nk == 0, adone = na == 0;
+    while (!(kdone && adone)) {
+        const int r = prefer == 0 ? (kdone ? 1 : 0) : (adone ? 0 : 1);
+        __syncthreads();  // every thread is done with the previous unit (s_unit and the stage's shared memory)
+        if (threadIdx.x == 0) s_unit = atomicAdd(pj.queue + r, 1u);
+        __syncthreads();
+        const size_t u = s_unit;
+        if (r == 0) {
+            if (u >= nk) {
+                kdone = true;
+            } else if (pj.kstage == 1) {
+                mask_unit<P>(pj.mask, u);
+            } else {
+                ctilde_unit<P>(pj.ct, u);
+            }
+        } else {
+            if (u >= na) {
+                adone = true;
+            } else if (pj.astage == 1) {
+                sign_w_unit<P, SHARED>(pj.w, u, reinterpret_cast<SignWSmem<P>*>(sm_raw));
+            } else {
+                sign_z_unit<P, SHARED>(pj.z, u, reinterpret_cast<SignSmem<P>*>(sm_raw));
+            }
+        }
+    }
+}
+
+constexpr int CTL_WORDS = 16;       // SignWs::nact: [4 * way + buffer] active counts, [8] ctx error flag
+constexpr int CTL_CTX_ERR = 8;
+constexpr int QUEUE_PAIRS = 2048;   // SignWs::queue: one (Keccak, arithmetic) counter pair per paired launch
+
 template <class P>
 static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
                               const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out)
@@ -437,17 +745,24 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     const size_t nkeys = shared ? 1 : n;
     const Tuning tn = tuning();
     const int D = ws.depth;
+    const bool paired = tn.pair != 0 && n >= 8192;  // small batches are latency-bound: keep the plain loop
+    const size_t nA = paired ? (n + 1) / 2 : n;     // way A = lanes [0, nA), way B = [nA, n)
     auto warp_grid = [&](size_t items) {
         return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16);
     };
     cudaError_t e;
-    int* ctx_err = reinterpret_cast<int*>(ws.nact + 2);
-    e = cudaMemsetAsync(ws.nact, 0, 16, st);
+    int* ctx_err = reinterpret_cast<int*>(ws.nact + CTL_CTX_ERR);
+    e = cudaMemsetAsync(ws.nact, 0, CTL_WORDS * 4, st);
     if (e != cudaSuccess) return e;
+    if (paired) {
+        e = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
+        if (e != cudaSuccess) return e;
+    }
     {
         KLaunch kl(KID_SIGN_PREP, st);
         sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
-                                                                        ws.kappa, ws.done, ws.act[0], ws.nact, ctx_err, D);
+                                                                        ws.kappa, ws.done, ws.act[0], ws.nact, nA,
+                                                                        ctx_err, D);
     }
     {
         KLaunch kl(KID_SIGN_KEY, st);
@@ -464,57 +779,140 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
         return cudaErrorInvalidValue;
     }
 
-    // Round loop.  The kernels read the live active-lane count from device memory (nact[cur]); the host
-    // only needs an upper bound to size the grids, so once the active set is small it re-reads the count
-    // every few rounds instead of stalling the stream after each one.
-    size_t bound = n;
-    int cur = 0, rounds = 0, since_sync = 0;
-    while (bound > 0) {
-        {
-            KLaunch kl(KID_MASK, st);
-            mask_kernel<P><<<capped_grid((bound * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(
-                ws.nact + cur, ws.act[cur], ws.rhopp, ws.kappa, ws.yraw, D);
-        }
-        {
-            KLaunch kl(KID_SIGN_W, st);
-            if (shared)
-                sign_w_kernel<P, true><<<warp_grid(bound * D), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
-                                                                                     ws.yraw, ws.w, ws.mw1, D);
-            else
-                sign_w_kernel<P, false><<<warp_grid(bound * D), SG_WARPS * 32, 0, st>>>(ws.nact + cur, ws.act[cur], ws.A,
-                                                                                      ws.yraw, ws.w, ws.mw1, D);
-        }
-        e = launch_ctilde(P::PS, st, bound * D, ws.nact + cur, ws.act[cur], D, ws.mw1, nullptr, nullptr, nullptr,
-                          ws.ctilde, ws.cmask);
-        if (e != cudaSuccess) return e;
-        {
-            KLaunch kl(KID_SIGN_Z, st);
-            if (shared)
-                sign_z_kernel<P, true><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
-                    ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
-                    ws.done, ws.rhopp, sig, iters, D);
-            else
-                sign_z_kernel<P, false><<<warp_grid(bound), SG_WARPS * 32, 0, st>>>(
-                    ws.nact + cur, ws.act[cur], ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa,
-                    ws.done, ws.rhopp, sig, iters, D);
-        }
-        e = cudaMemsetAsync(ws.nact + (cur ^ 1), 0, 4, st);
-        if (e != cudaSuccess) return e;
+    // Per-way state.  The kernels read the live active-lane count from device memory; the host only needs to
+    // know when a way has run dry, so it looks at the counters every few rounds.
+    struct Way {
+        size_t lo, bound;
+        int cur = 0;
+        const uint32_t* nact(const SignWs& w, int way) const { return w.nact + 4 * way + cur; }
+    } way[2];
+    way[0].lo = 0, way[0].bound = nA;
+    way[1].lo = nA, way[1].bound = n - nA;
+    auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D}; };
+    auto ct_job = [&](int v) { return CtildeJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.mw1, ws.ctilde, ws.cmask, D}; };
+    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D}; };
+    auto z_job = [&](int v) {
+        return SignZJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde,
+                        ws.cmask, ws.kappa, ws.done, ws.rhopp, sig, iters, D};
+    };
+    auto compact = [&](int v) -> cudaError_t {
+        Way& y = way[v];
+        uint32_t* nout = ws.nact + 4 * v + (y.cur ^ 1);
+        cudaError_t ce = cudaMemsetAsync(nout, 0, 4, st);
+        if (ce != cudaSuccess) return ce;
         {
             KLaunch kl(KID_COMPACT, st);
-            compact_kernel<<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(ws.nact + cur, ws.act[cur], ws.done,
-                                                                           ws.act[cur ^ 1], ws.nact + (cur ^ 1));
+            compact_kernel<<<(unsigned)((y.bound + 255) / 256) + 1, 256, 0, st>>>(y.nact(ws, v), ws.act[y.cur] + y.lo, ws.done,
+                                                                            ws.act[y.cur ^ 1] + y.lo, nout);
         }
-        cur ^= 1;
-        rounds++;
-        const int every = bound > 65536 ? 1 : (bound > 4096 ? 3 : 6);
-        if (++since_sync >= every) {
-            e = cudaMemcpyAsync(ws.h_nact, ws.nact + cur, 4, cudaMemcpyDeviceToHost, st);
+        y.cur ^= 1;
+        return cudaGetLastError();
+    };
+    auto read_bounds = [&]() -> cudaError_t {  // refresh the hosts's view of both ways' active counts
+        cudaError_t ce = cudaMemcpyAsync(ws.h_nact, ws.nact, 32, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return ce;
+        for (int v = 0; v < 2; v++) way[v].bound = ws.h_nact[4 * v + way[v].cur];
+        return cudaSuccess;
+    };
+    int rounds = 0;
+
+    if (!paired) {
+        Way& y = way[0];
+        int since_sync = 0;
+        while (y.bound > 0) {
+            {
+                KLaunch kl(KID_MASK, st);
+                mask_kernel<P><<<capped_grid((y.bound * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(mask_job(0));
+            }
+            if (tn.stage == 0) {
+                KLaunch kl(KID_SIGN_W, st);
+                if (shared) sign_w_kernel<P, true><<<warp_grid(y.bound * D), SG_WARPS * 32, 0, st>>>(w_job(0));
+                else sign_w_kernel<P, false><<<warp_grid(y.bound * D), SG_WARPS * 32, 0, st>>>(w_job(0));
+            } else {
+                const int cap = tn.acap > 0 ? tn.acap : 16;
+                if (D % 2 == 0 && tn.stage == 2)
+                    e = shared ? launch_sign_w_staged<P, true, 2>(st, w_job(0), y.bound * D, cap)
+                               : launch_sign_w_staged<P, false, 2>(st, w_job(0), y.bound * D, cap);
+                else
+                    e = shared ? launch_sign_w_staged<P, true, 1>(st, w_job(0), y.bound * D, cap)
+                               : launch_sign_w_staged<P, false, 1>(st, w_job(0), y.bound * D, cap);
+                if (e != cudaSuccess) return e;
+            }
+            e = launch_ctilde(P::PS, st, y.bound * D, y.nact(ws, 0), ws.act[y.cur], D, ws.mw1, nullptr, nullptr, nullptr,
+                              ws.ctilde, ws.cmask);
             if (e != cudaSuccess) return e;
-            e = cudaStreamSynchronize(st);
+            {
+                KLaunch kl(KID_SIGN_Z, st);
+                if (shared) sign_z_kernel<P, true><<<warp_grid(y.bound), SG_WARPS * 32, 0, st>>>(z_job(0));
+                else sign_z_kernel<P, false><<<warp_grid(y.bound), SG_WARPS * 32, 0, st>>>(z_job(0));
+            }
+            e = compact(0);
             if (e != cudaSuccess) return e;
-            bound = ws.h_nact[0];
-            since_sync = 0;
+            rounds++;
+            const int every = y.bound > 65536 ? 1 : (y.bound > 4096 ? 3 : 6);
+            if (++since_sync >= every) {
+                e = read_bounds();
+                if (e != cudaSuccess) return e;
+                since_sync = 0;
+            }
+        }
+    } else {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned grid = (unsigned)(sms * PAIR_CTAS_PER_SM);
+        const int kshare = tn.kshare > 0 && tn.kshare < PAIR_CTAS_PER_SM ? tn.kshare : 2;
+        int qi = 0;
+        auto launch_pair = [&](int kstage, int kv, int astage, int av) -> cudaError_t {
+            if (qi == QUEUE_PAIRS) {  // recycle the counters (stream order: every earlier launch is done with them)
+                cudaError_t ce = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
+                if (ce != cudaSuccess) return ce;
+                qi = 0;
+            }
+            PairJob pj{};
+            pj.kstage = kstage;
+            pj.astage = astage;
+            if (kstage == 1) pj.mask = mask_job(kv);
+            if (kstage == 2) pj.ct = ct_job(kv);
+            if (astage == 1) pj.w = w_job(av);
+            if (astage == 2) pj.z = z_job(av);
+            pj.queue = ws.queue + 2 * qi++;
+            pj.kshare = kshare;
+            KLaunch kl(KID_ROUND_PAIR, st);
+            if (shared) round_pair_kernel<P, true><<<grid, SG_WARPS * 32, 0, st>>>(pj);
+            else round_pair_kernel<P, false><<<grid, SG_WARPS * 32, 0, st>>>(pj);
+            return cudaGetLastError();
+        };
+        bool pending_zb = false;  // way B's sign_z of the previous round rides with way A's next mask
+        int since_sync = 0;
+        while (way[0].bound > 0 || way[1].bound > 0 || pending_zb) {
+            e = launch_pair(way[0].bound ? 1 : 0, 0, pending_zb ? 2 : 0, 1);
+            if (e != cudaSuccess) return e;
+            if (pending_zb) {
+                e = compact(1);
+                if (e != cudaSuccess) return e;
+                pending_zb = false;
+            }
+            e = launch_pair(way[1].bound ? 1 : 0, 1, way[0].bound ? 1 : 0, 0);
+            if (e != cudaSuccess) return e;
+            e = launch_pair(way[0].bound ? 2 : 0, 0, way[1].bound ? 1 : 0, 1);
+            if (e != cudaSuccess) return e;
+            e = launch_pair(way[1].bound ? 2 : 0, 1, way[0].bound ? 2 : 0, 0);
+            if (e != cudaSuccess) return e;
+            if (way[0].bound) {
+                e = compact(0);
+                if (e != cudaSuccess) return e;
+            }
+            pending_zb = way[1].bound > 0;
+            rounds++;
+            if (++since_sync >= 4 || (way[0].bound + way[1].bound) < 4096) {
+                // (the counts lag: way B's are from before its pending sign_z, which only makes them larger)
+                e = read_bounds();
+                if (e != cudaSuccess) return e;
+                since_sync = 0;
+            }
         }
     }
     if (rounds_out) *rounds_out = rounds;

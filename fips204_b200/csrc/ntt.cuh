@@ -34,6 +34,25 @@ __device__ __forceinline__ void gs_bfly(int32_t& a, int32_t& b, int32_t z, int32
     b = mont_mul_pre(t - b, z, zq);            // ntt.rs:130-133
 }
 
+
+// Per-lane twiddles of the B stage (len = 2, 1 forward / 1, 2 inverse) and per-row twiddles of the M stage
+// (len = 16, 8, 4 / 4, 8, 16) from the packed tables of zetas.inc: 3 + 4 contiguous 128-bit loads per transform.
+struct TwB { int2 za, zb, y0, y1, y2, y3; };
+struct TwM { int2 z8, za, zb, y0, y1, y2, y3; };
+__device__ __forceinline__ TwB load_twB(const int4* BA, const int4* BY0, const int4* BY1, int lane)
+{
+    const int4 a = __ldg(BA + lane), b = __ldg(BY0 + lane), c = __ldg(BY1 + lane);
+    return TwB{make_int2(a.x, a.y), make_int2(a.z, a.w), make_int2(b.x, b.y), make_int2(b.z, b.w), make_int2(c.x, c.y),
+               make_int2(c.z, c.w)};
+}
+__device__ __forceinline__ TwM load_twM(const int4 (*M)[4], int lane)
+{
+    const int4* p = M[lane >> 2];
+    const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    return TwM{make_int2(a.x, a.y), make_int2(a.z, a.w), make_int2(b.x, b.y), make_int2(b.z, b.w), make_int2(c.x, c.y),
+               make_int2(c.z, c.w), make_int2(d.x, d.y)};
+}
+
 // ---- tile <-> register moves (caller provides __syncwarp() ordering unless noted) ----
 __device__ __forceinline__ void tile_load_A(const int32_t* tile, int lane, int32_t (&v)[8])
 {
@@ -86,29 +105,23 @@ __device__ __forceinline__ void ntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int 
     __syncwarp();
     tile_load_M(tile, lane, v);
     {   // len = 16, 8, 4
-        const int r = lane >> 2;
-        const int2 z8 = __ldg(&ZETA_FWD[8 + r]);
-        ct_bfly(v[0], v[4], z8.x, z8.y); ct_bfly(v[1], v[5], z8.x, z8.y);
-        ct_bfly(v[2], v[6], z8.x, z8.y); ct_bfly(v[3], v[7], z8.x, z8.y);
-        const int2 za = __ldg(&ZETA_FWD[16 + 2 * r]), zb = __ldg(&ZETA_FWD[17 + 2 * r]);
-        ct_bfly(v[0], v[2], za.x, za.y); ct_bfly(v[1], v[3], za.x, za.y);
-        ct_bfly(v[4], v[6], zb.x, zb.y); ct_bfly(v[5], v[7], zb.x, zb.y);
-        const int2 y0 = __ldg(&ZETA_FWD[32 + 4 * r]), y1 = __ldg(&ZETA_FWD[33 + 4 * r]);
-        const int2 y2 = __ldg(&ZETA_FWD[34 + 4 * r]), y3 = __ldg(&ZETA_FWD[35 + 4 * r]);
-        ct_bfly(v[0], v[1], y0.x, y0.y); ct_bfly(v[2], v[3], y1.x, y1.y);
-        ct_bfly(v[4], v[5], y2.x, y2.y); ct_bfly(v[6], v[7], y3.x, y3.y);
+        const TwM w = load_twM(ZMP_FWD_M, lane);
+        ct_bfly(v[0], v[4], w.z8.x, w.z8.y); ct_bfly(v[1], v[5], w.z8.x, w.z8.y);
+        ct_bfly(v[2], v[6], w.z8.x, w.z8.y); ct_bfly(v[3], v[7], w.z8.x, w.z8.y);
+        ct_bfly(v[0], v[2], w.za.x, w.za.y); ct_bfly(v[1], v[3], w.za.x, w.za.y);
+        ct_bfly(v[4], v[6], w.zb.x, w.zb.y); ct_bfly(v[5], v[7], w.zb.x, w.zb.y);
+        ct_bfly(v[0], v[1], w.y0.x, w.y0.y); ct_bfly(v[2], v[3], w.y1.x, w.y1.y);
+        ct_bfly(v[4], v[5], w.y2.x, w.y2.y); ct_bfly(v[6], v[7], w.y3.x, w.y3.y);
     }
     tile_store_M(tile, lane, v);  // same addresses this lane just read
     __syncwarp();
     tile_load_B(tile, lane, v);
     {   // len = 2, 1
-        const int2 za = __ldg(&ZETA_FWD[64 + 2 * lane]), zb = __ldg(&ZETA_FWD[65 + 2 * lane]);
-        ct_bfly(v[0], v[2], za.x, za.y); ct_bfly(v[1], v[3], za.x, za.y);
-        ct_bfly(v[4], v[6], zb.x, zb.y); ct_bfly(v[5], v[7], zb.x, zb.y);
-        const int2 y0 = __ldg(&ZETA_FWD[128 + 4 * lane]), y1 = __ldg(&ZETA_FWD[129 + 4 * lane]);
-        const int2 y2 = __ldg(&ZETA_FWD[130 + 4 * lane]), y3 = __ldg(&ZETA_FWD[131 + 4 * lane]);
-        ct_bfly(v[0], v[1], y0.x, y0.y); ct_bfly(v[2], v[3], y1.x, y1.y);
-        ct_bfly(v[4], v[5], y2.x, y2.y); ct_bfly(v[6], v[7], y3.x, y3.y);
+        const TwB w = load_twB(ZMP_FWD_BA, ZMP_FWD_BY0, ZMP_FWD_BY1, lane);
+        ct_bfly(v[0], v[2], w.za.x, w.za.y); ct_bfly(v[1], v[3], w.za.x, w.za.y);
+        ct_bfly(v[4], v[6], w.zb.x, w.zb.y); ct_bfly(v[5], v[7], w.zb.x, w.zb.y);
+        ct_bfly(v[0], v[1], w.y0.x, w.y0.y); ct_bfly(v[2], v[3], w.y1.x, w.y1.y);
+        ct_bfly(v[4], v[5], w.y2.x, w.y2.y); ct_bfly(v[6], v[7], w.y3.x, w.y3.y);
     }
     __syncwarp();
 }
@@ -120,30 +133,24 @@ template <int32_t F>
 __device__ __forceinline__ void ntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane)
 {
     {   // len = 1, 2   (twiddle index counts down: m = 2*nb - 1 - block, ntt.rs:112-118)
-        const int2 y0 = __ldg(&ZETA_INV[255 - 4 * lane]), y1 = __ldg(&ZETA_INV[254 - 4 * lane]);
-        const int2 y2 = __ldg(&ZETA_INV[253 - 4 * lane]), y3 = __ldg(&ZETA_INV[252 - 4 * lane]);
-        gs_bfly(v[0], v[1], y0.x, y0.y); gs_bfly(v[2], v[3], y1.x, y1.y);
-        gs_bfly(v[4], v[5], y2.x, y2.y); gs_bfly(v[6], v[7], y3.x, y3.y);
-        const int2 za = __ldg(&ZETA_INV[127 - 2 * lane]), zb = __ldg(&ZETA_INV[126 - 2 * lane]);
-        gs_bfly(v[0], v[2], za.x, za.y); gs_bfly(v[1], v[3], za.x, za.y);
-        gs_bfly(v[4], v[6], zb.x, zb.y); gs_bfly(v[5], v[7], zb.x, zb.y);
+        const TwB w = load_twB(ZMP_INV_BA, ZMP_INV_BY0, ZMP_INV_BY1, lane);
+        gs_bfly(v[0], v[1], w.y0.x, w.y0.y); gs_bfly(v[2], v[3], w.y1.x, w.y1.y);
+        gs_bfly(v[4], v[5], w.y2.x, w.y2.y); gs_bfly(v[6], v[7], w.y3.x, w.y3.y);
+        gs_bfly(v[0], v[2], w.za.x, w.za.y); gs_bfly(v[1], v[3], w.za.x, w.za.y);
+        gs_bfly(v[4], v[6], w.zb.x, w.zb.y); gs_bfly(v[5], v[7], w.zb.x, w.zb.y);
     }
     __syncwarp();
     tile_store_B(tile, lane, v);
     __syncwarp();
     tile_load_M(tile, lane, v);
     {   // len = 4, 8, 16
-        const int r = lane >> 2;
-        const int2 y0 = __ldg(&ZETA_INV[63 - 4 * r]), y1 = __ldg(&ZETA_INV[62 - 4 * r]);
-        const int2 y2 = __ldg(&ZETA_INV[61 - 4 * r]), y3 = __ldg(&ZETA_INV[60 - 4 * r]);
-        gs_bfly(v[0], v[1], y0.x, y0.y); gs_bfly(v[2], v[3], y1.x, y1.y);
-        gs_bfly(v[4], v[5], y2.x, y2.y); gs_bfly(v[6], v[7], y3.x, y3.y);
-        const int2 za = __ldg(&ZETA_INV[31 - 2 * r]), zb = __ldg(&ZETA_INV[30 - 2 * r]);
-        gs_bfly(v[0], v[2], za.x, za.y); gs_bfly(v[1], v[3], za.x, za.y);
-        gs_bfly(v[4], v[6], zb.x, zb.y); gs_bfly(v[5], v[7], zb.x, zb.y);
-        const int2 z8 = __ldg(&ZETA_INV[15 - r]);
-        gs_bfly(v[0], v[4], z8.x, z8.y); gs_bfly(v[1], v[5], z8.x, z8.y);
-        gs_bfly(v[2], v[6], z8.x, z8.y); gs_bfly(v[3], v[7], z8.x, z8.y);
+        const TwM w = load_twM(ZMP_INV_M, lane);
+        gs_bfly(v[0], v[1], w.y0.x, w.y0.y); gs_bfly(v[2], v[3], w.y1.x, w.y1.y);
+        gs_bfly(v[4], v[5], w.y2.x, w.y2.y); gs_bfly(v[6], v[7], w.y3.x, w.y3.y);
+        gs_bfly(v[0], v[2], w.za.x, w.za.y); gs_bfly(v[1], v[3], w.za.x, w.za.y);
+        gs_bfly(v[4], v[6], w.zb.x, w.zb.y); gs_bfly(v[5], v[7], w.zb.x, w.zb.y);
+        gs_bfly(v[0], v[4], w.z8.x, w.z8.y); gs_bfly(v[1], v[5], w.z8.x, w.z8.y);
+        gs_bfly(v[2], v[6], w.z8.x, w.z8.y); gs_bfly(v[3], v[7], w.z8.x, w.z8.y);
     }
     tile_store_M(tile, lane, v);
     __syncwarp();
@@ -238,29 +245,23 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
     __syncwarp();
     tile_load_M(tile, lane, v);
     {
-        const int r = lane >> 2;
-        const int2 z8 = __ldg(&ZS_FWD[8 + r]);
-        ct_bfly_s(v[0], v[4], z8.x, z8.y); ct_bfly_s(v[1], v[5], z8.x, z8.y);
-        ct_bfly_s(v[2], v[6], z8.x, z8.y); ct_bfly_s(v[3], v[7], z8.x, z8.y);
-        const int2 za = __ldg(&ZS_FWD[16 + 2 * r]), zb = __ldg(&ZS_FWD[17 + 2 * r]);
-        ct_bfly_s(v[0], v[2], za.x, za.y); ct_bfly_s(v[1], v[3], za.x, za.y);
-        ct_bfly_s(v[4], v[6], zb.x, zb.y); ct_bfly_s(v[5], v[7], zb.x, zb.y);
-        const int2 y0 = __ldg(&ZS_FWD[32 + 4 * r]), y1 = __ldg(&ZS_FWD[33 + 4 * r]);
-        const int2 y2 = __ldg(&ZS_FWD[34 + 4 * r]), y3 = __ldg(&ZS_FWD[35 + 4 * r]);
-        ct_bfly_s(v[0], v[1], y0.x, y0.y); ct_bfly_s(v[2], v[3], y1.x, y1.y);
-        ct_bfly_s(v[4], v[5], y2.x, y2.y); ct_bfly_s(v[6], v[7], y3.x, y3.y);
+        const TwM w = load_twM(ZSP_FWD_M, lane);
+        ct_bfly_s(v[0], v[4], w.z8.x, w.z8.y); ct_bfly_s(v[1], v[5], w.z8.x, w.z8.y);
+        ct_bfly_s(v[2], v[6], w.z8.x, w.z8.y); ct_bfly_s(v[3], v[7], w.z8.x, w.z8.y);
+        ct_bfly_s(v[0], v[2], w.za.x, w.za.y); ct_bfly_s(v[1], v[3], w.za.x, w.za.y);
+        ct_bfly_s(v[4], v[6], w.zb.x, w.zb.y); ct_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
+        ct_bfly_s(v[0], v[1], w.y0.x, w.y0.y); ct_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
+        ct_bfly_s(v[4], v[5], w.y2.x, w.y2.y); ct_bfly_s(v[6], v[7], w.y3.x, w.y3.y);
     }
     tile_store_M(tile, lane, v);
     __syncwarp();
     tile_load_B(tile, lane, v);
     {
-        const int2 za = __ldg(&ZS_FWD[64 + 2 * lane]), zb = __ldg(&ZS_FWD[65 + 2 * lane]);
-        ct_bfly_s(v[0], v[2], za.x, za.y); ct_bfly_s(v[1], v[3], za.x, za.y);
-        ct_bfly_s(v[4], v[6], zb.x, zb.y); ct_bfly_s(v[5], v[7], zb.x, zb.y);
-        const int2 y0 = __ldg(&ZS_FWD[128 + 4 * lane]), y1 = __ldg(&ZS_FWD[129 + 4 * lane]);
-        const int2 y2 = __ldg(&ZS_FWD[130 + 4 * lane]), y3 = __ldg(&ZS_FWD[131 + 4 * lane]);
-        ct_bfly_s(v[0], v[1], y0.x, y0.y); ct_bfly_s(v[2], v[3], y1.x, y1.y);
-        ct_bfly_s(v[4], v[5], y2.x, y2.y); ct_bfly_s(v[6], v[7], y3.x, y3.y);
+        const TwB w = load_twB(ZSP_FWD_BA, ZSP_FWD_BY0, ZSP_FWD_BY1, lane);
+        ct_bfly_s(v[0], v[2], w.za.x, w.za.y); ct_bfly_s(v[1], v[3], w.za.x, w.za.y);
+        ct_bfly_s(v[4], v[6], w.zb.x, w.zb.y); ct_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
+        ct_bfly_s(v[0], v[1], w.y0.x, w.y0.y); ct_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
+        ct_bfly_s(v[4], v[5], w.y2.x, w.y2.y); ct_bfly_s(v[6], v[7], w.y3.x, w.y3.y);
     }
     __syncwarp();
 }
@@ -270,30 +271,24 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
 __device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane)
 {
     {
-        const int2 y0 = __ldg(&ZS_INV[255 - 4 * lane]), y1 = __ldg(&ZS_INV[254 - 4 * lane]);
-        const int2 y2 = __ldg(&ZS_INV[253 - 4 * lane]), y3 = __ldg(&ZS_INV[252 - 4 * lane]);
-        gs_bfly_s(v[0], v[1], y0.x, y0.y); gs_bfly_s(v[2], v[3], y1.x, y1.y);
-        gs_bfly_s(v[4], v[5], y2.x, y2.y); gs_bfly_s(v[6], v[7], y3.x, y3.y);
-        const int2 za = __ldg(&ZS_INV[127 - 2 * lane]), zb = __ldg(&ZS_INV[126 - 2 * lane]);
-        gs_bfly_s(v[0], v[2], za.x, za.y); gs_bfly_s(v[1], v[3], za.x, za.y);
-        gs_bfly_s(v[4], v[6], zb.x, zb.y); gs_bfly_s(v[5], v[7], zb.x, zb.y);
+        const TwB w = load_twB(ZSP_INV_BA, ZSP_INV_BY0, ZSP_INV_BY1, lane);
+        gs_bfly_s(v[0], v[1], w.y0.x, w.y0.y); gs_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
+        gs_bfly_s(v[4], v[5], w.y2.x, w.y2.y); gs_bfly_s(v[6], v[7], w.y3.x, w.y3.y);
+        gs_bfly_s(v[0], v[2], w.za.x, w.za.y); gs_bfly_s(v[1], v[3], w.za.x, w.za.y);
+        gs_bfly_s(v[4], v[6], w.zb.x, w.zb.y); gs_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
     }
     __syncwarp();
     tile_store_B(tile, lane, v);
     __syncwarp();
     tile_load_M(tile, lane, v);
     {
-        const int r = lane >> 2;
-        const int2 y0 = __ldg(&ZS_INV[63 - 4 * r]), y1 = __ldg(&ZS_INV[62 - 4 * r]);
-        const int2 y2 = __ldg(&ZS_INV[61 - 4 * r]), y3 = __ldg(&ZS_INV[60 - 4 * r]);
-        gs_bfly_s(v[0], v[1], y0.x, y0.y); gs_bfly_s(v[2], v[3], y1.x, y1.y);
-        gs_bfly_s(v[4], v[5], y2.x, y2.y); gs_bfly_s(v[6], v[7], y3.x, y3.y);
-        const int2 za = __ldg(&ZS_INV[31 - 2 * r]), zb = __ldg(&ZS_INV[30 - 2 * r]);
-        gs_bfly_s(v[0], v[2], za.x, za.y); gs_bfly_s(v[1], v[3], za.x, za.y);
-        gs_bfly_s(v[4], v[6], zb.x, zb.y); gs_bfly_s(v[5], v[7], zb.x, zb.y);
-        const int2 z8 = __ldg(&ZS_INV[15 - r]);
-        gs_bfly_s(v[0], v[4], z8.x, z8.y); gs_bfly_s(v[1], v[5], z8.x, z8.y);
-        gs_bfly_s(v[2], v[6], z8.x, z8.y); gs_bfly_s(v[3], v[7], z8.x, z8.y);
+        const TwM w = load_twM(ZSP_INV_M, lane);
+        gs_bfly_s(v[0], v[1], w.y0.x, w.y0.y); gs_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
+        gs_bfly_s(v[4], v[5], w.y2.x, w.y2.y); gs_bfly_s(v[6], v[7], w.y3.x, w.y3.y);
+        gs_bfly_s(v[0], v[2], w.za.x, w.za.y); gs_bfly_s(v[1], v[3], w.za.x, w.za.y);
+        gs_bfly_s(v[4], v[6], w.zb.x, w.zb.y); gs_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
+        gs_bfly_s(v[0], v[4], w.z8.x, w.z8.y); gs_bfly_s(v[1], v[5], w.z8.x, w.z8.y);
+        gs_bfly_s(v[2], v[6], w.z8.x, w.z8.y); gs_bfly_s(v[3], v[7], w.z8.x, w.z8.y);
     }
     // five doubling levels done: |v| < 64 q.  Back under q so that the last three stay inside int32.
 #pragma unroll

@@ -136,6 +136,10 @@ void mldsa_set_tuning(int ways, int kcap, int acap);
  * (default MLDSA_DEPTH, else 2).  Results never depend on it: candidates count in the reference's order
  * (src/ml_dsa.rs:212-330); a larger depth trades a little speculative work for fewer rounds and less A-hat traffic. */
 void mldsa_set_depth(int depth);
+/* pair != 0 (MLDSA_PAIR, default 0: measured no gain while the arithmetic stages are latency-bound): a sign chunk of >= 8192 lanes runs as two half-chunks whose rejection loops are
+ * staggered by one stage, each launch executing a Keccak stage of one half beside an arithmetic stage of the other on
+ * the same SMs; kshare (1..4, default 2, MLDSA_KSHARE) = CTAs out of 5 per SM that prefer the Keccak queue. */
+void mldsa_set_pairing(int pair, int kshare);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */
