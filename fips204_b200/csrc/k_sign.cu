@@ -21,6 +21,8 @@
 //     ctilde        thread/lane  c~ = H(mu || w1), c = SampleInBall(c~) as bit masks   ml_dsa.rs:233-237
 //     sign_z        warp/lane    c-hat, r0 / z / ct0 / hint checks, sigEncode          ml_dsa.rs:240-336
 //     compact       thread/lane  rebuild the active list
+#include <cmath>
+
 #include "engine.h"
 #include "keccak.cuh"
 #include "ntt.cuh"
@@ -494,12 +496,21 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
         const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
         int32_t* wl = wall + slot * (size_t)K * 256;
 
-        // first operands of the r0 phase stream in while c-hat is computed
-        if (lane < 16) {
-            const char* nxt = lane < 8 ? reinterpret_cast<const char*>(s2h_all + kn * (size_t)K * 256) + 128 * lane
-                                       : reinterpret_cast<const char*>(wl) + 128 * (lane - 8);
+        // the first w row and the first y polynomial stream into L2 while c-hat is computed
+        if (lane < 13) {
+            const char* nxt = lane < 8 ? reinterpret_cast<const char*>(wl) + 128 * lane
+                                       : reinterpret_cast<const char*>(yp) + 128 * (lane - 8);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
         }
+        rej = false;
+        int hcount = 0;
+        // operand row of step p: s2-hat[p], then s1-hat[p - K], then t0-hat[p - K - L]
+        auto row_ptr = [&](int p) {
+            const int32_t* r = p < K ? s2h_all + (kn * K + p) * 256
+                                     : (p < K + L ? s1h_all + (kn * L + (p - K)) * 256 : t0h_all + (kn * K + (p - K - L)) * 256);
+            return reinterpret_cast<const int4*>(r + 8 * lane);
+        };
+        int4 nx0 = __ldg(row_ptr(0)), nx1 = __ldg(row_ptr(0) + 1);  // in flight during the forward NTT of c
         // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240) centred, with its Shoup companion
         int32_t ch[8], chs[8];
         load_c_layoutA(cmask + slot * (size_t)CMASK_STRIDE, lane, ch);
@@ -509,24 +520,20 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
             ch[i] = center(freeze(ch[i]));
             chs[i] = shoup_companion(ch[i]);
         }
-
-        rej = false;
-        int hcount = 0;
 #pragma unroll 1
         for (int p = 0; p < 2 * K + L && !rej; p++) {
             const int phase = p < K ? 0 : (p < K + L ? 1 : 2);
             const int idx = phase == 0 ? p : (phase == 1 ? p - K : p - K - L);
-            const int32_t* src = phase == 0 ? s2h_all + (kn * K + idx) * 256
-                                            : (phase == 1 ? s1h_all + (kn * L + idx) * 256 : t0h_all + (kn * K + idx) * 256);
-            const int4* sp = reinterpret_cast<const int4*>(src + 8 * lane);
-            const int4 x = __ldg(sp), y4 = __ldg(sp + 1);
-            const int32_t sv[8] = {x.x, x.y, x.z, x.w, y4.x, y4.y, y4.z, y4.w};
-            // the s2-hat rows and w rows of one key / lane are contiguous: pull the next ones into L2
-            if (phase == 0 && lane < 16) {
-                const char* nxt = lane < 8 ? reinterpret_cast<const char*>(src + 256) + 128 * lane
-                                           : reinterpret_cast<const char*>(wl + 256 * (idx + 1)) + 128 * (lane - 8);
-                if (idx + 1 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            const int32_t sv[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+            if (p + 1 < 2 * K + L) {  // the next step's operand row loads while this step's inverse NTT runs
+                nx0 = __ldg(row_ptr(p + 1));
+                nx1 = __ldg(row_ptr(p + 1) + 1);
             }
+            // the w rows of a candidate are contiguous: pull the next one into L2
+            if (phase == 0 && lane < 8 && idx + 1 < K)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wl + 256 * (idx + 1)) + 128 * lane));
+            if (phase == 1 && lane < 5 && idx + 1 < L)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + (idx + 1) * 32 * P::ZBITS + 128 * lane));
             int32_t t[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) t[i] = shoup_mul(sv[i], ch[i], chs[i]);  // s-hat rows are prescaled by 1/256
@@ -819,44 +826,62 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     int rounds = 0;
 
     if (!paired) {
+        // The host never waits for a round: grids are sized from the EXPECTED number of survivors (every kernel is
+        // a grid-stride loop over the live count it reads from device memory, so any grid is correct), the rounds
+        // that almost surely suffice are enqueued in one go, and only then does the host look at the counter.
+        // A round rejects a lane with probability (1 - p)^D; p >= 0.19 for all three parameter sets (FIPS 204
+        // table 1: 4.25 / 5.1 / 3.85 expected iterations).
         Way& y = way[0];
-        int since_sync = 0;
-        while (y.bound > 0) {
+        const double keep = pow(1.0 - 0.19, (double)D);
+        double expect = (double)n;
+        auto one_round = [&](size_t sz) -> cudaError_t {
             {
                 KLaunch kl(KID_MASK, st);
-                mask_kernel<P><<<capped_grid((y.bound * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(mask_job(0));
+                mask_kernel<P><<<capped_grid((sz * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(mask_job(0));
             }
+            cudaError_t ce = cudaSuccess;
             if (tn.stage == 0) {
                 KLaunch kl(KID_SIGN_W, st);
-                if (shared) sign_w_kernel<P, true><<<warp_grid(y.bound * D), SG_WARPS * 32, 0, st>>>(w_job(0));
-                else sign_w_kernel<P, false><<<warp_grid(y.bound * D), SG_WARPS * 32, 0, st>>>(w_job(0));
+                if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(w_job(0));
+                else sign_w_kernel<P, false><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(w_job(0));
             } else {
                 const int cap = tn.acap > 0 ? tn.acap : 16;
                 if (D % 2 == 0 && tn.stage == 2)
-                    e = shared ? launch_sign_w_staged<P, true, 2>(st, w_job(0), y.bound * D, cap)
-                               : launch_sign_w_staged<P, false, 2>(st, w_job(0), y.bound * D, cap);
+                    ce = shared ? launch_sign_w_staged<P, true, 2>(st, w_job(0), sz * D, cap)
+                                : launch_sign_w_staged<P, false, 2>(st, w_job(0), sz * D, cap);
                 else
-                    e = shared ? launch_sign_w_staged<P, true, 1>(st, w_job(0), y.bound * D, cap)
-                               : launch_sign_w_staged<P, false, 1>(st, w_job(0), y.bound * D, cap);
-                if (e != cudaSuccess) return e;
+                    ce = shared ? launch_sign_w_staged<P, true, 1>(st, w_job(0), sz * D, cap)
+                                : launch_sign_w_staged<P, false, 1>(st, w_job(0), sz * D, cap);
+                if (ce != cudaSuccess) return ce;
             }
-            e = launch_ctilde(P::PS, st, y.bound * D, y.nact(ws, 0), ws.act[y.cur], D, ws.mw1, nullptr, nullptr, nullptr,
-                              ws.ctilde, ws.cmask);
-            if (e != cudaSuccess) return e;
+            ce = launch_ctilde(P::PS, st, sz * D, y.nact(ws, 0), ws.act[y.cur], D, ws.mw1, nullptr, nullptr, nullptr,
+                               ws.ctilde, ws.cmask);
+            if (ce != cudaSuccess) return ce;
             {
                 KLaunch kl(KID_SIGN_Z, st);
-                if (shared) sign_z_kernel<P, true><<<warp_grid(y.bound), SG_WARPS * 32, 0, st>>>(z_job(0));
-                else sign_z_kernel<P, false><<<warp_grid(y.bound), SG_WARPS * 32, 0, st>>>(z_job(0));
+                if (shared) sign_z_kernel<P, true><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(z_job(0));
+                else sign_z_kernel<P, false><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(z_job(0));
             }
-            e = compact(0);
+            y.bound = sz;
+            return compact(0);
+        };
+        while (expect > 0.01) {  // P(a lane is still active after these rounds) < 1 %
+            const size_t sz = (size_t)(expect * 1.25) + 256;
+            e = one_round(sz < n ? sz : n);
             if (e != cudaSuccess) return e;
             rounds++;
-            const int every = y.bound > 65536 ? 1 : (y.bound > 4096 ? 3 : 6);
-            if (++since_sync >= every) {
-                e = read_bounds();
+            expect *= keep;
+        }
+        e = read_bounds();
+        if (e != cudaSuccess) return e;
+        while (y.bound > 0) {  // stragglers beyond the estimate (rare): a few rounds at a time
+            for (int r = 0; r < 4; r++) {
+                e = one_round(y.bound);
                 if (e != cudaSuccess) return e;
-                since_sync = 0;
+                rounds++;
             }
+            e = read_bounds();
+            if (e != cudaSuccess) return e;
         }
     } else {
         int dev = 0, sms = 148;
