@@ -8,6 +8,7 @@
 #include "engine.h"
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -177,7 +178,7 @@ struct DeviceCtx {
             CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
         }
-        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 512, cudaHostAllocDefault));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 512, cudaHostAllocMapped | cudaHostAllocPortable));
         dev = d;
         return OK;
     }
@@ -797,6 +798,7 @@ static ChunkPlan plan_chunks(size_t arena_bytes, size_t n, size_t fixed, size_t 
 }
 
 }  // extern "C"
+
 // ph < 0: plain ML-DSA with `framing`; ph = 0/1/2: HashML-DSA with SHA-256 / SHA-512 / SHAKE128 pre-hash
 static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8_t* sk, size_t sk_stride,
                      const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
@@ -869,6 +871,9 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     // make sure nothing of a previous call is still in flight on the copy streams
     CK(cudaStreamSynchronize(cx->s_in));
     CK(cudaStreamSynchronize(cx->s_out));
+    const bool trace = env_int("MLDSA_TRACE", 0) != 0;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     rc = copy_in(0);
     if (rc) return rc;
     for (size_t i = 0; i < pl.nchunks(); i++) {
@@ -880,6 +885,10 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         }
         CK(cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0));
         if (i >= 2) CK(cudaStreamWaitEvent(st, cx->ev_out[i & 1], 0));  // D2H(i-2) has drained this set's outputs
+        if (trace) {
+            cudaEventSynchronize(cx->ev_in[i & 1]);
+            fprintf(stderr, "[mldsa trace] chunk %zu (%zu lanes): inputs on device at %.2f ms\n", i, m, now_ms());
+        }
         const uint8_t* cm = s.m - msg_off[lo];
         const uint64_t* cmo = s.mo;
         if (ph >= 0) {  // HashML-DSA: M' carries OID || PH(M) (src/lib.rs:310-342)
@@ -897,11 +906,13 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, st));  // secrets do not linger in the staging set
         CK(cudaMemsetAsync(s.rnd, 0, m * 32, st));
         CK(cudaStreamSynchronize(st));
+        if (trace) fprintf(stderr, "[mldsa trace] chunk %zu: signed at %.2f ms\n", i, now_ms());
         CK(cudaMemcpyAsync(sig + p.sig * lo, s.sig, m * p.sig, cudaMemcpyDeviceToHost, cx->s_out));
         if (iters) CK(cudaMemcpyAsync(iters + lo, s.it, m * 4, cudaMemcpyDeviceToHost, cx->s_out));
         CK(cudaEventRecord(cx->ev_out[i & 1], cx->s_out));
     }
     CK(cudaStreamSynchronize(cx->s_out));
+    if (trace) fprintf(stderr, "[mldsa trace] all signatures on the host at %.2f ms\n", now_ms());
     return OK;
 }
 

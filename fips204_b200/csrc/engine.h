@@ -39,7 +39,7 @@ void prof_collect();
 struct Tuning {
     int ways, kcap, acap;
     int depth;  // candidates tried per active lane and round of the sign loop (MLDSA_DEPTH, default 2)
-    int pair;   // 1: run a Keccak stage of one half-chunk beside an arithmetic stage of the other (MLDSA_PAIR, default 1)
+    int pair;   // 1: run a Keccak stage of one half-chunk beside an arithmetic stage of the other (MLDSA_PAIR, default 0)
     int stage;  // sign_w: 0 = A-hat rows straight from global memory, 1 = TMA-staged per warp, 2 = staged and shared by
                 // the two candidate warps of a lane when the depth is even (MLDSA_STAGE, default 2)
     int kshare; // paired kernel: CTAs out of 5 per SM that prefer the Keccak queue (MLDSA_KSHARE, default 2)

@@ -21,7 +21,10 @@
 //     ctilde        thread/lane  c~ = H(mu || w1), c = SampleInBall(c~) as bit masks   ml_dsa.rs:233-237
 //     sign_z        warp/lane    c-hat, r0 / z / ct0 / hint checks, sigEncode          ml_dsa.rs:240-336
 //     compact       thread/lane  rebuild the active list
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "engine.h"
 #include "keccak.cuh"
@@ -662,6 +665,15 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_z_kernel(SignZJob
     }
 }
 
+// Device -> host mailbox without the copy engine: the pinned mailbox is mapped into the device address space and a
+// one-warp kernel stores the control words there.  (A 4-byte cudaMemcpyAsync D2H queues behind any bulk D2H copy
+// that is in flight -- e.g. the previous chunk's signatures -- and stalled the sign stream for its whole duration.)
+__global__ void publish_kernel(const uint32_t* __restrict__ src, volatile uint32_t* __restrict__ dst_mapped, int nwords)
+{
+    if ((int)threadIdx.x < nwords) dst_mapped[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256)
 compact_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act_in,
                const uint8_t* __restrict__ done, uint32_t* __restrict__ act_out, uint32_t* __restrict__ nout)
@@ -758,6 +770,9 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
         return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16);
     };
     cudaError_t e;
+    const bool trace = getenv("MLDSA_TRACE") != nullptr && n >= 4096;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     int* ctx_err = reinterpret_cast<int*>(ws.nact + CTL_CTX_ERR);
     e = cudaMemsetAsync(ws.nact, 0, CTL_WORDS * 4, st);
     if (e != cudaSuccess) return e;
@@ -777,10 +792,10 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     }
     e = launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(ws.h_nact, ctx_err, 4, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
+    publish_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(ctx_err), ws.h_nact, 1);
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
+    if (trace) fprintf(stderr, "[mldsa trace] sign_run %zu lanes: setup done at %.2f ms\n", n, now_ms());
     if (ws.h_nact[0] != 0) {  // ctx too long: the caller maps this marker to -2 (lib.rs:274)
         ws.h_nact[1] = CTX_ERR_MARK;
         return cudaErrorInvalidValue;
@@ -816,9 +831,8 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
         return cudaGetLastError();
     };
     auto read_bounds = [&]() -> cudaError_t {  // refresh the hosts's view of both ways' active counts
-        cudaError_t ce = cudaMemcpyAsync(ws.h_nact, ws.nact, 32, cudaMemcpyDeviceToHost, st);
-        if (ce != cudaSuccess) return ce;
-        ce = cudaStreamSynchronize(st);
+        publish_kernel<<<1, 32, 0, st>>>(ws.nact, ws.h_nact, 8);
+        cudaError_t ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return ce;
         for (int v = 0; v < 2; v++) way[v].bound = ws.h_nact[4 * v + way[v].cur];
         return cudaSuccess;
@@ -872,8 +886,10 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
             rounds++;
             expect *= keep;
         }
+        if (trace) fprintf(stderr, "[mldsa trace] sign_run: %d rounds enqueued at %.2f ms\n", rounds, now_ms());
         e = read_bounds();
         if (e != cudaSuccess) return e;
+        if (trace) fprintf(stderr, "[mldsa trace] sign_run: rounds done at %.2f ms, %zu lanes left\n", now_ms(), y.bound);
         while (y.bound > 0) {  // stragglers beyond the estimate (rare): a few rounds at a time
             for (int r = 0; r < 4; r++) {
                 e = one_round(y.bound);
