@@ -69,7 +69,12 @@ void prof_collect()
 {
     if (t_events.empty()) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::vector<EvPair> pending;  // launched on a stream that is still running (pipelined chunks): keep for later
     for (auto& p : t_events) {
+        if (cudaEventQuery(p.b) == cudaErrorNotReady) {
+            pending.push_back(p);
+            continue;
+        }
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             g_prof_ms[p.id] += ms;
@@ -80,10 +85,11 @@ void prof_collect()
         t_evpool.push_back(p.a);
         t_evpool.push_back(p.b);
     }
-    t_events.clear();
+    t_events.swap(pending);
 }
 
-static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1}, g_pair{-1}, g_kshare{-1}, g_stage{-1};
+static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1}, g_pair{-1}, g_kshare{-1}, g_stage{-1},
+    g_tail_depth{-1}, g_tail_slots{-1};
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -106,7 +112,12 @@ Tuning tuning()
     if (ks < 0) g_kshare.store(ks = env_int("MLDSA_KSHARE", 2));
     int sg = g_stage.load();
     if (sg < 0) g_stage.store(sg = env_int("MLDSA_STAGE", 2));
-    return Tuning{w, k, a, d, pr, sg, ks};
+    int td = g_tail_depth.load(), ts = g_tail_slots.load();
+    if (td < 0) g_tail_depth.store(td = env_int("MLDSA_TAILDEPTH", 8));
+    if (ts < 0) g_tail_slots.store(ts = env_int("MLDSA_TAILSLOTS", 32768));
+    if (td > 16) td = 16;
+    if (ts < 0) ts = 0;
+    return Tuning{w, k, a, d, pr, sg, ks, td, ts};
 }
 unsigned capped_grid(size_t want_ctas, int cap_per_sm)
 {
@@ -155,28 +166,34 @@ static bool ps_info(int ps, PSInfo& o)
     return false;
 }
 
+constexpr int SIGN_SETS = 3;  // depth of the host entry points' chunk pipeline (staging sets, sign workspaces)
+
 struct DeviceCtx {
     std::mutex mu;
     int dev = -1;
     cudaStream_t stream = nullptr;
-    cudaStream_t way_stream[8] = {};  // extra streams for the concurrent ways of a sign chunk
+    cudaStream_t s_tail = nullptr;                 // high priority: the latency-bound tail rounds of a sign chunk
     cudaStream_t s_in = nullptr, s_out = nullptr;  // H2D / D2H streams of the chunk pipeline
-    cudaEvent_t ev_in[2] = {}, ev_out[2] = {};
+    cudaEvent_t ev_in[SIGN_SETS] = {}, ev_out[SIGN_SETS] = {}, ev_bulk[SIGN_SETS] = {}, ev_tail[SIGN_SETS] = {};
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
-    uint32_t* mailbox = nullptr;  // pinned, 4 words per way
+    uint32_t* mailbox = nullptr;  // mapped pinned memory, 16 control words per sign workspace
 
     int init(int d)
     {
         if (dev == d) return OK;
         CK(cudaSetDevice(d));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        for (auto& ws : way_stream) CK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&s_tail, cudaStreamNonBlocking, prio_hi));
         CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < SIGN_SETS; i++) {
             CK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_bulk[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_tail[i], cudaEventDisableTiming));
         }
         CK(cudaHostAlloc(reinterpret_cast<void**>(&mailbox), 512, cudaHostAllocMapped | cudaHostAllocPortable));
         dev = d;
@@ -278,7 +295,7 @@ static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared)
     const size_t nk = shared ? 1 : n, D = (size_t)tuning().depth;
     return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
            pad256(n * D * p.K * 1024) + pad256(n * D * p.L * 32 * p.zbits) + pad256(n * D * (64 + p.w1len)) +
-           pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64) + pad256(2 * 2048 * 4);
+           2 * pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64) + pad256(2 * 2048 * 4);
 }
 static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox)
 {
@@ -292,6 +309,7 @@ static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint
     w.w = c.take<int32_t>(n * D * p.K * 256);
     w.yraw = c.take<uint8_t>(n * D * p.L * 32 * p.zbits);
     w.mw1 = c.take<uint8_t>(n * D * (64 + p.w1len));
+    w.mu = c.take<uint8_t>(n * 64);
     w.rhopp = c.take<uint8_t>(n * 64);
     w.ctilde = c.take<uint8_t>(n * D * 64);
     w.cmask = c.take<uint8_t>(n * D * 64);
@@ -364,6 +382,18 @@ static int verify_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size
     return OK;
 }
 
+// secrets of a sign workspace that the kernels do not zero themselves: the shared key's s-hat rows, and
+// everything when a run stopped early (s1-hat .. yraw are contiguous in the carve)
+static void sign_wipe(const SignWs& ws, size_t m, bool shared, bool failed, cudaStream_t st)
+{
+    if (failed) {
+        cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.mw1 - (uint8_t*)ws.s1h), st);
+        cudaMemsetAsync(ws.rhopp, 0, m * 64, st);
+    } else if (shared) {
+        cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.w - (uint8_t*)ws.s1h), st);
+    }
+}
+
 static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t n, const uint8_t* d_sk,
                      size_t sk_stride, const uint8_t* d_msgs, const uint64_t* d_msg_off, const uint8_t* d_ctx,
                      const uint32_t* d_ctx_off, const uint8_t* d_rnd, uint8_t* d_sig, uint32_t* d_iters,
@@ -374,79 +404,28 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
     const bool shared = sk_stride == 0;
     const size_t fixed = sign_ws_bytes(p, 0, shared);
     const size_t per_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? fixed : 0)) / 1024 + 1;
-    int ways = tuning().ways;
-    if (n < (size_t)ways * 4096) ways = 1;  // small batches: concurrency only adds latency
-    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + (size_t)ways * (fixed + 4096), per_lane);
-    // worst-case carve: every way carries its own fixed part; lanes are split evenly
-    const size_t way_lanes = (chunk + ways - 1) / ways;
-    int rc = cx.reserve(arena_skip + (size_t)ways * sign_ws_bytes(p, way_lanes, shared), arena_skip);
+    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + fixed + 4096, per_lane);
+    int rc = cx.reserve(arena_skip + sign_ws_bytes(p, chunk, shared), arena_skip);
     if (rc) return rc;
     t_last_rounds = 0;
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    cudaEvent_t ready = nullptr;
-    if (ways > 1) {
-        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        CK(cudaEventRecord(ready, st));  // inputs staged on `st` must be visible to the other ways' streams
-    }
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
-        std::vector<int> rcs((size_t)ways, OK), rounds((size_t)ways, 0);
-        std::vector<std::string> errs((size_t)ways);
-        auto run_way = [&](int w) {
-            const size_t wlo = lo + m * (size_t)w / (size_t)ways, whi = lo + m * (size_t)(w + 1) / (size_t)ways;
-            const size_t wm = whi - wlo;
-            if (wm == 0) return;
-            cudaSetDevice(dev);
-            cudaStream_t ws_stream = w == 0 ? st : cx.way_stream[w];
-            if (w != 0) cudaStreamWaitEvent(ws_stream, ready, 0);
-            Carver c(cx.arena + arena_skip + (size_t)w * sign_ws_bytes(p, way_lanes, shared));
-            SignWs ws = sign_carve(c, p, wm, shared, cx.mailbox + 8 * w);
-            ws.h_nact[1] = 0;
-            MsgDesc md{d_msgs, d_msg_off + wlo, d_ctx, d_ctx_off ? d_ctx_off + wlo : nullptr, framing};
-            cudaError_t e = sign_run(ps, ws_stream, wm, d_sk + sk_stride * wlo, sk_stride, md, d_rnd + 32 * wlo,
-                                     d_sig + p.sig * wlo, d_iters ? d_iters + wlo : nullptr, ws, &rounds[(size_t)w]);
-            // Everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop) is zeroed by
-            // sign_z as each lane finishes; A-hat, mu||w1, c~ and the challenge are public.  What is left for
-            // the host: the shared key's s-hat rows, and everything if the run stopped early.
-            // (s1-hat .. yraw are contiguous in the carve.)
-            if (e != cudaSuccess) {
-                cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.mw1 - (uint8_t*)ws.s1h), ws_stream);
-                cudaMemsetAsync(ws.rhopp, 0, wm * 64, ws_stream);
-            } else if (shared) {
-                cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.w - (uint8_t*)ws.s1h), ws_stream);
-            }
-            cudaStreamSynchronize(ws_stream);
-            prof_collect();
-            if (e != cudaSuccess) {
-                if (ws.h_nact[1] == CTX_ERR_MARK) {
-                    rcs[(size_t)w] = E_CTX;
-                } else {
-                    rcs[(size_t)w] = cuda_fail(e, "sign_run");
-                    errs[(size_t)w] = t_cuda_err;
-                }
-            }
-        };
-        if (ways == 1) {
-            run_way(0);
-        } else {
-            std::vector<std::thread> th;
-            for (int w = 1; w < ways; w++) th.emplace_back(run_way, w);
-            run_way(0);
-            for (auto& t : th) t.join();
-        }
-        int worst = 0;
-        for (int w = 0; w < ways; w++) {
-            if (rounds[(size_t)w] > worst) worst = rounds[(size_t)w];
-            if (rcs[(size_t)w]) {
-                if (!errs[(size_t)w].empty()) t_cuda_err = errs[(size_t)w];
-                if (ready) cudaEventDestroy(ready);
-                return rcs[(size_t)w];
-            }
-        }
-        t_last_rounds += worst;
+        Carver c(cx.arena + arena_skip);
+        SignWs ws = sign_carve(c, p, m, shared, cx.mailbox);
+        MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
+        SignRun run;
+        cudaError_t e = sign_begin(ps, st, m, d_sk + sk_stride * lo, sk_stride, md, d_rnd + 32 * lo, d_sig + p.sig * lo,
+                                   d_iters ? d_iters + lo : nullptr, ws, 0, &run);
+        if (e == cudaSuccess) e = sign_tail(st, &run);
+        if (e == cudaSuccess) e = sign_finish(&run);
+        // Everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop) is zeroed by
+        // sign_z as each lane finishes; A-hat, mu||w1, c~ and the challenge are public.
+        sign_wipe(ws, m, shared, e != cudaSuccess, st);
+        cudaStreamSynchronize(st);
+        prof_collect();
+        t_last_rounds += run.rounds;
+        if (e != cudaSuccess) return run.ctx_err ? E_CTX : cuda_fail(e, "sign");
     }
-    if (ready) cudaEventDestroy(ready);
     CK(cudaStreamSynchronize(st));
     prof_collect();
     return OK;
@@ -544,6 +523,11 @@ void mldsa_host_free(void* p)
 }
 void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
 void mldsa_set_depth(int depth) { g_depth.store(depth < 1 ? 1 : (depth > 8 ? 8 : depth)); }
+void mldsa_set_tail(int tail_depth, int tail_slots)
+{
+    g_tail_depth.store(tail_depth < 0 ? 0 : (tail_depth > 16 ? 16 : tail_depth));
+    g_tail_slots.store(tail_slots < 0 ? 0 : tail_slots);
+}
 void mldsa_set_pairing(int pair, int kshare)
 {
     g_pair.store(pair ? 1 : 0);
@@ -773,14 +757,31 @@ static ChunkPlan plan_chunks(size_t arena_bytes, size_t n, size_t fixed, size_t 
     ChunkPlan pl;
     const size_t cap = pick_chunk(arena_bytes, n, fixed, per_lane);
     pl.lo.push_back(0);
-    if (n >= (size_t(1) << 17) && cap >= (n + 3) / 4) {
-        // Big batch that would fit in <= 4 chunks: use 1-3-4-4-3-1 sixteenths, so the exposed pipeline fill
-        // (first copy-in) and drain (last copy-out) are 1/16 of the traffic instead of 1/4.
-        static const int frac[6] = {1, 3, 4, 4, 3, 1};
+    // Big batch that would fit in a few chunks: ramp the chunk sizes up and down, so that the exposed pipeline fill
+    // (first copy-in) and drain (last tail + copy-out) are 1/32 of the work instead of 1/4.  MLDSA_PLAN overrides the
+    // shape ("1,3,4,4,3,1" = sixteenths).
+    std::vector<int> frac = {1, 2, 4, 6, 6, 6, 4, 2, 1};
+    if (const char* pe = getenv("MLDSA_PLAN")) {
+        std::vector<int> f;
+        for (const char* q = pe; *q;) {
+            char* end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v > 0 && v < 4096) f.push_back((int)v);
+            q = *end ? end + 1 : end;
+        }
+        if (!f.empty()) frac = f;
+    }
+    int total = 0, biggest = 0;
+    for (int f : frac) {
+        total += f;
+        if (f > biggest) biggest = f;
+    }
+    if (n >= (size_t(1) << 17) && cap >= (n * (size_t)biggest + total - 1) / total) {
         size_t acc = 0;
         for (int f : frac) {
             acc += f;
-            pl.lo.push_back(n * acc / 16);
+            pl.lo.push_back(n * acc / total);
         }
     } else {
         for (size_t lo = cap; lo < n; lo += cap) pl.lo.push_back(lo);
@@ -818,24 +819,26 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     DeviceCtx* cx = lock_ctx(dev, lk, rc);
     if (!cx) return rc;
     const bool shared = sk_stride == 0;
-    const int ways = tuning().ways;
     const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
     const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
-    const size_t fixed = (size_t)ways * (sign_ws_bytes(p, 0, shared) + 4096) + (shared ? 2 * pad256(p.sk) : 0) + 65536;
-    const size_t ws_lane = (sign_ws_bytes(p, 1024, shared) - (shared ? sign_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
-    const size_t io_lane = 2 * ((shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + avg_msg + avg_ctx);
+    // NS sets of staged inputs / outputs AND rejection-loop workspaces: chunk i's tail rounds and its copy-out run
+    // under the bulk rounds of chunks i+1 and i+2
+    constexpr size_t NS = SIGN_SETS;
+    const size_t fixed = NS * (sign_ws_bytes(p, 0, shared) + 4096) + (shared ? NS * pad256(p.sk) : 0) + 65536;
+    const size_t ws_lane = NS * ((sign_ws_bytes(p, 1024, shared) - (shared ? sign_ws_bytes(p, 0, true) : 0)) / 1024 + 1);
+    const size_t io_lane = NS * ((shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + avg_msg + avg_ctx + PREHASH_STRIDE + 8);
     const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
-    const size_t C = pl.max_lanes;
+    const size_t C = pl.max_lanes, N = pl.nchunks();
     struct Set {
         uint8_t *sk, *rnd, *sig, *m, *c, *pm;
         uint32_t *it, *co;
         uint64_t *mo, *po;
-    } set[2];
+    } set[NS];
     const size_t set_bytes = pad256(shared ? p.sk : C * p.sk) + pad256(C * 32) + pad256(C * p.sig) + pad256(C * 4) +
                              pad256((C + 1) * 8) + pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) +
                              pad256(pl.max_cbytes + 8) + pad256(C * PREHASH_STRIDE) + pad256((C + 1) * 8);
-    const size_t way_lanes = (C + ways - 1) / ways;
-    rc = cx->reserve(2 * set_bytes + (size_t)ways * sign_ws_bytes(p, way_lanes, shared) + 4096);
+    const size_t ws_bytes = pad256(sign_ws_bytes(p, C, shared)) + 4096;
+    rc = cx->reserve(NS * (set_bytes + ws_bytes));
     if (rc) return rc;
     Carver c(cx->arena);
     for (auto& s : set) {
@@ -850,13 +853,38 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         s.pm = c.take<uint8_t>(C * PREHASH_STRIDE);
         s.po = c.take<uint64_t>(C + 1);
     }
-    const size_t io = c.off;
-    cudaStream_t st = cx->stream;
+    uint8_t* ws_base[NS];
+    for (size_t k = 0; k < NS; k++) ws_base[k] = cx->arena + c.off + k * ws_bytes;
+    cudaStream_t B = cx->stream, T = cx->s_tail;
+    // the bulk rounds stop when about this many lanes are expected to be live: below it the kernels no longer fill
+    // the device and a round costs its (fixed) latency
+    const size_t tail_lanes = N > 1 ? (size_t)env_int("MLDSA_TAIL", 16384) : 0;
+    SignRun run[NS];
+    size_t lanes_of[NS] = {};
+    bool started[NS] = {};
+    const bool trace = env_int("MLDSA_TRACE", 0) != 0;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    // MLDSA_TRACE=1: device-side timeline of the pipeline (timing events on every stream, printed at the end)
+    enum { TR_IN0, TR_IN1, TR_BULK0, TR_BULK1, TR_TAIL1, TR_OUT0, TR_OUT1, TR_N };
+    std::vector<cudaEvent_t> tr;
+    cudaEvent_t tr_origin = nullptr;
+    auto mark = [&](size_t i, int what, cudaStream_t st) {
+        if (trace) cudaEventRecord(tr[i * TR_N + what], st);
+    };
+    if (trace) {
+        tr.resize(N * TR_N);
+        for (auto& e : tr) cudaEventCreate(&e);
+        cudaEventCreate(&tr_origin);
+    }
+
     auto copy_in = [&](size_t i) -> int {
         const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
-        Set& s = set[i & 1];
+        Set& s = set[i % NS];
         const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
+        if (i >= NS) CK(cudaStreamWaitEvent(cx->s_in, cx->ev_bulk[i % NS], 0));  // the previous user of this set has consumed its inputs
+        mark(i, TR_IN0, cx->s_in);
         CK(cudaMemcpyAsync(s.sk, sk + sk_stride * lo, shared ? p.sk : m * p.sk, cudaMemcpyHostToDevice, cx->s_in));
         CK(cudaMemcpyAsync(s.rnd, rnd + 32 * lo, m * 32, cudaMemcpyHostToDevice, cx->s_in));
         CK(cudaMemcpyAsync(s.mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, cx->s_in));
@@ -865,54 +893,116 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
             CK(cudaMemcpyAsync(s.co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, cx->s_in));
             if (cbytes) CK(cudaMemcpyAsync(s.c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, cx->s_in));
         }
-        CK(cudaEventRecord(cx->ev_in[i & 1], cx->s_in));
+        CK(cudaEventRecord(cx->ev_in[i % NS], cx->s_in));
+        mark(i, TR_IN1, cx->s_in);
         return OK;
     };
-    // make sure nothing of a previous call is still in flight on the copy streams
-    CK(cudaStreamSynchronize(cx->s_in));
-    CK(cudaStreamSynchronize(cx->s_out));
-    const bool trace = env_int("MLDSA_TRACE", 0) != 0;
-    const auto t_start = std::chrono::steady_clock::now();
-    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
-    rc = copy_in(0);
-    if (rc) return rc;
-    for (size_t i = 0; i < pl.nchunks(); i++) {
+    // set-up and bulk rounds of chunk i on the work stream; nothing here waits for the device
+    auto enqueue_bulk = [&](size_t i) -> int {
         const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
-        Set& s = set[i & 1];
-        if (i + 1 < pl.nchunks()) {
-            rc = copy_in(i + 1);  // overlaps with this chunk's compute
-            if (rc) return rc;
+        Set& s = set[i % NS];
+        CK(cudaStreamWaitEvent(B, cx->ev_in[i % NS], 0));
+        if (i >= NS) {
+            CK(cudaStreamWaitEvent(B, cx->ev_out[i % NS], 0));   // the copy-out of the set's previous chunk has drained its outputs
+            CK(cudaStreamWaitEvent(B, cx->ev_tail[i % NS], 0));  // ... and that chunk is done with the workspace
         }
-        CK(cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0));
-        if (i >= 2) CK(cudaStreamWaitEvent(st, cx->ev_out[i & 1], 0));  // D2H(i-2) has drained this set's outputs
-        if (trace) {
-            cudaEventSynchronize(cx->ev_in[i & 1]);
-            fprintf(stderr, "[mldsa trace] chunk %zu (%zu lanes): inputs on device at %.2f ms\n", i, m, now_ms());
-        }
+        mark(i, TR_BULK0, B);
         const uint8_t* cm = s.m - msg_off[lo];
         const uint64_t* cmo = s.mo;
         if (ph >= 0) {  // HashML-DSA: M' carries OID || PH(M) (src/lib.rs:310-342)
-            CK(launch_prehash(st, ph, m, cm, cmo, s.pm, s.po));
+            CK(launch_prehash(B, ph, m, cm, cmo, s.pm, s.po));
             cm = s.pm;
             cmo = s.po;
         }
-        rc = sign_core(*cx, st, ps, framing, m, s.sk, sk_stride, cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr,
-                       ctx_off ? s.co : nullptr, s.rnd, s.sig, s.it, io);
-        if (rc) {
-            cudaStreamSynchronize(cx->s_in);
-            cudaStreamSynchronize(cx->s_out);
-            return rc;
+        Carver wc(ws_base[i % NS]);
+        const SignWs ws = sign_carve(wc, p, m, shared, cx->mailbox + 16 * (i % NS));
+        const MsgDesc md{cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, framing};
+        lanes_of[i % NS] = m;
+        started[i % NS] = true;
+        cudaError_t e = sign_begin(ps, B, m, s.sk, sk_stride, md, s.rnd, s.sig, s.it, ws, tail_lanes, &run[i % NS]);
+        if (e != cudaSuccess) return run[i % NS].ctx_err ? E_CTX : cuda_fail(e, "sign_begin");
+        CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, B));  // secrets do not linger in the staging set
+        CK(cudaMemsetAsync(s.rnd, 0, m * 32, B));
+        CK(cudaEventRecord(cx->ev_bulk[i % NS], B));
+        mark(i, TR_BULK1, B);
+        return OK;
+    };
+    auto enqueue_tail = [&](size_t i) -> int {
+        CK(cudaStreamWaitEvent(T, cx->ev_bulk[i % NS], 0));
+        cudaError_t e = sign_tail(T, &run[i % NS]);
+        return e == cudaSuccess ? OK : cuda_fail(e, "sign_tail");
+    };
+    auto finish = [&](size_t i) -> int {
+        SignRun& r = run[i % NS];
+        cudaError_t e = sign_finish(&r);  // the host waits here, with chunk i+1's bulk already queued behind
+        if (e != cudaSuccess) return r.ctx_err ? E_CTX : cuda_fail(e, "sign_finish");
+        sign_wipe(r.ws, lanes_of[i % NS], shared, false, T);
+        CK(cudaEventRecord(cx->ev_tail[i % NS], T));
+        mark(i, TR_TAIL1, T);
+        started[i % NS] = false;
+        t_last_rounds += r.rounds;
+        prof_collect();
+        return OK;
+    };
+    auto bail = [&](int code) -> int {  // stop everything, leave no secrets behind
+        const std::string err = t_cuda_err;
+        cudaStreamSynchronize(cx->s_in);
+        cudaStreamSynchronize(B);
+        cudaStreamSynchronize(T);
+        cudaStreamSynchronize(cx->s_out);
+        for (size_t k = 0; k < NS; k++) {
+            if (started[k]) sign_wipe(run[k].ws, lanes_of[k], shared, true, B);
+            cudaMemsetAsync(set[k].sk, 0, shared ? p.sk : C * p.sk, B);
+            cudaMemsetAsync(set[k].rnd, 0, C * 32, B);
         }
-        CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, st));  // secrets do not linger in the staging set
-        CK(cudaMemsetAsync(s.rnd, 0, m * 32, st));
-        CK(cudaStreamSynchronize(st));
-        if (trace) fprintf(stderr, "[mldsa trace] chunk %zu: signed at %.2f ms\n", i, now_ms());
-        CK(cudaMemcpyAsync(sig + p.sig * lo, s.sig, m * p.sig, cudaMemcpyDeviceToHost, cx->s_out));
-        if (iters) CK(cudaMemcpyAsync(iters + lo, s.it, m * 4, cudaMemcpyDeviceToHost, cx->s_out));
-        CK(cudaEventRecord(cx->ev_out[i & 1], cx->s_out));
-    }
+        cudaStreamSynchronize(B);
+        cudaGetLastError();
+        prof_collect();
+        t_cuda_err = err;
+        return code;
+    };
+
+    // make sure nothing of a previous call is still in flight on the copy streams
+    CK(cudaStreamSynchronize(cx->s_in));
     CK(cudaStreamSynchronize(cx->s_out));
-    if (trace) fprintf(stderr, "[mldsa trace] all signatures on the host at %.2f ms\n", now_ms());
+    t_last_rounds = 0;
+    if (trace) cudaEventRecord(tr_origin, cx->s_in);
+    if ((rc = copy_in(0))) return bail(rc);
+    if (N > 1 && (rc = copy_in(1))) return bail(rc);
+    if ((rc = enqueue_bulk(0))) return bail(rc);
+    for (size_t i = 0; i < N; i++) {
+        const size_t lo = pl.lo[i], m = pl.lo[i + 1] - lo;
+        Set& s = set[i % NS];
+        if ((rc = enqueue_tail(i))) return bail(rc);
+        if (i + 1 < N && (rc = enqueue_bulk(i + 1))) return bail(rc);
+        if (i + 2 < N && (rc = copy_in(i + 2))) return bail(rc);
+        if ((rc = finish(i))) return bail(rc);
+        if (trace) fprintf(stderr, "[mldsa trace] chunk %zu (%zu lanes): signed at %.2f ms, %d rounds\n", i, m, now_ms(), run[i % NS].rounds);
+        mark(i, TR_OUT0, cx->s_out);
+        if (cudaMemcpyAsync(sig + p.sig * lo, s.sig, m * p.sig, cudaMemcpyDeviceToHost, cx->s_out) != cudaSuccess ||
+            (iters && cudaMemcpyAsync(iters + lo, s.it, m * 4, cudaMemcpyDeviceToHost, cx->s_out) != cudaSuccess) ||
+            cudaEventRecord(cx->ev_out[i % NS], cx->s_out) != cudaSuccess)
+            return bail(cuda_fail(cudaGetLastError(), "copy out"));
+        mark(i, TR_OUT1, cx->s_out);
+    }
+    cudaError_t e = cudaStreamSynchronize(cx->s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(T);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(B);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "sign pipeline"));
+    prof_collect();
+    if (trace) {
+        fprintf(stderr, "[mldsa trace] all signatures on the host at %.2f ms\n", now_ms());
+        fprintf(stderr, "[mldsa trace] chunk   lanes |  H2D start..end | bulk start..end | tail end | D2H start..end   (device ms)\n");
+        for (size_t i = 0; i < N; i++) {
+            float t[TR_N];
+            for (int k = 0; k < TR_N; k++) cudaEventElapsedTime(&t[k], tr_origin, tr[i * TR_N + k]);
+            fprintf(stderr, "[mldsa trace] %5zu %7zu | %7.2f %7.2f | %7.2f %7.2f | %7.2f | %7.2f %7.2f\n", i, pl.lo[i + 1] - pl.lo[i],
+                    t[TR_IN0], t[TR_IN1], t[TR_BULK0], t[TR_BULK1], t[TR_TAIL1], t[TR_OUT0], t[TR_OUT1]);
+        }
+        for (auto& e : tr) cudaEventDestroy(e);
+        cudaEventDestroy(tr_origin);
+        cudaGetLastError();
+    }
     return OK;
 }
 

@@ -14,7 +14,6 @@ constexpr int SIB_BYTES = 136;   // one SHAKE256 block of H(c~) for SampleInBall
 constexpr int CMASK_STRIDE = 64;  // bytes per lane of the challenge masks
 constexpr int MU_BYTES = 64;
 constexpr int PREHASH_STRIDE = 80;  // OID (11) || PH(M) (<= 64), padded
-constexpr uint32_t CTX_ERR_MARK = 0xC7C7C7C7u;  // SignWs::h_nact[1] when sign_run saw |ctx| > 255
 
 // Kernel classes for launch telemetry (mldsa_kernel_launches) and the optional per-kernel device
 // timing (mldsa_profile_*): CUDA events recorded around every launch on the launching stream.
@@ -43,6 +42,8 @@ struct Tuning {
     int stage;  // sign_w: 0 = A-hat rows straight from global memory, 1 = TMA-staged per warp, 2 = staged and shared by
                 // the two candidate warps of a lane when the depth is even (MLDSA_STAGE, default 2)
     int kshare; // paired kernel: CTAs out of 5 per SM that prefer the Keccak queue (MLDSA_KSHARE, default 2)
+    int tail_depth;  // sign: deepest speculation of the under-filled last rounds (MLDSA_TAILDEPTH, default 8; <= depth: off)
+    int tail_slots;  // sign: candidate slots of the shared tail region (MLDSA_TAILSLOTS, default 32768)
 };
 Tuning tuning();
 unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event pairs into the per-kernel totals (call after a stream sync)
@@ -123,6 +124,7 @@ struct SignWs {
     int32_t* w;        // [n][D][K][256]
     uint8_t* yraw;     // [n][D][L][32*ZBITS]
     uint8_t* mw1;      // [n][D][64 + W1_LEN]  mu || w1
+    uint8_t* mu;       // [n][64]
     uint8_t* rhopp;    // [n][64]
     uint8_t* ctilde;   // [n][D][64]
     uint8_t* cmask;    // [n][D][64]
@@ -131,15 +133,41 @@ struct SignWs {
     uint32_t* act[2];  // [n] active lane lists (ping-pong)
     uint32_t* nact;    // [16] device control words: [4 * way + buffer] active counts, [8] ctx error flag
     uint32_t* queue;   // [2 * 2048] work-unit counters of the paired round launches
-    uint32_t* h_nact;  // pinned host mirror [2]: [0] active count / ctx flag, [1] CTX_ERR_MARK
+    uint32_t* h_nact;  // mapped pinned host mirror of the 16 control words (written by publish_kernel)
     static size_t bytes_per_lane(int K, int L, int zbits, int w1len, bool shared)
     {
         return (shared ? 0 : (size_t)(K * L + L + 2 * K) * 1024) + (size_t)K * 1024 + (size_t)L * 32 * zbits + 64 +
                w1len + 64 + 64 + SIB_BYTES + 4 + 1 + 8 + 16;
     }
 };
-// returns cudaSuccess; *rounds_out = number of rejection-loop rounds executed
-cudaError_t sign_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
-                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out);
+// Host-side state of one chunk's rejection loop between its three phases (k_sign.cu).
+struct SignRun {
+    int ps = 0;
+    size_t n = 0;
+    bool shared = false;
+    uint8_t* sig = nullptr;
+    uint32_t* iters = nullptr;
+    SignWs ws{};
+    int cur = 0;            // which of ws.act[] / ws.nact[] holds the live list
+    size_t bound = 0;       // host's upper bound on the live lanes
+    double expect = 0;      // expected live lanes after the rounds enqueued so far
+    int rounds = 0;         // rounds enqueued
+    size_t tail_slots = 0;  // size of the shared tail region in candidate slots (0 = no deeper tail rounds)
+    int tail_depth = 0;     // deepest speculation of the tail rounds
+    size_t slot_w_bytes = 0, slot_y_bytes = 0;
+    bool used_tail = false;
+    bool finished = false;
+    bool ctx_err = false;   // a lane's ctx was longer than 255 bytes (src/lib.rs:274)
+    cudaStream_t tail_stream = nullptr;
+};
+// sign_begin: set-up kernels and the bulk rounds (until the expected live count drops to tail_lanes; 0 = all the
+// rounds that almost surely suffice) on `st`, no host wait.  sign_tail: the remaining rounds on `st` (may differ
+// from the bulk stream; the caller orders them).  sign_finish: waits for the tail stream, runs straggler rounds
+// until no lane is live.  cudaErrorInvalidValue with run->ctx_err set = ctx too long.
+cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                       const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, size_t tail_lanes,
+                       SignRun* run);
+cudaError_t sign_tail(cudaStream_t st, SignRun* run);
+cudaError_t sign_finish(SignRun* run);
 
 }  // namespace mldsa

@@ -38,9 +38,9 @@ namespace mldsa {
 template <class P>
 __global__ void __launch_bounds__(128)
 sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
-                 const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mw1, uint8_t* __restrict__ rhopp,
+                 const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mu_out, uint8_t* __restrict__ rhopp,
                  uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
-                 uint32_t* __restrict__ ctl, size_t n_way_a, int* __restrict__ ctx_err, int depth)
+                 uint32_t* __restrict__ ctl, size_t n_way_a, int* __restrict__ ctx_err)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -53,8 +53,8 @@ sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, Msg
     if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
     uint64_t mu[8];
     sp.out_words(mu, 8);
-    for (int j = 0; j < depth; j++) {  // every candidate row starts with mu (the input row of the c~ hash)
-        uint64_t* mo = reinterpret_cast<uint64_t*>(mw1 + (i * depth + j) * (size_t)(MU_BYTES + P::W1_LEN));
+    {  // sign_w copies mu in front of every candidate's w1 (the input row of the c~ hash)
+        uint64_t* mo = reinterpret_cast<uint64_t*>(mu_out + i * (size_t)MU_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; k++) mo[k] = mu[k];
     }
@@ -119,19 +119,25 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
 // ---- per-stage jobs.  Every stage is written as a function of a WORK UNIT (what one 128-thread CTA does in one
 // step: 128 Keccak streams, or one item per warp), so that the same body runs in the stand-alone kernels
 // (grid-stride over units) and in the paired round kernel (units handed out from two queues).
+// Candidate scratch (yraw, w, mw1, ctilde, cmask) is addressed by SLOT.  pos = 0: slot = lane * depth + candidate.
+// pos = 1 (tail rounds with a deeper speculation than the workspace was carved for): slot = position of the lane
+// in the active list * depth + candidate -- the few live lanes share the low end of the candidate buffers.
 struct MaskJob {
-    const uint32_t* nact; const uint32_t* act; const uint8_t* rhopp; const uint32_t* kappa; uint8_t* yraw; int depth;
+    const uint32_t* nact; const uint32_t* act; const uint8_t* rhopp; const uint32_t* kappa; uint8_t* yraw; int depth; int pos;
 };
 struct CtildeJob {
     const uint32_t* nact; const uint32_t* act; const uint8_t* mw1; uint8_t* ctilde; uint8_t* cmask; int depth;
 };
 struct SignWJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* A; const uint8_t* yraw; int32_t* w; uint8_t* mw1; int depth;
+    const uint8_t* mu; int pos;
 };
 struct SignZJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* s1h; const int32_t* s2h; const int32_t* t0h;
     const uint8_t* yraw; int32_t* w; const uint8_t* ctilde; const uint8_t* cmask; uint32_t* kappa; uint8_t* done;
     uint8_t* rhopp; uint8_t* sig; uint32_t* iters; int depth;
+    int pos; int depth0; size_t tail_slots;  // pos = 1: the lane's stale slots of the carved depth0 are zeroed on accept
+                                             // too, unless they lie in the shared tail region [0, tail_slots)
 };
 
 // ExpandMask: one thread per (active lane, r) SHAKE256 stream; the squeezed bytes ARE the packed y.
@@ -145,7 +151,8 @@ __device__ __forceinline__ void mask_unit(const MaskJob& j, size_t unit)
     const size_t nstreams = (size_t)*j.nact * L;
     const size_t q = unit * 128 + threadIdx.x;
     if (q >= nstreams) return;
-    const size_t ln = j.act[q / L];
+    const size_t li = q / L;
+    const size_t ln = j.act[li];
     const uint32_t r = (uint32_t)(q % L);
     const uint64_t* rp = reinterpret_cast<const uint64_t*>(j.rhopp + 64 * ln);
     uint64_t a[25];
@@ -156,7 +163,7 @@ __device__ __forceinline__ void mask_unit(const MaskJob& j, size_t unit)
 #pragma unroll
     for (int i = 9; i < 25; i++) a[i] = 0;
     a[16] = 0x8000000000000000ULL;
-    uint64_t* out = reinterpret_cast<uint64_t*>(j.yraw + (ln * L + r) * (size_t)(YW * 8));
+    uint64_t* out = reinterpret_cast<uint64_t*>(j.yraw + ((j.pos ? li : ln) * L + r) * (size_t)(YW * 8));
 #pragma unroll 1
     for (int b = 0; b < (YW + 16) / 17; b++) {
         keccak_f1600(a);
@@ -218,11 +225,13 @@ __device__ __forceinline__ void sign_w_unit(const SignWJob& j, size_t unit, Sign
     const size_t ai = unit * SG_WARPS + warp;
     if (ai < nact) {
         const size_t ln = act[ai / depth];
-        const size_t slot = ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
+        const size_t slot = j.pos ? ai : ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
         const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
         const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
         int32_t* wo = wall + slot * (size_t)K * 256;
         uint8_t* w1o = mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
+        if (lane < 8)  // mu || w1 is the input row of the c~ hash
+            reinterpret_cast<uint64_t*>(w1o - MU_BYTES)[lane] = reinterpret_cast<const uint64_t*>(j.mu + ln * (size_t)MU_BYTES)[lane];
         __syncwarp();
         warp_prefetch_l2(A, 2 * L * 1024, lane);  // rows 0 and 1 of A-hat stream in during the forward NTTs
         uint32_t yw[2][(P::ZBITS + 3) / 4];       // packed y of the next polynomial is in flight during an NTT
@@ -349,11 +358,13 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
         const size_t ai = u * SG_WARPS + warp;
         if (ai >= nitems) continue;  // G = 2 needs an even depth, so both warps of a group skip together
         const size_t ln = j.act[ai / depth];
-        const size_t slot = ln * depth + ai % depth;
+        const size_t slot = j.pos ? ai : ln * depth + ai % depth;
         const int32_t* A = j.A + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
         const uint8_t* yp = j.yraw + slot * (size_t)(L * 32 * P::ZBITS);
         int32_t* wo = j.w + slot * (size_t)K * 256;
         uint8_t* w1o = j.mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
+        if (lane < 8)  // mu || w1 is the input row of the c~ hash
+            reinterpret_cast<uint64_t*>(w1o - MU_BYTES)[lane] = reinterpret_cast<const uint64_t*>(j.mu + ln * (size_t)MU_BYTES)[lane];
         // Every warp of the group reports "done reading the staged row"; the last one to report starts the next copy.
         auto release_and_fetch = [&](int row) {
             __syncwarp();
@@ -489,13 +500,14 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
     if (ai < nact) {
         const size_t ln = act[ai];
         const size_t kn = SHARED ? 0 : ln;
+        const size_t sbase = (j.pos ? ai : ln) * depth;  // first candidate slot of this lane
         uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
         bool rej = true;
         int cand = 0;
         // the lane's candidates in the reference's order: the first one that passes every check is the signature
 #pragma unroll 1
         for (; cand < depth && rej; cand++) {
-        const size_t slot = ln * depth + cand;
+        const size_t slot = sbase + cand;
         const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
         int32_t* wl = wall + slot * (size_t)K * 256;
 
@@ -634,7 +646,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
         // accept: c~ and hints complete the signature                            encodings.rs:254, 273
         __syncwarp();
         warp_copy_out(sg + LO::SIG_H, sm.stage, P::OMEGA + K, lane);
-        warp_copy_bytes(sg, ctilde + (ln * depth + cand) * 64, P::CTILDE, lane);
+        warp_copy_bytes(sg, ctilde + (sbase + cand) * 64, P::CTILDE, lane);
         if (lane == 0) {
             done[ln] = 1;
             if (iters) iters[ln] = kappa[ln] / L + cand + 1;
@@ -642,8 +654,14 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
         // The lane is finished: zero everything it derived from the secret key and the mask (y, w - c*s2, rho'',
         // and its own s1-hat / s2-hat / t0-hat) right here, where the stores hide behind other warps' arithmetic,
         // instead of a 27 GB cudaMemset after the last round (src/types.rs:19 ZeroizeOnDrop analogue).
-        warp_zero16(wall + ln * (size_t)depth * K * 256, depth * K * 1024, lane);
-        warp_zero16(const_cast<uint8_t*>(yraw) + ln * (size_t)depth * (L * 32 * P::ZBITS), depth * L * 32 * P::ZBITS, lane);
+        warp_zero16(wall + sbase * (size_t)K * 256, depth * K * 1024, lane);
+        warp_zero16(const_cast<uint8_t*>(yraw) + sbase * (size_t)(L * 32 * P::ZBITS), depth * L * 32 * P::ZBITS, lane);
+        if (j.pos && ln * (size_t)j.depth0 >= j.tail_slots) {
+            // what the lane's last rejected candidates left in its own slots (the tail region itself, which other
+            // live lanes are using right now, is cleared by the host after the last round)
+            warp_zero16(wall + ln * (size_t)j.depth0 * K * 256, j.depth0 * K * 1024, lane);
+            warp_zero16(const_cast<uint8_t*>(yraw) + ln * (size_t)j.depth0 * (L * 32 * P::ZBITS), j.depth0 * L * 32 * P::ZBITS, lane);
+        }
         warp_zero16(rhopp + ln * 64, 64, lane);
         if (!SHARED) {
             warp_zero16(const_cast<int32_t*>(s1h_all) + ln * (size_t)L * 256, L * 1024, lane);
@@ -755,54 +773,147 @@ constexpr int CTL_WORDS = 16;       // SignWs::nact: [4 * way + buffer] active c
 constexpr int CTL_CTX_ERR = 8;
 constexpr int QUEUE_PAIRS = 2048;   // SignWs::queue: one (Keccak, arithmetic) counter pair per paired launch
 
+// ---- the rejection loop of one chunk, in three host phases ------------------------------------------------
+//   sign_begin   set-up kernels + the BULK rounds (while the expected number of live lanes is above `tail_lanes`)
+//   sign_tail    the remaining rounds that almost surely suffice + publication of the control words
+//   sign_finish  the only host wait: read the live count, run straggler rounds until it is zero
+// No phase before sign_finish waits for the device, and the tail may be enqueued on another stream than the bulk
+// (the caller orders the two with an event): the host entry point runs chunk i's latency-bound tail (a few
+// thousand lanes, ~100 dependent small launches) on a high-priority stream UNDER chunk i+1's bulk rounds.
+// Every kernel is a grid-stride loop over the live count it reads from device memory, so grids are sized from
+// the EXPECTED number of survivors: a round rejects a lane with probability (1 - p)^D, p >= 0.19 for all three
+// parameter sets (FIPS 204 table 1: 4.25 / 5.1 / 3.85 expected iterations).
 template <class P>
-static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
-                              const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out)
+static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                                const uint8_t* rnd, size_t nA)
 {
     constexpr int K = P::K, L = P::L;
-    const bool shared = sk_stride == 0;
-    const size_t nkeys = shared ? 1 : n;
+    const SignWs& ws = r.ws;
+    const size_t n = r.n, nkeys = r.shared ? 1 : n;
     const Tuning tn = tuning();
-    const int D = ws.depth;
-    const bool paired = tn.pair != 0 && n >= 8192;  // small batches are latency-bound: keep the plain loop
-    const size_t nA = paired ? (n + 1) / 2 : n;     // way A = lanes [0, nA), way B = [nA, n)
-    auto warp_grid = [&](size_t items) {
-        return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16);
-    };
-    cudaError_t e;
-    const bool trace = getenv("MLDSA_TRACE") != nullptr && n >= 4096;
-    const auto t_start = std::chrono::steady_clock::now();
-    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     int* ctx_err = reinterpret_cast<int*>(ws.nact + CTL_CTX_ERR);
-    e = cudaMemsetAsync(ws.nact, 0, CTL_WORDS * 4, st);
+    cudaError_t e = cudaMemsetAsync(ws.nact, 0, CTL_WORDS * 4, st);
     if (e != cudaSuccess) return e;
-    if (paired) {
-        e = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
-        if (e != cudaSuccess) return e;
-    }
     {
         KLaunch kl(KID_SIGN_PREP, st);
-        sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mw1, ws.rhopp,
+        sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mu, ws.rhopp,
                                                                         ws.kappa, ws.done, ws.act[0], ws.nact, nA,
-                                                                        ctx_err, D);
+                                                                        ctx_err);
     }
     {
         KLaunch kl(KID_SIGN_KEY, st);
-        sign_key_kernel<P><<<warp_grid(nkeys), SG_WARPS * 32, 0, st>>>(nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
+        sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16), SG_WARPS * 32, 0, st>>>(
+            nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
     }
-    e = launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
-    if (e != cudaSuccess) return e;
-    publish_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(ctx_err), ws.h_nact, 1);
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    if (trace) fprintf(stderr, "[mldsa trace] sign_run %zu lanes: setup done at %.2f ms\n", n, now_ms());
-    if (ws.h_nact[0] != 0) {  // ctx too long: the caller maps this marker to -2 (lib.rs:274)
-        ws.h_nact[1] = CTX_ERR_MARK;
-        return cudaErrorInvalidValue;
-    }
+    return launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
+}
 
-    // Per-way state.  The kernels read the live active-lane count from device memory; the host only needs to
-    // know when a way has run dry, so it looks at the counters every few rounds.
+// Speculation depth of a round over (at most) sz live lanes: the carved depth D while the candidates fill the
+// device; once sz * d candidates fit in the tail region (the low tail_slots slots of the candidate buffers), the
+// deepest d in {16, 8, 4} allowed -- the device is under-filled there and a round costs its fixed latency, so
+// extra speculative candidates are free and the number of rounds (dependent launches) drops with log(0.81^d).
+static int round_depth(const SignRun& r, size_t sz)
+{
+    const int D = r.ws.depth;
+    if (r.tail_slots)
+        for (int d = 16; d > D; d >>= 1)
+            if (d <= r.tail_depth && sz * (size_t)d <= r.tail_slots) return d;
+    return D;
+}
+
+// one round over (at most) sz live lanes of the un-paired loop
+template <class P>
+static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
+{
+    constexpr int L = P::L;
+    const SignWs& ws = r.ws;
+    const Tuning tn = tuning();
+    const int D = round_depth(r, sz);
+    const int pos = D != ws.depth ? 1 : 0;
+    if (pos) r.used_tail = true;
+    const bool shared = r.shared;
+    const uint32_t* nact = ws.nact + r.cur;
+    const uint32_t* act = ws.act[r.cur];
+    auto warp_grid = [&](size_t items) { return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : 16); };
+    {
+        KLaunch kl(KID_MASK, st);
+        mask_kernel<P><<<capped_grid((sz * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(
+            MaskJob{nact, act, ws.rhopp, ws.kappa, ws.yraw, D, pos});
+    }
+    cudaError_t ce = cudaSuccess;
+    const SignWJob wj{nact, act, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, pos};
+    if (tn.stage == 0) {
+        KLaunch kl(KID_SIGN_W, st);
+        if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
+        else sign_w_kernel<P, false><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
+    } else {
+        const int cap = tn.acap > 0 ? tn.acap : 16;
+        if (D % 2 == 0 && tn.stage == 2)
+            ce = shared ? launch_sign_w_staged<P, true, 2>(st, wj, sz * D, cap) : launch_sign_w_staged<P, false, 2>(st, wj, sz * D, cap);
+        else
+            ce = shared ? launch_sign_w_staged<P, true, 1>(st, wj, sz * D, cap) : launch_sign_w_staged<P, false, 1>(st, wj, sz * D, cap);
+        if (ce != cudaSuccess) return ce;
+    }
+    // pos: rows are the positions themselves (act = nullptr)
+    ce = launch_ctilde(P::PS, st, sz * D, nact, pos ? nullptr : act, D, ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.cmask);
+    if (ce != cudaSuccess) return ce;
+    {
+        const SignZJob zj{nact, act, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done, ws.rhopp,
+                          r.sig, r.iters, D, pos, ws.depth, r.tail_slots};
+        KLaunch kl(KID_SIGN_Z, st);
+        if (shared) sign_z_kernel<P, true><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(zj);
+        else sign_z_kernel<P, false><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(zj);
+    }
+    // re-queue the rejected lanes into the other list
+    uint32_t* nout = ws.nact + (r.cur ^ 1);
+    ce = cudaMemsetAsync(nout, 0, 4, st);
+    if (ce != cudaSuccess) return ce;
+    {
+        KLaunch kl(KID_COMPACT, st);
+        compact_kernel<<<(unsigned)((sz + 255) / 256) + 1, 256, 0, st>>>(nact, act, ws.done, ws.act[r.cur ^ 1], nout);
+    }
+    r.cur ^= 1;
+    r.bound = sz;
+    r.rounds++;
+    return cudaGetLastError();
+}
+static cudaError_t sign_round(cudaStream_t st, SignRun& r, size_t sz)
+{
+    switch (r.ps) {
+    case 44: return sign_round_t<Params<44>>(st, r, sz);
+    case 65: return sign_round_t<Params<65>>(st, r, sz);
+    case 87: return sign_round_t<Params<87>>(st, r, sz);
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t sign_rounds_until(cudaStream_t st, SignRun& r, double stop_at)
+{
+    while (r.expect > stop_at) {
+        size_t sz = (size_t)(r.expect * 1.25) + 256;
+        if (sz > r.n) sz = r.n;
+        const double keep = pow(1.0 - 0.19, (double)round_depth(r, sz));
+        cudaError_t e = sign_round(st, r, sz);
+        if (e != cudaSuccess) return e;
+        r.expect *= keep;
+    }
+    return cudaSuccess;
+}
+
+// Paired round loop (MLDSA_PAIR=1): synchronous, everything happens inside sign_begin.
+template <class P>
+static cudaError_t sign_paired_t(cudaStream_t st, SignRun& r, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                                 const uint8_t* rnd)
+{
+    const SignWs& ws = r.ws;
+    const size_t n = r.n;
+    const bool shared = r.shared;
+    const Tuning tn = tuning();
+    const int D = ws.depth;
+    const size_t nA = (n + 1) / 2;  // way A = lanes [0, nA), way B = [nA, n)
+    cudaError_t e = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
+    if (e != cudaSuccess) return e;
+    e = sign_setup_t<P>(st, r, sk, sk_stride, md, rnd, nA);
+    if (e != cudaSuccess) return e;
     struct Way {
         size_t lo, bound;
         int cur = 0;
@@ -810,12 +921,12 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
     } way[2];
     way[0].lo = 0, way[0].bound = nA;
     way[1].lo = nA, way[1].bound = n - nA;
-    auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D}; };
+    auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D, 0}; };
     auto ct_job = [&](int v) { return CtildeJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.mw1, ws.ctilde, ws.cmask, D}; };
-    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D}; };
+    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, 0}; };
     auto z_job = [&](int v) {
         return SignZJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde,
-                        ws.cmask, ws.kappa, ws.done, ws.rhopp, sig, iters, D};
+                        ws.cmask, ws.kappa, ws.done, ws.rhopp, r.sig, r.iters, D, 0, D, 0};
     };
     auto compact = [&](int v) -> cudaError_t {
         Way& y = way[v];
@@ -830,147 +941,167 @@ static cudaError_t sign_run_t(cudaStream_t st, size_t n, const uint8_t* sk, size
         y.cur ^= 1;
         return cudaGetLastError();
     };
-    auto read_bounds = [&]() -> cudaError_t {  // refresh the hosts's view of both ways' active counts
-        publish_kernel<<<1, 32, 0, st>>>(ws.nact, ws.h_nact, 8);
+    auto read_bounds = [&]() -> cudaError_t {  // refresh the host's view of both ways' active counts
+        publish_kernel<<<1, 32, 0, st>>>(ws.nact, ws.h_nact, CTL_WORDS);
         cudaError_t ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return ce;
         for (int v = 0; v < 2; v++) way[v].bound = ws.h_nact[4 * v + way[v].cur];
         return cudaSuccess;
     };
-    int rounds = 0;
-
-    if (!paired) {
-        // The host never waits for a round: grids are sized from the EXPECTED number of survivors (every kernel is
-        // a grid-stride loop over the live count it reads from device memory, so any grid is correct), the rounds
-        // that almost surely suffice are enqueued in one go, and only then does the host look at the counter.
-        // A round rejects a lane with probability (1 - p)^D; p >= 0.19 for all three parameter sets (FIPS 204
-        // table 1: 4.25 / 5.1 / 3.85 expected iterations).
-        Way& y = way[0];
-        const double keep = pow(1.0 - 0.19, (double)D);
-        double expect = (double)n;
-        auto one_round = [&](size_t sz) -> cudaError_t {
-            {
-                KLaunch kl(KID_MASK, st);
-                mask_kernel<P><<<capped_grid((sz * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(mask_job(0));
-            }
-            cudaError_t ce = cudaSuccess;
-            if (tn.stage == 0) {
-                KLaunch kl(KID_SIGN_W, st);
-                if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(w_job(0));
-                else sign_w_kernel<P, false><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(w_job(0));
-            } else {
-                const int cap = tn.acap > 0 ? tn.acap : 16;
-                if (D % 2 == 0 && tn.stage == 2)
-                    ce = shared ? launch_sign_w_staged<P, true, 2>(st, w_job(0), sz * D, cap)
-                                : launch_sign_w_staged<P, false, 2>(st, w_job(0), sz * D, cap);
-                else
-                    ce = shared ? launch_sign_w_staged<P, true, 1>(st, w_job(0), sz * D, cap)
-                                : launch_sign_w_staged<P, false, 1>(st, w_job(0), sz * D, cap);
-                if (ce != cudaSuccess) return ce;
-            }
-            ce = launch_ctilde(P::PS, st, sz * D, y.nact(ws, 0), ws.act[y.cur], D, ws.mw1, nullptr, nullptr, nullptr,
-                               ws.ctilde, ws.cmask);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(sms * PAIR_CTAS_PER_SM);
+    const int kshare = tn.kshare > 0 && tn.kshare < PAIR_CTAS_PER_SM ? tn.kshare : 2;
+    int qi = 0;
+    auto launch_pair = [&](int kstage, int kv, int astage, int av) -> cudaError_t {
+        if (qi == QUEUE_PAIRS) {  // recycle the counters (stream order: every earlier launch is done with them)
+            cudaError_t ce = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
             if (ce != cudaSuccess) return ce;
-            {
-                KLaunch kl(KID_SIGN_Z, st);
-                if (shared) sign_z_kernel<P, true><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(z_job(0));
-                else sign_z_kernel<P, false><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(z_job(0));
-            }
-            y.bound = sz;
-            return compact(0);
-        };
-        while (expect > 0.01) {  // P(a lane is still active after these rounds) < 1 %
-            const size_t sz = (size_t)(expect * 1.25) + 256;
-            e = one_round(sz < n ? sz : n);
-            if (e != cudaSuccess) return e;
-            rounds++;
-            expect *= keep;
+            qi = 0;
         }
-        if (trace) fprintf(stderr, "[mldsa trace] sign_run: %d rounds enqueued at %.2f ms\n", rounds, now_ms());
-        e = read_bounds();
+        PairJob pj{};
+        pj.kstage = kstage;
+        pj.astage = astage;
+        if (kstage == 1) pj.mask = mask_job(kv);
+        if (kstage == 2) pj.ct = ct_job(kv);
+        if (astage == 1) pj.w = w_job(av);
+        if (astage == 2) pj.z = z_job(av);
+        pj.queue = ws.queue + 2 * qi++;
+        pj.kshare = kshare;
+        KLaunch kl(KID_ROUND_PAIR, st);
+        if (shared) round_pair_kernel<P, true><<<grid, SG_WARPS * 32, 0, st>>>(pj);
+        else round_pair_kernel<P, false><<<grid, SG_WARPS * 32, 0, st>>>(pj);
+        return cudaGetLastError();
+    };
+    bool pending_zb = false;  // way B's sign_z of the previous round rides with way A's next mask
+    int since_sync = 0;
+    while (way[0].bound > 0 || way[1].bound > 0 || pending_zb) {
+        e = launch_pair(way[0].bound ? 1 : 0, 0, pending_zb ? 2 : 0, 1);
         if (e != cudaSuccess) return e;
-        if (trace) fprintf(stderr, "[mldsa trace] sign_run: rounds done at %.2f ms, %zu lanes left\n", now_ms(), y.bound);
-        while (y.bound > 0) {  // stragglers beyond the estimate (rare): a few rounds at a time
-            for (int r = 0; r < 4; r++) {
-                e = one_round(y.bound);
-                if (e != cudaSuccess) return e;
-                rounds++;
-            }
+        if (pending_zb) {
+            e = compact(1);
+            if (e != cudaSuccess) return e;
+            pending_zb = false;
+        }
+        e = launch_pair(way[1].bound ? 1 : 0, 1, way[0].bound ? 1 : 0, 0);
+        if (e != cudaSuccess) return e;
+        e = launch_pair(way[0].bound ? 2 : 0, 0, way[1].bound ? 1 : 0, 1);
+        if (e != cudaSuccess) return e;
+        e = launch_pair(way[1].bound ? 2 : 0, 1, way[0].bound ? 2 : 0, 0);
+        if (e != cudaSuccess) return e;
+        if (way[0].bound) {
+            e = compact(0);
+            if (e != cudaSuccess) return e;
+        }
+        pending_zb = way[1].bound > 0;
+        r.rounds++;
+        if (++since_sync >= 4 || (way[0].bound + way[1].bound) < 4096) {
+            // (the counts lag: way B's are from before its pending sign_z, which only makes them larger)
             e = read_bounds();
             if (e != cudaSuccess) return e;
-        }
-    } else {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const unsigned grid = (unsigned)(sms * PAIR_CTAS_PER_SM);
-        const int kshare = tn.kshare > 0 && tn.kshare < PAIR_CTAS_PER_SM ? tn.kshare : 2;
-        int qi = 0;
-        auto launch_pair = [&](int kstage, int kv, int astage, int av) -> cudaError_t {
-            if (qi == QUEUE_PAIRS) {  // recycle the counters (stream order: every earlier launch is done with them)
-                cudaError_t ce = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
-                if (ce != cudaSuccess) return ce;
-                qi = 0;
-            }
-            PairJob pj{};
-            pj.kstage = kstage;
-            pj.astage = astage;
-            if (kstage == 1) pj.mask = mask_job(kv);
-            if (kstage == 2) pj.ct = ct_job(kv);
-            if (astage == 1) pj.w = w_job(av);
-            if (astage == 2) pj.z = z_job(av);
-            pj.queue = ws.queue + 2 * qi++;
-            pj.kshare = kshare;
-            KLaunch kl(KID_ROUND_PAIR, st);
-            if (shared) round_pair_kernel<P, true><<<grid, SG_WARPS * 32, 0, st>>>(pj);
-            else round_pair_kernel<P, false><<<grid, SG_WARPS * 32, 0, st>>>(pj);
-            return cudaGetLastError();
-        };
-        bool pending_zb = false;  // way B's sign_z of the previous round rides with way A's next mask
-        int since_sync = 0;
-        while (way[0].bound > 0 || way[1].bound > 0 || pending_zb) {
-            e = launch_pair(way[0].bound ? 1 : 0, 0, pending_zb ? 2 : 0, 1);
-            if (e != cudaSuccess) return e;
-            if (pending_zb) {
-                e = compact(1);
-                if (e != cudaSuccess) return e;
-                pending_zb = false;
-            }
-            e = launch_pair(way[1].bound ? 1 : 0, 1, way[0].bound ? 1 : 0, 0);
-            if (e != cudaSuccess) return e;
-            e = launch_pair(way[0].bound ? 2 : 0, 0, way[1].bound ? 1 : 0, 1);
-            if (e != cudaSuccess) return e;
-            e = launch_pair(way[1].bound ? 2 : 0, 1, way[0].bound ? 2 : 0, 0);
-            if (e != cudaSuccess) return e;
-            if (way[0].bound) {
-                e = compact(0);
-                if (e != cudaSuccess) return e;
-            }
-            pending_zb = way[1].bound > 0;
-            rounds++;
-            if (++since_sync >= 4 || (way[0].bound + way[1].bound) < 4096) {
-                // (the counts lag: way B's are from before its pending sign_z, which only makes them larger)
-                e = read_bounds();
-                if (e != cudaSuccess) return e;
-                since_sync = 0;
-            }
+            since_sync = 0;
         }
     }
-    if (rounds_out) *rounds_out = rounds;
+    if (ws.h_nact[CTL_CTX_ERR] != 0) {  // ctx too long (lib.rs:274)
+        r.ctx_err = true;
+        return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
-cudaError_t sign_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
-                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, int* rounds_out)
+cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
+                       const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, size_t tail_lanes,
+                       SignRun* run)
 {
-    if (rounds_out) *rounds_out = 0;
-    if (n == 0) return cudaSuccess;
-    switch (ps) {
-    case 44: return sign_run_t<Params<44>>(st, n, sk, sk_stride, md, rnd, sig, iters, ws, rounds_out);
-    case 65: return sign_run_t<Params<65>>(st, n, sk, sk_stride, md, rnd, sig, iters, ws, rounds_out);
-    case 87: return sign_run_t<Params<87>>(st, n, sk, sk_stride, md, rnd, sig, iters, ws, rounds_out);
+    SignRun& r = *run;
+    r = SignRun{};
+    r.ps = ps;
+    r.n = n;
+    r.shared = sk_stride == 0;
+    r.sig = sig;
+    r.iters = iters;
+    r.ws = ws;
+    r.expect = (double)n;
+    r.tail_stream = st;
+    {
+        // tail region: the low slots of the candidate buffers, shared by the few live lanes of the last rounds
+        const Tuning tn = tuning();
+        size_t slots = n * (size_t)ws.depth;
+        if (slots > (size_t)tn.tail_slots) slots = (size_t)tn.tail_slots;
+        slots -= slots % (size_t)(16 * ws.depth);  // whole lanes of the carved depth, whole lanes of every tail depth
+        r.tail_slots = tn.tail_depth > ws.depth ? slots : 0;
+        r.tail_depth = tn.tail_depth;
+        const int K = ps == 44 ? 4 : (ps == 65 ? 6 : 8), L = ps == 44 ? 4 : (ps == 65 ? 5 : 7), zbits = ps == 44 ? 18 : 20;
+        r.slot_w_bytes = (size_t)K * 1024;
+        r.slot_y_bytes = (size_t)L * 32 * zbits;
     }
-    return cudaErrorInvalidValue;
+    if (n == 0) {
+        r.finished = true;
+        return cudaSuccess;
+    }
+    cudaError_t e;
+    if (tuning().pair != 0 && n >= 8192) {  // small batches are latency-bound: keep the plain loop
+        r.finished = true;
+        switch (ps) {
+        case 44: return sign_paired_t<Params<44>>(st, r, sk, sk_stride, md, rnd);
+        case 65: return sign_paired_t<Params<65>>(st, r, sk, sk_stride, md, rnd);
+        case 87: return sign_paired_t<Params<87>>(st, r, sk, sk_stride, md, rnd);
+        }
+        return cudaErrorInvalidValue;
+    }
+    switch (ps) {
+    case 44: e = sign_setup_t<Params<44>>(st, r, sk, sk_stride, md, rnd, n); break;
+    case 65: e = sign_setup_t<Params<65>>(st, r, sk, sk_stride, md, rnd, n); break;
+    case 87: e = sign_setup_t<Params<87>>(st, r, sk, sk_stride, md, rnd, n); break;
+    default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    return sign_rounds_until(st, r, tail_lanes > 0 ? (double)tail_lanes : 0.01);
+}
+
+cudaError_t sign_tail(cudaStream_t st, SignRun* run)
+{
+    SignRun& r = *run;
+    r.tail_stream = st;
+    if (r.finished) return cudaSuccess;
+    cudaError_t e = sign_rounds_until(st, r, 0.01);  // P(a lane is still active after these rounds) < 1 %
+    if (e != cudaSuccess) return e;
+    publish_kernel<<<1, 32, 0, st>>>(r.ws.nact, r.ws.h_nact, CTL_WORDS);
+    return cudaGetLastError();
+}
+
+cudaError_t sign_finish(SignRun* run)
+{
+    SignRun& r = *run;
+    if (r.finished) return cudaSuccess;
+    cudaStream_t st = r.tail_stream;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    if (r.ws.h_nact[CTL_CTX_ERR] != 0) {  // ctx too long: the caller maps this to -2 (lib.rs:274)
+        r.ctx_err = true;
+        r.finished = true;
+        return cudaErrorInvalidValue;
+    }
+    r.bound = r.ws.h_nact[r.cur];
+    while (r.bound > 0) {  // stragglers beyond the estimate (rare): a few rounds at a time
+        const size_t sz = r.bound;
+        for (int k = 0; k < 4; k++) {
+            e = sign_round(st, r, sz);
+            if (e != cudaSuccess) return e;
+        }
+        publish_kernel<<<1, 32, 0, st>>>(r.ws.nact, r.ws.h_nact, CTL_WORDS);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return e;
+        r.bound = r.ws.h_nact[r.cur];
+    }
+    if (r.used_tail) {  // rejected candidates of the tail rounds (y, w - c*s2) may be left in the shared tail region
+        e = cudaMemsetAsync(r.ws.w, 0, r.tail_slots * r.slot_w_bytes, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(r.ws.yraw, 0, r.tail_slots * r.slot_y_bytes, st);
+        if (e != cudaSuccess) return e;
+    }
+    r.finished = true;
+    return cudaSuccess;
 }
 
 }  // namespace mldsa

@@ -128,14 +128,19 @@ int mldsa_shake_batch(int dev, int bits /*128|256*/, size_t n, const uint8_t* in
 /* ---- tuning / telemetry ------------------------------------------------------------------ */
 /* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 96 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);
-/* launch tuning: a sign chunk runs as `ways` concurrent sub-batches on separate streams; kcap / acap cap
- * the CTAs per SM of the Keccak / arithmetic kernels so kernels of different ways share an SM
- * (0 = uncapped).  Defaults come from MLDSA_WAYS / MLDSA_KCAP / MLDSA_ACAP, else 1 / 0 / 0. */
+/* launch tuning: kcap / acap cap the CTAs per SM of the (grid-stride) Keccak / arithmetic kernels (0 = default:
+ * uncapped / 16).  Defaults come from MLDSA_KCAP / MLDSA_ACAP.  `ways` is accepted and ignored: running a chunk as
+ * concurrent sub-batches on separate streams was measured to gain nothing and was removed. */
 void mldsa_set_tuning(int ways, int kcap, int acap);
 /* candidates (kappa, kappa + L, ...) every still-active lane tries per round of the sign rejection loop, 1..8
  * (default MLDSA_DEPTH, else 2).  Results never depend on it: candidates count in the reference's order
  * (src/ml_dsa.rs:212-330); a larger depth trades a little speculative work for fewer rounds and less A-hat traffic. */
 void mldsa_set_depth(int depth);
+/* the last, under-filled rounds of the sign rejection loop (a few thousand live lanes; a round then costs its fixed
+ * latency) speculate deeper: once live_lanes * d candidates fit in `tail_slots` candidate slots, a round tries the
+ * largest d in {4, 8, 16} with d <= tail_depth.  Results never depend on it (same argument as mldsa_set_depth).
+ * Defaults MLDSA_TAILDEPTH / MLDSA_TAILSLOTS, else 8 / 32768; tail_depth <= depth switches it off. */
+void mldsa_set_tail(int tail_depth, int tail_slots);
 /* pair != 0 (MLDSA_PAIR, default 0: measured no gain while the arithmetic stages are latency-bound): a sign chunk of >= 8192 lanes runs as two half-chunks whose rejection loops are
  * staggered by one stage, each launch executing a Keccak stage of one half beside an arithmetic stage of the other on
  * the same SMs; kshare (1..4, default 2, MLDSA_KSHARE) = CTAs out of 5 per SM that prefer the Keccak queue. */

@@ -401,3 +401,31 @@ def test_sign_speculation_depth_does_not_change_bytes(F, depth):
             assert (one == oone).all()
     finally:
         L.mldsa_set_depth(2)
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_sign_tail_rounds_speculate_deeper(F, ps):
+    """The last, under-filled rounds of the rejection loop try up to 16 candidates per lane in slots addressed by
+    the lane's position in the active list (mldsa_set_tail).  Signatures and iteration counts must still be the
+    reference's sequential loop (src/ml_dsa.rs:212-330), with the tail region small enough here that depths 4, 8
+    and 16 are all used, through both entry points and for a shared key."""
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    m = F.PARAM_SETS[ps]
+    n = 5000
+    pks, sks = O.keygen_batch(ps, synth_block(f"tk{ps}", n, 32))
+    msgs = [synth("tm", i, i % 40) for i in range(n)]
+    rnds = synth_rows("tr", n, 32)
+    osig, oit = O.sign_batch(ps, sks, msgs, rnds)
+    try:
+        for tail_depth, slots in ((16, 8192), (8, 32768), (4, 1024), (0, 0)):
+            L.mldsa_set_tail(tail_depth, slots)
+            sig, it = m.sign_batch(sks, msgs, rnds, want_iters=True)
+            assert (sig == osig).all() and (it == oit).all(), (ps, tail_depth, slots)
+        L.mldsa_set_tail(16, 8192)
+        one = m.sign_batch(sks[9].tobytes(), msgs[:1500], rnds[:1500], shared_key=True)
+        oone, _ = O.sign_batch(ps, sks[9], msgs[:1500], rnds[:1500], shared_key=True)
+        assert (one == oone).all()
+        assert m.verify_batch(pks, msgs, sig).all()
+    finally:
+        L.mldsa_set_tail(8, 32768)
