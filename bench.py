@@ -306,6 +306,17 @@ def main():
                     "frac": (tk["hbm_gbs"] or 0) / hbm_peak, "peak_source": hbm_src},
             "traffic": None,
         }
+        # DRAM bytes of that kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to
+        # this launch's lanes: dram__bytes_read.sum + dram__bytes_write.sum per launch
+        tf = ROOT / "profiles" / "ncu_traffic.json"
+        if tf.exists():
+            rec = json.load(open(tf)).get(f"{top}:{args.ps}")
+            if rec:
+                per_unit = (rec["dram_read_bytes"] + rec["dram_write_bytes"]) / rec["units"]
+                units_per_launch = {"expand_a": n}.get(top, iters_total / launches_top)
+                roofline["traffic"] = per_unit * units_per_launch
+                roofline["traffic_source"] = rec["source"]
+                roofline["traffic_over_algorithmic"] = roofline["traffic"] / (byts / launches_top) if byts else None
     whole_ops = sum(v[0] for k, v in work.items() if k != "round_pair")
 
     # ---- correctness guards outside the timed region: all signatures verify on the GPU, and a sample is
@@ -315,7 +326,12 @@ def main():
     all_verify = bool(d_ok.all().item())
     check = {"all_signatures_verify": all_verify}
     verify_obj = None
+    h_sig = torch.empty((n, m.SIG_LEN), dtype=torch.uint8).pin_memory()
+    h_msg = d_msg.cpu().pin_memory()
+    h_moff = d_moff.cpu().to(torch.int64).pin_memory()
     if not args.no_verify_leg:
+        h_pk = d_pk.cpu().pin_memory()
+        h_ok = torch.zeros(n, dtype=torch.uint8).pin_memory()
         vev = []
         for shared in (False, True):
             if shared:
@@ -341,19 +357,44 @@ def main():
                 ms = float(t.item())
             assert bool(d_ok.all().item())
             vops = verify_work(args.ps, n, shared)
-            vev.append({"keys": "shared" if shared else "distinct", "value": world * n / (ms * 1e-3),
-                        "unit": "verifies/s", "ms_per_step": ms,
-                        "int32_tops": vops / (ms * 1e-3) / 1e12, "frac_of_int32_peak": vops / (ms * 1e-3) / peaks["both"]})
-        verify_obj = {"value": vev[0]["value"], "unit": "verifies/s", "legs": vev}
+            leg = {"keys": "shared" if shared else "distinct", "value": world * n / (ms * 1e-3),
+                   "unit": "verifies/s", "ms_per_step": ms,
+                   "int32_tops": vops / (ms * 1e-3) / 1e12, "frac_of_int32_peak": vops / (ms * 1e-3) / peaks["both"]}
+            # the same leg end to end: host-pointer C-ABI call, pinned buffers, pk + msg + sig in, verdicts out
+            h_sig.copy_(d_sig)
+            torch.cuda.synchronize()
+
+            def verify_host():
+                _lib.check(L.mldsa_verify_batch(args.ps, local, 0, n, ptr(h_pk), stride, ptr(h_msg), ptr(h_moff), None,
+                                                None, ptr(h_sig), ptr(h_ok)))
+
+            verify_host()
+            barrier()
+            t0 = time.perf_counter()
+            vsteps = max(1, min(args.steps, 3))
+            for _ in range(vsteps):
+                verify_host()
+            barrier()
+            vs = (time.perf_counter() - t0) / vsteps
+            if world > 1:
+                t = torch.tensor([vs], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                vs = float(t.item())
+            assert bool(h_ok.all().item())
+            h2d = int((m.PK_LEN if shared else h_pk.numel()) + h_msg.numel() + h_moff.numel() * 8 + h_sig.numel())
+            leg["e2e"] = {"value": world * n / vs, "unit": "verifies/s", "ms_per_step": vs * 1e3,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_ok.numel()),
+                          "h2d_gbs": h2d / vs / 1e9, "host_buffers": "pinned", "api": "mldsa_verify_batch (host pointers)",
+                          "note": "PCIe-bound: the packed pk + sig bytes of a lane cross the link once"}
+            vev.append(leg)
+        verify_obj = {"value": vev[0]["value"], "unit": "verifies/s", "e2e": vev[0]["e2e"], "legs": vev}
+        del h_pk, h_ok
         # restore the distinct-key signatures for the e2e / oracle checks
         sign_dev()
 
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region
     h_sk = d_sk.cpu().pin_memory()
-    h_msg = d_msg.cpu().pin_memory()
     h_rnd = d_rnd.cpu().pin_memory()
-    h_moff = d_moff.cpu().to(torch.int64).pin_memory()
-    h_sig = torch.empty((n, m.SIG_LEN), dtype=torch.uint8).pin_memory()
     h_iters = torch.zeros(n, dtype=torch.int32).pin_memory()
 
     def sign_host():

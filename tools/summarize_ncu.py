@@ -89,12 +89,39 @@ def full(rep, out):
     out.write("\n")
 
 
+def traffic(rep, tag, lanes, ps):
+    """profiles/ncu_traffic.json: DRAM bytes per launch of the kernels whose launch covers exactly `lanes` units
+    (expand_a: keys, sign_key: keys), read by bench.py for roofline.traffic."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, data = rows[0], rows[2:]
+    dst = ROOT / "profiles" / "ncu_traffic.json"
+    rec = json.load(open(dst)) if dst.exists() else {}
+    for r in data:
+        name = short(r[hdr.index("Kernel Name")])
+        for key in ("expand_a", "sign_key"):
+            if name.startswith(key):
+                rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
+                wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
+                u = hdr.index("dram__bytes_read.sum")
+                unit = rows[1][u]
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+                wscale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[rows[1][hdr.index("dram__bytes_write.sum")]]
+                rec[f"{key}:{ps}"] = {"dram_read_bytes": rd * scale, "dram_write_bytes": wr * wscale, "units": lanes,
+                                      "source": f"profiles/{tag}.md (ncu --set full, {Path(rep).name}, {lanes} keys per launch)"}
+    json.dump(rec, open(dst, "w"), indent=1)
+    print(dst)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
     ap.add_argument("--launches")
     ap.add_argument("--rep")
     ap.add_argument("--note", default="")
+    ap.add_argument("--traffic-lanes", type=int, default=0, help="lanes per launch of the captured run: also write ncu_traffic.json")
+    ap.add_argument("--ps", type=int, default=65)
     a = ap.parse_args()
     dst = ROOT / "profiles" / f"{a.tag}.md"
     with open(dst, "w") as out:
@@ -104,3 +131,5 @@ if __name__ == "__main__":
         if a.rep:
             full(a.rep, out)
     print(dst)
+    if a.rep and a.traffic_lanes:
+        traffic(a.rep, a.tag, a.traffic_lanes, a.ps)
