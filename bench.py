@@ -403,21 +403,27 @@ def main():
 
     del d_ok
     sign_host()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    # every call is timed on its own (barrier on both sides); the reported step time is the MEDIAN of the calls:
+    # on the shared boxes one call in five is 30-50 ms slower for host-side reasons (all samples are in the line)
+    e2e_steps = max(3, args.steps)
+    e2e_samples = []
     for _ in range(e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
         sign_host()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_samples.append(dt)
+    e2e_s = float(np.median(e2e_samples))
     check["e2e_equals_device_resident"] = bool(torch.equal(h_sig, d_sig.cpu()))
     e2e = {"value": world * n / e2e_s, "unit": "signs/s",
            "h2d_bytes_per_step": int(h_sk.numel() + h_msg.numel() + h_rnd.numel() + h_moff.numel() * 8),
            "d2h_bytes_per_step": int(h_sig.numel() + h_iters.numel() * 4), "ms_per_step": e2e_s * 1e3,
+           "steps": e2e_steps, "step_ms_all": [round(x * 1e3, 2) for x in e2e_samples], "statistic": "median of the steps",
            "host_buffers": "pinned", "api": "mldsa_sign_batch (host pointers)"}
 
     cpu_baseline = None
