@@ -46,6 +46,11 @@ struct Tuning {
     int tail_slots;  // sign: candidate slots of the shared tail region (MLDSA_TAILSLOTS, default 32768)
 };
 Tuning tuning();
+// CTAs per SM of the grid-stride arithmetic (warp-per-lane) kernels.  6-10 are resident at a time; with 16 the last
+// wave ran a partly empty machine (measured, sign at 2^20 lanes: 16 -> 37.5 / 32.7 / 7.5 ms for sign_w / sign_z /
+// sign_key, 120-400 -> 35.8 / 30.6 / 6.8 ms, one CTA per unit -> 36.3 / 34.5 / 6.8 ms).  MLDSA_ACAP overrides.
+constexpr int ACAP_DEFAULT = 192;
+inline int arith_cap() { const int a = tuning().acap; return a > 0 ? a : ACAP_DEFAULT; }
 unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event pairs into the per-kernel totals (call after a stream sync)
 
 // ---- k_common.cu ----

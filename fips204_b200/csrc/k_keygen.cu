@@ -240,7 +240,7 @@ static cudaError_t sk_to_pk_run_t(cudaStream_t st, size_t n, const uint8_t* sk, 
     if (e != cudaSuccess) return e;
     {
         KLaunch kl(KID_SK2PK, st);
-        sk_to_pk_kernel<P><<<capped_grid((n + KG_WARPS - 1) / KG_WARPS, 16), KG_WARPS * 32, 0, st>>>(n, sk, ws.A, pk);
+        sk_to_pk_kernel<P><<<capped_grid((n + KG_WARPS - 1) / KG_WARPS, arith_cap()), KG_WARPS * 32, 0, st>>>(n, sk, ws.A, pk);
     }
     return cudaGetLastError();
 }
@@ -273,11 +273,7 @@ static cudaError_t keygen_run_t(cudaStream_t st, size_t n, const uint8_t* xi, ui
     }
     cudaError_t e = launch_expand_a(st, K, L, ws.seeds, 128, n, ws.A);
     if (e != cudaSuccess) return e;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t want = (n + KG_WARPS - 1) / KG_WARPS;
-    const unsigned grid = (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
+    const unsigned grid = capped_grid((n + KG_WARPS - 1) / KG_WARPS, arith_cap());
     {
         KLaunch kl(KID_KG_ARITH, st);
         kg_arith_kernel<P><<<grid, KG_WARPS * 32, 0, st>>>(n, ws.seeds, ws.s, ws.A, pk, sk);

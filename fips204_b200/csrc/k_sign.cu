@@ -70,10 +70,6 @@ sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, Msg
 }
 
 constexpr int SG_WARPS = 4;
-// CTAs per SM of the grid-stride arithmetic kernels (sign_key, sign_w, sign_z).  6-10 are resident at a time; with the
-// former 16 the last wave ran a partly empty machine (measured at 2^20 lanes: 16 -> 37.5 / 32.7 / 7.5 ms,
-// 120-400 -> 35.8 / 30.6 / 6.8 ms, one CTA per unit -> 36.3 / 34.5 / 6.8 ms).
-constexpr int ACAP_DEFAULT = 192;
 #ifndef SG_MINB
 #define SG_MINB 6   // sign_w: its shared memory (y-hat rows, staged A-hat row, NTT tile: 8.8 KB per warp) admits 6 CTAs per SM
 #endif
@@ -812,7 +808,7 @@ static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, 
     }
     {
         KLaunch kl(KID_SIGN_KEY, st);
-        sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : ACAP_DEFAULT), SG_WARPS * 32, 0, st>>>(
+        sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
             nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
     }
     return launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
@@ -844,7 +840,7 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
     const bool shared = r.shared;
     const uint32_t* nact = ws.nact + r.cur;
     const uint32_t* act = ws.act[r.cur];
-    auto warp_grid = [&](size_t items) { return capped_grid((items + SG_WARPS - 1) / SG_WARPS, tn.acap > 0 ? tn.acap : ACAP_DEFAULT); };
+    auto warp_grid = [&](size_t items) { return capped_grid((items + SG_WARPS - 1) / SG_WARPS, arith_cap()); };
     {
         KLaunch kl(KID_MASK, st);
         mask_kernel<P><<<capped_grid((sz * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(
@@ -857,7 +853,7 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
         if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
         else sign_w_kernel<P, false><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
     } else {
-        const int cap = tn.acap > 0 ? tn.acap : ACAP_DEFAULT;
+        const int cap = arith_cap();
         if (D % 2 == 0 && tn.stage == 2)
             ce = shared ? launch_sign_w_staged<P, true, 2>(st, wj, sz * D, cap) : launch_sign_w_staged<P, false, 2>(st, wj, sz * D, cap);
         else
