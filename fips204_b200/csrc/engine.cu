@@ -717,27 +717,70 @@ int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk
     int rc = OK;
     DeviceCtx* cx = lock_ctx(dev, lk, rc);
     if (!cx) return rc;
-    const size_t io_lane = 32 + p.pk + p.sk;
-    const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, keygen_ws_bytes(p, 1024) / 1024 + io_lane + 1);
-    const size_t io = pad256(chunk * 32) + pad256(chunk * p.pk) + pad256(chunk * p.sk);
-    rc = cx->reserve(io + keygen_ws_bytes(p, chunk));
+    // Keygen is copy-OUT bound (32 bytes in, pk + sk = 3.9 / 6.0 / 7.5 KB out per key against ~60 ns of compute),
+    // so the chunks' kernels run ahead on the work stream and the copy-out stream never idles: NS output staging
+    // sets, one workspace (kernels are stream-ordered), no host wait until the end.
+    constexpr size_t NS = SIGN_SETS;
+    const size_t io_lane = NS * (32 + p.pk + p.sk);
+    size_t chunk = pick_chunk(cx->arena_bytes, n, 65536, keygen_ws_bytes(p, 1024) / 1024 + io_lane + 1);
+    if (n >= (size_t(1) << 17) && chunk > (n + 15) / 16) chunk = (n + 15) / 16;  // >= 16 chunks: short fill and drain
+    const size_t set_bytes = pad256(chunk * 32) + pad256(chunk * p.pk) + pad256(chunk * p.sk);
+    rc = cx->reserve(NS * set_bytes + keygen_ws_bytes(p, chunk));
     if (rc) return rc;
-    cudaStream_t st = cx->stream;
-    for (size_t lo = 0; lo < n; lo += chunk) {
-        const size_t m = n - lo < chunk ? n - lo : chunk;
-        Carver c(cx->arena);
-        uint8_t* d_xi = c.take<uint8_t>(chunk * 32);
-        uint8_t* d_pk = c.take<uint8_t>(chunk * p.pk);
-        uint8_t* d_sk = c.take<uint8_t>(chunk * p.sk);
-        CK(cudaMemcpyAsync(d_xi, xi + 32 * lo, m * 32, cudaMemcpyHostToDevice, st));
-        rc = keygen_core(*cx, st, ps, m, d_xi, d_pk, d_sk, io);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(pk + p.pk * lo, d_pk, m * p.pk, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(sk + p.sk * lo, d_sk, m * p.sk, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemsetAsync(d_xi, 0, m * 32, st));
-        CK(cudaMemsetAsync(d_sk, 0, m * p.sk, st));
-        CK(cudaStreamSynchronize(st));
+    struct Set {
+        uint8_t *xi, *pk, *sk;
+    } set[NS];
+    Carver c(cx->arena);
+    for (auto& s : set) {
+        s.xi = c.take<uint8_t>(chunk * 32);
+        s.pk = c.take<uint8_t>(chunk * p.pk);
+        s.sk = c.take<uint8_t>(chunk * p.sk);
     }
+    uint8_t* const ws_base = cx->arena + c.off;
+    cudaStream_t st = cx->stream;
+    cudaEvent_t* ev_cmp = cx->ev_bulk;
+    auto drain = [&](int code) -> int {
+        const std::string err = t_cuda_err;
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(cx->s_out);
+        for (auto& s : set) {
+            cudaMemsetAsync(s.xi, 0, chunk * 32, st);
+            cudaMemsetAsync(s.sk, 0, chunk * p.sk, st);
+        }
+        cudaMemsetAsync(ws_base, 0, keygen_ws_bytes(p, chunk), st);
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
+        prof_collect();
+        t_cuda_err = err;
+        return code;
+    };
+    auto enqueue = [&](size_t i, size_t lo, size_t m) -> int {
+        Set& s = set[i % NS];
+        if (i >= NS) CK(cudaStreamWaitEvent(st, cx->ev_out[i % NS], 0));  // the set's previous keys are on the host
+        CK(cudaMemcpyAsync(s.xi, xi + 32 * lo, m * 32, cudaMemcpyHostToDevice, st));
+        Carver wc(ws_base);
+        const KeygenWs ws = keygen_carve(wc, p, m);
+        CK(keygen_run(ps, st, m, s.xi, s.pk, s.sk, ws));
+        // xi, rho', K, s1, s2 are secret: zero the scratch (mirrors ZeroizeOnDrop, src/types.rs:19)
+        CK(cudaMemsetAsync(s.xi, 0, m * 32, st));
+        CK(cudaMemsetAsync(ws.seeds, 0, m * 128, st));
+        CK(cudaMemsetAsync(ws.s, 0, m * (size_t)(p.K + p.L) * 256, st));
+        CK(cudaEventRecord(ev_cmp[i % NS], st));
+        CK(cudaStreamWaitEvent(cx->s_out, ev_cmp[i % NS], 0));
+        CK(cudaMemcpyAsync(pk + p.pk * lo, s.pk, m * p.pk, cudaMemcpyDeviceToHost, cx->s_out));
+        CK(cudaMemcpyAsync(sk + p.sk * lo, s.sk, m * p.sk, cudaMemcpyDeviceToHost, cx->s_out));
+        CK(cudaMemsetAsync(s.sk, 0, m * p.sk, cx->s_out));
+        CK(cudaEventRecord(cx->ev_out[i % NS], cx->s_out));
+        return OK;
+    };
+    CK(cudaStreamSynchronize(cx->s_out));
+    size_t i = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, i++)
+        if ((rc = enqueue(i, lo, n - lo < chunk ? n - lo : chunk))) return drain(rc);
+    cudaError_t e = cudaStreamSynchronize(cx->s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return drain(cuda_fail(e, "keygen pipeline"));
+    prof_collect();
     return OK;
 }
 
