@@ -34,6 +34,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 PS = 65
 MSG_LEN = 32
+_JSON_OUT = sys.stdout
 # SURVEY.md 8(d) conversion constants (algorithmic int32 ops)
 KECCAK_F, NTT_OPS, INTT_OPS, MAC_OPS = 4320, 6144, 7168, 5
 PARAMS = {44: dict(K=4, L=4, ct_blocks=7, zbytes=576, w1=768, pk=1312, sk=2560, sig=2420, tr_blocks=10),
@@ -59,6 +60,8 @@ def parse():
 # clocks sampler (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class Clocks:
+    # One sample per 400 ms: every NVML query can stall a launch or a sync of the sampled GPU for several ms
+    # (tools/smi_probe.py: 164 ms steps become 170-190 ms when a query lands in them), so the sampler is kept sparse.
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -69,7 +72,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "400", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -170,7 +173,8 @@ def reference_arm(args, rank, world):
         "verify": {"value": sample / tv, "unit": "verifies/s", "keys": "distinct"},
         "gpu_launches": 0, "mean_iters": float(iters.mean()),
     }
-    print(json.dumps(line), flush=True)
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def workload_config(args, lanes):
@@ -182,6 +186,12 @@ def workload_config(args, lanes):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under torchrun)
+    # are sent to stderr for the duration of the run
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -466,7 +476,8 @@ def main():
             "int32_peaks_tops": {k: v / 1e12 for k, v in peaks.items()},
             "kernels": kernels, "check": check,
         }
-        print(json.dumps(line), flush=True)
+        _JSON_OUT.write(json.dumps(line) + "\n")
+        _JSON_OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
