@@ -45,6 +45,7 @@ SIGNATURES = {
     "mldsa_set_tuning": (None, [C.c_int, C.c_int, C.c_int]),
     "mldsa_set_depth": (None, [C.c_int]),
     "mldsa_set_tail": (None, [C.c_int, C.c_int]),
+    "mldsa_debug_secret_residue": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mldsa_set_pairing": (None, [C.c_int, C.c_int]),
     "mldsa_kernel_launches": (C.c_uint64, []),
     "mldsa_last_sign_rounds": (C.c_int, []),

@@ -178,6 +178,44 @@ struct DeviceCtx {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     uint32_t* mailbox = nullptr;  // mapped pinned memory, 16 control words per sign workspace
+    // device ranges that held secret-derived data during the most recent keygen / sign call on this device; all of
+    // them must read as zero once the call has returned (mldsa_debug_secret_residue)
+    std::vector<std::pair<const uint8_t*, size_t>> secret_ranges;
+    std::vector<int> secret_slot;  // pipeline slot of each range: a later chunk in the same slot replaces the entries
+    int cur_slot = 0;
+    void begin_slot(int slot)
+    {
+        cur_slot = slot;
+        for (size_t i = secret_ranges.size(); i-- > 0;)
+            if (secret_slot[i] == slot) {
+                secret_ranges.erase(secret_ranges.begin() + (long)i);
+                secret_slot.erase(secret_slot.begin() + (long)i);
+            }
+    }
+    void clear_secrets()
+    {
+        secret_ranges.clear();
+        secret_slot.clear();
+        cur_slot = 0;
+    }
+    void note_secret(const void* p, size_t bytes)
+    {
+        if (p && bytes) {
+            secret_ranges.emplace_back(static_cast<const uint8_t*>(p), bytes);
+            secret_slot.push_back(cur_slot);
+        }
+    }
+    // the secret-derived arrays of a sign workspace, for the n lanes a chunk used (K, L, zbits: parameter set)
+    void note_sign_ws(const SignWs& w, size_t n, bool shared, int K, int L, int zbits)
+    {
+        const size_t nk = shared ? 1 : n, D = (size_t)w.depth;
+        note_secret(w.s1h, nk * (size_t)L * 1024);
+        note_secret(w.s2h, nk * (size_t)K * 1024);
+        note_secret(w.t0h, nk * (size_t)K * 1024);
+        note_secret(w.w, n * D * K * 1024);                 // w - c*s2
+        note_secret(w.yraw, n * D * L * 32 * (size_t)zbits);  // y
+        note_secret(w.rhopp, n * 64);
+    }
 
     int init(int d)
     {
@@ -349,10 +387,14 @@ static int keygen_core(DeviceCtx& cx, cudaStream_t st, int ps, size_t n, const u
     const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip, per_lane);
     int rc = cx.reserve(arena_skip + keygen_ws_bytes(p, chunk), arena_skip);
     if (rc) return rc;
+    cx.clear_secrets();
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
         Carver c(cx.arena + arena_skip);
-        KeygenWs ws = keygen_carve(c, p, m);
+        KeygenWs ws = keygen_carve(c, p, chunk);  // same layout for every chunk
+        cx.begin_slot(0);
+        cx.note_secret(ws.seeds, m * 128);
+        cx.note_secret(ws.s, m * (size_t)(p.K + p.L) * 256);
         CK(keygen_run(ps, st, m, d_xi + 32 * lo, d_pk + p.pk * lo, d_sk + p.sk * lo, ws));
         // rho', K, s1, s2 are secret: zero the scratch (mirrors ZeroizeOnDrop, src/types.rs:19)
         CK(cudaMemsetAsync(ws.seeds, 0, m * 128, st));
@@ -420,10 +462,13 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
     int rc = cx.reserve(arena_skip + sign_ws_bytes(p, chunk, shared), arena_skip);
     if (rc) return rc;
     t_last_rounds = 0;
+    cx.clear_secrets();
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
         Carver c(cx.arena + arena_skip);
-        SignWs ws = sign_carve(c, p, m, shared, cx.mailbox);
+        SignWs ws = sign_carve(c, p, chunk, shared, cx.mailbox);  // same layout for every chunk
+        cx.begin_slot(0);
+        cx.note_sign_ws(ws, m, shared, p.K, p.L, p.zbits);
         MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
         SignRun run;
         cudaError_t e = sign_begin(ps, st, m, d_sk + sk_stride * lo, sk_stride, md, d_rnd + 32 * lo, d_sig + p.sig * lo,
@@ -644,6 +689,39 @@ int mldsa_int32_peak_probe(int mode, double* ops_per_sec)
 }
 int mldsa_last_sign_rounds(void) { return t_last_rounds; }
 
+// Test hook for the ZeroizeOnDrop analogue (src/types.rs:19): bytes that are not zero in the device ranges which held
+// secret-derived data (staged sk / xi / rnd, rho', K, s1, s2, their NTT images, y, w - c*s2, rho'') during the most
+// recent keygen or sign call on `dev`.  Must be 0 after every call, successful or not.
+int mldsa_debug_secret_residue(int dev, uint64_t* nonzero_bytes, uint64_t* scanned_bytes)
+{
+    if (!nonzero_bytes) return E_PARAM;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    unsigned long long* d_cnt = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_cnt), 8));
+    CK(cudaMemsetAsync(d_cnt, 0, 8, cx->stream));
+    uint64_t scanned = 0;
+    for (auto& r : cx->secret_ranges) {
+        if (r.first < cx->arena || r.first + r.second > cx->arena + cx->arena_bytes) continue;  // arena was re-made
+        cudaError_t e = launch_count_nonzero(cx->stream, r.first, r.second, d_cnt);
+        if (e != cudaSuccess) {
+            cudaFree(d_cnt);
+            return cuda_fail(e, "count_nonzero");
+        }
+        scanned += r.second;
+    }
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, cx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cx->stream);
+    cudaFree(d_cnt);
+    if (e != cudaSuccess) return cuda_fail(e, "secret residue");
+    *nonzero_bytes = h;
+    if (scanned_bytes) *scanned_bytes = scanned;
+    return OK;
+}
+
 // ---------------------------------------------------------------- device-pointer entry points
 int mldsa_keygen_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_xi, uint8_t* d_pk, uint8_t* d_sk)
 {
@@ -749,6 +827,20 @@ int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk
         s.sk = c.take<uint8_t>(chunk * p.sk);
     }
     uint8_t* const ws_base = cx->arena + c.off;
+    cx->clear_secrets();
+    size_t used[NS] = {};  // most lanes any chunk put into each set (only what this call touched is registered)
+    auto note_used = [&]() {
+        size_t most = 0;
+        for (size_t k = 0; k < NS; k++) {
+            cx->note_secret(set[k].xi, used[k] * 32);
+            cx->note_secret(set[k].sk, used[k] * p.sk);
+            if (used[k] > most) most = used[k];
+        }
+        Carver wc(ws_base);
+        const KeygenWs w0 = keygen_carve(wc, p, chunk);
+        cx->note_secret(w0.seeds, most * 128);
+        cx->note_secret(w0.s, most * (size_t)(p.K + p.L) * 256);
+    };
     cudaStream_t st = cx->stream;
     cudaEvent_t* ev_cmp = cx->ev_bulk;
     auto drain = [&](int code) -> int {
@@ -763,15 +855,17 @@ int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk
         cudaStreamSynchronize(st);
         cudaGetLastError();
         prof_collect();
+        note_used();
         t_cuda_err = err;
         return code;
     };
     auto enqueue = [&](size_t i, size_t lo, size_t m) -> int {
         Set& s = set[i % NS];
+        if (m > used[i % NS]) used[i % NS] = m;
         if (i >= NS) CK(cudaStreamWaitEvent(st, cx->ev_out[i % NS], 0));  // the set's previous keys are on the host
         CK(cudaMemcpyAsync(s.xi, xi + 32 * lo, m * 32, cudaMemcpyHostToDevice, st));
         Carver wc(ws_base);
-        const KeygenWs ws = keygen_carve(wc, p, m);
+        const KeygenWs ws = keygen_carve(wc, p, chunk);  // same layout for every chunk
         CK(keygen_run(ps, st, m, s.xi, s.pk, s.sk, ws));
         // xi, rho', K, s1, s2 are secret: zero the scratch (mirrors ZeroizeOnDrop, src/types.rs:19)
         CK(cudaMemsetAsync(s.xi, 0, m * 32, st));
@@ -793,6 +887,7 @@ int mldsa_keygen_batch(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return drain(cuda_fail(e, "keygen pipeline"));
     prof_collect();
+    note_used();
     return OK;
 }
 
@@ -910,6 +1005,7 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     }
     uint8_t* ws_base[NS];
     for (size_t k = 0; k < NS; k++) ws_base[k] = cx->arena + c.off + k * ws_bytes;
+    cx->clear_secrets();
     cudaStream_t B = cx->stream, T = cx->s_tail;
     // the bulk rounds stop when about this many lanes are expected to be live: below it the kernels no longer fill
     // the device and a round costs its (fixed) latency
@@ -970,10 +1066,14 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
             cmo = s.po;
         }
         Carver wc(ws_base[i % NS]);
-        const SignWs ws = sign_carve(wc, p, m, shared, cx->mailbox + 16 * (i % NS));
+        const SignWs ws = sign_carve(wc, p, C, shared, cx->mailbox + 16 * (i % NS));  // same layout for every chunk
         const MsgDesc md{cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, framing};
         lanes_of[i % NS] = m;
         started[i % NS] = true;
+        cx->begin_slot((int)(i % NS));  // (a later chunk re-carves the slot: only its ranges are meaningful)
+        cx->note_sign_ws(ws, m, shared, p.K, p.L, p.zbits);
+        cx->note_secret(s.sk, shared ? p.sk : m * p.sk);
+        cx->note_secret(s.rnd, m * 32);
         cudaError_t e = sign_begin(ps, B, m, s.sk, sk_stride, md, s.rnd, s.sig, s.it, ws, tail_lanes, &run[i % NS]);
         if (e != cudaSuccess) return run[i % NS].ctx_err ? E_CTX : cuda_fail(e, "sign_begin");
         CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, B));  // secrets do not linger in the staging set

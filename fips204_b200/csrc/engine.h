@@ -69,6 +69,8 @@ cudaError_t launch_keccak_probe(cudaStream_t st, int variant, int blocks, int re
 // HashML-DSA: out rows = OID || PH(M_i) with out_off[i] = i * PREHASH_STRIDE .. (message framing 2)
 cudaError_t launch_prehash(cudaStream_t st, int ph, size_t n, const uint8_t* msgs, const uint64_t* msg_off,
                            uint8_t* out, uint64_t* out_off);
+// *count += number of non-zero bytes in [p, p + bytes)   (test hook: secret residue scan)
+cudaError_t launch_count_nonzero(cudaStream_t st, const uint8_t* p, size_t bytes, unsigned long long* count);
 cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops);
 // A[key][r*L+s][256] = RejNTTPoly(rho_key || s || r)          (src/hashing.rs:225-239)
 cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, size_t rho_stride, size_t nkeys,

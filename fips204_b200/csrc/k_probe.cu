@@ -42,4 +42,33 @@ cudaError_t launch_keccak_probe(cudaStream_t st, int variant, int blocks, int re
     return cudaGetLastError();
 }
 
+// Test hook: count the non-zero bytes of a device range (the ranges that held secrets must be all zero after a call).
+__global__ void count_nonzero_kernel(const uint8_t* __restrict__ p, size_t bytes, unsigned long long* __restrict__ count)
+{
+    unsigned long long local = 0;
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;  // bytes before the first aligned int4
+    const size_t nvec = bytes > head ? (bytes - head) / 16 : 0;
+    const int4* v = reinterpret_cast<const int4*>(p + head);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 x = v[i];
+        if (x.x | x.y | x.z | x.w) {
+            const uint32_t w[4] = {(uint32_t)x.x, (uint32_t)x.y, (uint32_t)x.z, (uint32_t)x.w};
+            for (int k = 0; k < 4; k++)
+                for (int b = 0; b < 4; b++) local += ((w[k] >> (8 * b)) & 0xFF) != 0;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t i = 0; i < (head < bytes ? head : bytes); i++) local += p[i] != 0;
+        for (size_t i = head + nvec * 16; i < bytes; i++) local += p[i] != 0;
+    }
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+cudaError_t launch_count_nonzero(cudaStream_t st, const uint8_t* p, size_t bytes, unsigned long long* count)
+{
+    if (bytes == 0) return cudaSuccess;
+    count_nonzero_kernel<<<148 * 8, 256, 0, st>>>(p, bytes, count);
+    return cudaGetLastError();
+}
+
 }  // namespace mldsa

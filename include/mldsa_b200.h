@@ -145,6 +145,11 @@ void mldsa_set_tail(int tail_depth, int tail_slots);
  * staggered by one stage, each launch executing a Keccak stage of one half beside an arithmetic stage of the other on
  * the same SMs; kshare (1..4, default 2, MLDSA_KSHARE) = CTAs out of 5 per SM that prefer the Keccak queue. */
 void mldsa_set_pairing(int pair, int kshare);
+/* test hook for the ZeroizeOnDrop analogue (src/types.rs:19-41): number of non-zero bytes left in the device ranges
+ * that held secret-derived data (staged xi / sk / rnd, rho', K, s1, s2 and their NTT images, y, w - c*s2, rho'')
+ * during the most recent keygen or sign call on `dev`; *scanned_bytes (optional) = size of those ranges.  0 after
+ * every call, successful or not. */
+int mldsa_debug_secret_residue(int dev, uint64_t* nonzero_bytes, uint64_t* scanned_bytes);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */

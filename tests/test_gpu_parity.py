@@ -429,3 +429,39 @@ def test_sign_tail_rounds_speculate_deeper(F, ps):
         assert m.verify_batch(pks, msgs, sig).all()
     finally:
         L.mldsa_set_tail(8, 32768)
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_no_secret_residue_on_device(F, ps):
+    """ZeroizeOnDrop analogue (src/types.rs:19-41): once keygen / sign has returned, every device range that held
+    secret-derived data (staged xi / sk / rnd, rho', K, s1, s2 and their NTT images, y, w - c*s2, rho'') reads as
+    zero -- for distinct and shared keys, one and many chunks, and with the deeper tail rounds in their shared slots."""
+    import ctypes as C
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    m = F.PARAM_SETS[ps]
+
+    def residue():
+        nz, sc = C.c_uint64(), C.c_uint64()
+        _lib.check(L.mldsa_debug_secret_residue(0, C.byref(nz), C.byref(sc)))
+        assert sc.value > 0, "no secret ranges were registered"
+        return nz.value
+
+    n = 3000
+    xi = synth_block(f"zk{ps}", n, 32)
+    pks, sks = m.keygen_batch(xi)
+    assert residue() == 0
+    msgs = [synth("zm", i, i % 60) for i in range(n)]
+    rnds = synth_rows("zr", n, 32)
+    try:
+        for tail_depth, slots, limit in ((8, 32768, 0), (16, 2048, 0), (0, 0, 0), (16, 1024, 48 << 20)):
+            L.mldsa_set_tail(tail_depth, slots)
+            L.mldsa_set_workspace_limit(limit)
+            sig = m.sign_batch(sks, msgs, rnds)
+            assert residue() == 0, (ps, tail_depth, slots, limit)
+            one = m.sign_batch(sks[3].tobytes(), msgs, rnds, shared_key=True)
+            assert residue() == 0, (ps, tail_depth, slots, limit, "shared")
+        assert m.verify_batch(pks, msgs, sig).all() and m.verify_batch(pks[3].tobytes(), msgs, one, shared_key=True).all()
+    finally:
+        L.mldsa_set_tail(8, 32768)
+        L.mldsa_set_workspace_limit(0)
