@@ -21,6 +21,7 @@ Error behaviour follows the reference: signing with |ctx| > 255 raises ValueErro
 too long") (lib.rs:274), an RNG failure raises ValueError("... random number generator failed")
 (lib.rs:283, ml_dsa.rs:41), verify never raises for malformed input and returns False (lib.rs:368-370).
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -252,6 +253,14 @@ class _ParamSet:
     def hash_verify_batch(self, pks, msgs, sigs, ph, **kw):
         return self.verify_batch(pks, msgs, sigs, ph=ph, **kw)
 
+    def load_private_keys(self, sks, dev=0):
+        """n x SK_LEN packed keys -> PrivateKeySet: the keys expanded once (PrivateKey::try_from_bytes ->
+        expand_private, lib.rs:462-468, ml_dsa.rs:445-469) and resident in HBM for any number of sign calls."""
+        sk = _u8(sks).reshape(-1, self.SK_LEN)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mldsa_sk_load(self.PS, dev, sk.shape[0], _ptr(sk), C.byref(h)))
+        return PrivateKeySet(self, h)
+
     def sk_to_pk_batch(self, sks, dev=0):
         """Signer::get_public_key over a batch: n x SK_LEN -> pk[n, PK_LEN] (ml_dsa.rs:502-563)."""
         sk = _u8(sks).reshape(-1, self.SK_LEN)
@@ -280,6 +289,58 @@ class _ParamSet:
         _lib.check(fn(self.PS, dev, framing if ph is None else int(ph), n, _ptr(pk), 0 if shared_key else self.PK_LEN,
                       _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(sg), _ptr(ok)))
         return ok
+
+
+class PrivateKeySet:
+    """Expanded secret keys resident on the device (mldsa_sk_load); zeroized by free() / on garbage collection
+    (ZeroizeOnDrop, types.rs:19)."""
+
+    def __init__(self, mod, handle):
+        self._mod, self._h = mod, handle
+
+    def __len__(self):
+        return int(_lib.lib().mldsa_keyset_size(self._h)) if self._h else 0
+
+    @property
+    def device_bytes(self):
+        return int(_lib.lib().mldsa_keyset_device_bytes(self._h)) if self._h else 0
+
+    def sign_batch(self, msgs, rnds, ctxs=None, key_idx=None, framing=0, want_iters=False):
+        """Lane i signs msgs[i] with key key_idx[i] (default: key i).  Same bytes as _ParamSet.sign_batch."""
+        if not self._h:
+            raise ValueError("key set was freed")
+        m, n = self._mod, len(msgs)
+        rnd = _u8(rnds)
+        if rnd.size != 32 * n:
+            raise ValueError("rnd must be n x 32 bytes")
+        mb, mo = _ragged(msgs, np.uint64)
+        cb = co = None
+        if ctxs is not None:
+            if any(len(c) > 255 for c in ctxs):
+                raise ValueError("ML-DSA.Sign: ctx too long")
+            cb, co = _ragged(ctxs, np.uint32)
+        ki = None if key_idx is None else np.ascontiguousarray(key_idx, dtype=np.uint32)
+        if ki is not None and ki.size != n:
+            raise ValueError("key_idx must have n entries")
+        sig = np.empty((n, m.SIG_LEN), dtype=np.uint8)
+        iters = np.zeros(n, dtype=np.uint32)
+        rc = _lib.lib().mldsa_sign_batch_keys(self._h, framing, n, _ptr(ki), _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co),
+                                              _ptr(rnd), _ptr(sig), _ptr(iters))
+        if rc == -2:
+            raise ValueError("ML-DSA.Sign: ctx too long")
+        _lib.check(rc)
+        return (sig, iters) if want_iters else sig
+
+    def free(self):
+        if self._h:
+            _lib.lib().mldsa_keyset_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 ml_dsa_44 = _ParamSet(44, 4, 4, 1312, 2560, 2420)

@@ -45,6 +45,12 @@ SIGNATURES = {
     "mldsa_set_tuning": (None, [C.c_int, C.c_int, C.c_int]),
     "mldsa_set_depth": (None, [C.c_int]),
     "mldsa_set_tail": (None, [C.c_int, C.c_int]),
+    "mldsa_sk_load": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mldsa_keyset_size": (C.c_size_t, [C.c_void_p]),
+    "mldsa_keyset_device_bytes": (C.c_size_t, [C.c_void_p]),
+    "mldsa_keyset_free": (None, [C.c_void_p]),
+    "mldsa_sign_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mldsa_debug_secret_residue": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mldsa_set_pairing": (None, [C.c_int, C.c_int]),
     "mldsa_kernel_launches": (C.c_uint64, []),

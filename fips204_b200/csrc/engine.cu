@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -269,6 +270,18 @@ struct DeviceCtx {
 constexpr int MAX_DEV = 64;
 static DeviceCtx g_ctx[MAX_DEV];
 
+// A set of secret keys expanded once and kept in HBM (mldsa_sk_load): what the reference's PrivateKey struct caches
+// (s1-hat, s2-hat, t0-hat, K, tr; src/types.rs:19-28, built by expand_private, src/ml_dsa.rs:445-469) plus A-hat, which
+// the reference re-derives from rho on every sign (src/ml_dsa.rs:181).  Own allocation, not part of the arena.
+struct KeySet {
+    uint32_t magic = 0x4B534554;  // "KSET"
+    int ps = 0, dev = 0;
+    size_t n = 0, bytes = 0;
+    uint8_t* base = nullptr;
+    int32_t *A = nullptr, *s1h = nullptr, *s2h = nullptr, *t0h = nullptr;
+    uint8_t* mini = nullptr;  // [n][128] rho || K || tr
+};
+
 // bump allocator over the arena, 256-byte granules
 struct Carver {
     uint8_t* base;
@@ -328,16 +341,17 @@ static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n, bool shared)
     w.pre_ok = c.take<uint8_t>(n);
     return w;
 }
-static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared)
+// resident: A-hat and the s-hat rows live in a loaded key set (mldsa_sk_load), not in the workspace
+static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared, bool resident = false)
 {
-    const size_t nk = shared ? 1 : n, D = (size_t)tuning().depth;
+    const size_t nk = resident ? 0 : (shared ? 1 : n), D = (size_t)tuning().depth;
     return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
            pad256(n * D * p.K * 1024) + pad256(n * D * p.L * 32 * p.zbits) + pad256(n * D * (64 + p.w1len)) +
            2 * pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64) + pad256(2 * 2048 * 4);
 }
-static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox)
+static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox, bool resident = false)
 {
-    const size_t nk = shared ? 1 : n, D = (size_t)tuning().depth;
+    const size_t nk = resident ? 0 : (shared ? 1 : n), D = (size_t)tuning().depth;
     SignWs w;
     w.depth = (int)D;
     w.A = c.take<int32_t>(nk * (size_t)p.K * p.L * 256);
@@ -951,16 +965,26 @@ static ChunkPlan plan_chunks(size_t arena_bytes, size_t n, size_t fixed, size_t 
 }  // extern "C"
 
 // ph < 0: plain ML-DSA with `framing`; ph = 0/1/2: HashML-DSA with SHA-256 / SHA-512 / SHAKE128 pre-hash
+// ks != nullptr: the keys are a resident key set; lane i signs with key key_idx[i] (nullptr: key i), sk is unused
 static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8_t* sk, size_t sk_stride,
                      const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
-                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters)
+                     const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const KeySet* ks = nullptr,
+                     const uint32_t* key_idx = nullptr)
 {
     PSInfo p;
     if (!ps_info(ps, p) || (framing != 0 && framing != 1) || ph > 2) return E_PARAM;
     if (ph >= 0) framing = 2;
-    if (sk_stride != 0 && sk_stride != p.sk) return E_PARAM;
-    if (n && (!sk || !rnd || !sig || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
+    if (!ks && sk_stride != 0 && sk_stride != p.sk) return E_PARAM;
+    if (n && ((!ks && !sk) || !rnd || !sig || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
     if (n == 0) return OK;
+    if (ks) {
+        if (ks->ps != ps || ks->dev != dev) return E_PARAM;
+        if (!key_idx && n > ks->n) return E_PARAM;
+        if (key_idx)
+            for (size_t i = 0; i < n; i++)
+                if (key_idx[i] >= ks->n) return E_PARAM;
+        sk_stride = 128;
+    }
     if (ctx_off)
         for (size_t i = 0; i < n; i++)
             if (ctx_off[i + 1] - ctx_off[i] > 255) return E_CTX;  // src/lib.rs:274
@@ -968,15 +992,17 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     int rc = OK;
     DeviceCtx* cx = lock_ctx(dev, lk, rc);
     if (!cx) return rc;
-    const bool shared = sk_stride == 0;
+    const bool shared = sk_stride == 0, resident = ks != nullptr;
+    const size_t sk_lane = resident ? (key_idx ? 4 : 0) : p.sk;  // staged bytes per lane: packed sk, or a key index
     const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
     const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
     // NS sets of staged inputs / outputs AND rejection-loop workspaces: chunk i's tail rounds and its copy-out run
     // under the bulk rounds of chunks i+1 and i+2
     constexpr size_t NS = SIGN_SETS;
-    const size_t fixed = NS * (sign_ws_bytes(p, 0, shared) + 4096) + (shared ? NS * pad256(p.sk) : 0) + 65536;
-    const size_t ws_lane = NS * ((sign_ws_bytes(p, 1024, shared) - (shared ? sign_ws_bytes(p, 0, true) : 0)) / 1024 + 1);
-    const size_t io_lane = NS * ((shared ? 0 : p.sk) + 32 + p.sig + 4 + 8 + 4 + avg_msg + avg_ctx + PREHASH_STRIDE + 8);
+    const size_t fixed = NS * (sign_ws_bytes(p, 0, shared, resident) + 4096) + (shared ? NS * pad256(p.sk) : 0) + 65536;
+    const size_t ws_lane =
+        NS * ((sign_ws_bytes(p, 1024, shared, resident) - (shared ? sign_ws_bytes(p, 0, true) : sign_ws_bytes(p, 0, false, resident))) / 1024 + 1);
+    const size_t io_lane = NS * ((shared ? 0 : sk_lane) + 32 + p.sig + 4 + 8 + 4 + avg_msg + avg_ctx + PREHASH_STRIDE + 8);
     const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
     const size_t C = pl.max_lanes, N = pl.nchunks();
     struct Set {
@@ -984,15 +1010,16 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         uint32_t *it, *co;
         uint64_t *mo, *po;
     } set[NS];
-    const size_t set_bytes = pad256(shared ? p.sk : C * p.sk) + pad256(C * 32) + pad256(C * p.sig) + pad256(C * 4) +
+    const size_t sk_set = shared ? p.sk : C * sk_lane + 16;
+    const size_t set_bytes = pad256(sk_set) + pad256(C * 32) + pad256(C * p.sig) + pad256(C * 4) +
                              pad256((C + 1) * 8) + pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) +
                              pad256(pl.max_cbytes + 8) + pad256(C * PREHASH_STRIDE) + pad256((C + 1) * 8);
-    const size_t ws_bytes = pad256(sign_ws_bytes(p, C, shared)) + 4096;
+    const size_t ws_bytes = pad256(sign_ws_bytes(p, C, shared, resident)) + 4096;
     rc = cx->reserve(NS * (set_bytes + ws_bytes));
     if (rc) return rc;
     Carver c(cx->arena);
     for (auto& s : set) {
-        s.sk = c.take<uint8_t>(shared ? p.sk : C * p.sk);
+        s.sk = c.take<uint8_t>(sk_set);  // packed secret keys -- or, for a resident key set, the lanes' key indices
         s.rnd = c.take<uint8_t>(C * 32);
         s.sig = c.take<uint8_t>(C * p.sig);
         s.it = c.take<uint32_t>(C);
@@ -1036,7 +1063,10 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
         if (i >= NS) CK(cudaStreamWaitEvent(cx->s_in, cx->ev_bulk[i % NS], 0));  // the previous user of this set has consumed its inputs
         mark(i, TR_IN0, cx->s_in);
-        CK(cudaMemcpyAsync(s.sk, sk + sk_stride * lo, shared ? p.sk : m * p.sk, cudaMemcpyHostToDevice, cx->s_in));
+        if (!resident)
+            CK(cudaMemcpyAsync(s.sk, sk + sk_stride * lo, shared ? p.sk : m * p.sk, cudaMemcpyHostToDevice, cx->s_in));
+        else if (key_idx)
+            CK(cudaMemcpyAsync(s.sk, key_idx + lo, m * 4, cudaMemcpyHostToDevice, cx->s_in));
         CK(cudaMemcpyAsync(s.rnd, rnd + 32 * lo, m * 32, cudaMemcpyHostToDevice, cx->s_in));
         CK(cudaMemcpyAsync(s.mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, cx->s_in));
         if (mbytes) CK(cudaMemcpyAsync(s.m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, cx->s_in));
@@ -1066,17 +1096,33 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
             cmo = s.po;
         }
         Carver wc(ws_base[i % NS]);
-        const SignWs ws = sign_carve(wc, p, C, shared, cx->mailbox + 16 * (i % NS));  // same layout for every chunk
+        SignWs ws = sign_carve(wc, p, C, shared, cx->mailbox + 16 * (i % NS), resident);  // same layout for every chunk
         const MsgDesc md{cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, framing};
         lanes_of[i % NS] = m;
         started[i % NS] = true;
         cx->begin_slot((int)(i % NS));  // (a later chunk re-carves the slot: only its ranges are meaningful)
-        cx->note_sign_ws(ws, m, shared, p.K, p.L, p.zbits);
-        cx->note_secret(s.sk, shared ? p.sk : m * p.sk);
+        const uint8_t* key_rows = s.sk;
+        if (resident) {
+            // lanes [lo, lo + m) use keys key_idx[lo ..] -- or keys lo .. lo + m - 1 of the set
+            const size_t k0 = key_idx ? 0 : lo;
+            ws.keys_resident = true;
+            ws.kidx = key_idx ? reinterpret_cast<const uint32_t*>(s.sk) : nullptr;
+            ws.A = ks->A + k0 * (size_t)p.K * p.L * 256;
+            ws.s1h = ks->s1h + k0 * (size_t)p.L * 256;
+            ws.s2h = ks->s2h + k0 * (size_t)p.K * 256;
+            ws.t0h = ks->t0h + k0 * (size_t)p.K * 256;
+            key_rows = ks->mini + k0 * 128;
+            cx->note_secret(ws.w, m * (size_t)ws.depth * p.K * 1024);
+            cx->note_secret(ws.yraw, m * (size_t)ws.depth * p.L * 32 * p.zbits);
+            cx->note_secret(ws.rhopp, m * 64);
+        } else {
+            cx->note_sign_ws(ws, m, shared, p.K, p.L, p.zbits);
+            cx->note_secret(s.sk, shared ? p.sk : m * p.sk);
+        }
         cx->note_secret(s.rnd, m * 32);
-        cudaError_t e = sign_begin(ps, B, m, s.sk, sk_stride, md, s.rnd, s.sig, s.it, ws, tail_lanes, &run[i % NS]);
+        cudaError_t e = sign_begin(ps, B, m, key_rows, sk_stride, md, s.rnd, s.sig, s.it, ws, tail_lanes, &run[i % NS]);
         if (e != cudaSuccess) return run[i % NS].ctx_err ? E_CTX : cuda_fail(e, "sign_begin");
-        CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, B));  // secrets do not linger in the staging set
+        if (!resident) CK(cudaMemsetAsync(s.sk, 0, shared ? p.sk : m * p.sk, B));  // secrets do not linger in the staging set
         CK(cudaMemsetAsync(s.rnd, 0, m * 32, B));
         CK(cudaEventRecord(cx->ev_bulk[i % NS], B));
         mark(i, TR_BULK1, B);
@@ -1091,7 +1137,7 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         SignRun& r = run[i % NS];
         cudaError_t e = sign_finish(&r);  // the host waits here, with chunk i+1's bulk already queued behind
         if (e != cudaSuccess) return r.ctx_err ? E_CTX : cuda_fail(e, "sign_finish");
-        sign_wipe(r.ws, lanes_of[i % NS], shared, false, T);
+        if (!resident) sign_wipe(r.ws, lanes_of[i % NS], shared, false, T);
         CK(cudaEventRecord(cx->ev_tail[i % NS], T));
         mark(i, TR_TAIL1, T);
         started[i % NS] = false;
@@ -1106,8 +1152,12 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
         cudaStreamSynchronize(T);
         cudaStreamSynchronize(cx->s_out);
         for (size_t k = 0; k < NS; k++) {
-            if (started[k]) sign_wipe(run[k].ws, lanes_of[k], shared, true, B);
-            cudaMemsetAsync(set[k].sk, 0, shared ? p.sk : C * p.sk, B);
+            if (started[k] && !resident) sign_wipe(run[k].ws, lanes_of[k], shared, true, B);
+            if (started[k] && resident) {  // the key set stays; y, w - c*s2 and rho'' of the unfinished lanes go
+                cudaMemsetAsync(run[k].ws.w, 0, (size_t)((uint8_t*)run[k].ws.mw1 - (uint8_t*)run[k].ws.w), B);
+                cudaMemsetAsync(run[k].ws.rhopp, 0, lanes_of[k] * 64, B);
+            }
+            if (!resident) cudaMemsetAsync(set[k].sk, 0, sk_set, B);
             cudaMemsetAsync(set[k].rnd, 0, C * 32, B);
         }
         cudaStreamSynchronize(B);
@@ -1298,6 +1348,125 @@ int mldsa_hash_verify_batch(int ps, int dev, int ph, size_t n, const uint8_t* pk
 {
     if (ph < 0 || ph > 2) return E_PARAM;
     return verify_host(ps, dev, 0, ph, n, pk, pk_stride, msgs, msg_off, ctx, ctx_off, sig, ok);
+}
+
+// ---------------------------------------------------------------- resident key sets
+// PrivateKey::try_from_bytes + expand_private (src/lib.rs:462-468, src/ml_dsa.rs:445-469) for n keys at once, kept on
+// the device: later sign calls skip the H2D copy of the packed keys, sk_decode, the L + 2K forward NTTs and ExpandA.
+int mldsa_sk_load(int ps, int dev, size_t n, const uint8_t* sk, mldsa_keyset** out)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || !out || n == 0 || !sk) return E_PARAM;
+    *out = nullptr;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    KeySet* ks = new (std::nothrow) KeySet;
+    if (!ks) return E_NOMEM;
+    ks->ps = ps;
+    ks->dev = dev;
+    ks->n = n;
+    const size_t a_b = pad256(n * (size_t)p.K * p.L * 1024), s1_b = pad256(n * (size_t)p.L * 1024),
+                 s2_b = pad256(n * (size_t)p.K * 1024), mini_b = pad256(n * 128);
+    ks->bytes = a_b + s1_b + 2 * s2_b + mini_b;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ks->base), ks->bytes);
+    if (e != cudaSuccess) {
+        delete ks;
+        return cuda_fail(e, "key set allocation");
+    }
+    Carver c(ks->base);
+    ks->A = c.take<int32_t>(n * (size_t)p.K * p.L * 256);
+    ks->s1h = c.take<int32_t>(n * (size_t)p.L * 256);
+    ks->s2h = c.take<int32_t>(n * (size_t)p.K * 256);
+    ks->t0h = c.take<int32_t>(n * (size_t)p.K * 256);
+    ks->mini = c.take<uint8_t>(n * 128);
+    // packed keys pass through the arena in chunks (two staging buffers: copy-in of chunk i+1 under the kernels of i)
+    size_t chunk = pick_chunk(cx->arena_bytes, n, 65536, 2 * p.sk);
+    if (chunk > (size_t(1) << 17)) chunk = size_t(1) << 17;
+    rc = cx->reserve(2 * pad256(chunk * p.sk));
+    cudaStream_t st = cx->stream;
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(cx->s_in);
+        cudaStreamSynchronize(st);
+        cudaMemset(ks->base, 0, ks->bytes);
+        cudaFree(ks->base);
+        if (cx->arena) cudaMemset(cx->arena, 0, 2 * pad256(chunk * p.sk) < cx->arena_bytes ? 2 * pad256(chunk * p.sk) : cx->arena_bytes);
+        cudaGetLastError();
+        delete ks;
+        return code;
+    };
+    if (rc) return fail(rc);
+    uint8_t* stage[2] = {cx->arena, cx->arena + pad256(chunk * p.sk)};
+    cx->clear_secrets();
+    cx->note_secret(stage[0], chunk < n ? chunk * p.sk : n * p.sk);
+    if (n > chunk) cx->note_secret(stage[1], (n - chunk < chunk ? n - chunk : chunk) * p.sk);
+    size_t i = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, i++) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        uint8_t* d_sk = stage[i & 1];
+        if (i >= 2 && cudaStreamWaitEvent(cx->s_in, cx->ev_bulk[i & 1], 0) != cudaSuccess) return fail(E_CUDA);
+        e = cudaMemcpyAsync(d_sk, sk + p.sk * lo, m * p.sk, cudaMemcpyHostToDevice, cx->s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_in[i & 1], cx->s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0);
+        if (e == cudaSuccess)
+            e = sign_expand_keys(ps, st, m, d_sk, ks->A + lo * (size_t)p.K * p.L * 256, ks->s1h + lo * (size_t)p.L * 256,
+                                 ks->s2h + lo * (size_t)p.K * 256, ks->t0h + lo * (size_t)p.K * 256);
+        if (e == cudaSuccess)  // rho || K || tr: the first 128 bytes of every packed key (src/encodings.rs:168-176)
+            e = cudaMemcpy2DAsync(ks->mini + 128 * lo, 128, d_sk, p.sk, 128, m, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_sk, 0, m * p.sk, st);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_bulk[i & 1], st);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "key set load"));
+    }
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "key set load"));
+    prof_collect();
+    *out = reinterpret_cast<mldsa_keyset*>(ks);
+    return OK;
+}
+
+static KeySet* as_keyset(const mldsa_keyset* h)
+{
+    KeySet* ks = reinterpret_cast<KeySet*>(const_cast<mldsa_keyset*>(h));
+    return ks && ks->magic == 0x4B534554 ? ks : nullptr;
+}
+
+size_t mldsa_keyset_size(const mldsa_keyset* h)
+{
+    const KeySet* ks = as_keyset(h);
+    return ks ? ks->n : 0;
+}
+size_t mldsa_keyset_device_bytes(const mldsa_keyset* h)
+{
+    const KeySet* ks = as_keyset(h);
+    return ks ? ks->bytes : 0;
+}
+
+// Zeroize + ZeroizeOnDrop of the expanded keys (src/types.rs:19)
+void mldsa_keyset_free(mldsa_keyset* h)
+{
+    KeySet* ks = as_keyset(h);
+    if (!ks) return;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    if (lock_ctx(ks->dev, lk, rc)) {
+        cudaMemset(ks->base, 0, ks->bytes);
+        cudaFree(ks->base);
+        cudaGetLastError();
+    }
+    ks->magic = 0;
+    delete ks;
+}
+
+// Signer::try_sign_with_rng on an expanded PrivateKey (src/lib.rs:268-296): lane i signs msgs[i] with key key_idx[i]
+// of the set (key_idx == NULL: key i; then n <= number of keys)
+int mldsa_sign_batch_keys(const mldsa_keyset* h, int framing, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                          const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                          uint8_t* sig, uint32_t* iters)
+{
+    const KeySet* ks = as_keyset(h);
+    if (!ks) return E_PARAM;
+    return sign_host(ks->ps, ks->dev, framing, -1, n, nullptr, 128, msgs, msg_off, ctx, ctx_off, rnd, sig, iters, ks, key_idx);
 }
 
 // Signer::get_public_key (src/lib.rs:344-346 -> src/ml_dsa.rs:502-563): pk bytes from sk bytes

@@ -141,6 +141,10 @@ struct SignWs {
     uint32_t* nact;    // [16] device control words: [4 * way + buffer] active counts, [8] ctx error flag
     uint32_t* queue;   // [2 * 2048] work-unit counters of the paired round launches
     uint32_t* h_nact;  // mapped pinned host mirror of the 16 control words (written by publish_kernel)
+    // Resident key set (mldsa_sk_load): A / s1h / s2h / t0h point into the key set, the `sk` passed to sign_begin is
+    // its 128-byte rho || K || tr rows, lane i uses key kidx[i] (nullptr: i), and nothing of the keys is wiped.
+    bool keys_resident = false;
+    const uint32_t* kidx = nullptr;
     static size_t bytes_per_lane(int K, int L, int zbits, int w1len, bool shared)
     {
         return (shared ? 0 : (size_t)(K * L + L + 2 * K) * 1024) + (size_t)K * 1024 + (size_t)L * 32 * zbits + 64 +
@@ -175,6 +179,9 @@ cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, siz
                        const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, size_t tail_lanes,
                        SignRun* run);
 cudaError_t sign_tail(cudaStream_t st, SignRun* run);
+// expand_private (src/ml_dsa.rs:445-469) for nkeys packed secret keys: A-hat, s1-hat, s2-hat, t0-hat
+cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
+                             int32_t* t0h);
 cudaError_t sign_finish(SignRun* run);
 
 }  // namespace mldsa

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128)
 sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
                  const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mu_out, uint8_t* __restrict__ rhopp,
                  uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
-                 uint32_t* __restrict__ ctl, size_t n_way_a, int* __restrict__ ctx_err)
+                 uint32_t* __restrict__ ctl, size_t n_way_a, int* __restrict__ ctx_err, const uint32_t* __restrict__ kidx)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -48,7 +48,7 @@ sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, Msg
         ctl[0] = (uint32_t)n_way_a;
         ctl[4] = (uint32_t)(n - n_way_a);
     }
-    const uint8_t* key = sk + i * sk_stride;
+    const uint8_t* key = sk + (kidx ? (size_t)kidx[i] : i) * sk_stride;  // rho || K || tr || ... (only K and tr are read)
     Sponge<SHAKE256_RATE> sp;
     if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
     uint64_t mu[8];
@@ -137,6 +137,7 @@ struct CtildeJob {
 struct SignWJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* A; const uint8_t* yraw; int32_t* w; uint8_t* mw1; int depth;
     const uint8_t* mu; int pos;
+    const uint32_t* kidx;  // resident key set: key of lane ln = kidx[ln] (nullptr: ln)
 };
 struct SignZJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* s1h; const int32_t* s2h; const int32_t* t0h;
@@ -144,6 +145,8 @@ struct SignZJob {
     uint8_t* rhopp; uint8_t* sig; uint32_t* iters; int depth;
     int pos; int depth0; size_t tail_slots;  // pos = 1: the lane's stale slots of the carved depth0 are zeroed on accept
                                              // too, unless they lie in the shared tail region [0, tail_slots)
+    const uint32_t* kidx;  // resident key set: key of lane ln = kidx[ln] (nullptr: ln)
+    int wipe_keys;         // 1: s1-hat / s2-hat / t0-hat belong to this call and are zeroed when the lane is accepted
 };
 
 // ExpandMask: one thread per (active lane, r) SHAKE256 stream; the squeezed bytes ARE the packed y.
@@ -232,7 +235,7 @@ __device__ __forceinline__ void sign_w_unit(const SignWJob& j, size_t unit, Sign
     if (ai < nact) {
         const size_t ln = act[ai / depth];
         const size_t slot = j.pos ? ai : ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
-        const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
+        const int32_t* A = Aall + (SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln) * (size_t)(K * L) * 256);
         const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
         int32_t* wo = wall + slot * (size_t)K * 256;
         uint8_t* w1o = mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
         if (ai >= nitems) continue;  // G = 2 needs an even depth, so both warps of a group skip together
         const size_t ln = j.act[ai / depth];
         const size_t slot = j.pos ? ai : ln * depth + ai % depth;
-        const int32_t* A = j.A + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
+        const int32_t* A = j.A + (SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln) * (size_t)(K * L) * 256);
         const uint8_t* yp = j.yraw + slot * (size_t)(L * 32 * P::ZBITS);
         int32_t* wo = j.w + slot * (size_t)K * 256;
         uint8_t* w1o = j.mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
@@ -505,7 +508,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
     const size_t ai = unit * SG_WARPS + warp;
     if (ai < nact) {
         const size_t ln = act[ai];
-        const size_t kn = SHARED ? 0 : ln;
+        const size_t kn = SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln);
         const size_t sbase = (j.pos ? ai : ln) * depth;  // first candidate slot of this lane
         uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
         bool rej = true;
@@ -669,10 +672,10 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
             warp_zero16(const_cast<uint8_t*>(yraw) + ln * (size_t)j.depth0 * (L * 32 * P::ZBITS), j.depth0 * L * 32 * P::ZBITS, lane);
         }
         warp_zero16(rhopp + ln * 64, 64, lane);
-        if (!SHARED) {
-            warp_zero16(const_cast<int32_t*>(s1h_all) + ln * (size_t)L * 256, L * 1024, lane);
-            warp_zero16(const_cast<int32_t*>(s2h_all) + ln * (size_t)K * 256, K * 1024, lane);
-            warp_zero16(const_cast<int32_t*>(t0h_all) + ln * (size_t)K * 256, K * 1024, lane);
+        if (!SHARED && j.wipe_keys) {
+            warp_zero16(const_cast<int32_t*>(s1h_all) + kn * (size_t)L * 256, L * 1024, lane);
+            warp_zero16(const_cast<int32_t*>(s2h_all) + kn * (size_t)K * 256, K * 1024, lane);
+            warp_zero16(const_cast<int32_t*>(t0h_all) + kn * (size_t)K * 256, K * 1024, lane);
         }
         __syncwarp();
     }
@@ -804,8 +807,9 @@ static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, 
         KLaunch kl(KID_SIGN_PREP, st);
         sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mu, ws.rhopp,
                                                                         ws.kappa, ws.done, ws.act[0], ws.nact, nA,
-                                                                        ctx_err);
+                                                                        ctx_err, ws.kidx);
     }
+    if (ws.keys_resident) return cudaGetLastError();  // A-hat and the s-hat rows come from a loaded key set
     {
         KLaunch kl(KID_SIGN_KEY, st);
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
@@ -847,7 +851,7 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
             MaskJob{nact, act, ws.rhopp, ws.kappa, ws.yraw, D, pos});
     }
     cudaError_t ce = cudaSuccess;
-    const SignWJob wj{nact, act, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, pos};
+    const SignWJob wj{nact, act, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, pos, ws.kidx};
     if (tn.stage == 0) {
         KLaunch kl(KID_SIGN_W, st);
         if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
@@ -865,7 +869,7 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
     if (ce != cudaSuccess) return ce;
     {
         const SignZJob zj{nact, act, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done, ws.rhopp,
-                          r.sig, r.iters, D, pos, ws.depth, r.tail_slots};
+                          r.sig, r.iters, D, pos, ws.depth, r.tail_slots, ws.kidx, ws.keys_resident ? 0 : 1};
         KLaunch kl(KID_SIGN_Z, st);
         if (shared) sign_z_kernel<P, true><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(zj);
         else sign_z_kernel<P, false><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(zj);
@@ -929,10 +933,10 @@ static cudaError_t sign_paired_t(cudaStream_t st, SignRun& r, const uint8_t* sk,
     way[1].lo = nA, way[1].bound = n - nA;
     auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D, 0}; };
     auto ct_job = [&](int v) { return CtildeJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.mw1, ws.ctilde, ws.cmask, D}; };
-    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, 0}; };
+    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, 0, ws.kidx}; };
     auto z_job = [&](int v) {
         return SignZJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde,
-                        ws.cmask, ws.kappa, ws.done, ws.rhopp, r.sig, r.iters, D, 0, D, 0};
+                        ws.cmask, ws.kappa, ws.done, ws.rhopp, r.sig, r.iters, D, 0, D, 0, ws.kidx, ws.keys_resident ? 0 : 1};
     };
     auto compact = [&](int v) -> cudaError_t {
         Way& y = way[v];
@@ -1016,6 +1020,30 @@ static cudaError_t sign_paired_t(cudaStream_t st, SignRun& r, const uint8_t* sk,
     return cudaGetLastError();
 }
 
+// expand_private for a key set (src/ml_dsa.rs:445-469): A-hat and s1-hat / s2-hat / t0-hat of nkeys packed secret keys
+template <class P>
+static cudaError_t sign_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
+                                      int32_t* t0h)
+{
+    {
+        KLaunch kl(KID_SIGN_KEY, st);
+        sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
+            nkeys, sk, P::SK_LEN, s1h, s2h, t0h);
+    }
+    return launch_expand_a(st, P::K, P::L, sk, P::SK_LEN, nkeys, A);
+}
+cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
+                             int32_t* t0h)
+{
+    if (nkeys == 0) return cudaSuccess;
+    switch (ps) {
+    case 44: return sign_expand_keys_t<Params<44>>(st, nkeys, sk, A, s1h, s2h, t0h);
+    case 65: return sign_expand_keys_t<Params<65>>(st, nkeys, sk, A, s1h, s2h, t0h);
+    case 87: return sign_expand_keys_t<Params<87>>(st, nkeys, sk, A, s1h, s2h, t0h);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
                        const uint8_t* rnd, uint8_t* sig, uint32_t* iters, const SignWs& ws, size_t tail_lanes,
                        SignRun* run)
@@ -1047,7 +1075,7 @@ cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, siz
         return cudaSuccess;
     }
     cudaError_t e;
-    if (tuning().pair != 0 && n >= 8192) {  // small batches are latency-bound: keep the plain loop
+    if (tuning().pair != 0 && n >= 8192 && !ws.keys_resident) {  // small batches are latency-bound: keep the plain loop
         r.finished = true;
         switch (ps) {
         case 44: return sign_paired_t<Params<44>>(st, r, sk, sk_stride, md, rnd);

@@ -125,6 +125,26 @@ int mldsa_expand_a_batch_dev(void* stream, size_t n, const uint8_t* d_seed34, in
 int mldsa_shake_batch(int dev, int bits /*128|256*/, size_t n, const uint8_t* in, size_t in_len, uint8_t* out,
                       size_t out_len);
 
+/* ---- resident key sets ----------------------------------------------------------------------
+ * The reference's PrivateKey is the EXPANDED key: rho, K, tr and the NTT images of s1, s2, t0 (src/types.rs:19-28),
+ * built once by try_from_bytes -> expand_private (src/lib.rs:462-468, src/ml_dsa.rs:445-469) and reused by every
+ * sign call.  mldsa_sk_load is that step for n keys at once; the expanded keys (plus A-hat, which the reference
+ * re-derives from rho on every sign, src/ml_dsa.rs:181) stay in HBM until mldsa_keyset_free, which zeroizes them
+ * (ZeroizeOnDrop, src/types.rs:19).  Signing with a key set moves 64 bytes + the message per lane over PCIe
+ * instead of the packed key as well, and skips sk_decode, L + 2K forward NTTs and ExpandA.
+ * Device memory: 29 / 47 / 79 KiB per key for ML-DSA-44 / 65 / 87. */
+typedef struct mldsa_keyset mldsa_keyset;
+int mldsa_sk_load(int ps, int dev, size_t n, const uint8_t* sk /* n x SK_LEN, host */, mldsa_keyset** out);
+size_t mldsa_keyset_size(const mldsa_keyset* ks);          /* number of keys */
+size_t mldsa_keyset_device_bytes(const mldsa_keyset* ks);
+void mldsa_keyset_free(mldsa_keyset* ks);
+/* Signer::try_sign_with_rng on expanded keys (src/lib.rs:268-296): lane i signs with key key_idx[i] of the set
+ * (key_idx == NULL: key i, n <= number of keys).  Same bytes as mldsa_sign_batch with those keys.  Other
+ * arguments and return codes as mldsa_sign_batch; -1 if a key index is out of range. */
+int mldsa_sign_batch_keys(const mldsa_keyset* ks, int framing, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                          const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                          uint8_t* sig, uint32_t* iters);
+
 /* ---- tuning / telemetry ------------------------------------------------------------------ */
 /* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 96 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);

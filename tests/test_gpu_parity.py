@@ -465,3 +465,47 @@ def test_no_secret_residue_on_device(F, ps):
     finally:
         L.mldsa_set_tail(8, 32768)
         L.mldsa_set_workspace_limit(0)
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_resident_key_set_signs_like_packed_keys(F, ps):
+    """mldsa_sk_load / mldsa_sign_batch_keys: keys expanded once and kept on the device (the reference's expanded
+    PrivateKey, src/types.rs:19-28, src/ml_dsa.rs:445-469).  Signatures and iteration counts equal the oracle's for
+    the identity mapping and for an arbitrary key index per lane, over repeated calls (nothing of the set is wiped),
+    in one chunk and in many."""
+    import ctypes as C
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    m = F.PARAM_SETS[ps]
+    nk, n = 700, 2600
+    pks, sks = O.keygen_batch(ps, synth_block(f"rk{ps}", nk, 32))
+    ks = m.load_private_keys(sks)
+    assert len(ks) == nk and ks.device_bytes >= nk * (m.K * m.L + m.L + 2 * m.K) * 1024
+    nz = C.c_uint64()
+    _lib.check(L.mldsa_debug_secret_residue(0, C.byref(nz), None))
+    assert nz.value == 0                                   # the staged packed keys are gone
+    msgs = [synth("rm", i, i % 70) for i in range(n)]
+    ctxs = [synth("rc", i, i % 9) for i in range(n)]
+    rnds = synth_rows("rr", n, 32)
+    idx = (np.arange(n, dtype=np.uint64) * 2654435761 % nk).astype(np.uint32)
+    want, wit = O.sign_batch(ps, sks[idx], msgs, rnds, ctxs=ctxs)
+    try:
+        for limit in (0, 40 << 20):
+            L.mldsa_set_workspace_limit(limit)
+            for _ in range(2):
+                sig, it = ks.sign_batch(msgs, rnds, ctxs=ctxs, key_idx=idx, want_iters=True)
+                assert (sig == want).all() and (it == wit).all(), (ps, limit)
+            sig1 = ks.sign_batch(msgs[:nk], rnds[:nk])         # identity mapping: lane i, key i
+            want1, _ = O.sign_batch(ps, sks, msgs[:nk], rnds[:nk])
+            assert (sig1 == want1).all()
+            _lib.check(L.mldsa_debug_secret_residue(0, C.byref(nz), None))
+            assert nz.value == 0
+        assert m.verify_batch(pks[idx], msgs, sig, ctxs=ctxs).all()
+        with pytest.raises(F.MldsaError):
+            ks.sign_batch(msgs[:4], rnds[:4], key_idx=np.array([0, 1, nk, 2], dtype=np.uint32))
+        with pytest.raises(ValueError, match="ctx too long"):
+            ks.sign_batch(msgs[:1], rnds[:1], ctxs=[bytes(256)])
+    finally:
+        L.mldsa_set_workspace_limit(0)
+        ks.free()
+    assert len(ks) == 0
