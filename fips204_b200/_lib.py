@@ -45,6 +45,7 @@ SIGNATURES = {
     "mldsa_set_tuning": (None, [C.c_int, C.c_int, C.c_int]),
     "mldsa_set_depth": (None, [C.c_int]),
     "mldsa_set_tail": (None, [C.c_int, C.c_int]),
+    "mldsa_debug_set_max_rounds": (None, [C.c_int]),
     "mldsa_sk_load": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mldsa_keyset_size": (C.c_size_t, [C.c_void_p]),
     "mldsa_keyset_device_bytes": (C.c_size_t, [C.c_void_p]),

@@ -90,7 +90,7 @@ void prof_collect()
 }
 
 static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1}, g_pair{-1}, g_kshare{-1}, g_stage{-1},
-    g_tail_depth{-1}, g_tail_slots{-1};
+    g_tail_depth{-1}, g_tail_slots{-1}, g_max_rounds{0};
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -118,7 +118,7 @@ Tuning tuning()
     if (ts < 0) g_tail_slots.store(ts = env_int("MLDSA_TAILSLOTS", 32768));
     if (td > 16) td = 16;
     if (ts < 0) ts = 0;
-    return Tuning{w, k, a, d, pr, sg, ks, td, ts};
+    return Tuning{w, k, a, d, pr, sg, ks, td, ts, g_max_rounds.load()};
 }
 unsigned capped_grid(size_t want_ctas, int cap_per_sm)
 {
@@ -495,7 +495,7 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
         cudaStreamSynchronize(st);
         prof_collect();
         t_last_rounds += run.rounds;
-        if (e != cudaSuccess) return run.ctx_err ? E_CTX : cuda_fail(e, "sign");
+        if (e != cudaSuccess) return run.ctx_err ? E_CTX : (run.incomplete ? E_UNSUPPORTED : cuda_fail(e, "sign"));
     }
     CK(cudaStreamSynchronize(st));
     prof_collect();
@@ -594,6 +594,7 @@ void mldsa_host_free(void* p)
 }
 void mldsa_set_workspace_limit(size_t bytes) { g_ws_limit.store(bytes); }
 void mldsa_set_depth(int depth) { g_depth.store(depth < 1 ? 1 : (depth > 8 ? 8 : depth)); }
+void mldsa_debug_set_max_rounds(int rounds) { g_max_rounds.store(rounds < 0 ? 0 : rounds); }
 void mldsa_set_tail(int tail_depth, int tail_slots)
 {
     g_tail_depth.store(tail_depth < 0 ? 0 : (tail_depth > 16 ? 16 : tail_depth));
@@ -1136,7 +1137,7 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     auto finish = [&](size_t i) -> int {
         SignRun& r = run[i % NS];
         cudaError_t e = sign_finish(&r);  // the host waits here, with chunk i+1's bulk already queued behind
-        if (e != cudaSuccess) return r.ctx_err ? E_CTX : cuda_fail(e, "sign_finish");
+        if (e != cudaSuccess) return r.ctx_err ? E_CTX : (r.incomplete ? E_UNSUPPORTED : cuda_fail(e, "sign_finish"));
         if (!resident) sign_wipe(r.ws, lanes_of[i % NS], shared, false, T);
         CK(cudaEventRecord(cx->ev_tail[i % NS], T));
         mark(i, TR_TAIL1, T);

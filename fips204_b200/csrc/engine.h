@@ -44,6 +44,7 @@ struct Tuning {
     int kshare; // paired kernel: CTAs out of 5 per SM that prefer the Keccak queue (MLDSA_KSHARE, default 2)
     int tail_depth;  // sign: deepest speculation of the under-filled last rounds (MLDSA_TAILDEPTH, default 8; <= depth: off)
     int tail_slots;  // sign: candidate slots of the shared tail region (MLDSA_TAILSLOTS, default 32768)
+    int max_rounds;  // test hook (mldsa_debug_set_max_rounds): stop a chunk's loop after this many rounds (0 = off)
 };
 Tuning tuning();
 // CTAs per SM of the grid-stride arithmetic (warp-per-lane) kernels.  6-10 are resident at a time; with 16 the last
@@ -168,6 +169,7 @@ struct SignRun {
     size_t slot_w_bytes = 0, slot_y_bytes = 0;
     bool used_tail = false;
     bool finished = false;
+    bool incomplete = false;  // stopped by the max_rounds test hook with lanes still live
     bool ctx_err = false;   // a lane's ctx was longer than 255 bytes (src/lib.rs:274)
     cudaStream_t tail_stream = nullptr;
 };

@@ -898,7 +898,9 @@ static cudaError_t sign_round(cudaStream_t st, SignRun& r, size_t sz)
 }
 static cudaError_t sign_rounds_until(cudaStream_t st, SignRun& r, double stop_at)
 {
+    const int max_rounds = tuning().max_rounds;
     while (r.expect > stop_at) {
+        if (max_rounds > 0 && r.rounds >= max_rounds) break;  // test hook: fixed number of rounds
         size_t sz = (size_t)(r.expect * 1.25) + 256;
         if (sz > r.n) sz = r.n;
         const double keep = pow(1.0 - 0.19, (double)round_depth(r, sz));
@@ -1118,6 +1120,11 @@ cudaError_t sign_finish(SignRun* run)
         return cudaErrorInvalidValue;
     }
     r.bound = r.ws.h_nact[r.cur];
+    if (tuning().max_rounds > 0 && r.bound > 0) {  // test hook: the caller wipes the unfinished lanes' state
+        r.incomplete = true;
+        r.finished = true;
+        return cudaErrorNotReady;
+    }
     while (r.bound > 0) {  // stragglers beyond the estimate (rare): a few rounds at a time
         const size_t sz = r.bound;
         for (int k = 0; k < 4; k++) {

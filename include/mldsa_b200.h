@@ -170,6 +170,10 @@ void mldsa_set_pairing(int pair, int kshare);
  * during the most recent keygen or sign call on `dev`; *scanned_bytes (optional) = size of those ranges.  0 after
  * every call, successful or not. */
 int mldsa_debug_secret_residue(int dev, uint64_t* nonzero_bytes, uint64_t* scanned_bytes);
+/* test hook for the timing probe (tools/ct_probe.py): a sign call stops every chunk's rejection loop after `rounds`
+ * rounds (0 = off, the default), wipes the unfinished lanes' state and returns -5; with rounds = 1 every kernel of
+ * the loop runs exactly once over all lanes, so per-kernel device times can be compared between input classes. */
+void mldsa_debug_set_max_rounds(int rounds);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */
