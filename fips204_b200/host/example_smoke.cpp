@@ -22,6 +22,13 @@ template <class M> static int run(const char* name, int want_pk0)
         threw = std::string(e.what()) == "ML-DSA.Sign: ctx too long";
     }
     ok = ok && threw && pk.into_bytes()[0] == want_pk0;  // lib.rs:543-545
+    // the same key expanded once and kept on the device signs the same bytes
+    typename M::PrivateKeySet set(1, sk.bytes.data());
+    std::vector<std::vector<uint8_t>> msgs{m1, m2, m1};
+    const uint32_t idx[3] = {0, 0, 0};
+    std::vector<uint8_t> rnd(3 * 32, 12);
+    auto sigs = set.sign_batch(msgs, nullptr, rnd.data(), idx);
+    ok = ok && set.size() == 1 && sigs[0] == sig && sigs[2] == sig && pk.verify(m2, sigs[1], {});
     std::printf("%s: %s\n", name, ok ? "ok" : "FAILED");
     return ok ? 0 : 1;
 }

@@ -113,6 +113,45 @@ struct ParamSet {
         return ok;
     }
 
+    // ---- expanded secret keys resident on the device ----------------------------------------------
+    // What the reference's PrivateKey struct holds (rho, K, tr, NTT(s1), NTT(s2), NTT(t0): types.rs:19-28, built once by
+    // try_from_bytes -> expand_private, lib.rs:462-468, ml_dsa.rs:445-469), for n keys, plus A-hat.  Zeroized on
+    // destruction (ZeroizeOnDrop).  sign_batch: lane i signs msgs[i] with key key_idx[i] (nullptr: key i).
+    struct PrivateKeySet {
+        mldsa_keyset* handle = nullptr;
+        PrivateKeySet(size_t n, const uint8_t* sk, int dev = 0) { check(mldsa_sk_load(PS, dev, n, sk, &handle)); }
+        ~PrivateKeySet() { mldsa_keyset_free(handle); }
+        PrivateKeySet(const PrivateKeySet&) = delete;
+        PrivateKeySet& operator=(const PrivateKeySet&) = delete;
+        size_t size() const { return mldsa_keyset_size(handle); }
+        std::vector<Signature> sign_batch(const std::vector<Bytes>& msgs, const std::vector<Bytes>* ctxs, const uint8_t* rnd,
+                                          const uint32_t* key_idx = nullptr, int framing = 0,
+                                          std::vector<uint32_t>* iters = nullptr) const
+        {
+            const size_t n = msgs.size();
+            std::vector<uint8_t> mb, cb;
+            std::vector<uint64_t> mo(n + 1, 0);
+            std::vector<uint32_t> co(n + 1, 0);
+            for (size_t i = 0; i < n; i++) {
+                mb.insert(mb.end(), msgs[i].begin(), msgs[i].end());
+                mo[i + 1] = mb.size();
+                if (ctxs) {
+                    if ((*ctxs)[i].size() > 255) throw Error(MLDSA_E_CTX, "ML-DSA.Sign: ctx too long");  // lib.rs:274
+                    cb.insert(cb.end(), (*ctxs)[i].begin(), (*ctxs)[i].end());
+                    co[i + 1] = static_cast<uint32_t>(cb.size());
+                }
+            }
+            mb.push_back(0);
+            cb.push_back(0);
+            std::vector<Signature> sig(n);
+            if (iters) iters->assign(n, 0);
+            check(mldsa_sign_batch_keys(handle, framing, n, key_idx, mb.data(), mo.data(), ctxs ? cb.data() : nullptr,
+                                        ctxs ? co.data() : nullptr, rnd, reinterpret_cast<uint8_t*>(sig.data()),
+                                        iters ? iters->data() : nullptr));
+            return sig;
+        }
+    };
+
     // ---- the reference's types ----------------------------------------------------------------
     struct PublicKey {  // types.rs:35-41 (here: canonical bytes)
         std::array<uint8_t, PK> bytes{};

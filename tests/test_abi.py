@@ -69,3 +69,33 @@ def test_host_mirror_argument_rules(built):
         m.try_keygen_with_rng(BadRng())
     with pytest.raises(ValueError, match="random number generator failed"):  # src/lib.rs:283
         sk.try_sign_with_rng(BadRng(), b"m", b"")
+
+
+def _build_cpp_example():
+    import subprocess
+    host = ROOT / "fips204_b200" / "host"
+    exe = host / "example_smoke"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", str(host / "example_smoke.cpp"),
+                           "-L" + str(ROOT / "fips204_b200"), "-lmldsa_b200", "-Wl,-rpath," + str(ROOT / "fips204_b200"),
+                           "-o", str(exe)])
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_links(built):
+    """fips204_b200/host/fips204.hpp (the C++ mirror of the reference surface, incl. PrivateKeySet) compiles without
+    warnings against include/mldsa_b200.h and links against the library; without a GPU the program reports the
+    library's error instead of computing anything on the CPU."""
+    import subprocess
+    exe = _build_cpp_example()
+    import fips204_b200 as F
+    if F.device_count() == 0:
+        r = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert r.returncode == 2 and "error -3" in r.stdout, (r.returncode, r.stdout)
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_smoke_on_gpu(built):
+    """the reference's in-crate smoke test (src/lib.rs:503-551) through the C++ mirror, on the device"""
+    import subprocess
+    r = subprocess.run([str(_build_cpp_example())], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count(": ok") == 3, (r.returncode, r.stdout, r.stderr)
