@@ -509,3 +509,28 @@ def test_resident_key_set_signs_like_packed_keys(F, ps):
         L.mldsa_set_workspace_limit(0)
         ks.free()
     assert len(ks) == 0
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_edge_shapes_vs_oracle(F, ps):
+    """Empty batch, single lane, empty and block-boundary message lengths (mu absorbs tr || 0 || |ctx| || ctx || M:
+    the SHAKE256 rate boundary falls at |ctx| + |M| = 70, 206, ...), a 100 kB message, the longest legal ctx."""
+    m = F.PARAM_SETS[ps]
+    pk, sk = O.keygen(ps, synth("edge-xi", ps, 32))
+    assert m.sign_batch(sk, [], np.zeros((0, 32), np.uint8), shared_key=True).shape == (0, m.SIG_LEN)
+    assert m.verify_batch(pk, [], np.zeros((0, m.SIG_LEN), np.uint8), shared_key=True).shape == (0,)
+    pk0, sk0 = m.keygen_batch(np.zeros((0, 32), np.uint8))
+    assert pk0.shape == (0, m.PK_LEN) and sk0.shape == (0, m.SK_LEN)
+    lens = [0, 1, 69, 70, 71, 72, 135, 136, 137, 205, 206, 207, 341, 342, 343, 5000, 100000]
+    msgs = [synth("edge-m", i, n) for i, n in enumerate(lens)]
+    ctxs = [b"" if i % 3 == 0 else synth("edge-c", i, 255 if i % 3 == 1 else i) for i in range(len(lens))]
+    rnds = synth_rows("edge-r", len(lens), 32)
+    sig, it = m.sign_batch(sk, msgs, rnds, ctxs=ctxs, shared_key=True, want_iters=True)
+    for i in range(len(lens)):
+        want, wit = O.sign(ps, sk, msgs[i], rnds[i].tobytes(), ctx=ctxs[i], want_iters=True)
+        assert sig[i].tobytes() == want and it[i] == wit, (ps, lens[i], len(ctxs[i]))
+        one = m.sign_batch(sk, [msgs[i]], rnds[i], ctxs=[ctxs[i]], shared_key=True)   # n = 1
+        assert one[0].tobytes() == want
+    assert m.verify_batch(pk, msgs, sig, ctxs=ctxs, shared_key=True).all()
+    swapped = [ctxs[1], ctxs[0]] + ctxs[2:]
+    assert list(m.verify_batch(pk, msgs, sig, ctxs=swapped, shared_key=True)[:2]) == [0, 0]
