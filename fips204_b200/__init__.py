@@ -261,6 +261,13 @@ class _ParamSet:
         _lib.check(_lib.lib().mldsa_sk_load(self.PS, dev, sk.shape[0], _ptr(sk), C.byref(h)))
         return PrivateKeySet(self, h)
 
+    def load_public_keys(self, pks, dev=0):
+        """n x PK_LEN packed keys -> PublicKeySet: expand_public (ml_dsa.rs:477-498) done once, resident in HBM."""
+        pk = _u8(pks).reshape(-1, self.PK_LEN)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mldsa_pk_load(self.PS, dev, pk.shape[0], _ptr(pk), C.byref(h)))
+        return PublicKeySet(self, h)
+
     def sk_to_pk_batch(self, sks, dev=0):
         """Signer::get_public_key over a batch: n x SK_LEN -> pk[n, PK_LEN] (ml_dsa.rs:502-563)."""
         sk = _u8(sks).reshape(-1, self.SK_LEN)
@@ -341,6 +348,34 @@ class PrivateKeySet:
             self.free()
         except Exception:
             pass
+
+
+class PublicKeySet(PrivateKeySet):
+    """Expanded public keys resident on the device (mldsa_pk_load): A-hat, tr, NTT(t1 * 2^d) per key."""
+
+    def sign_batch(self, *a, **kw):
+        raise ValueError("a public-key set cannot sign")
+
+    def verify_batch(self, msgs, sigs, ctxs=None, key_idx=None, framing=0):
+        """-> uint8[n]; lane i is checked under key key_idx[i] (default: key i).  Same verdicts as
+        _ParamSet.verify_batch."""
+        if not self._h:
+            raise ValueError("key set was freed")
+        m, n = self._mod, len(msgs)
+        sg = _u8(b"".join(bytes(s) for s in sigs)) if isinstance(sigs, (list, tuple)) else _u8(sigs)
+        if sg.size != n * m.SIG_LEN:
+            raise ValueError("incorrect signature length")
+        mb, mo = _ragged(msgs, np.uint64)
+        cb = co = None
+        if ctxs is not None:
+            cb, co = _ragged(ctxs, np.uint32)
+        ki = None if key_idx is None else np.ascontiguousarray(key_idx, dtype=np.uint32)
+        if ki is not None and ki.size != n:
+            raise ValueError("key_idx must have n entries")
+        ok = np.zeros(n, dtype=np.uint8)
+        _lib.check(_lib.lib().mldsa_verify_batch_keys(self._h, framing, n, _ptr(ki), _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co),
+                                                      _ptr(sg), _ptr(ok)))
+        return ok
 
 
 ml_dsa_44 = _ParamSet(44, 4, 4, 1312, 2560, 2420)

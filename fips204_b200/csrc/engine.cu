@@ -278,8 +278,11 @@ struct KeySet {
     int ps = 0, dev = 0;
     size_t n = 0, bytes = 0;
     uint8_t* base = nullptr;
+    bool is_public = false;   // false: secret keys (sign), true: public keys (verify)
     int32_t *A = nullptr, *s1h = nullptr, *s2h = nullptr, *t0h = nullptr;
-    uint8_t* mini = nullptr;  // [n][128] rho || K || tr
+    uint8_t* mini = nullptr;  // secret keys: [n][128] rho || K || tr
+    int32_t* t1h = nullptr;   // public keys: [n][K][256] NTT(t1 * 2^d), the reference's t1_d2_hat_mont (src/types.rs:40)
+    uint8_t* tr = nullptr;    // public keys: [n][64]
 };
 
 // bump allocator over the arena, 256-byte granules
@@ -979,7 +982,7 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     if (n && ((!ks && !sk) || !rnd || !sig || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
     if (n == 0) return OK;
     if (ks) {
-        if (ks->ps != ps || ks->dev != dev) return E_PARAM;
+        if (ks->ps != ps || ks->dev != dev || ks->is_public) return E_PARAM;
         if (!key_idx && n > ks->n) return E_PARAM;
         if (key_idx)
             for (size_t i = 0; i < n; i++)
@@ -1212,16 +1215,25 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
     return OK;
 }
 
+// ks != nullptr: the keys are a resident public-key set; lane i verifies under key key_idx[i] (nullptr: key i)
 static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uint8_t* pk, size_t pk_stride,
                        const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
-                       const uint8_t* sig, uint8_t* ok)
+                       const uint8_t* sig, uint8_t* ok, const KeySet* ks = nullptr, const uint32_t* key_idx = nullptr)
 {
     PSInfo p;
     if (!ps_info(ps, p) || (framing != 0 && framing != 1) || ph > 2) return E_PARAM;
     if (ph >= 0) framing = 2;
-    if (pk_stride != 0 && pk_stride != p.pk) return E_PARAM;
-    if (n && (!pk || !sig || !ok || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
+    if (!ks && pk_stride != 0 && pk_stride != p.pk) return E_PARAM;
+    if (n && ((!ks && !pk) || !sig || !ok || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
     if (n == 0) return OK;
+    if (ks) {
+        if (ks->ps != ps || ks->dev != dev || !ks->is_public) return E_PARAM;
+        if (!key_idx && n > ks->n) return E_PARAM;
+        if (key_idx)
+            for (size_t i = 0; i < n; i++)
+                if (key_idx[i] >= ks->n) return E_PARAM;
+        pk_stride = p.pk;
+    }
     std::unique_lock<std::mutex> lk;
     int rc = OK;
     DeviceCtx* cx = lock_ctx(dev, lk, rc);
@@ -1231,12 +1243,15 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
     // stream-ordered), verdicts out on s_out, ordered by events.  The packed pk + sig bytes make this path PCIe-bound
     // (5.3 KB per lane against 56 ns of compute), so what matters is that the copy-in stream never idles.
     constexpr size_t NS = SIGN_SETS;
-    const bool shared = pk_stride == 0;
+    const bool resident = ks != nullptr, shared = !resident && pk_stride == 0;
+    const size_t pk_lane = resident ? (key_idx ? 4 : 0) : p.pk;  // staged bytes per lane: packed pk, or a key index
     const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
     const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
-    const size_t fixed = verify_ws_bytes(p, 0, shared) + (shared ? NS * pad256(p.pk) : 0) + 65536;
-    const size_t ws_lane = (verify_ws_bytes(p, 1024, shared) - (shared ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
-    const size_t io_lane = NS * ((shared ? 0 : p.pk) + p.sig + 1 + 8 + 4 + avg_msg + avg_ctx + PREHASH_STRIDE + 8);
+    // a resident key set brings its own A-hat / t1-hat / tr: the workspace is sized like the shared-key one
+    const bool small_ws = shared || resident;
+    const size_t fixed = verify_ws_bytes(p, 0, small_ws) + (shared ? NS * pad256(p.pk) : 0) + 65536;
+    const size_t ws_lane = (verify_ws_bytes(p, 1024, small_ws) - (small_ws ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
+    const size_t io_lane = NS * ((shared ? 0 : pk_lane) + p.sig + 1 + 8 + 4 + avg_msg + avg_ctx + PREHASH_STRIDE + 8);
     const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
     const size_t C = pl.max_lanes, N = pl.nchunks();
     struct Set {
@@ -1244,14 +1259,15 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
         uint32_t* co;
         uint64_t *mo, *po;
     } set[NS];
-    const size_t set_bytes = pad256(shared ? p.pk : C * p.pk) + pad256(C * p.sig) + pad256(C) + pad256((C + 1) * 8) +
+    const size_t pk_set = shared ? p.pk : C * pk_lane + 16;
+    const size_t set_bytes = pad256(pk_set) + pad256(C * p.sig) + pad256(C) + pad256((C + 1) * 8) +
                              pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) + pad256(pl.max_cbytes + 8) +
                              pad256(C * PREHASH_STRIDE) + pad256((C + 1) * 8);
-    rc = cx->reserve(NS * set_bytes + verify_ws_bytes(p, C, shared) + 4096);
+    rc = cx->reserve(NS * set_bytes + verify_ws_bytes(p, C, small_ws) + 4096);
     if (rc) return rc;
     Carver c(cx->arena);
     for (auto& s : set) {
-        s.pk = c.take<uint8_t>(shared ? p.pk : C * p.pk);
+        s.pk = c.take<uint8_t>(pk_set);  // packed public keys -- or, for a resident key set, the lanes' key indices
         s.sig = c.take<uint8_t>(C * p.sig);
         s.ok = c.take<uint8_t>(C);
         s.mo = c.take<uint64_t>(C + 1);
@@ -1281,7 +1297,10 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
         const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
         // copy-in
         if (i >= NS) CK(cudaStreamWaitEvent(cx->s_in, ev_cmp[i % NS], 0));  // the set's previous chunk is computed
-        CK(cudaMemcpyAsync(s.pk, pk + pk_stride * lo, shared ? p.pk : m * p.pk, cudaMemcpyHostToDevice, cx->s_in));
+        if (!resident)
+            CK(cudaMemcpyAsync(s.pk, pk + pk_stride * lo, shared ? p.pk : m * p.pk, cudaMemcpyHostToDevice, cx->s_in));
+        else if (key_idx)
+            CK(cudaMemcpyAsync(s.pk, key_idx + lo, m * 4, cudaMemcpyHostToDevice, cx->s_in));
         CK(cudaMemcpyAsync(s.sig, sig + p.sig * lo, m * p.sig, cudaMemcpyHostToDevice, cx->s_in));
         CK(cudaMemcpyAsync(s.mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, cx->s_in));
         if (mbytes) CK(cudaMemcpyAsync(s.m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, cx->s_in));
@@ -1301,7 +1320,15 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
             cmo = s.po;
         }
         Carver wc(ws_base);
-        const VerifyWs ws = verify_carve(wc, p, m, shared);
+        VerifyWs ws = verify_carve(wc, p, m, small_ws);
+        if (resident) {  // lanes [lo, lo + m) use keys key_idx[lo ..] -- or keys lo .. lo + m - 1 of the set
+            const size_t k0 = key_idx ? 0 : lo;
+            ws.keys_resident = true;
+            ws.kidx = key_idx ? reinterpret_cast<const uint32_t*>(s.pk) : nullptr;
+            ws.A = ks->A + k0 * (size_t)p.K * p.L * 256;
+            ws.t1h = ks->t1h + k0 * (size_t)p.K * 256;
+            ws.tr = ks->tr + k0 * 64;
+        }
         const MsgDesc md{cm, cmo, ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, framing};
         CK(verify_run(ps, st, m, s.pk, pk_stride, md, s.sig, s.ok, ws));
         CK(cudaEventRecord(ev_cmp[i % NS], st));
@@ -1468,6 +1495,80 @@ int mldsa_sign_batch_keys(const mldsa_keyset* h, int framing, size_t n, const ui
     const KeySet* ks = as_keyset(h);
     if (!ks) return E_PARAM;
     return sign_host(ks->ps, ks->dev, framing, -1, n, nullptr, 128, msgs, msg_off, ctx, ctx_off, rnd, sig, iters, ks, key_idx);
+}
+
+// PublicKey::try_from_bytes + expand_public (src/lib.rs:469-474, src/ml_dsa.rs:477-498) for n keys, kept on the device:
+// rho-derived A-hat, tr = H(pk) and NTT(t1 * 2^d) -- the fields of the reference's PublicKey (src/types.rs:35-41) plus
+// A-hat.  Later verify calls send only signatures and messages.
+int mldsa_pk_load(int ps, int dev, size_t n, const uint8_t* pk, mldsa_keyset** out)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || !out || n == 0 || !pk) return E_PARAM;
+    *out = nullptr;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    KeySet* ks = new (std::nothrow) KeySet;
+    if (!ks) return E_NOMEM;
+    ks->ps = ps;
+    ks->dev = dev;
+    ks->n = n;
+    ks->is_public = true;
+    ks->bytes = pad256(n * (size_t)p.K * p.L * 1024) + pad256(n * (size_t)p.K * 1024) + pad256(n * 64);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ks->base), ks->bytes);
+    if (e != cudaSuccess) {
+        delete ks;
+        return cuda_fail(e, "key set allocation");
+    }
+    Carver c(ks->base);
+    ks->A = c.take<int32_t>(n * (size_t)p.K * p.L * 256);
+    ks->t1h = c.take<int32_t>(n * (size_t)p.K * 256);
+    ks->tr = c.take<uint8_t>(n * 64);
+    size_t chunk = pick_chunk(cx->arena_bytes, n, 65536, 2 * p.pk);
+    if (chunk > (size_t(1) << 17)) chunk = size_t(1) << 17;
+    rc = cx->reserve(2 * pad256(chunk * p.pk));
+    cudaStream_t st = cx->stream;
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(cx->s_in);
+        cudaStreamSynchronize(st);
+        cudaFree(ks->base);
+        cudaGetLastError();
+        delete ks;
+        return code;
+    };
+    if (rc) return fail(rc);
+    uint8_t* stage[2] = {cx->arena, cx->arena + pad256(chunk * p.pk)};
+    size_t i = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, i++) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        uint8_t* d_pk = stage[i & 1];
+        if (i >= 2 && cudaStreamWaitEvent(cx->s_in, cx->ev_bulk[i & 1], 0) != cudaSuccess) return fail(E_CUDA);
+        e = cudaMemcpyAsync(d_pk, pk + p.pk * lo, m * p.pk, cudaMemcpyHostToDevice, cx->s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_in[i & 1], cx->s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0);
+        if (e == cudaSuccess)
+            e = verify_expand_keys(ps, st, m, d_pk, ks->A + lo * (size_t)p.K * p.L * 256, ks->t1h + lo * (size_t)p.K * 256,
+                                   ks->tr + lo * 64);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_bulk[i & 1], st);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "key set load"));
+    }
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "key set load"));
+    prof_collect();
+    *out = reinterpret_cast<mldsa_keyset*>(ks);
+    return OK;
+}
+
+// Verifier::verify on expanded PublicKeys (src/lib.rs:364-380): lane i is checked under key key_idx[i] of the set
+// (key_idx == NULL: key i; then n <= number of keys)
+int mldsa_verify_batch_keys(const mldsa_keyset* h, int framing, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                            const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
+                            uint8_t* ok)
+{
+    const KeySet* ks = as_keyset(h);
+    if (!ks) return E_PARAM;
+    return verify_host(ks->ps, ks->dev, framing, -1, n, nullptr, 0, msgs, msg_off, ctx, ctx_off, sig, ok, ks, key_idx);
 }
 
 // Signer::get_public_key (src/lib.rs:344-346 -> src/ml_dsa.rs:502-563): pk bytes from sk bytes

@@ -114,6 +114,9 @@ struct VerifyWs {
     uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1'
     uint8_t* cmask;    // [n][64]   c = SampleInBall(c~) as nonzero / negative bit masks
     uint8_t* pre_ok;   // [n]
+    // Resident key set (mldsa_pk_load): A / t1h / tr point into the key set (per key), lane i uses key kidx[i] (nullptr: i)
+    bool keys_resident = false;
+    const uint32_t* kidx = nullptr;
     static size_t bytes_per_lane(int K, int L, int w1len, bool shared)
     {
         return (shared ? 0 : (size_t)K * L * 1024 + 64) + 64 + w1len + SIB_BYTES + 8;
@@ -121,6 +124,8 @@ struct VerifyWs {
 };
 cudaError_t verify_run(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,
                        const uint8_t* sig, uint8_t* ok, const VerifyWs& ws);
+// expand_public (src/ml_dsa.rs:477-498) for nkeys packed public keys: A-hat, NTT(t1 * 2^d), tr
+cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr);
 
 // ---- k_sign.cu ----
 struct SignWs {

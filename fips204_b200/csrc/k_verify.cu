@@ -20,15 +20,16 @@ template <class P>
 __global__ void __launch_bounds__(128)
 verify_pre_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ tr_shared,
                   MsgDesc md, const uint8_t* __restrict__ sig, uint8_t* __restrict__ mw1, uint8_t* __restrict__ cmask,
-                  uint8_t* __restrict__ pre_ok)
+                  uint8_t* __restrict__ pre_ok, size_t tr_stride, const uint32_t* __restrict__ kidx)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Sponge<SHAKE256_RATE> sp;
     uint64_t tr[8];
-    if (tr_shared) {
+    if (tr_shared) {  // cached tr: one shared key (tr_stride 0) or a resident key set (64-byte rows, key kidx[i] or i)
+        const uint64_t* row = reinterpret_cast<const uint64_t*>(tr_shared + (kidx ? (size_t)kidx[i] : i) * tr_stride);
 #pragma unroll
-        for (int k = 0; k < 8; k++) tr[k] = reinterpret_cast<const uint64_t*>(tr_shared)[k];
+        for (int k = 0; k < 8; k++) tr[k] = row[k];
     } else {
         sp.init();
         sp.absorb(pk + i * pk_stride, P::PK_LEN);  // ml_dsa.rs:486-488
@@ -79,6 +80,25 @@ t1hat_kernel(const uint8_t* __restrict__ pk, int32_t* __restrict__ t1h)
     }
 }
 
+// NTT(t1 * 2^d) for every polynomial of nkeys public keys (expand_public, src/ml_dsa.rs:490-495): warp per polynomial
+template <class P>
+__global__ void __launch_bounds__(128)
+t1hat_batch_kernel(size_t nkeys, const uint8_t* __restrict__ pk, int32_t* __restrict__ t1h)
+{
+    __shared__ __align__(16) int32_t tiles[4][NTT_TILE_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t npoly = nkeys * P::K;
+    for (size_t q = (size_t)blockIdx.x * 4 + warp; q < npoly; q += (size_t)gridDim.x * 4) {
+        const size_t key = q / P::K;
+        const int k = (int)(q % P::K);
+        int32_t v[8];
+        load_t1_hat(pk + key * (size_t)P::PK_LEN + 32 + 320 * k, v, tiles[warp], lane);
+        int4* o = reinterpret_cast<int4*>(t1h + q * 256 + 8 * lane);
+        o[0] = make_int4(v[0], v[1], v[2], v[3]);
+        o[1] = make_int4(v[4], v[5], v[6], v[7]);
+    }
+}
+
 constexpr int VF_WARPS = 4;
 
 template <class P>
@@ -89,14 +109,19 @@ struct alignas(16) VerifySmem {
     alignas(16) int32_t zh[P::L][256];              // z-hat, NTT domain, natural order
 };
 
-template <class P, bool SHARED>
+// MODE 0: per-lane packed public keys (A-hat per lane in the workspace, t1-hat computed from the key bytes);
+// MODE 1: one shared key (A-hat, t1-hat cached once); MODE 2: resident key set (A-hat, t1-hat cached per key, lane
+// ln uses key kidx[ln] or ln) -- what the reference's PublicKey struct caches (src/types.rs:35-41).
+template <class P, int MODE>
 __global__ void __launch_bounds__(VF_WARPS * 32)
 verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ sig,
                     const int32_t* __restrict__ Aall, const int32_t* __restrict__ t1h_shared,
-                    const uint8_t* __restrict__ cmask, uint8_t* __restrict__ mw1, uint8_t* __restrict__ pre_ok)
+                    const uint8_t* __restrict__ cmask, uint8_t* __restrict__ mw1, uint8_t* __restrict__ pre_ok,
+                    const uint32_t* __restrict__ kidx)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
+    constexpr bool SHARED = MODE == 1;
     __shared__ __align__(16) VerifySmem<P> sm_all[VF_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     VerifySmem<P>& sm = sm_all[warp];
@@ -104,8 +129,10 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
     const size_t stride = (size_t)gridDim.x * VF_WARPS;
     for (size_t ln = (size_t)blockIdx.x * VF_WARPS + warp; ln < n; ln += stride) {
         const uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
-        const uint8_t* pkl = pk + (SHARED ? 0 : ln * pk_stride);
-        const int32_t* A = Aall + (SHARED ? 0 : ln * (size_t)(K * L) * 256);
+        const size_t key = MODE == 2 ? (kidx ? (size_t)kidx[ln] : ln) : ln;
+        const uint8_t* pkl = MODE == 0 ? pk + ln * pk_stride : pk;
+        const int32_t* A = Aall + (SHARED ? 0 : key * (size_t)(K * L) * 256);
+        const int32_t* t1h = t1h_shared + (MODE == 2 ? key * (size_t)K * 256 : 0);
         uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
         __syncwarp();
 
@@ -179,8 +206,8 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
         for (int k = 0; k < K; k++) {
             if (!SHARED && k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
             int32_t t1v[8];
-            if (SHARED) {
-                const int4* tp = reinterpret_cast<const int4*>(t1h_shared + 256 * k + 8 * lane);
+            if (MODE != 0) {
+                const int4* tp = reinterpret_cast<const int4*>(t1h + 256 * k + 8 * lane);
                 const int4 x = __ldg(tp), y = __ldg(tp + 1);
                 t1v[0] = x.x; t1v[1] = x.y; t1v[2] = x.z; t1v[3] = x.w;
                 t1v[4] = y.x; t1v[5] = y.y; t1v[6] = y.z; t1v[7] = y.w;
@@ -220,9 +247,11 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
                                 const uint8_t* sig, uint8_t* ok, const VerifyWs& ws)
 {
     constexpr int K = P::K, L = P::L;
-    const bool shared = pk_stride == 0;
+    const bool resident = ws.keys_resident, shared = !resident && pk_stride == 0;
     cudaError_t e;
-    if (shared) {
+    if (resident) {
+        // A-hat, t1-hat and tr of every key were built by verify_expand_keys
+    } else if (shared) {
         e = launch_expand_a(st, K, L, pk, 0, 1, ws.A);
         if (e != cudaSuccess) return e;
         e = launch_shake256_rows(st, pk, 0, P::PK_LEN, 1, ws.tr, 64, 64);
@@ -237,24 +266,54 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
     }
     {
         KLaunch kl(KID_VERIFY_PRE, st);
-        verify_pre_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, pk, pk_stride, shared ? ws.tr : nullptr,
-                                                                         md, sig, ws.mw1, ws.cmask, ws.pre_ok);
+        verify_pre_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
+            n, pk, pk_stride, (shared || resident) ? ws.tr : nullptr, md, sig, ws.mw1, ws.cmask, ws.pre_ok,
+            resident ? (size_t)64 : 0, resident ? ws.kidx : nullptr);
     }
-    // shared key: every CTA stages the key's A-hat and t1-hat once, so few long-lived CTAs (measured at 2^20 lanes,
-    // ML-DSA-65: 16 per SM -> 10.9 ms, 192 per SM -> 24.4 ms); distinct keys: many short ones (no partly empty last wave)
+    // One shared key: few long-lived CTAs (measured at 2^20 lanes, ML-DSA-65: 16 per SM -> 10.9 ms, 192 per SM ->
+    // 24.4 ms: the key's 36 KiB of A-hat / t1-hat stay hot in each SM's L1); per-lane keys: many short CTAs (no partly
+    // empty last wave)
     const unsigned grid = capped_grid((n + VF_WARPS - 1) / VF_WARPS, shared ? 16 : arith_cap());
     {
         KLaunch kl(KID_VERIFY_ARITH, st);
-        if (shared)
-            verify_arith_kernel<P, true><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h,
-                                                                         ws.cmask, ws.mw1, ws.pre_ok);
+        if (resident)
+            verify_arith_kernel<P, 2><<<grid, VF_WARPS * 32, 0, st>>>(n, nullptr, 0, sig, ws.A, ws.t1h, ws.cmask, ws.mw1,
+                                                                      ws.pre_ok, ws.kidx);
+        else if (shared)
+            verify_arith_kernel<P, 1><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h, ws.cmask,
+                                                                      ws.mw1, ws.pre_ok, nullptr);
         else
-            verify_arith_kernel<P, false><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr,
-                                                                          ws.cmask, ws.mw1, ws.pre_ok);
+            verify_arith_kernel<P, 0><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr, ws.cmask,
+                                                                      ws.mw1, ws.pre_ok, nullptr);
     }
     e = launch_ctilde(P::PS, st, n, nullptr, nullptr, 1, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
+}
+
+// expand_public (src/ml_dsa.rs:477-498) for nkeys packed public keys: A-hat, NTT(t1 * 2^d), tr = H(pk)
+template <class P>
+static cudaError_t verify_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr)
+{
+    cudaError_t e = launch_expand_a(st, P::K, P::L, pk, P::PK_LEN, nkeys, A);
+    if (e != cudaSuccess) return e;
+    e = launch_shake256_rows(st, pk, P::PK_LEN, P::PK_LEN, nkeys, tr, 64, 64);
+    if (e != cudaSuccess) return e;
+    {
+        KLaunch kl(KID_T1HAT, st);
+        t1hat_batch_kernel<P><<<capped_grid((nkeys * P::K + 3) / 4, arith_cap()), 128, 0, st>>>(nkeys, pk, t1h);
+    }
+    return cudaGetLastError();
+}
+cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr)
+{
+    if (nkeys == 0) return cudaSuccess;
+    switch (ps) {
+    case 44: return verify_expand_keys_t<Params<44>>(st, nkeys, pk, A, t1h, tr);
+    case 65: return verify_expand_keys_t<Params<65>>(st, nkeys, pk, A, t1h, tr);
+    case 87: return verify_expand_keys_t<Params<87>>(st, nkeys, pk, A, t1h, tr);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t verify_run(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,

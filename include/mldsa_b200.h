@@ -145,6 +145,18 @@ int mldsa_sign_batch_keys(const mldsa_keyset* ks, int framing, size_t n, const u
                           const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
                           uint8_t* sig, uint32_t* iters);
 
+/* The same for public keys: PublicKey::try_from_bytes -> expand_public (src/lib.rs:469-474, src/ml_dsa.rs:477-498)
+ * for n keys at once; rho-derived A-hat, tr = H(pk) and NTT(t1 * 2^d) (the reference's PublicKey, src/types.rs:35-41)
+ * stay in HBM (36 KiB per ML-DSA-65 key) and verify calls send only signatures and messages.  Same handle type,
+ * same mldsa_keyset_size / _device_bytes / _free; a secret-key set cannot verify and a public-key set cannot sign
+ * (-1). */
+int mldsa_pk_load(int ps, int dev, size_t n, const uint8_t* pk /* n x PK_LEN, host */, mldsa_keyset** out);
+/* Verifier::verify on expanded keys (src/lib.rs:364-380): lane i is checked under key key_idx[i] (NULL: key i).
+ * Same verdicts as mldsa_verify_batch with those keys. */
+int mldsa_verify_batch_keys(const mldsa_keyset* ks, int framing, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                            const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
+                            uint8_t* ok);
+
 /* ---- tuning / telemetry ------------------------------------------------------------------ */
 /* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 96 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);

@@ -534,3 +534,51 @@ def test_edge_shapes_vs_oracle(F, ps):
     assert m.verify_batch(pk, msgs, sig, ctxs=ctxs, shared_key=True).all()
     swapped = [ctxs[1], ctxs[0]] + ctxs[2:]
     assert list(m.verify_batch(pk, msgs, sig, ctxs=swapped, shared_key=True)[:2]) == [0, 0]
+
+
+@pytest.mark.parametrize("ps", [44, 65, 87])
+def test_resident_public_key_set_verifies_like_packed_keys(F, ps):
+    """mldsa_pk_load / mldsa_verify_batch_keys: expand_public done once per key (the reference's PublicKey,
+    src/types.rs:35-41, src/ml_dsa.rs:477-498).  Verdicts equal the oracle's on valid and mutated signatures, for
+    the identity mapping and for a key index per lane, in one chunk and in many; wrong key -> false."""
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    m = F.PARAM_SETS[ps]
+    nk, n = 300, 2100
+    pks, sks = O.keygen_batch(ps, synth_block(f"pk{ps}", nk, 32))
+    ks = m.load_public_keys(pks)
+    assert len(ks) == nk
+    msgs = [synth("pm", i, i % 45) for i in range(n)]
+    ctxs = [synth("pc", i, i % 7) for i in range(n)]
+    rnds = synth_rows("pr", n, 32)
+    idx = (np.arange(n, dtype=np.uint64) * 40503 % nk).astype(np.uint32)
+    sig, _ = O.sign_batch(ps, sks[idx], msgs, rnds, ctxs=ctxs)
+    bad = sig.copy()
+    hint_off = m.SIG_LEN - (O.params(ps).omega + m.K)
+    bad[0::7, 3] ^= 1                       # c~
+    bad[1::7, 80] ^= 4                      # z
+    bad[2::7, m.SIG_LEN - 1] = 255          # hint count > omega
+    bad[3::7, hint_off + 1] ^= 1            # hint index / padding
+    want = O.verify_batch(ps, pks[idx], msgs, bad, ctxs=ctxs)
+    assert 0 < want.sum() < n
+    try:
+        for limit in (0, 24 << 20):
+            L.mldsa_set_workspace_limit(limit)
+            assert ks.verify_batch(msgs, sig, ctxs=ctxs, key_idx=idx).all()
+            assert (ks.verify_batch(msgs, bad, ctxs=ctxs, key_idx=idx) == want).all(), (ps, limit)
+            wrong = (idx + 1) % nk
+            assert not ks.verify_batch(msgs, sig, ctxs=ctxs, key_idx=wrong).any()
+            s1, _ = O.sign_batch(ps, sks, msgs[:nk], rnds[:nk])
+            assert ks.verify_batch(msgs[:nk], s1).all()                      # identity mapping
+        with pytest.raises(ValueError):
+            ks.sign_batch(msgs[:1], rnds[:1])
+        with pytest.raises(F.MldsaError):
+            ks.verify_batch(msgs[:2], sig[:2], key_idx=np.array([0, nk], dtype=np.uint32))
+        sks_set = m.load_private_keys(sks[:4])
+        with pytest.raises(F.MldsaError):                                    # a secret-key set cannot verify
+            _lib.check(L.mldsa_verify_batch_keys(sks_set._h, 0, 1, None, None, np.zeros(2, np.uint64).ctypes.data, None, None,
+                                                 sig[:1].ctypes.data, np.zeros(1, np.uint8).ctypes.data))
+        sks_set.free()
+    finally:
+        L.mldsa_set_workspace_limit(0)
+        ks.free()
