@@ -60,28 +60,71 @@ def parse():
 # clocks sampler (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class Clocks:
-    # One sample per 400 ms: every NVML query can stall a launch or a sync of the sampled GPU for several ms
-    # (tools/smi_probe.py: 164 ms steps become 170-190 ms when a query lands in them), so the sampler is kept sparse.
+    """SM clock and throttle reasons sampled DURING the timed region.  Every NVML clock / reason query stalls the
+    sampled GPU for ~10 ms (tools/smi_probe.py: 164 ms steps become 172-178 ms when a query lands in them; the power
+    query is free), so the sampler takes TWO samples, at 1/3 and 2/3 of the expected length of the region, through
+    NVML in-process; without pynvml it falls back to the recipe's `nvidia-smi --query-gpu ... -lms` line."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, expected_s):
+        self.idx, self.rows, self.proc, self.expected = gpu_index, [], None, max(expected_s, 0.05)
+        self.samples, self.thread, self.stop_flag, self.nv = [], None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
+            period = max(200, int(self.expected * 1e3 / 3))
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "400", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(period), "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _pump_nvml(self):
+        nv, t0 = self.nv, time.perf_counter()
+        for frac in (1 / 3, 2 / 3):
+            while not self.stop_flag and time.perf_counter() - t0 < frac * self.expected:
+                time.sleep(0.002)
+            if self.stop_flag:
+                return
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1e3))
+            except Exception:
+                return
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            reasons = sorted({k for _, r, _ in self.samples for k, b in bits.items() if r & b})
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "power_w": max((s[2] for s in self.samples), default=None),
+                    "sampler": "NVML in-process, at 1/3 and 2/3 of the timed region (a clock query stalls the GPU ~10 ms)"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -93,7 +136,7 @@ class Clocks:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "sampler": "nvidia-smi --query-gpu -lms"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,14 +294,18 @@ def main():
         peaks[name] = v.value
 
     # ---- warm-up, then K timed steps between barriers; CUDA events on the launching stream
+    warm_s = 0.2
     for _ in range(max(args.warmup, 3)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         sign_dev()
+        warm_s = time.perf_counter() - t0
     L.mldsa_profile_reset()
     L.mldsa_profile_enable(1)
     launches0 = L.mldsa_kernel_launches()
-    clocks = Clocks(local)
-    clocks.start()
+    clocks = Clocks(local, warm_s * args.steps)
     barrier()
+    clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     rounds = 0
     for a, b in ev:
@@ -436,6 +483,34 @@ def main():
            "steps": e2e_steps, "step_ms_all": [round(x * 1e3, 2) for x in e2e_samples], "statistic": "median of the steps",
            "host_buffers": "pinned", "api": "mldsa_sign_batch (host pointers)"}
 
+    # ---- the same batch with the keys resident on the device (mldsa_sk_load once, untimed): the
+    # reference's expanded PrivateKey.  Extra information, not the headline: the key expansion is outside the timed calls.
+    e2e_keys = None
+    if not args.no_verify_leg:
+        hks = C.c_void_p()
+        _lib.check(L.mldsa_sk_load(args.ps, local, n, ptr(h_sk), C.byref(hks)))
+        ks_samples = []
+        for k in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            _lib.check(L.mldsa_sign_batch_keys(hks, 0, n, None, ptr(h_msg), ptr(h_moff), None, None, ptr(h_rnd), ptr(h_sig),
+                                               ptr(h_iters)))
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            if k:
+                ks_samples.append(dt)
+        L.mldsa_keyset_free(hks)
+        check["resident_keys_equal_device_resident"] = bool(torch.equal(h_sig, d_sig.cpu()))
+        ks_s = float(np.median(ks_samples))
+        e2e_keys = {"value": world * n / ks_s, "unit": "signs/s", "ms_per_step": ks_s * 1e3,
+                    "h2d_bytes_per_step": int(h_msg.numel() + h_rnd.numel() + h_moff.numel() * 8),
+                    "d2h_bytes_per_step": int(h_sig.numel() + h_iters.numel() * 4),
+                    "api": "mldsa_sign_batch_keys (keys expanded once by mldsa_sk_load, outside the timed calls)"}
+
     cpu_baseline = None
     if rank == 0:
         import oracle_lib as O
@@ -467,7 +542,8 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args, n),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_resident_keys": e2e_keys,
+            "gpu_launches": int(launches),
             "clocks": clk, "verify": verify_obj,
             "sign": {"mean_iters": iters_total / n, "rounds_per_step": rounds / args.steps,
                      "algorithmic_int32_ops_per_sign": whole_ops / n,

@@ -225,7 +225,7 @@ struct DeviceCtx {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CK(cudaStreamCreateWithPriority(&s_tail, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&s_tail, cudaStreamNonBlocking, env_int("MLDSA_TAILPRIO", 1) ? prio_hi : prio_lo));
         CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         for (int i = 0; i < SIGN_SETS; i++) {

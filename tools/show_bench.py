@@ -4,7 +4,10 @@ import json
 import sys
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(f"{d['metric']}: {d['value']:.0f} {d['unit']}  ({d['ms_per_step']:.1f} ms/step)  e2e {d['e2e']['value']:.0f}")
+print(f"{d['metric']}: {d['value']:.0f} {d['unit']}  ({d['ms_per_step']:.1f} ms/step)  e2e {d['e2e']['value']:.0f}"
+      f"  e2e resident keys {(d.get('e2e_resident_keys') or {}).get('value', 0):.0f}")
+for leg in (d.get("verify") or {}).get("legs", []):
+    print(f"  verify {leg['keys']:9s} {leg['value']:.0f}/s device-resident  {leg.get('e2e', {}).get('value', 0):.0f}/s e2e")
 if d.get("verify"):
     print("verify:", [(l["keys"], round(l["value"])) for l in d["verify"]["legs"]])
 for k, v in sorted(d.get("kernels", {}).items(), key=lambda kv: -kv[1]["ms_per_step"]):

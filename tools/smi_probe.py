@@ -27,16 +27,28 @@ def run(tag):
 for _ in range(2): sign()
 run("no sampler")
 q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-pr = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", "0"], stdout=subprocess.DEVNULL)
-time.sleep(0.5); run("nvidia-smi -lms 200"); pr.terminate(); pr.wait()
-pr = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active", "--format=csv,noheader,nounits", "-lms", "200", "-i", "0"], stdout=subprocess.DEVNULL)
-time.sleep(0.5); run("nvidia-smi 3 fields"); pr.terminate(); pr.wait()
 import pynvml
-pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0); stop = False; rows = []
-def pump():
-    while not stop:
-        rows.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
-        time.sleep(0.1)
-th = threading.Thread(target=pump); th.start(); time.sleep(0.3); run("pynvml thread 100 ms"); stop = True; th.join()
-print(len(rows), rows[:3], pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-run("no sampler")
+pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
+def with_thread(tag, fn, period):
+    global stop
+    stop = False
+    cnt = [0]
+    def pump():
+        while not stop:
+            fn(); cnt[0] += 1
+            time.sleep(period)
+    th = threading.Thread(target=pump); th.start(); time.sleep(0.3)
+    out = []
+    for _ in range(12):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); sign(); out.append(1e3 * (time.perf_counter() - t0))
+    stop = True; th.join()
+    print(f"{tag:34s} mean {sum(out)/len(out):7.2f}  max {max(out):7.2f}  ({cnt[0]} queries)", flush=True)
+with_thread("no query (sleep only)", lambda: None, 0.1)
+with_thread("clock SM @100ms", lambda: pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), 0.1)
+with_thread("event reasons @100ms", lambda: pynvml.nvmlDeviceGetCurrentClocksEventReasons(h), 0.1)
+with_thread("power @100ms", lambda: pynvml.nvmlDeviceGetPowerUsage(h), 0.1)
+with_thread("clock+reasons @400ms", lambda: (pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)), 0.4)
+pr = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "400", "-i", "0"], stdout=subprocess.DEVNULL)
+time.sleep(0.5)
+with_thread("nvidia-smi -lms 400 (9 fields)", lambda: None, 0.1)
+pr.terminate(); pr.wait()
