@@ -319,6 +319,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ uint32_t atom_add_acq_rel_cta(uint32_t* p, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
@@ -375,13 +381,18 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
         if (lane < 8)  // mu || w1 is the input row of the c~ hash
             reinterpret_cast<uint64_t*>(w1o - MU_BYTES)[lane] = reinterpret_cast<const uint64_t*>(j.mu + ln * (size_t)MU_BYTES)[lane];
         // Every warp of the group reports "done reading the staged row"; the last one to report starts the next copy.
+        // Ordering: a warp's reads of the row precede its (release) arrival; the last arriver's (acquire) arrival
+        // precedes the copy it issues; the proxy fence orders those generic-proxy accesses before the async-proxy
+        // write of the TMA unit.  (compute-sanitizer racecheck does not model completion through an mbarrier and
+        // still reports the copy against the reads of the PREVIOUS row as a hazard.)
         auto release_and_fetch = [&](int row) {
             __syncwarp();
             if (lane == 0) {
                 bool last = true;
-                if (G > 1) last = atomicAdd(&sm.cnt[grp], 1u) == (uint32_t)(G - 1);
+                if (G > 1) last = atom_add_acq_rel_cta(&sm.cnt[grp], 1u) == (uint32_t)(G - 1);
                 if (last) {
                     if (G > 1) atomicExch(&sm.cnt[grp], 0u);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_expect_tx(&sm.full[grp], ROW_BYTES);
                     bulk_g2s(sm.arow[grp], A + (size_t)row * L * 256, ROW_BYTES, &sm.full[grp]);
                 }
