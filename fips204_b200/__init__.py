@@ -29,7 +29,7 @@ import numpy as np
 from . import _lib
 from ._lib import MldsaError
 
-__all__ = ["ml_dsa_44", "ml_dsa_65", "ml_dsa_87", "Ph", "MldsaError", "micro", "device_count", "kernel_launches"]
+__all__ = ["ml_dsa_44", "ml_dsa_65", "ml_dsa_87", "Ph", "MldsaError", "micro", "device_count", "kernel_launches", "bind_host_to_device"]
 
 
 class Ph:
@@ -39,6 +39,28 @@ class Ph:
 
 def device_count():
     return _lib.lib().mldsa_device_count()
+
+
+def bind_host_to_device(dev=0):
+    """Pin the calling process to the CPU cores that are local to GPU `dev` (NVML's CPU affinity of the device), so
+    that the pinned host buffers it allocates afterwards live on that NUMA node and its copies do not cross the
+    socket interconnect.  One process per GPU (torchrun) on a two-socket box otherwise lands most ranks' buffers on
+    the wrong socket.  Returns the list of cores, or [] when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else dev
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1 and i in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
 
 
 def kernel_launches():

@@ -8,6 +8,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import fips204_b200 as F
 from fips204_b200 import _lib
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+if os.environ.get("MG_BIND") == "1":
+    print(f"rank {rank} bound to cores {F.bind_host_to_device(local)}", flush=True)
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
 L = _lib.lib(); ps = 65; m = F.PARAM_SETS[ps]; n = 1 << 20
@@ -34,4 +36,7 @@ t(verify, "verify, 9 GB pinned alive"); t(sign, "sign, 9 GB pinned alive")
 hp = pk.cpu().pin_memory(); hs = sig.cpu().pin_memory(); hm = msg.cpu().pin_memory(); hmo = moff.cpu().pin_memory(); hok = torch.zeros(n, dtype=torch.uint8).pin_memory()
 def vhost(): _lib.check(L.mldsa_verify_batch(ps, local, 0, n, p(hp), m.PK_LEN, p(hm), p(hmo), None, None, p(hs), p(hok)))
 t(vhost, "verify e2e"); t(verify, "verify after e2e")
+hsk = sk.cpu().pin_memory(); hr = rnd.cpu().pin_memory(); hsig = torch.empty((n, m.SIG_LEN), dtype=torch.uint8).pin_memory()
+def shost(): _lib.check(L.mldsa_sign_batch(ps, local, 0, n, p(hsk), m.SK_LEN, p(hm), p(hmo), None, None, p(hr), p(hsig), None))
+t(shost, "sign e2e")
 if world > 1: dist.destroy_process_group()
