@@ -716,16 +716,21 @@ __global__ void __launch_bounds__(256)
 compact_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict__ act_in,
                const uint8_t* __restrict__ done, uint32_t* __restrict__ act_out, uint32_t* __restrict__ nout)
 {
+    // grid-stride over the LIVE count (whole warps per trip): the grid is sized from the host's estimate of that
+    // count, and a lane must never be dropped from the list if the estimate was low
     const size_t nact = *nact_dev;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool keep = i < nact && !done[act_in[i]];
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(nout, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (keep) act_out[base + __popc(m & ((1u << lane) - 1))] = act_in[i];
+    const size_t span = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < nact; base += span) {
+        const size_t i = base + threadIdx.x;
+        const bool keep = i < nact && !done[act_in[i]];
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0) continue;
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t pos = 0;
+        if (lane == leader) pos = atomicAdd(nout, (uint32_t)__popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (keep) act_out[pos + __popc(m & ((1u << lane) - 1))] = act_in[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
