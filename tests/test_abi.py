@@ -99,3 +99,23 @@ def test_cpp_host_mirror_smoke_on_gpu(built):
     import subprocess
     r = subprocess.run([str(_build_cpp_example())], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.count(": ok") == 3, (r.returncode, r.stdout, r.stderr)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: exactly one JSON line on
+    stdout with the contract's keys, the oracle as a `port` baseline, and e2e equal to the line's own value."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-sample", "32"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+    assert "workload" in d["config"] and d["unit"] == "signs/s"
