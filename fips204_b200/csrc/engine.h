@@ -62,7 +62,7 @@ unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event 
 // depth: rows per lane (sign: candidates per round; row = act[i / depth] * depth + i % depth), 1 for verify.
 cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act, int depth,
                           const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
-                          uint8_t* ctilde_out, uint8_t* cmask_out);
+                          uint8_t* ctilde_out, uint8_t* cmask_out, size_t row_cap = ~size_t(0));
 
 int keccak_probe_variants();
 uint32_t keccak_probe_mask(int v);

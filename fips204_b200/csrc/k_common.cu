@@ -251,9 +251,10 @@ template <class P, bool SIGN>
 __global__ void __launch_bounds__(128, 4)
 ctilde_kernel(size_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ act, int depth,
               const uint8_t* __restrict__ mw1, const uint8_t* __restrict__ sig, const uint8_t* __restrict__ pre_ok,
-              uint8_t* __restrict__ ok, uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ cmask_out)
+              uint8_t* __restrict__ ok, uint8_t* __restrict__ ctilde_out, uint8_t* __restrict__ cmask_out, size_t row_cap)
 {
     if (n_dev) n = (size_t)*n_dev * depth;  // sign rounds: live (active lane, candidate) count; n only bounds the launch
+    if (n > row_cap) n = row_cap - row_cap % depth;  // tail rounds: whole lanes inside the shared tail region
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t row = act ? (size_t)act[idx / depth] * depth + idx % depth : idx;  // row = lane * depth + candidate
         ctilde_row<P, SIGN>(row, mw1, sig, pre_ok, ok, ctilde_out, cmask_out);
@@ -263,28 +264,28 @@ ctilde_kernel(size_t n, const uint32_t* __restrict__ n_dev, const uint32_t* __re
 template <class P>
 static cudaError_t launch_ctilde_t(cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act, int depth,
                                    const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
-                                   uint8_t* ctilde_out, uint8_t* sib_out)
+                                   uint8_t* ctilde_out, uint8_t* sib_out, size_t row_cap)
 {
     const unsigned grid = capped_grid((n + 127) / 128, tuning().kcap);
     {
         KLaunch kl(KID_CTILDE, st);
         if (ctilde_out)
-            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+            ctilde_kernel<P, true><<<grid, 128, 0, st>>>(n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out, row_cap);
         else
-            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+            ctilde_kernel<P, false><<<grid, 128, 0, st>>>(n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out, row_cap);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_ctilde(int ps, cudaStream_t st, size_t n, const uint32_t* n_dev, const uint32_t* act, int depth,
                           const uint8_t* mw1, const uint8_t* sig, const uint8_t* pre_ok, uint8_t* ok,
-                          uint8_t* ctilde_out, uint8_t* sib_out)
+                          uint8_t* ctilde_out, uint8_t* sib_out, size_t row_cap)
 {
     if (n == 0) return cudaSuccess;
     switch (ps) {
-    case 44: return launch_ctilde_t<Params<44>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    case 65: return launch_ctilde_t<Params<65>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
-    case 87: return launch_ctilde_t<Params<87>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out);
+    case 44: return launch_ctilde_t<Params<44>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out, row_cap);
+    case 65: return launch_ctilde_t<Params<65>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out, row_cap);
+    case 87: return launch_ctilde_t<Params<87>>(st, n, n_dev, act, depth, mw1, sig, pre_ok, ok, ctilde_out, sib_out, row_cap);
     }
     return cudaErrorInvalidValue;
 }

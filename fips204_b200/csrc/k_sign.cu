@@ -130,6 +130,7 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
 // in the active list * depth + candidate -- the few live lanes share the low end of the candidate buffers.
 struct MaskJob {
     const uint32_t* nact; const uint32_t* act; const uint8_t* rhopp; const uint32_t* kappa; uint8_t* yraw; int depth; int pos;
+    size_t cap;  // pos = 1: candidate slots of the tail region; lanes whose slots would lie beyond it sit the round out
 };
 struct CtildeJob {
     const uint32_t* nact; const uint32_t* act; const uint8_t* mw1; uint8_t* ctilde; uint8_t* cmask; int depth;
@@ -138,6 +139,7 @@ struct SignWJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* A; const uint8_t* yraw; int32_t* w; uint8_t* mw1; int depth;
     const uint8_t* mu; int pos;
     const uint32_t* kidx;  // resident key set: key of lane ln = kidx[ln] (nullptr: ln)
+    size_t cap;            // as MaskJob::cap
 };
 struct SignZJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* s1h; const int32_t* s2h; const int32_t* t0h;
@@ -161,6 +163,7 @@ __device__ __forceinline__ void mask_unit(const MaskJob& j, size_t unit)
     const size_t q = unit * 128 + threadIdx.x;
     if (q >= nstreams) return;
     const size_t li = q / L;
+    if (j.pos && (li + 1) * (size_t)j.depth > j.cap) return;  // (only if the host's estimate of the live count was low)
     const size_t ln = j.act[li];
     const uint32_t r = (uint32_t)(q % L);
     const uint64_t* rp = reinterpret_cast<const uint64_t*>(j.rhopp + 64 * ln);
@@ -232,7 +235,7 @@ __device__ __forceinline__ void sign_w_unit(const SignWJob& j, size_t unit, Sign
     SignWSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
     const size_t ai = unit * SG_WARPS + warp;
-    if (ai < nact) {
+    if (ai < nact && !(j.pos && (ai / depth + 1) * (size_t)depth > j.cap)) {
         const size_t ln = act[ai / depth];
         const size_t slot = j.pos ? ai : ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
         const int32_t* A = Aall + (SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln) * (size_t)(K * L) * 256);
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
     for (size_t u = blockIdx.x; u < nu; u += gridDim.x) {
         const size_t ai = u * SG_WARPS + warp;
         if (ai >= nitems) continue;  // G = 2 needs an even depth, so both warps of a group skip together
+        if (j.pos && (ai / depth + 1) * (size_t)depth > j.cap) continue;  // whole lanes (all warps of a group) sit out
         const size_t ln = j.act[ai / depth];
         const size_t slot = j.pos ? ai : ln * depth + ai % depth;
         const int32_t* A = j.A + (SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln) * (size_t)(K * L) * 256);
@@ -517,7 +521,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
     int32_t* tile = sm.tile;
     uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
     const size_t ai = unit * SG_WARPS + warp;
-    if (ai < nact) {
+    if (ai < nact && !(j.pos && (ai + 1) * (size_t)depth > j.tail_slots)) {  // (a lane without slots sits the round out)
         const size_t ln = act[ai];
         const size_t kn = SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln);
         const size_t sbase = (j.pos ? ai : ln) * depth;  // first candidate slot of this lane
@@ -864,10 +868,10 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
     {
         KLaunch kl(KID_MASK, st);
         mask_kernel<P><<<capped_grid((sz * L * D + 127) / 128, tn.kcap), 128, 0, st>>>(
-            MaskJob{nact, act, ws.rhopp, ws.kappa, ws.yraw, D, pos});
+            MaskJob{nact, act, ws.rhopp, ws.kappa, ws.yraw, D, pos, r.tail_slots});
     }
     cudaError_t ce = cudaSuccess;
-    const SignWJob wj{nact, act, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, pos, ws.kidx};
+    const SignWJob wj{nact, act, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, pos, ws.kidx, r.tail_slots};
     if (tn.stage == 0) {
         KLaunch kl(KID_SIGN_W, st);
         if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
@@ -881,7 +885,8 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
         if (ce != cudaSuccess) return ce;
     }
     // pos: rows are the positions themselves (act = nullptr)
-    ce = launch_ctilde(P::PS, st, sz * D, nact, pos ? nullptr : act, D, ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.cmask);
+    ce = launch_ctilde(P::PS, st, sz * D, nact, pos ? nullptr : act, D, ws.mw1, nullptr, nullptr, nullptr, ws.ctilde, ws.cmask,
+                       pos ? r.tail_slots : ~size_t(0));
     if (ce != cudaSuccess) return ce;
     {
         const SignZJob zj{nact, act, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done, ws.rhopp,
@@ -915,9 +920,12 @@ static cudaError_t sign_round(cudaStream_t st, SignRun& r, size_t sz)
 static cudaError_t sign_rounds_until(cudaStream_t st, SignRun& r, double stop_at)
 {
     const int max_rounds = tuning().max_rounds;
+    // test hook: MLDSA_EST_SCALE < 1 makes the host UNDER-estimate the live count, which exercises what must then still
+    // hold -- grid-stride kernels and compaction over the true count, lanes without a tail slot sitting a round out
+    static const double est_scale = getenv("MLDSA_EST_SCALE") ? atof(getenv("MLDSA_EST_SCALE")) : 1.0;
     while (r.expect > stop_at) {
         if (max_rounds > 0 && r.rounds >= max_rounds) break;  // test hook: fixed number of rounds
-        size_t sz = (size_t)(r.expect * 1.25) + 256;
+        size_t sz = (size_t)(r.expect * 1.25 * est_scale) + (est_scale < 1.0 ? 1 : 256);
         if (sz > r.n) sz = r.n;
         const double keep = pow(1.0 - 0.19, (double)round_depth(r, sz));
         cudaError_t e = sign_round(st, r, sz);
@@ -949,9 +957,9 @@ static cudaError_t sign_paired_t(cudaStream_t st, SignRun& r, const uint8_t* sk,
     } way[2];
     way[0].lo = 0, way[0].bound = nA;
     way[1].lo = nA, way[1].bound = n - nA;
-    auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D, 0}; };
+    auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D, 0, 0}; };
     auto ct_job = [&](int v) { return CtildeJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.mw1, ws.ctilde, ws.cmask, D}; };
-    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, 0, ws.kidx}; };
+    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, 0, ws.kidx, 0}; };
     auto z_job = [&](int v) {
         return SignZJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde,
                         ws.cmask, ws.kappa, ws.done, ws.rhopp, r.sig, r.iters, D, 0, D, 0, ws.kidx, ws.keys_resident ? 0 : 1};

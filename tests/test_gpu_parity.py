@@ -582,3 +582,38 @@ def test_resident_public_key_set_verifies_like_packed_keys(F, ps):
     finally:
         L.mldsa_set_workspace_limit(0)
         ks.free()
+
+
+def test_sign_survives_a_low_live_count_estimate():
+    """The host sizes every round's grids (and picks the tail depth) from an ESTIMATE of the live-lane count.
+    MLDSA_EST_SCALE=0.3 makes that estimate far too low: the kernels must still cover the true count (grid-stride
+    loops, grid-stride compaction), lanes that find no slot in the shared tail region must sit the round out
+    untouched, and the straggler rounds must finish the batch -- with the reference's bytes and iteration counts."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+import numpy as np
+import fips204_b200 as F, oracle_lib as O
+from fips204_b200 import _lib
+from synth import synth, synth_block, synth_rows
+L = _lib.lib()
+for ps in (44, 65, 87):
+    m = F.PARAM_SETS[ps]
+    n = 4000
+    pks, sks = O.keygen_batch(ps, synth_block(f"est{ps}", n, 32))
+    msgs = [synth("em", i, i % 33) for i in range(n)]
+    rnds = synth_rows("er", n, 32)
+    want, wit = O.sign_batch(ps, sks, msgs, rnds)
+    for td, slots in ((16, 1024), (8, 32768), (0, 0)):
+        L.mldsa_set_tail(td, slots)
+        sig, it = m.sign_batch(sks, msgs, rnds, want_iters=True)
+        assert (sig == want).all() and (it == wit).all(), (ps, td, slots)
+print("ok")
+'''
+    env = dict(os.environ, MLDSA_EST_SCALE="0.3")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                       cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent), timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-300:], r.stderr[-1500:])
