@@ -617,3 +617,44 @@ print("ok")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                        cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent), timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-300:], r.stderr[-1500:])
+
+
+def test_multi_device_entry_points_split_contiguously(F):
+    """mldsa_*_batch_multi: one host thread per listed device, contiguous lane ranges, disjoint output slices, ragged
+    message / ctx blobs addressed by absolute offsets.  Runs over every visible GPU -- or three shards on device 0 when
+    there is only one (the shards then serialise on the device context, the splitting logic is the same)."""
+    import ctypes as C
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    ps = 65
+    m = F.PARAM_SETS[ps]
+    ndev = F.device_count()
+    devs = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    darr = (C.c_int * len(devs))(*devs)
+    n = 1000 + 7
+    xi = synth_block("md-xi", n, 32)
+    pk = np.empty((n, m.PK_LEN), np.uint8)
+    sk = np.empty((n, m.SK_LEN), np.uint8)
+    _lib.check(L.mldsa_keygen_batch_multi(ps, darr, len(devs), n, xi.ctypes.data, pk.ctypes.data, sk.ctypes.data))
+    opk, osk = O.keygen_batch(ps, xi)
+    assert (pk == opk).all() and (sk == osk).all()
+    msgs = [synth("md-m", i, i % 53) for i in range(n)]
+    ctxs = [synth("md-c", i, i % 5) for i in range(n)]
+    rnd = synth_rows("md-r", n, 32)
+    mb = np.frombuffer(b"".join(msgs) + b"\0", np.uint8).copy()
+    mo = np.zeros(n + 1, np.uint64)
+    mo[1:] = np.cumsum([len(x) for x in msgs])
+    cb = np.frombuffer(b"".join(ctxs) + b"\0", np.uint8).copy()
+    co = np.zeros(n + 1, np.uint32)
+    co[1:] = np.cumsum([len(x) for x in ctxs])
+    sig = np.empty((n, m.SIG_LEN), np.uint8)
+    it = np.zeros(n, np.uint32)
+    _lib.check(L.mldsa_sign_batch_multi(ps, darr, len(devs), 0, n, sk.ctypes.data, m.SK_LEN, mb.ctypes.data, mo.ctypes.data,
+                                        cb.ctypes.data, co.ctypes.data, rnd.ctypes.data, sig.ctypes.data, it.ctypes.data))
+    osig, oit = O.sign_batch(ps, sk, msgs, rnd, ctxs=ctxs)
+    assert (sig == osig).all() and (it == oit).all()
+    sig[[0, 500, n - 1], 9] ^= 2
+    ok = np.zeros(n, np.uint8)
+    _lib.check(L.mldsa_verify_batch_multi(ps, darr, len(devs), 0, n, pk.ctypes.data, m.PK_LEN, mb.ctypes.data,
+                                          mo.ctypes.data, cb.ctypes.data, co.ctypes.data, sig.ctypes.data, ok.ctypes.data))
+    assert list(np.nonzero(ok == 0)[0]) == [0, 500, n - 1]
