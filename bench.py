@@ -551,6 +551,12 @@ def main():
                      "whole_step_frac_of_int32_peak": whole_ops / (ms_per_step * 1e-3) / peaks["both"]},
             "int32_peaks_tops": {k: v / 1e12 for k, v in peaks.items()},
             "kernels": kernels, "check": check,
+            # the only figures that are the reference's own (benches/README.md:16-26: one core of an i7-7700K @ 4.2 GHz,
+            # pre-expanded keys); the cpu_baseline above is this repo's C oracle on the GPU box's host cores
+            "reference_published": {"sign_us": {"44": 226.32, "65": 352.89, "87": 385.05}[str(args.ps)],
+                                    "verify_us": {"44": 21.016, "65": 27.996, "87": 36.468}[str(args.ps)],
+                                    "keygen_us": {"44": 104.89, "65": 194.80, "87": 290.24}[str(args.ps)],
+                                    "hardware": "Intel i7-7700K, 1 core", "source": "benches/README.md:16-26"},
         }
         _JSON_OUT.write(json.dumps(line) + "\n")
         _JSON_OUT.flush()

@@ -658,3 +658,28 @@ def test_multi_device_entry_points_split_contiguously(F):
     _lib.check(L.mldsa_verify_batch_multi(ps, darr, len(devs), 0, n, pk.ctypes.data, m.PK_LEN, mb.ctypes.data,
                                           mo.ctypes.data, cb.ctypes.data, co.ctypes.data, sig.ctypes.data, ok.ctypes.data))
     assert list(np.nonzero(ok == 0)[0]) == [0, 500, n - 1]
+
+
+def test_config1_reference_benchmark_inputs(F):
+    """BASELINE configs[0]: the inputs of the reference's own benchmark (benches/benchmark.rs: counter RNG, keys from
+    draws 0 / 1 / 2, message 00..07, sign with ctx = [], verify of a ctx = [0] signature under ctx = [] -> false)
+    through the engine, byte for byte against the oracle (tools/bench_config1.py times the same lanes on the CPU)."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench_config1", Path(__file__).resolve().parent.parent / "tools" / "bench_config1.py")
+    c1 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c1)
+    assert c1.draw(0x01020304)[:6] == bytes([1, 2, 3, 4, 4, 4]) and c1.draw(7) == bytes([0, 0, 0, 7] + [7] * 28)
+    n = 96
+    for ps in (44, 65, 87):
+        m = F.PARAM_SETS[ps]
+        xi, pk, sk, rnd, sig0 = c1.workload(ps, n)
+        opk, osk = O.keygen_batch(ps, xi)
+        gpk, gsk = m.keygen_batch(xi)
+        assert (gpk == opk).all() and (gsk == osk).all()
+        osig, oit = O.sign_batch(ps, np.frombuffer(sk, np.uint8), [c1.MSG] * n, rnd, ctxs=[b""] * n, shared_key=True)
+        gsig, git = m.sign_batch(sk, [c1.MSG] * n, rnd, ctxs=[b""] * n, shared_key=True, want_iters=True)
+        assert (gsig == osig).all() and (git == oit).all()
+        sigs = np.tile(np.frombuffer(sig0, np.uint8), (n, 1))
+        assert not m.verify_batch(pk, [c1.MSG] * n, sigs, ctxs=[b""] * n, shared_key=True).any()      # benchmark.rs:58
+        assert m.verify_batch(pk, [c1.MSG] * n, sigs, ctxs=[b"\0"] * n, shared_key=True).all()
