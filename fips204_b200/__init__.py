@@ -334,8 +334,9 @@ class PrivateKeySet:
     def device_bytes(self):
         return int(_lib.lib().mldsa_keyset_device_bytes(self._h)) if self._h else 0
 
-    def sign_batch(self, msgs, rnds, ctxs=None, key_idx=None, framing=0, want_iters=False):
-        """Lane i signs msgs[i] with key key_idx[i] (default: key i).  Same bytes as _ParamSet.sign_batch."""
+    def sign_batch(self, msgs, rnds, ctxs=None, key_idx=None, framing=0, want_iters=False, ph=None):
+        """Lane i signs msgs[i] with key key_idx[i] (default: key i).  Same bytes as _ParamSet.sign_batch; ph = Ph.*
+        selects HashML-DSA."""
         if not self._h:
             raise ValueError("key set was freed")
         m, n = self._mod, len(msgs)
@@ -353,8 +354,9 @@ class PrivateKeySet:
             raise ValueError("key_idx must have n entries")
         sig = np.empty((n, m.SIG_LEN), dtype=np.uint8)
         iters = np.zeros(n, dtype=np.uint32)
-        rc = _lib.lib().mldsa_sign_batch_keys(self._h, framing, n, _ptr(ki), _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co),
-                                              _ptr(rnd), _ptr(sig), _ptr(iters))
+        fn = _lib.lib().mldsa_sign_batch_keys if ph is None else _lib.lib().mldsa_hash_sign_batch_keys
+        rc = fn(self._h, framing if ph is None else int(ph), n, _ptr(ki), _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co), _ptr(rnd),
+                _ptr(sig), _ptr(iters))
         if rc == -2:
             raise ValueError("ML-DSA.Sign: ctx too long")
         _lib.check(rc)
@@ -378,9 +380,9 @@ class PublicKeySet(PrivateKeySet):
     def sign_batch(self, *a, **kw):
         raise ValueError("a public-key set cannot sign")
 
-    def verify_batch(self, msgs, sigs, ctxs=None, key_idx=None, framing=0):
+    def verify_batch(self, msgs, sigs, ctxs=None, key_idx=None, framing=0, ph=None):
         """-> uint8[n]; lane i is checked under key key_idx[i] (default: key i).  Same verdicts as
-        _ParamSet.verify_batch."""
+        _ParamSet.verify_batch; ph = Ph.* selects HashML-DSA."""
         if not self._h:
             raise ValueError("key set was freed")
         m, n = self._mod, len(msgs)
@@ -395,8 +397,9 @@ class PublicKeySet(PrivateKeySet):
         if ki is not None and ki.size != n:
             raise ValueError("key_idx must have n entries")
         ok = np.zeros(n, dtype=np.uint8)
-        _lib.check(_lib.lib().mldsa_verify_batch_keys(self._h, framing, n, _ptr(ki), _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co),
-                                                      _ptr(sg), _ptr(ok)))
+        fn = _lib.lib().mldsa_verify_batch_keys if ph is None else _lib.lib().mldsa_hash_verify_batch_keys
+        _lib.check(fn(self._h, framing if ph is None else int(ph), n, _ptr(ki), _ptr(mb), _ptr(mo), _ptr(cb), _ptr(co),
+                      _ptr(sg), _ptr(ok)))
         return ok
 
 

@@ -50,6 +50,10 @@ SIGNATURES = {
     "mldsa_pk_load": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mldsa_verify_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mldsa_hash_sign_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mldsa_hash_verify_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mldsa_keyset_size": (C.c_size_t, [C.c_void_p]),
     "mldsa_keyset_device_bytes": (C.c_size_t, [C.c_void_p]),
     "mldsa_keyset_free": (None, [C.c_void_p]),

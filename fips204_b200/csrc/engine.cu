@@ -1453,6 +1453,25 @@ int mldsa_sk_load(int ps, int dev, size_t n, const uint8_t* sk, mldsa_keyset** o
     return OK;
 }
 
+static KeySet* as_keyset(const mldsa_keyset* h);
+// HashML-DSA on expanded keys (src/lib.rs:310-342, :391-411): ph = 0 / 1 / 2 = SHA-256 / SHA-512 / SHAKE128 pre-hash
+int mldsa_hash_sign_batch_keys(const mldsa_keyset* h, int ph, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                               const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                               uint8_t* sig, uint32_t* iters)
+{
+    const KeySet* ks = as_keyset(h);
+    if (!ks || ph < 0 || ph > 2) return E_PARAM;
+    return sign_host(ks->ps, ks->dev, 0, ph, n, nullptr, 128, msgs, msg_off, ctx, ctx_off, rnd, sig, iters, ks, key_idx);
+}
+int mldsa_hash_verify_batch_keys(const mldsa_keyset* h, int ph, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                                 const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
+                                 uint8_t* ok)
+{
+    const KeySet* ks = as_keyset(h);
+    if (!ks || ph < 0 || ph > 2) return E_PARAM;
+    return verify_host(ks->ps, ks->dev, 0, ph, n, nullptr, 0, msgs, msg_off, ctx, ctx_off, sig, ok, ks, key_idx);
+}
+
 static KeySet* as_keyset(const mldsa_keyset* h)
 {
     KeySet* ks = reinterpret_cast<KeySet*>(const_cast<mldsa_keyset*>(h));

@@ -157,6 +157,15 @@ int mldsa_verify_batch_keys(const mldsa_keyset* ks, int framing, size_t n, const
                             const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
                             uint8_t* ok);
 
+/* HashML-DSA on resident key sets (try_hash_sign_with_rng src/lib.rs:310-342, hash_verify :391-411): ph as in
+ * mldsa_hash_sign_batch (0 SHA-256, 1 SHA-512, 2 SHAKE128), the pre-hash runs on the device. */
+int mldsa_hash_sign_batch_keys(const mldsa_keyset* ks, int ph, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                               const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                               uint8_t* sig, uint32_t* iters);
+int mldsa_hash_verify_batch_keys(const mldsa_keyset* ks, int ph, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
+                                 const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
+                                 uint8_t* ok);
+
 /* ---- tuning / telemetry ------------------------------------------------------------------ */
 /* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 96 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);

@@ -683,3 +683,29 @@ def test_config1_reference_benchmark_inputs(F):
         sigs = np.tile(np.frombuffer(sig0, np.uint8), (n, 1))
         assert not m.verify_batch(pk, [c1.MSG] * n, sigs, ctxs=[b""] * n, shared_key=True).any()      # benchmark.rs:58
         assert m.verify_batch(pk, [c1.MSG] * n, sigs, ctxs=[b"\0"] * n, shared_key=True).all()
+
+
+def test_hash_ml_dsa_on_resident_key_sets(F):
+    """try_hash_sign* / hash_verify (src/lib.rs:310-342, :391-411) on expanded keys: same bytes as the packed-key
+    HashML-DSA path and the oracle, for all three pre-hash functions and a key index per lane."""
+    ps = 65
+    m = F.PARAM_SETS[ps]
+    nk, n = 40, 300
+    pks, sks = O.keygen_batch(ps, synth_block("hk", nk, 32))
+    sset, pset = m.load_private_keys(sks), m.load_public_keys(pks)
+    msgs = [synth("hkm", i, (i * 13) % 400) for i in range(n)]
+    ctxs = [synth("hkc", i, i % 12) for i in range(n)]
+    rnds = synth_rows("hkr", n, 32)
+    idx = (np.arange(n) * 7 % nk).astype(np.uint32)
+    try:
+        for ph in (F.Ph.SHA256, F.Ph.SHA512, F.Ph.SHAKE128):
+            sig = sset.sign_batch(msgs, rnds, ctxs=ctxs, key_idx=idx, ph=ph)
+            assert (sig == m.hash_sign_batch(sks[idx], msgs, rnds, ph, ctxs=ctxs)).all()
+            for i in (0, 17, n - 1):
+                assert sig[i].tobytes() == O.sign(ps, sks[idx[i]].tobytes(), msgs[i], rnds[i].tobytes(), ctx=ctxs[i], framing=2, ph=ph)
+            assert pset.verify_batch(msgs, sig, ctxs=ctxs, key_idx=idx, ph=ph).all()
+            assert not pset.verify_batch(msgs, sig, ctxs=ctxs, key_idx=idx).any()           # not a pure ML-DSA signature
+            assert not pset.verify_batch(msgs, sig, ctxs=ctxs, key_idx=idx, ph=(ph + 1) % 3).any()
+    finally:
+        sset.free()
+        pset.free()
