@@ -166,7 +166,13 @@ int mldsa_hash_verify_batch_keys(const mldsa_keyset* ks, int ph, size_t n, const
                                  const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
                                  uint8_t* ok);
 
-/* ---- tuning / telemetry ------------------------------------------------------------------ */
+/* ---- tuning / telemetry ------------------------------------------------------------------
+ * Environment knobs (read once; the setters below override them): MLDSA_DEPTH, MLDSA_TAILDEPTH, MLDSA_TAILSLOTS,
+ * MLDSA_KCAP, MLDSA_ACAP, MLDSA_STAGE, MLDSA_PAIR, MLDSA_KSHARE as documented at the setters; host pipelines:
+ * MLDSA_PLAN (chunk sizes of a large batch, e.g. "1,2,4,6,6,6,4,2,1"), MLDSA_TAIL (live lanes at which a sign chunk
+ * hands over to the tail stream, default 16384), MLDSA_TAILPRIO (0: low-priority tail stream), MLDSA_NCAP (CTAs per
+ * SM of the standalone NTT), MLDSA_TRACE=1 (device-side timeline of the host pipelines on stderr); test hook:
+ * MLDSA_EST_SCALE (< 1 makes the host under-estimate the live-lane counts of the sign rounds). */
 /* upper bound for the per-call device scratch, bytes (0 = default: 60% of free memory, <= 96 GiB) */
 void mldsa_set_workspace_limit(size_t bytes);
 /* launch tuning: kcap / acap cap the CTAs per SM of the (grid-stride) Keccak / arithmetic kernels (0 = default:
