@@ -486,9 +486,11 @@ def main():
     # ---- the same batch with the keys resident on the device (mldsa_sk_load once, untimed): the
     # reference's expanded PrivateKey.  Extra information, not the headline: the key expansion is outside the timed calls.
     e2e_keys = None
-    if not args.no_verify_leg:
-        hks = C.c_void_p()
-        _lib.check(L.mldsa_sk_load(args.ps, local, n, ptr(h_sk), C.byref(hks)))
+    hks = C.c_void_p()
+    if not args.no_verify_leg and L.mldsa_sk_load(args.ps, local, n, ptr(h_sk), C.byref(hks)) != 0:
+        # (2^20 expanded ML-DSA-87 keys next to the cached 96 GiB arena do not fit in 180 GB: the leg is skipped)
+        e2e_keys, hks = {"unavailable": "key set + cached workspace exceed device memory"}, C.c_void_p()
+    if hks:
         ks_samples = []
         for k in range(4):
             barrier()
