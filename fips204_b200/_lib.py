@@ -46,6 +46,7 @@ SIGNATURES = {
     "mldsa_set_depth": (None, [C.c_int]),
     "mldsa_set_tail": (None, [C.c_int, C.c_int]),
     "mldsa_debug_set_max_rounds": (None, [C.c_int]),
+    "mldsa_debug_chunk_plan": (C.c_size_t, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
     "mldsa_sk_load": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mldsa_pk_load": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mldsa_verify_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

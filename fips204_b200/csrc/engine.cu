@@ -7,6 +7,7 @@
 // synchronous and re-entrant; calls on different devices run concurrently from different threads.
 #include "engine.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -550,6 +551,63 @@ static bool check_msgs(size_t n, const uint8_t* msgs, const uint64_t* msg_off, c
 
 using namespace mldsa;
 
+// Lanes per chunk of a host-pipeline call over n lanes when at most `cap` lanes fit the workspace; empty = no plan
+// (the caller falls back to chunks of `cap`).
+static std::vector<size_t> plan_sizes(size_t n, size_t cap)
+{
+    // Chunks ramp up and down in units of 32 768 lanes (1, 2, 4, then at most 6 units = 196 608 lanes, mirrored at the
+    // end): the exposed pipeline fill (first copy-in) and drain (last tail + copy-out) are one unit's worth, the bulk
+    // rounds of a 32 768-lane chunk are as efficient as those of a large one (161 ns per lane, timeline in
+    // profiles/r06_e2e_timeline.md), and a chunk's latency-bound tail hides under the next chunk's bulk.  2^20 lanes:
+    // 1-2-4-6-6-6-4-2-1; 2^17 lanes: 1-2-1; below two units: one chunk.  MLDSA_PLAN overrides the shape with explicit
+    // proportions ("1,3,4,4,3,1" = sixteenths).
+    constexpr size_t UNIT = 32768;
+    std::vector<size_t> sizes;  // lanes per chunk
+    if (const char* pe = getenv("MLDSA_PLAN")) {
+        std::vector<size_t> f;
+        size_t total = 0;
+        for (const char* q = pe; *q;) {
+            char* end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v > 0 && v < 4096) {
+                f.push_back((size_t)v);
+                total += (size_t)v;
+            }
+            q = *end ? end + 1 : end;
+        }
+        if (!f.empty() && n >= 2 * UNIT) {
+            size_t acc = 0, prev = 0;
+            for (size_t v : f) {
+                acc += v;
+                sizes.push_back(n * acc / total - prev);
+                prev = n * acc / total;
+            }
+        }
+    } else if (n >= 2 * UNIT && cap >= 2 * UNIT) {
+        const size_t units = n / UNIT, rest = n % UNIT;
+        const size_t step_cap = std::min<size_t>(6, (cap - (UNIT - 1)) / UNIT);  // the largest chunk also takes `rest`
+        std::vector<size_t> left, right;
+        size_t rem = units, step = 1;
+        while (rem > 0) {
+            const size_t a = std::min(step, rem);
+            left.push_back(a);
+            rem -= a;
+            if (rem == 0) break;
+            const size_t b = std::min(step, rem);
+            right.insert(right.begin(), b);
+            rem -= b;
+            step = std::min(step * 2, step_cap);
+        }
+        left.insert(left.end(), right.begin(), right.end());
+        size_t big = left.size() / 2;  // the remainder goes to the largest chunk, the middle one among equals
+        for (size_t i = 0; i < left.size(); i++)
+            if (left[i] > left[big]) big = i;
+        for (size_t i = 0; i < left.size(); i++) sizes.push_back(left[i] * UNIT + (i == big ? rest : 0));
+    }
+    return sizes;
+}
+
 extern "C" {
 
 int mldsa_device_count(void)
@@ -706,6 +764,18 @@ int mldsa_int32_peak_probe(int mode, double* ops_per_sec)
     return OK;
 }
 int mldsa_last_sign_rounds(void) { return t_last_rounds; }
+
+// Test hook: the chunk sizes the host pipelines would use for n lanes when `cap` lanes fit the workspace (no device
+// needed).  Returns the number of chunks (0: no ramp plan, the caller cuts chunks of `cap`), at most max_out are written.
+size_t mldsa_debug_chunk_plan(size_t n, size_t cap, size_t* out, size_t max_out)
+{
+    const std::vector<size_t> sizes = plan_sizes(n, cap);
+    bool fits = !sizes.empty();
+    for (size_t m : sizes) fits = fits && m > 0 && m <= cap;
+    if (!fits) return 0;
+    for (size_t i = 0; i < sizes.size() && i < max_out; i++) out[i] = sizes[i];
+    return sizes.size();
+}
 
 // Test hook for the ZeroizeOnDrop analogue (src/types.rs:19): bytes that are not zero in the device ranges which held
 // secret-derived data (staged sk / xi / rnd, rho', K, s1, s2, their NTT images, y, w - c*s2, rho'') during the most
@@ -925,31 +995,14 @@ static ChunkPlan plan_chunks(size_t arena_bytes, size_t n, size_t fixed, size_t 
     ChunkPlan pl;
     const size_t cap = pick_chunk(arena_bytes, n, fixed, per_lane);
     pl.lo.push_back(0);
-    // Big batch that would fit in a few chunks: ramp the chunk sizes up and down, so that the exposed pipeline fill
-    // (first copy-in) and drain (last tail + copy-out) are 1/32 of the work instead of 1/4.  MLDSA_PLAN overrides the
-    // shape ("1,3,4,4,3,1" = sixteenths).
-    std::vector<int> frac = {1, 2, 4, 6, 6, 6, 4, 2, 1};
-    if (const char* pe = getenv("MLDSA_PLAN")) {
-        std::vector<int> f;
-        for (const char* q = pe; *q;) {
-            char* end = nullptr;
-            const long v = strtol(q, &end, 10);
-            if (end == q) break;
-            if (v > 0 && v < 4096) f.push_back((int)v);
-            q = *end ? end + 1 : end;
-        }
-        if (!f.empty()) frac = f;
-    }
-    int total = 0, biggest = 0;
-    for (int f : frac) {
-        total += f;
-        if (f > biggest) biggest = f;
-    }
-    if (n >= (size_t(1) << 17) && cap >= (n * (size_t)biggest + total - 1) / total) {
+    std::vector<size_t> sizes = plan_sizes(n, cap);
+    bool fits = !sizes.empty();
+    for (size_t m : sizes) fits = fits && m > 0 && m <= cap;
+    if (fits) {
         size_t acc = 0;
-        for (int f : frac) {
-            acc += f;
-            pl.lo.push_back(n * acc / total);
+        for (size_t m : sizes) {
+            acc += m;
+            pl.lo.push_back(acc);
         }
     } else {
         for (size_t lo = cap; lo < n; lo += cap) pl.lo.push_back(lo);

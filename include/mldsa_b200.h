@@ -201,6 +201,9 @@ int mldsa_debug_secret_residue(int dev, uint64_t* nonzero_bytes, uint64_t* scann
  * rounds (0 = off, the default), wipes the unfinished lanes' state and returns -5; with rounds = 1 every kernel of
  * the loop runs exactly once over all lanes, so per-kernel device times can be compared between input classes. */
 void mldsa_debug_set_max_rounds(int rounds);
+/* test hook: chunk sizes (lanes) the host pipelines use for an n-lane call when `cap` lanes fit the workspace; returns
+ * the number of chunks (0 = plain chunks of `cap`), writes at most max_out of them.  Needs no device. */
+size_t mldsa_debug_chunk_plan(size_t n, size_t cap, size_t* out, size_t max_out);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */

@@ -119,3 +119,27 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
     assert "workload" in d["config"] and d["unit"] == "signs/s"
+
+
+def test_host_pipeline_chunk_plan(built):
+    """Chunk sizes of the host entry points (mldsa_debug_chunk_plan, no device needed): units of 32 768 lanes ramping
+    1-2-4-6...6-4-2-1, every lane covered exactly once, no chunk above the workspace capacity, small batches in one
+    chunk, and a fallback (0) when not even two units fit."""
+    import ctypes as C
+    from fips204_b200 import _lib
+    L = _lib.lib()
+
+    def plan(n, cap):
+        out = (C.c_size_t * 256)()
+        k = L.mldsa_debug_chunk_plan(n, cap, out, 256)
+        return list(out[:k])
+
+    U = 32768
+    assert plan(1 << 20, 1 << 20) == [U * x for x in (1, 2, 4, 6, 6, 6, 4, 2, 1)]
+    assert plan(1 << 17, 1 << 20) == [U, 2 * U, U]
+    assert plan(1 << 16, 1 << 20) == [U, U]
+    assert plan(50000, 1 << 20) == [] and plan(1 << 20, 40000) == []          # one chunk / plain chunks of cap
+    for n, cap in ((3000001, 455000), (1 << 20, 100000), (200000, 70000), (65537, 1 << 20), (10 ** 7, 1 << 19)):
+        p = plan(n, cap)
+        assert p and sum(p) == n and max(p) <= cap and min(p) >= U, (n, cap, p)
+        assert max(p) <= 6 * U + U - 1 and (len(p) < 3 or (p[0] == U and p[-1] == U)), (n, cap, p)
