@@ -29,6 +29,14 @@ template <class M> static int run(const char* name, int want_pk0)
     std::vector<uint8_t> rnd(3 * 32, 12);
     auto sigs = set.sign_batch(msgs, nullptr, rnd.data(), idx);
     ok = ok && set.size() == 1 && sigs[0] == sig && sigs[2] == sig && pk.verify(m2, sigs[1], {});
+    // ... and the expanded public key verifies them; the signature of m1 is not one of m2
+    typename M::PublicKeySet pset(1, pk.bytes.data());
+    std::vector<uint8_t> flat;
+    for (auto& s : sigs) flat.insert(flat.end(), s.begin(), s.end());
+    auto v = pset.verify_batch(msgs, nullptr, flat.data(), idx);
+    std::vector<std::vector<uint8_t>> swapped{m2, m2, m1};
+    auto w = pset.verify_batch(swapped, nullptr, flat.data(), idx);
+    ok = ok && v[0] && v[1] && v[2] && !w[0] && w[1] && w[2];
     std::printf("%s: %s\n", name, ok ? "ok" : "FAILED");
     return ok ? 0 : 1;
 }

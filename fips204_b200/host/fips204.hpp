@@ -152,6 +152,39 @@ struct ParamSet {
         }
     };
 
+    // Expanded public keys resident on the device: rho-derived A-hat, tr, NTT(t1 * 2^d) per key -- the fields of the
+    // reference's PublicKey (types.rs:35-41, built by expand_public, ml_dsa.rs:477-498).  verify_batch: lane i is
+    // checked under key key_idx[i] (nullptr: key i); never throws for malformed signatures (lib.rs:368-370).
+    struct PublicKeySet {
+        mldsa_keyset* handle = nullptr;
+        PublicKeySet(size_t n, const uint8_t* pk, int dev = 0) { check(mldsa_pk_load(PS, dev, n, pk, &handle)); }
+        ~PublicKeySet() { mldsa_keyset_free(handle); }
+        PublicKeySet(const PublicKeySet&) = delete;
+        PublicKeySet& operator=(const PublicKeySet&) = delete;
+        size_t size() const { return mldsa_keyset_size(handle); }
+        std::vector<uint8_t> verify_batch(const std::vector<Bytes>& msgs, const std::vector<Bytes>* ctxs, const uint8_t* sigs,
+                                          const uint32_t* key_idx = nullptr, int framing = 0) const
+        {
+            const size_t n = msgs.size();
+            std::vector<uint8_t> mb, cb, ok(n, 0);
+            std::vector<uint64_t> mo(n + 1, 0);
+            std::vector<uint32_t> co(n + 1, 0);
+            for (size_t i = 0; i < n; i++) {
+                mb.insert(mb.end(), msgs[i].begin(), msgs[i].end());
+                mo[i + 1] = mb.size();
+                if (ctxs) {
+                    cb.insert(cb.end(), (*ctxs)[i].begin(), (*ctxs)[i].end());
+                    co[i + 1] = static_cast<uint32_t>(cb.size());
+                }
+            }
+            mb.push_back(0);
+            cb.push_back(0);
+            check(mldsa_verify_batch_keys(handle, framing, n, key_idx, mb.data(), mo.data(), ctxs ? cb.data() : nullptr,
+                                          ctxs ? co.data() : nullptr, sigs, ok.data()));
+            return ok;
+        }
+    };
+
     // ---- the reference's types ----------------------------------------------------------------
     struct PublicKey {  // types.rs:35-41 (here: canonical bytes)
         std::array<uint8_t, PK> bytes{};
