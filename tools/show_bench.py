@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """Pretty-print the last JSON line of a bench.py output file."""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` closes the pipe early
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(f"{d['metric']}: {d['value']:.0f} {d['unit']}  ({d['ms_per_step']:.1f} ms/step)  e2e {d['e2e']['value']:.0f}"
