@@ -188,7 +188,7 @@ def reference_arm(args, rank, world):
     import oracle_lib as O
     from synth import synth_block
     cores = O.ncores()
-    sample = args.ref_sample or max(256, min(args.lanes, cores * 96))
+    sample = args.ref_sample or max(256, min(args.lanes, cores * 1024))  # ~0.7 s of work per step on every core
     xi = synth_block("bench-xi", sample, 32)
     pk, sk = O.keygen_batch(args.ps, xi)
     msgs = [bytes(m) for m in synth_block("bench-msg", sample, MSG_LEN)]
