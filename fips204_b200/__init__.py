@@ -290,6 +290,57 @@ class _ParamSet:
         _lib.check(_lib.lib().mldsa_pk_load(self.PS, dev, pk.shape[0], _ptr(pk), C.byref(h)))
         return PublicKeySet(self, h)
 
+    def keygen_to_keysets(self, xis, dev=0, want_pk=True, want_private=True, want_public=True):
+        """n x 32 seeds -> (pk bytes or None, PrivateKeySet or None, PublicKeySet or None): KG::keygen_from_seed whose
+        expanded keys stay on the device (mldsa_keygen_to_keyset); no packed secret key crosses PCIe."""
+        xi = _u8(xis).reshape(-1, 32)
+        n = xi.shape[0]
+        pk = np.empty((n, self.PK_LEN), dtype=np.uint8) if want_pk else None
+        hs, hp = C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib().mldsa_keygen_to_keyset(self.PS, dev, n, _ptr(xi), _ptr(pk), C.byref(hs) if want_private else None,
+                                                     C.byref(hp) if want_public else None))
+        return pk, (PrivateKeySet(self, hs) if want_private else None), (PublicKeySet(self, hp) if want_public else None)
+
+    def pipeline_batch(self, xis, msgs, rnds, ctxs=None, framing=0, devs=(0,), want_sk=False, want_iters=False,
+                       want_stage_ms=False):
+        """keygen -> sign -> verify chained on the device(s) (the flow of lib.rs:503-551 as one batch call): lane i
+        derives its key pair from xis[i], signs msgs[i] and verifies the result.  -> dict(pk, sig, ok[, sk, iters,
+        stage_ms]).  Same bytes as keygen_batch / sign_batch / verify_batch called one after the other."""
+        xi = _u8(xis).reshape(-1, 32)
+        n = xi.shape[0]
+        if len(msgs) != n:
+            raise ValueError("msgs must have n entries")
+        rnd = _u8(rnds)
+        if rnd.size != 32 * n:
+            raise ValueError("rnd must be n x 32 bytes")
+        mb, mo = _ragged(msgs, np.uint64)
+        cb = co = None
+        if ctxs is not None:
+            if len(ctxs) != n:
+                raise ValueError("ctxs must have n entries")
+            if any(len(c) > 255 for c in ctxs):
+                raise ValueError("ML-DSA.Sign: ctx too long")
+            cb, co = _ragged(ctxs, np.uint32)
+        out = {"pk": np.empty((n, self.PK_LEN), dtype=np.uint8), "sig": np.empty((n, self.SIG_LEN), dtype=np.uint8),
+               "ok": np.zeros(n, dtype=np.uint8)}
+        sk = np.empty((n, self.SK_LEN), dtype=np.uint8) if want_sk else None
+        iters = np.zeros(n, dtype=np.uint32) if want_iters else None
+        ms = (C.c_double * 3)() if want_stage_ms else None
+        dv = np.ascontiguousarray(list(devs), dtype=np.int32)
+        rc = _lib.lib().mldsa_pipeline_batch_multi(self.PS, _ptr(dv), len(dv), framing, n, _ptr(xi), _ptr(mb), _ptr(mo), _ptr(cb),
+                                                   _ptr(co), _ptr(rnd), _ptr(out["pk"]), _ptr(sk), _ptr(out["sig"]),
+                                                   _ptr(out["ok"]), _ptr(iters), C.cast(ms, C.c_void_p) if ms else None)
+        if rc == -2:
+            raise ValueError("ML-DSA.Sign: ctx too long")
+        _lib.check(rc)
+        if want_sk:
+            out["sk"] = sk
+        if want_iters:
+            out["iters"] = iters
+        if want_stage_ms:
+            out["stage_ms"] = [float(x) for x in ms]
+        return out
+
     def sk_to_pk_batch(self, sks, dev=0):
         """Signer::get_public_key over a batch: n x SK_LEN -> pk[n, PK_LEN] (ml_dsa.rs:502-563)."""
         sk = _u8(sks).reshape(-1, self.SK_LEN)

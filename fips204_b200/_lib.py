@@ -55,13 +55,16 @@ SIGNATURES = {
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mldsa_hash_verify_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mldsa_keygen_to_keyset": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p)]),
+    "mldsa_pipeline_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, sz] + [vp] * 12),
+    "mldsa_pipeline_batch_multi": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, sz] + [vp] * 12),
     "mldsa_keyset_size": (C.c_size_t, [C.c_void_p]),
     "mldsa_keyset_device_bytes": (C.c_size_t, [C.c_void_p]),
     "mldsa_keyset_free": (None, [C.c_void_p]),
     "mldsa_sign_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mldsa_debug_secret_residue": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "mldsa_set_pairing": (None, [C.c_int, C.c_int]),
     "mldsa_kernel_launches": (C.c_uint64, []),
     "mldsa_last_sign_rounds": (C.c_int, []),
     "mldsa_profile_enable": (None, [C.c_int]),

@@ -32,7 +32,7 @@ static uint64_t g_prof_n[KID_COUNT];
 static const char* const KERNEL_NAMES[KID_COUNT] = {
     "expand_a", "ntt", "intt", "shake_rows", "ctilde", "kg_seed", "rej_bounded", "kg_arith", "verify_pre",
     "t1hat", "verify_arith", "sign_prep", "sign_key", "mask", "sign_w", "sign_z", "compact", "int_probe", "prehash",
-    "sk_to_pk", "round_pair"};
+    "sk_to_pk"};
 
 struct EvPair {
     int id;
@@ -90,8 +90,7 @@ void prof_collect()
     t_events.swap(pending);
 }
 
-static std::atomic<int> g_ways{-1}, g_kcap{-1}, g_acap{-1}, g_depth{-1}, g_pair{-1}, g_kshare{-1}, g_stage{-1},
-    g_tail_depth{-1}, g_tail_slots{-1}, g_max_rounds{0};
+static std::atomic<int> g_kcap{-1}, g_acap{-1}, g_depth{-1}, g_tail_depth{-1}, g_tail_slots{-1}, g_max_rounds{0};
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -99,36 +98,30 @@ static int env_int(const char* name, int dflt)
 }
 Tuning tuning()
 {
-    int w = g_ways.load(), k = g_kcap.load(), a = g_acap.load();
-    if (w < 0) g_ways.store(w = env_int("MLDSA_WAYS", 1));
+    int k = g_kcap.load(), a = g_acap.load();
     if (k < 0) g_kcap.store(k = env_int("MLDSA_KCAP", 0));
     if (a < 0) g_acap.store(a = env_int("MLDSA_ACAP", 0));
-    if (w < 1) w = 1;
-    if (w > 8) w = 8;
     int d = g_depth.load();
     if (d < 0) g_depth.store(d = env_int("MLDSA_DEPTH", 2));
     if (d < 1) d = 1;
     if (d > 8) d = 8;
-    int pr = g_pair.load(), ks = g_kshare.load();
-    if (pr < 0) g_pair.store(pr = env_int("MLDSA_PAIR", 0));
-    if (ks < 0) g_kshare.store(ks = env_int("MLDSA_KSHARE", 2));
-    int sg = g_stage.load();
-    if (sg < 0) g_stage.store(sg = env_int("MLDSA_STAGE", 2));
     int td = g_tail_depth.load(), ts = g_tail_slots.load();
     if (td < 0) g_tail_depth.store(td = env_int("MLDSA_TAILDEPTH", 8));
     if (ts < 0) g_tail_slots.store(ts = env_int("MLDSA_TAILSLOTS", 32768));
     if (td > 16) td = 16;
     if (ts < 0) ts = 0;
-    return Tuning{w, k, a, d, pr, sg, ks, td, ts, g_max_rounds.load()};
+    return Tuning{k, a, d, td, ts, g_max_rounds.load()};
 }
 unsigned capped_grid(size_t want_ctas, int cap_per_sm)
 {
-    static int sms = 0;
+    static std::atomic<int> sm_count[64];  // per device: a box may mix parts
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = dev >= 0 && dev < 64 ? sm_count[dev].load(std::memory_order_relaxed) : 0;
     if (sms == 0) {
-        int dev = 0, n = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        sms = n;
+        sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (dev >= 0 && dev < 64) sm_count[dev].store(sms, std::memory_order_relaxed);
     }
     if (want_ctas < 1) want_ctas = 1;
     if (cap_per_sm > 0 && want_ctas > (size_t)sms * cap_per_sm) want_ctas = (size_t)sms * cap_per_sm;
@@ -246,7 +239,10 @@ struct DeviceCtx {
         if (bytes <= arena_bytes) return OK;
         const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
         uint8_t* fresh = nullptr;
+        // Scratch that held secrets is zeroed by every entry point before it returns; the old arena is wiped once more
+        // before it goes back to the driver, so that nothing depends on that invariant (ZeroizeOnDrop, src/types.rs:19).
         if (keep == 0 && arena) {
+            cudaMemset(arena, 0, arena_bytes);
             cudaFree(arena);
             arena = nullptr;
             arena_bytes = 0;
@@ -254,6 +250,7 @@ struct DeviceCtx {
         CK(cudaMalloc(reinterpret_cast<void**>(&fresh), want));
         if (arena) {
             cudaError_t e = cudaMemcpy(fresh, arena, keep, cudaMemcpyDeviceToDevice);
+            cudaMemset(arena, 0, arena_bytes);
             cudaFree(arena);
             if (e != cudaSuccess) {
                 cudaFree(fresh);
@@ -351,7 +348,7 @@ static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared, bool residen
     const size_t nk = resident ? 0 : (shared ? 1 : n), D = (size_t)tuning().depth;
     return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
            pad256(n * D * p.K * 1024) + pad256(n * D * p.L * 32 * p.zbits) + pad256(n * D * (64 + p.w1len)) +
-           2 * pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64) + pad256(2 * 2048 * 4);
+           2 * pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64);
 }
 static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint32_t* mailbox, bool resident = false)
 {
@@ -374,7 +371,6 @@ static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint
     w.act[0] = c.take<uint32_t>(n);
     w.act[1] = c.take<uint32_t>(n);
     w.nact = c.take<uint32_t>(16);
-    w.queue = c.take<uint32_t>(2 * 2048);
     w.h_nact = mailbox;
     return w;
 }
@@ -481,6 +477,15 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
     if (rc) return rc;
     t_last_rounds = 0;
     cx.clear_secrets();
+    if (d_ctx_off) {
+        // ctx longer than 255 bytes fails the whole call (src/lib.rs:274) BEFORE any candidate is computed: the rounds
+        // write z of not-yet-accepted candidates into d_sig, and mu of such a lane would lack the ctx framing
+        uint32_t* flag = cx.mailbox + 64;
+        *flag = 0;
+        CK(launch_ctx_check(st, n, d_ctx_off, flag));
+        CK(cudaStreamSynchronize(st));
+        if (*flag) return E_CTX;
+    }
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
         Carver c(cx.arena + arena_skip);
@@ -496,6 +501,7 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
         // Everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop) is zeroed by
         // sign_z as each lane finishes; A-hat, mu||w1, c~ and the challenge are public.
         sign_wipe(ws, m, shared, e != cudaSuccess, st);
+        if (e != cudaSuccess) cudaMemsetAsync(d_sig, 0, n * p.sig, st);  // no partial output next to an error code
         cudaStreamSynchronize(st);
         prof_collect();
         t_last_rounds += run.rounds;
@@ -542,6 +548,12 @@ static bool check_msgs(size_t n, const uint8_t* msgs, const uint64_t* msg_off, c
                        const uint32_t* ctx_off)
 {
     if (!msg_off) return false;
+    // offsets must not decrease: a non-monotone pair would underflow the unsigned length arithmetic below
+    for (size_t i = 0; i < n; i++)
+        if (msg_off[i + 1] < msg_off[i]) return false;
+    if (ctx_off)
+        for (size_t i = 0; i < n; i++)
+            if (ctx_off[i + 1] < ctx_off[i]) return false;
     if (!msgs && n && msg_off[n] != msg_off[0]) return false;
     if ((ctx == nullptr) != (ctx_off == nullptr)) return ctx_off == nullptr || ctx_off[n] == ctx_off[0];
     return true;
@@ -661,14 +673,9 @@ void mldsa_set_tail(int tail_depth, int tail_slots)
     g_tail_depth.store(tail_depth < 0 ? 0 : (tail_depth > 16 ? 16 : tail_depth));
     g_tail_slots.store(tail_slots < 0 ? 0 : tail_slots);
 }
-void mldsa_set_pairing(int pair, int kshare)
-{
-    g_pair.store(pair ? 1 : 0);
-    g_kshare.store(kshare < 1 ? 2 : (kshare > 4 ? 4 : kshare));
-}
 void mldsa_set_tuning(int ways, int kcap, int acap)
 {
-    g_ways.store(ways < 1 ? 1 : ways);
+    (void)ways;
     g_kcap.store(kcap < 0 ? 0 : kcap);
     g_acap.store(acap < 0 ? 0 : acap);
 }
@@ -1216,6 +1223,7 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
             }
             if (!resident) cudaMemsetAsync(set[k].sk, 0, sk_set, B);
             cudaMemsetAsync(set[k].rnd, 0, C * 32, B);
+            cudaMemsetAsync(set[k].sig, 0, C * p.sig, B);  // z of candidates that were never accepted
         }
         cudaStreamSynchronize(B);
         cudaGetLastError();
@@ -1643,6 +1651,393 @@ int mldsa_verify_batch_keys(const mldsa_keyset* h, int framing, size_t n, const 
     return verify_host(ks->ps, ks->dev, framing, -1, n, nullptr, 0, msgs, msg_off, ctx, ctx_off, sig, ok, ks, key_idx);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------- device-side key provisioning and the chained pipeline
+static KeySet* keyset_new(const PSInfo& p, int ps, int dev, size_t n, bool is_public, int* rc)
+{
+    KeySet* ks = new (std::nothrow) KeySet;
+    if (!ks) {
+        *rc = E_NOMEM;
+        return nullptr;
+    }
+    ks->ps = ps;
+    ks->dev = dev;
+    ks->n = n;
+    ks->is_public = is_public;
+    const size_t a_b = pad256(n * (size_t)p.K * p.L * 1024), k_b = pad256(n * (size_t)p.K * 1024);
+    ks->bytes = is_public ? a_b + k_b + pad256(n * 64) : a_b + pad256(n * (size_t)p.L * 1024) + 2 * k_b + pad256(n * 128);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ks->base), ks->bytes);
+    if (e != cudaSuccess) {
+        delete ks;
+        *rc = cuda_fail(e, "key set allocation");
+        return nullptr;
+    }
+    Carver c(ks->base);
+    ks->A = c.take<int32_t>(n * (size_t)p.K * p.L * 256);
+    if (is_public) {
+        ks->t1h = c.take<int32_t>(n * (size_t)p.K * 256);
+        ks->tr = c.take<uint8_t>(n * 64);
+    } else {
+        ks->s1h = c.take<int32_t>(n * (size_t)p.L * 256);
+        ks->s2h = c.take<int32_t>(n * (size_t)p.K * 256);
+        ks->t0h = c.take<int32_t>(n * (size_t)p.K * 256);
+        ks->mini = c.take<uint8_t>(n * 128);
+    }
+    return ks;
+}
+static void keyset_drop(KeySet* ks)  // zeroize + free (the caller holds the device's lock)
+{
+    if (!ks) return;
+    cudaMemset(ks->base, 0, ks->bytes);
+    cudaFree(ks->base);
+    cudaGetLastError();
+    ks->magic = 0;
+    delete ks;
+}
+
+extern "C" {
+
+// KG::keygen_from_seed (src/lib.rs:247-251, src/ml_dsa.rs:57-134) straight into EXPANDED keys that stay on the device
+// (expand_private / expand_public, src/ml_dsa.rs:445-498): a signing service provisions its keys from seeds and never
+// moves a packed secret key over PCIe.  Only xi goes in; the packed public keys come back if `pk` is given.
+int mldsa_keygen_to_keyset(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk, mldsa_keyset** sk_set,
+                           mldsa_keyset** pk_set)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || n == 0 || !xi || (!sk_set && !pk_set)) return E_PARAM;
+    if (sk_set) *sk_set = nullptr;
+    if (pk_set) *pk_set = nullptr;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    KeySet* sks = sk_set ? keyset_new(p, ps, dev, n, false, &rc) : nullptr;
+    if (rc) return rc;
+    KeySet* pks = pk_set ? keyset_new(p, ps, dev, n, true, &rc) : nullptr;
+    if (rc) {
+        keyset_drop(sks);
+        return rc;
+    }
+    constexpr size_t NS = 2;
+    const size_t KL = (size_t)p.K * p.L, KpL = (size_t)(p.K + p.L);
+    size_t chunk = pick_chunk(cx->arena_bytes, n, 65536, NS * (32 + p.pk + p.sk) + 128 + KpL * 256 + 64);
+    if (chunk > (size_t(1) << 17)) chunk = size_t(1) << 17;  // the pk copy-out of chunk i runs under the kernels of i + 1
+    const size_t set_bytes = pad256(chunk * 32) + pad256(chunk * p.pk) + pad256(chunk * p.sk);
+    struct Set {
+        uint8_t *xi, *pk, *sk;
+    } set[NS];
+    uint8_t* seeds = nullptr;
+    int8_t* sbuf = nullptr;
+    cudaStream_t st = cx->stream;
+    auto fail = [&](int code) {
+        const std::string err = t_cuda_err;
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(cx->s_out);
+        if (cx->arena && seeds) cudaMemset(cx->arena, 0, NS * set_bytes + pad256(chunk * 128) + pad256(chunk * KpL * 256));
+        keyset_drop(sks);
+        keyset_drop(pks);
+        cudaGetLastError();
+        t_cuda_err = err;
+        return code;
+    };
+    rc = cx->reserve(NS * set_bytes + pad256(chunk * 128) + pad256(chunk * KpL * 256));
+    if (rc) return fail(rc);
+    Carver c(cx->arena);
+    for (auto& s : set) {
+        s.xi = c.take<uint8_t>(chunk * 32);
+        s.pk = c.take<uint8_t>(chunk * p.pk);
+        s.sk = c.take<uint8_t>(chunk * p.sk);
+    }
+    seeds = c.take<uint8_t>(chunk * 128);
+    sbuf = c.take<int8_t>(chunk * KpL * 256);
+    cx->clear_secrets();
+    const size_t first = n < chunk ? n : chunk;
+    for (size_t k = 0; k < NS; k++) {
+        const size_t used = k == 0 ? first : (n > chunk ? (n - chunk < chunk ? n - chunk : chunk) : 0);
+        cx->note_secret(set[k].xi, used * 32);
+        cx->note_secret(set[k].sk, used * p.sk);
+    }
+    cx->note_secret(seeds, first * 128);
+    cx->note_secret(sbuf, first * KpL * 256);
+    int32_t* const A_all = sks ? sks->A : pks->A;
+    CK(cudaStreamSynchronize(cx->s_out));
+    size_t i = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, i++) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        Set& s = set[i % NS];
+        cudaError_t e = cudaSuccess;
+        if (i >= NS) e = cudaStreamWaitEvent(st, cx->ev_out[i % NS], 0);  // the set's previous public keys are on the host
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.xi, xi + 32 * lo, m * 32, cudaMemcpyHostToDevice, st);
+        KeygenWs ws{seeds, sbuf, A_all + lo * KL * 256};  // A-hat is written once, straight into the key set
+        if (e == cudaSuccess) e = keygen_run(ps, st, m, s.xi, s.pk, s.sk, ws);
+        if (e == cudaSuccess && sks) {
+            e = sign_expand_keys(ps, st, m, s.sk, nullptr, sks->s1h + lo * (size_t)p.L * 256, sks->s2h + lo * (size_t)p.K * 256,
+                                 sks->t0h + lo * (size_t)p.K * 256, /*with_A*/ false);
+            if (e == cudaSuccess)  // rho || K || tr rows (src/encodings.rs:168-176)
+                e = cudaMemcpy2DAsync(sks->mini + 128 * lo, 128, s.sk, p.sk, 128, m, cudaMemcpyDeviceToDevice, st);
+        }
+        if (e == cudaSuccess && pks) {
+            if (sks)
+                e = cudaMemcpyAsync(pks->A + lo * KL * 256, sks->A + lo * KL * 256, m * KL * 1024, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess)
+                e = verify_expand_keys(ps, st, m, s.pk, nullptr, pks->t1h + lo * (size_t)p.K * 256, nullptr, false, false);
+            if (e == cudaSuccess)  // tr = H(pk) is bytes 64..127 of the secret key keygen just wrote (src/ml_dsa.rs:99-101)
+                e = cudaMemcpy2DAsync(pks->tr + 64 * lo, 64, s.sk + 64, p.sk, 64, m, cudaMemcpyDeviceToDevice, st);
+        }
+        // xi, rho', K, s1, s2 and the packed secret key are secret: nothing of them outlives the chunk
+        if (e == cudaSuccess) e = cudaMemsetAsync(s.xi, 0, m * 32, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(seeds, 0, m * 128, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sbuf, 0, m * KpL * 256, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(s.sk, 0, m * p.sk, st);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_bulk[i % NS], st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cx->s_out, cx->ev_bulk[i % NS], 0);
+        if (e == cudaSuccess && pk) e = cudaMemcpyAsync(pk + p.pk * lo, s.pk, m * p.pk, cudaMemcpyDeviceToHost, cx->s_out);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_out[i % NS], cx->s_out);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "keygen_to_keyset"));
+    }
+    cudaError_t e = cudaStreamSynchronize(cx->s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "keygen_to_keyset"));
+    prof_collect();
+    if (sk_set) *sk_set = reinterpret_cast<mldsa_keyset*>(sks);
+    if (pk_set) *pk_set = reinterpret_cast<mldsa_keyset*>(pks);
+    return OK;
+}
+
+}  // extern "C"
+
+// keygen -> sign -> verify chained on one device, keys and signatures staying in HBM between the stages (the smoke flow
+// of src/lib.rs:503-551 as a batch).  A-hat is expanded ONCE per key, by keygen, and reused by sign and verify (the
+// reference re-derives it in all three, src/ml_dsa.rs:78, :181, :360).  stage_ms (optional, 3 doubles): device time of the
+// keygen / sign / verify stage summed over the chunks.
+static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* xi, const uint8_t* msgs, const uint64_t* msg_off,
+                         const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd, uint8_t* pk, uint8_t* sk, uint8_t* sig,
+                         uint8_t* ok, uint32_t* iters, double* stage_ms)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || (framing != 0 && framing != 1)) return E_PARAM;
+    if (n && (!xi || !rnd || !pk || !sig || !ok || !check_msgs(n, msgs, msg_off, ctx, ctx_off))) return E_PARAM;
+    if (stage_ms) stage_ms[0] = stage_ms[1] = stage_ms[2] = 0;
+    if (n == 0) return OK;
+    if (ctx_off)
+        for (size_t i = 0; i < n; i++)
+            if (ctx_off[i + 1] - ctx_off[i] > 255) return E_CTX;  // src/lib.rs:274
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    constexpr size_t NS = 2;
+    const size_t KL = (size_t)p.K * p.L, KpL = (size_t)(p.K + p.L);
+    const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
+    const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
+    auto ws_bytes_for = [&](size_t C) {
+        return pad256(C * 128) + pad256(C * KpL * 256) + pad256(C * KL * 1024) + pad256(C * (size_t)p.L * 1024) +
+               2 * pad256(C * (size_t)p.K * 1024) + pad256(sign_ws_bytes(p, C, false, true)) + 4096 +
+               verify_ws_bytes(p, C, true) + pad256(C * (size_t)p.K * 1024) + pad256(C * 64);
+    };
+    const size_t ws_lane = ws_bytes_for(1024) / 1024 + 1;
+    const size_t io_lane = NS * (64 + p.pk + p.sk + p.sig + 1 + 4 + 8 + 4 + avg_msg + avg_ctx + 16);
+    const size_t cap = pick_chunk(cx->arena_bytes, n, ws_bytes_for(0) + 65536, ws_lane + io_lane);
+    // chunks of >= 32768 lanes (as efficient as large ones, profiles/r06_e2e_timeline.md), at least ~8 per call so that
+    // the copy-out of chunk i hides under the stages of chunk i + 1
+    size_t C = n;
+    if (n >= 65536) C = std::max<size_t>(32768, (n + 7) / 8);
+    if (C > cap) C = cap;
+    const size_t N = (n + C - 1) / C;
+    size_t max_mbytes = 0, max_cbytes = 0;
+    for (size_t lo = 0; lo < n; lo += C) {
+        const size_t m = n - lo < C ? n - lo : C;
+        max_mbytes = std::max(max_mbytes, (size_t)(msg_off[lo + m] - msg_off[lo]));
+        if (ctx_off) max_cbytes = std::max(max_cbytes, (size_t)(ctx_off[lo + m] - ctx_off[lo]));
+    }
+    struct Set {
+        uint8_t *xi, *rnd, *pk, *sk, *sig, *ok, *m, *c;
+        uint32_t *it, *co;
+        uint64_t* mo;
+    } set[NS];
+    const size_t set_bytes = 2 * pad256(C * 32) + pad256(C * p.pk) + pad256(C * p.sk) + pad256(C * p.sig) + pad256(C) +
+                             pad256(C * 4) + pad256((C + 1) * 4) + pad256((C + 1) * 8) + pad256(max_mbytes + 8) +
+                             pad256(max_cbytes + 8);
+    rc = cx->reserve(NS * set_bytes + ws_bytes_for(C) + 4096);
+    if (rc) return rc;
+    Carver c(cx->arena);
+    for (auto& s : set) {
+        s.xi = c.take<uint8_t>(C * 32);
+        s.rnd = c.take<uint8_t>(C * 32);
+        s.pk = c.take<uint8_t>(C * p.pk);
+        s.sk = c.take<uint8_t>(C * p.sk);
+        s.sig = c.take<uint8_t>(C * p.sig);
+        s.ok = c.take<uint8_t>(C);
+        s.it = c.take<uint32_t>(C);
+        s.co = c.take<uint32_t>(C + 1);
+        s.mo = c.take<uint64_t>(C + 1);
+        s.m = c.take<uint8_t>(max_mbytes + 8);
+        s.c = c.take<uint8_t>(max_cbytes + 8);
+    }
+    uint8_t* const ws_base = cx->arena + c.off;
+    KeygenWs kws;
+    kws.seeds = c.take<uint8_t>(C * 128);
+    kws.s = c.take<int8_t>(C * KpL * 256);
+    kws.A = c.take<int32_t>(C * KL * 256);
+    int32_t* s1h = c.take<int32_t>(C * (size_t)p.L * 256);
+    int32_t* s2h = c.take<int32_t>(C * (size_t)p.K * 256);
+    int32_t* t0h = c.take<int32_t>(C * (size_t)p.K * 256);
+    SignWs sws = sign_carve(c, p, C, false, cx->mailbox, /*resident*/ true);
+    sws.keys_resident = true;  // A-hat and the s-hat rows are this pipeline's own arrays, wiped after the stage
+    sws.A = kws.A;
+    sws.s1h = s1h;
+    sws.s2h = s2h;
+    sws.t0h = t0h;
+    c.take<uint8_t>(4096);
+    VerifyWs vws0 = verify_carve(c, p, C, true);
+    int32_t* t1h = c.take<int32_t>(C * (size_t)p.K * 256);
+    uint8_t* tr = c.take<uint8_t>(C * 64);
+    uint8_t* const ws_end = cx->arena + c.off;
+    cx->clear_secrets();
+    cudaStream_t B = cx->stream;
+    std::vector<cudaEvent_t> tev;
+    if (stage_ms) {
+        tev.resize(N * 4);
+        for (auto& e : tev) cudaEventCreate(&e);
+    }
+    auto bail = [&](int code) -> int {  // stop everything, leave no secrets behind
+        const std::string err = t_cuda_err;
+        cudaStreamSynchronize(cx->s_in);
+        cudaStreamSynchronize(B);
+        cudaStreamSynchronize(cx->s_out);
+        cudaMemsetAsync(ws_base, 0, (size_t)(ws_end - ws_base), B);
+        for (auto& s : set) {
+            cudaMemsetAsync(s.xi, 0, C * 32, B);
+            cudaMemsetAsync(s.rnd, 0, C * 32, B);
+            cudaMemsetAsync(s.sk, 0, C * p.sk, B);
+            cudaMemsetAsync(s.sig, 0, C * p.sig, B);
+        }
+        cudaStreamSynchronize(B);
+        for (auto& e : tev) cudaEventDestroy(e);
+        cudaGetLastError();
+        prof_collect();
+        t_cuda_err = err;
+        return code;
+    };
+    auto copy_in = [&](size_t i) -> int {
+        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        Set& s = set[i % NS];
+        const size_t mbytes = (size_t)(msg_off[lo + m] - msg_off[lo]);
+        const size_t cbytes = ctx_off ? (size_t)(ctx_off[lo + m] - ctx_off[lo]) : 0;
+        if (i >= NS) CK(cudaStreamWaitEvent(cx->s_in, cx->ev_bulk[i % NS], 0));  // the set's previous chunk is computed
+        CK(cudaMemcpyAsync(s.xi, xi + 32 * lo, m * 32, cudaMemcpyHostToDevice, cx->s_in));
+        CK(cudaMemcpyAsync(s.rnd, rnd + 32 * lo, m * 32, cudaMemcpyHostToDevice, cx->s_in));
+        CK(cudaMemcpyAsync(s.mo, msg_off + lo, (m + 1) * 8, cudaMemcpyHostToDevice, cx->s_in));
+        if (mbytes) CK(cudaMemcpyAsync(s.m, msgs + msg_off[lo], mbytes, cudaMemcpyHostToDevice, cx->s_in));
+        if (ctx_off) {
+            CK(cudaMemcpyAsync(s.co, ctx_off + lo, (m + 1) * 4, cudaMemcpyHostToDevice, cx->s_in));
+            if (cbytes) CK(cudaMemcpyAsync(s.c, ctx + ctx_off[lo], cbytes, cudaMemcpyHostToDevice, cx->s_in));
+        }
+        CK(cudaEventRecord(cx->ev_in[i % NS], cx->s_in));
+        return OK;
+    };
+    CK(cudaStreamSynchronize(cx->s_in));
+    CK(cudaStreamSynchronize(cx->s_out));
+    t_last_rounds = 0;
+    if ((rc = copy_in(0))) return bail(rc);
+    for (size_t i = 0; i < N; i++) {
+        const size_t lo = i * C, m = n - lo < C ? n - lo : C;
+        Set& s = set[i % NS];
+        auto mark = [&](int k) {
+            if (stage_ms) cudaEventRecord(tev[i * 4 + k], B);
+        };
+        cudaError_t e = cudaStreamWaitEvent(B, cx->ev_in[i % NS], 0);
+        if (e == cudaSuccess && i >= NS) e = cudaStreamWaitEvent(B, cx->ev_out[i % NS], 0);  // its previous outputs are on the host
+        if (e != cudaSuccess) return bail(cuda_fail(e, "pipeline"));
+        cx->begin_slot((int)(i % NS));
+        cx->note_secret(s.xi, m * 32);
+        cx->note_secret(s.rnd, m * 32);
+        cx->note_secret(s.sk, m * p.sk);
+        cx->note_secret(kws.seeds, m * 128);
+        cx->note_secret(kws.s, m * KpL * 256);
+        cx->note_secret(s1h, m * (size_t)p.L * 1024);
+        cx->note_secret(s2h, m * (size_t)p.K * 1024);
+        cx->note_secret(t0h, m * (size_t)p.K * 1024);
+        cx->note_secret(sws.w, m * (size_t)sws.depth * p.K * 1024);
+        cx->note_secret(sws.yraw, m * (size_t)sws.depth * p.L * 32 * p.zbits);
+        cx->note_secret(sws.rhopp, m * 64);
+        // ---- stage 1: keygen (src/ml_dsa.rs:57-134); A-hat stays in kws.A for the next two stages
+        mark(0);
+        e = keygen_run(ps, B, m, s.xi, s.pk, s.sk, kws);
+        if (e == cudaSuccess) e = cudaMemsetAsync(s.xi, 0, m * 32, B);
+        if (e == cudaSuccess) e = cudaMemsetAsync(kws.seeds, 0, m * 128, B);
+        if (e == cudaSuccess) e = cudaMemsetAsync(kws.s, 0, m * KpL * 256, B);
+        mark(1);
+        // ---- stage 2: sign (src/ml_dsa.rs:153-337) with the packed keys where keygen left them
+        if (e == cudaSuccess) e = sign_expand_keys(ps, B, m, s.sk, nullptr, s1h, s2h, t0h, /*with_A*/ false);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "pipeline keygen"));
+        const MsgDesc md{s.m - msg_off[lo], s.mo, ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, framing};
+        SignRun run;
+        e = sign_begin(ps, B, m, s.sk, p.sk, md, s.rnd, s.sig, s.it, sws, 0, &run);
+        if (e == cudaSuccess) e = sign_tail(B, &run);
+        if (e != cudaSuccess) return bail(run.ctx_err ? E_CTX : cuda_fail(e, "pipeline sign"));
+        if (i + 1 < N && (rc = copy_in(i + 1))) return bail(rc);  // the next chunk's inputs move while this one signs
+        e = sign_finish(&run);  // the one host wait of a chunk
+        if (e != cudaSuccess) return bail(run.ctx_err ? E_CTX : (run.incomplete ? E_UNSUPPORTED : cuda_fail(e, "pipeline sign")));
+        t_last_rounds += run.rounds;
+        e = cudaMemsetAsync(s1h, 0, (size_t)((uint8_t*)sws.w - (uint8_t*)s1h), B);  // s1-hat, s2-hat, t0-hat (contiguous)
+        if (e == cudaSuccess) e = cudaMemsetAsync(s.rnd, 0, m * 32, B);
+        mark(2);
+        // ---- stage 3: verify (src/ml_dsa.rs:351-437) under the public keys keygen wrote
+        if (e == cudaSuccess) e = verify_expand_keys(ps, B, m, s.pk, nullptr, t1h, nullptr, false, false);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(tr, 64, s.sk + 64, p.sk, 64, m, cudaMemcpyDeviceToDevice, B);  // tr = sk[64..128)
+        if (e == cudaSuccess) {
+            VerifyWs vws = vws0;
+            vws.keys_resident = true;
+            vws.kidx = nullptr;
+            vws.A = kws.A;
+            vws.t1h = t1h;
+            vws.tr = tr;
+            e = verify_run(ps, B, m, s.pk, p.pk, md, s.sig, s.ok, vws);
+        }
+        mark(3);
+        if (e == cudaSuccess && !sk) e = cudaMemsetAsync(s.sk, 0, m * p.sk, B);
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_bulk[i % NS], B);
+        // ---- results out: packed pk, sig, verdicts (and sk / trip counts when asked for)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cx->s_out, cx->ev_bulk[i % NS], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pk + p.pk * lo, s.pk, m * p.pk, cudaMemcpyDeviceToHost, cx->s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sig + p.sig * lo, s.sig, m * p.sig, cudaMemcpyDeviceToHost, cx->s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ok + lo, s.ok, m, cudaMemcpyDeviceToHost, cx->s_out);
+        if (e == cudaSuccess && iters) e = cudaMemcpyAsync(iters + lo, s.it, m * 4, cudaMemcpyDeviceToHost, cx->s_out);
+        if (e == cudaSuccess && sk) {
+            e = cudaMemcpyAsync(sk + p.sk * lo, s.sk, m * p.sk, cudaMemcpyDeviceToHost, cx->s_out);
+            if (e == cudaSuccess) e = cudaMemsetAsync(s.sk, 0, m * p.sk, cx->s_out);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(cx->ev_out[i % NS], cx->s_out);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "pipeline"));
+        prof_collect();
+    }
+    cudaError_t e = cudaStreamSynchronize(cx->s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(B);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "pipeline"));
+    prof_collect();
+    if (stage_ms) {
+        for (size_t i = 0; i < N; i++)
+            for (int k = 0; k < 3; k++) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, tev[i * 4 + k], tev[i * 4 + k + 1]) == cudaSuccess) stage_ms[k] += ms;
+            }
+        for (auto& ev : tev) cudaEventDestroy(ev);
+        cudaGetLastError();
+    }
+    return OK;
+}
+
+extern "C" {
+
+int mldsa_pipeline_batch(int ps, int dev, int framing, size_t n, const uint8_t* xi, const uint8_t* msgs, const uint64_t* msg_off,
+                         const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd, uint8_t* pk, uint8_t* sk, uint8_t* sig,
+                         uint8_t* ok, uint32_t* iters, double* stage_ms)
+{
+    return pipeline_host(ps, dev, framing, n, xi, msgs, msg_off, ctx, ctx_off, rnd, pk, sk, sig, ok, iters, stage_ms);
+}
+
 // Signer::get_public_key (src/lib.rs:344-346 -> src/ml_dsa.rs:502-563): pk bytes from sk bytes
 int mldsa_sk_to_pk_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_sk, uint8_t* d_pk)
 {
@@ -1682,18 +2077,29 @@ int mldsa_sk_to_pk_batch(int ps, int dev, size_t n, const uint8_t* sk, uint8_t* 
     const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, per_lane);
     rc = cx->reserve(pad256(chunk * p.sk) + pad256(chunk * p.pk) + pad256(chunk * (size_t)p.K * p.L * 1024));
     if (rc) return rc;
+    Carver c(cx->arena);
+    uint8_t* d_sk = c.take<uint8_t>(chunk * p.sk);
+    uint8_t* d_pk = c.take<uint8_t>(chunk * p.pk);
+    KeygenWs ws{};
+    ws.A = c.take<int32_t>(chunk * (size_t)p.K * p.L * 256);
+    cx->clear_secrets();
+    cx->note_secret(d_sk, (n < chunk ? n : chunk) * p.sk);
+    auto wipe = [&](int code) {  // the staged secret keys never outlive the call, whatever happened
+        const std::string err = t_cuda_err;
+        cudaMemsetAsync(d_sk, 0, chunk * p.sk, st);
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
+        t_cuda_err = err;
+        return code;
+    };
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
-        Carver c(cx->arena);
-        uint8_t* d_sk = c.take<uint8_t>(chunk * p.sk);
-        uint8_t* d_pk = c.take<uint8_t>(chunk * p.pk);
-        KeygenWs ws{};
-        ws.A = c.take<int32_t>(chunk * (size_t)p.K * p.L * 256);
-        CK(cudaMemcpyAsync(d_sk, sk + p.sk * lo, m * p.sk, cudaMemcpyHostToDevice, st));
-        CK(sk_to_pk_run(ps, st, m, d_sk, d_pk, ws));
-        CK(cudaMemcpyAsync(pk + p.pk * lo, d_pk, m * p.pk, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemsetAsync(d_sk, 0, m * p.sk, st));
-        CK(cudaStreamSynchronize(st));
+        cudaError_t e = cudaMemcpyAsync(d_sk, sk + p.sk * lo, m * p.sk, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = sk_to_pk_run(ps, st, m, d_sk, d_pk, ws);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pk + p.pk * lo, d_pk, m * p.pk, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_sk, 0, m * p.sk, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return wipe(cuda_fail(e, "sk_to_pk"));
     }
     prof_collect();
     return OK;
@@ -1749,6 +2155,29 @@ int mldsa_verify_batch_multi(int ps, const int* devs, int ndev, int framing, siz
         return mldsa_verify_batch(ps, dev, framing, m, pk + pk_stride * lo, pk_stride, msgs, msg_off + lo, ctx,
                                   ctx_off ? ctx_off + lo : nullptr, sig + p.sig * lo, ok + lo);
     });
+}
+
+// stage_ms: per stage, the slowest device's time
+int mldsa_pipeline_batch_multi(int ps, const int* devs, int ndev, int framing, size_t n, const uint8_t* xi, const uint8_t* msgs,
+                               const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                               uint8_t* pk, uint8_t* sk, uint8_t* sig, uint8_t* ok, uint32_t* iters, double* stage_ms)
+{
+    PSInfo p;
+    if (!ps_info(ps, p) || !msg_off || ndev <= 0 || ndev > MAX_DEV) return E_PARAM;
+    std::vector<double> ms((size_t)ndev * 3, 0.0);
+    std::atomic<int> slot{0};
+    const int rc = run_sharded(devs, ndev, n, [&](int dev, size_t lo, size_t m) {
+        const int g = slot.fetch_add(1);
+        return mldsa_pipeline_batch(ps, dev, framing, m, xi + 32 * lo, msgs, msg_off + lo, ctx, ctx_off ? ctx_off + lo : nullptr,
+                                    rnd + 32 * lo, pk + p.pk * lo, sk ? sk + p.sk * lo : nullptr, sig + p.sig * lo, ok + lo,
+                                    iters ? iters + lo : nullptr, stage_ms ? &ms[(size_t)g * 3] : nullptr);
+    });
+    if (stage_ms)
+        for (int k = 0; k < 3; k++) {
+            stage_ms[k] = 0;
+            for (int g = 0; g < ndev; g++) stage_ms[k] = std::max(stage_ms[k], ms[(size_t)g * 3 + k]);
+        }
+    return rc;
 }
 
 static int micro_host(int dev, size_t n, const void* in, size_t in_bytes, void* out, size_t out_bytes, int which)

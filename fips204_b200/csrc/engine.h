@@ -20,7 +20,7 @@ constexpr int PREHASH_STRIDE = 80;  // OID (11) || PH(M) (<= 64), padded
 enum KernelId : int {
     KID_EXPAND_A = 0, KID_NTT, KID_INTT, KID_SHAKE_ROWS, KID_CTILDE, KID_KG_SEED, KID_REJ_BOUNDED, KID_KG_ARITH,
     KID_VERIFY_PRE, KID_T1HAT, KID_VERIFY_ARITH, KID_SIGN_PREP, KID_SIGN_KEY, KID_MASK, KID_SIGN_W, KID_SIGN_Z,
-    KID_COMPACT, KID_PROBE, KID_PREHASH, KID_SK2PK, KID_ROUND_PAIR, KID_COUNT
+    KID_COMPACT, KID_PROBE, KID_PREHASH, KID_SK2PK, KID_COUNT
 };
 struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<...>>>(...); }`
     int id;
@@ -28,20 +28,13 @@ struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<
     KLaunch(int id, cudaStream_t st);
     ~KLaunch();
 };
-void prof_collect();
+void prof_collect();  // fold finished event pairs into the per-kernel totals (call after a stream sync)
 
-// Launch tunables (mldsa_set_tuning / MLDSA_WAYS, MLDSA_KCAP, MLDSA_ACAP).  A sign chunk is split into
-// `ways` independent sub-batches that run concurrently on separate streams, so the ALU-pipe-bound Keccak
-// kernels of one way overlap the FMA/DRAM-bound arithmetic kernels of another.  kcap / acap cap the
-// CTAs per SM of the (grid-stride) Keccak / arithmetic kernels so that kernels of different ways can be
-// co-resident on an SM (0 = no cap).
+// Launch tunables (mldsa_set_tuning / MLDSA_KCAP, MLDSA_ACAP): kcap / acap cap the CTAs per SM of the (grid-stride)
+// Keccak / arithmetic kernels (0 = default).
 struct Tuning {
-    int ways, kcap, acap;
+    int kcap, acap;
     int depth;  // candidates tried per active lane and round of the sign loop (MLDSA_DEPTH, default 2)
-    int pair;   // 1: run a Keccak stage of one half-chunk beside an arithmetic stage of the other (MLDSA_PAIR, default 0)
-    int stage;  // sign_w: 0 = A-hat rows straight from global memory, 1 = TMA-staged per warp, 2 = staged and shared by
-                // the two candidate warps of a lane when the depth is even (MLDSA_STAGE, default 2)
-    int kshare; // paired kernel: CTAs out of 5 per SM that prefer the Keccak queue (MLDSA_KSHARE, default 2)
     int tail_depth;  // sign: deepest speculation of the under-filled last rounds (MLDSA_TAILDEPTH, default 8; <= depth: off)
     int tail_slots;  // sign: candidate slots of the shared tail region (MLDSA_TAILSLOTS, default 32768)
     int max_rounds;  // test hook (mldsa_debug_set_max_rounds): stop a chunk's loop after this many rounds (0 = off)
@@ -52,7 +45,7 @@ Tuning tuning();
 // sign_key, 120-400 -> 35.8 / 30.6 / 6.8 ms, one CTA per unit -> 36.3 / 34.5 / 6.8 ms).  MLDSA_ACAP overrides.
 constexpr int ACAP_DEFAULT = 192;
 inline int arith_cap() { const int a = tuning().acap; return a > 0 ? a : ACAP_DEFAULT; }
-unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // fold finished event pairs into the per-kernel totals (call after a stream sync)
+unsigned capped_grid(size_t want_ctas, int cap_per_sm);  // grid of a grid-stride kernel on the CURRENT device
 
 // ---- k_common.cu ----
 // Commitment hash.  Verify mode (ctilde_out == nullptr): ok[i] = pre_ok[i] && H(mu||w1')[0..CT) == sig_i[0..CT)
@@ -70,6 +63,8 @@ cudaError_t launch_keccak_probe(cudaStream_t st, int variant, int blocks, int re
 // HashML-DSA: out rows = OID || PH(M_i) with out_off[i] = i * PREHASH_STRIDE .. (message framing 2)
 cudaError_t launch_prehash(cudaStream_t st, int ph, size_t n, const uint8_t* msgs, const uint64_t* msg_off,
                            uint8_t* out, uint64_t* out_off);
+// *flag = 1 if any ctx_off[i + 1] - ctx_off[i] > 255 (src/lib.rs:274); flag may be mapped host memory
+cudaError_t launch_ctx_check(cudaStream_t st, size_t n, const uint32_t* ctx_off, uint32_t* flag);
 // *count += number of non-zero bytes in [p, p + bytes)   (test hook: secret residue scan)
 cudaError_t launch_count_nonzero(cudaStream_t st, const uint8_t* p, size_t bytes, unsigned long long* count);
 cudaError_t launch_int_probe(cudaStream_t st, int mode, int blocks, int iters, uint32_t* scratch, double* ops);
@@ -125,7 +120,9 @@ struct VerifyWs {
 cudaError_t verify_run(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,
                        const uint8_t* sig, uint8_t* ok, const VerifyWs& ws);
 // expand_public (src/ml_dsa.rs:477-498) for nkeys packed public keys: A-hat, NTT(t1 * 2^d), tr
-cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr);
+// with_A / with_tr = false: the caller already holds A-hat (from keygen) / tr (bytes 64..127 of the secret key)
+cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr,
+                               bool with_A = true, bool with_tr = true);
 
 // ---- k_sign.cu ----
 struct SignWs {
@@ -144,8 +141,7 @@ struct SignWs {
     uint32_t* kappa;   // [n]
     uint8_t* done;     // [n]
     uint32_t* act[2];  // [n] active lane lists (ping-pong)
-    uint32_t* nact;    // [16] device control words: [4 * way + buffer] active counts, [8] ctx error flag
-    uint32_t* queue;   // [2 * 2048] work-unit counters of the paired round launches
+    uint32_t* nact;    // [16] device control words: [buffer] active counts, [8] ctx error flag
     uint32_t* h_nact;  // mapped pinned host mirror of the 16 control words (written by publish_kernel)
     // Resident key set (mldsa_sk_load): A / s1h / s2h / t0h point into the key set, the `sk` passed to sign_begin is
     // its 128-byte rho || K || tr rows, lane i uses key kidx[i] (nullptr: i), and nothing of the keys is wiped.
@@ -188,7 +184,7 @@ cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, siz
 cudaError_t sign_tail(cudaStream_t st, SignRun* run);
 // expand_private (src/ml_dsa.rs:445-469) for nkeys packed secret keys: A-hat, s1-hat, s2-hat, t0-hat
 cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
-                             int32_t* t0h);
+                             int32_t* t0h, bool with_A = true);
 cudaError_t sign_finish(SignRun* run);
 
 }  // namespace mldsa

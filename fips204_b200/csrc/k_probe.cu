@@ -71,4 +71,22 @@ cudaError_t launch_count_nonzero(cudaStream_t st, const uint8_t* p, size_t bytes
     return cudaGetLastError();
 }
 
+// ctx longer than 255 bytes anywhere in the batch (src/lib.rs:274): checked before a device-pointer sign call starts
+__global__ void __launch_bounds__(256) ctx_check_kernel(size_t n, const uint32_t* __restrict__ ctx_off, volatile uint32_t* flag)
+{
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bad |= ctx_off[i + 1] - ctx_off[i] > 255u;
+    if (bad) {
+        *flag = 1;
+        __threadfence_system();
+    }
+}
+cudaError_t launch_ctx_check(cudaStream_t st, size_t n, const uint32_t* ctx_off, uint32_t* flag)
+{
+    if (n == 0) return cudaSuccess;
+    ctx_check_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(n, ctx_off, flag);
+    return cudaGetLastError();
+}
+
 }  // namespace mldsa

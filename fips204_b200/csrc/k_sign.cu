@@ -21,6 +21,7 @@
 //     ctilde        thread/lane  c~ = H(mu || w1), c = SampleInBall(c~) as bit masks   ml_dsa.rs:233-237
 //     sign_z        warp/lane    c-hat, r0 / z / ct0 / hint checks, sigEncode          ml_dsa.rs:240-336
 //     compact       thread/lane  rebuild the active list
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -40,14 +41,11 @@ __global__ void __launch_bounds__(128)
 sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, MsgDesc md,
                  const uint8_t* __restrict__ rnd, uint8_t* __restrict__ mu_out, uint8_t* __restrict__ rhopp,
                  uint32_t* __restrict__ kappa, uint8_t* __restrict__ done, uint32_t* __restrict__ act0,
-                 uint32_t* __restrict__ ctl, size_t n_way_a, int* __restrict__ ctx_err, const uint32_t* __restrict__ kidx)
+                 uint32_t* __restrict__ ctl, int* __restrict__ ctx_err, const uint32_t* __restrict__ kidx)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (i == 0) {  // active counts of the two ways: lanes [0, n_way_a) and [n_way_a, n)
-        ctl[0] = (uint32_t)n_way_a;
-        ctl[4] = (uint32_t)(n - n_way_a);
-    }
+    if (i == 0) ctl[0] = (uint32_t)n;  // live count of the first active list
     const uint8_t* key = sk + (kidx ? (size_t)kidx[i] : i) * sk_stride;  // rho || K || tr || ... (only K and tr are read)
     Sponge<SHAKE256_RATE> sp;
     if (!absorb_mu(sp, key + 64, md, i)) *ctx_err = 1;  // lib.rs:274 -> whole call fails with -2
@@ -122,18 +120,14 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
     }
 }
 
-// ---- per-stage jobs.  Every stage is written as a function of a WORK UNIT (what one 128-thread CTA does in one
-// step: 128 Keccak streams, or one item per warp), so that the same body runs in the stand-alone kernels
-// (grid-stride over units) and in the paired round kernel (units handed out from two queues).
+// ---- per-stage jobs.  Every stage is a grid-stride loop over WORK UNITS (what one 128-thread CTA does in one
+// step: 128 Keccak streams, or one item per warp) counted from the live lane count in device memory.
 // Candidate scratch (yraw, w, mw1, ctilde, cmask) is addressed by SLOT.  pos = 0: slot = lane * depth + candidate.
 // pos = 1 (tail rounds with a deeper speculation than the workspace was carved for): slot = position of the lane
 // in the active list * depth + candidate -- the few live lanes share the low end of the candidate buffers.
 struct MaskJob {
     const uint32_t* nact; const uint32_t* act; const uint8_t* rhopp; const uint32_t* kappa; uint8_t* yraw; int depth; int pos;
     size_t cap;  // pos = 1: candidate slots of the tail region; lanes whose slots would lie beyond it sit the round out
-};
-struct CtildeJob {
-    const uint32_t* nact; const uint32_t* act; const uint8_t* mw1; uint8_t* ctilde; uint8_t* cmask; int depth;
 };
 struct SignWJob {
     const uint32_t* nact; const uint32_t* act; const int32_t* A; const uint8_t* yraw; int32_t* w; uint8_t* mw1; int depth;
@@ -191,17 +185,6 @@ __global__ void __launch_bounds__(128, 4) mask_kernel(MaskJob j)
     for (size_t u = blockIdx.x; u < nu; u += gridDim.x) mask_unit<P>(j, u);
 }
 
-template <class P>
-__device__ __forceinline__ size_t ctilde_units(const CtildeJob& j) { return ((size_t)*j.nact * j.depth + 127) / 128; }
-template <class P>
-__device__ __forceinline__ void ctilde_unit(const CtildeJob& j, size_t unit)
-{
-    const size_t idx = unit * 128 + threadIdx.x;
-    if (idx >= (size_t)*j.nact * j.depth) return;
-    const size_t row = (size_t)j.act[idx / j.depth] * j.depth + idx % j.depth;
-    ctilde_row<P, true>(row, j.mw1, nullptr, nullptr, nullptr, j.ctilde, j.cmask);
-}
-
 // y (layout B regs) from the packed mask bytes: BitUnpack(gamma1 - 1, gamma1)
 template <class P>
 __device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (&y)[8])
@@ -210,95 +193,6 @@ __device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (
     load_span<P::ZBITS>(ypoly + P::ZBITS * lane, w);
 #pragma unroll
     for (int i = 0; i < 8; i++) y[i] = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(w, i);
-}
-
-template <class P>
-struct alignas(16) SignWSmem {
-    int32_t tile[NTT_TILE_WORDS];
-    alignas(16) int32_t yh[P::L][256];  // y-hat, NTT domain, natural order (lane t owns words 8t..8t+7 of each row)
-};
-
-template <class P>
-__device__ __forceinline__ size_t sign_w_units(const SignWJob& j) { return ((size_t)*j.nact * j.depth + SG_WARPS - 1) / SG_WARPS; }
-template <class P, bool SHARED>
-__device__ __forceinline__ void sign_w_unit(const SignWJob& j, size_t unit, SignWSmem<P>* sm_all)
-{
-    constexpr int K = P::K, L = P::L;
-    const uint32_t* __restrict__ act = j.act;
-    const int32_t* __restrict__ Aall = j.A;
-    const uint8_t* __restrict__ yraw = j.yraw;
-    int32_t* __restrict__ wall = j.w;
-    uint8_t* __restrict__ mw1 = j.mw1;
-    const int depth = j.depth;
-    const size_t nact = (size_t)*j.nact * depth;  // work items: (active lane, candidate)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SignWSmem<P>& sm = sm_all[warp];
-    int32_t* tile = sm.tile;
-    const size_t ai = unit * SG_WARPS + warp;
-    if (ai < nact && !(j.pos && (ai / depth + 1) * (size_t)depth > j.cap)) {
-        const size_t ln = act[ai / depth];
-        const size_t slot = j.pos ? ai : ln * depth + ai % depth;  // neighbouring warps hold the candidates of one lane
-        const int32_t* A = Aall + (SHARED ? 0 : (j.kidx ? (size_t)j.kidx[ln] : ln) * (size_t)(K * L) * 256);
-        const uint8_t* yp = yraw + slot * (size_t)(L * 32 * P::ZBITS);
-        int32_t* wo = wall + slot * (size_t)K * 256;
-        uint8_t* w1o = mw1 + slot * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
-        if (lane < 8)  // mu || w1 is the input row of the c~ hash
-            reinterpret_cast<uint64_t*>(w1o - MU_BYTES)[lane] = reinterpret_cast<const uint64_t*>(j.mu + ln * (size_t)MU_BYTES)[lane];
-        __syncwarp();
-        warp_prefetch_l2(A, 2 * L * 1024, lane);  // rows 0 and 1 of A-hat stream in during the forward NTTs
-        uint32_t yw[2][(P::ZBITS + 3) / 4];       // packed y of the next polynomial is in flight during an NTT
-        load_span<P::ZBITS>(yp + P::ZBITS * lane, yw[0]);
-#pragma unroll
-        for (int l = 0; l < L; l++) {
-            if (l + 1 < L) load_span<P::ZBITS>(yp + (l + 1) * 32 * P::ZBITS + P::ZBITS * lane, yw[(l + 1) & 1]);
-            int32_t y[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) y[i] = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(yw[l & 1], i);
-            sntt_fwd_B2B(y, tile, lane);
-            row_store(sm.yh[l], lane, y);  // only this lane reads these words back
-        }
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {
-            if (k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
-            int64_t acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = 0;
-#pragma unroll
-            for (int l = 0; l < L; l++) {
-                const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
-                const int4 x = __ldg(ap), y = __ldg(ap + 1);
-                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-                int32_t yv[8];
-                row_load(sm.yh[l], lane, yv);
-#pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * yv[i];
-            }
-            int32_t t[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
-            sntt_inv_B2B(t, tile, lane);  // w[k], canonical (A-hat is prescaled by 2^32 / 256)
-            int4* o = reinterpret_cast<int4*>(wo + 256 * k + 8 * lane);
-            o[0] = make_int4(t[0], t[1], t[2], t[3]);
-            o[1] = make_int4(t[4], t[5], t[6], t[7]);
-            uint32_t f[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                int32_t r0;
-                f[i] = (uint32_t)decompose<P::GAMMA2>(t[i], r0);  // HighBits (ml_dsa.rs:225-226)
-            }
-            uint32_t w[(P::W1BITS + 3) / 4];
-            pack_fields<P::W1BITS>(f, w);
-            store_span<P::W1BITS>(w1o + k * 32 * P::W1BITS + P::W1BITS * lane, w);
-        }
-    }
-}
-
-template <class P, bool SHARED>
-__global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_kernel(SignWJob j)
-{
-    __shared__ __align__(16) SignWSmem<P> sm_all[SG_WARPS];
-    const size_t nu = sign_w_units<P>(j);
-    for (size_t u = blockIdx.x; u < nu; u += gridDim.x) sign_w_unit<P, SHARED>(j, u, sm_all);
 }
 
 // ---- sign_w with A-hat rows staged through shared memory by the TMA unit --------------------------------
@@ -471,13 +365,17 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
 template <class P, bool SHARED, int G>
 static cudaError_t launch_sign_w_staged(cudaStream_t st, const SignWJob& j, size_t items, int cap_per_sm)
 {
-    static bool configured = false;  // one attribute call per instantiation (idempotent; a benign race at worst)
+    // The dynamic shared-memory limit is a PER-DEVICE function attribute: one call per instantiation and device
+    // (callers on different devices run on different host threads).
+    static std::atomic<uint64_t> configured{0};
     constexpr size_t SMEM = sizeof(SignWStage<P, G>);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sign_w_staged_kernel<P, SHARED, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)SMEM);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1)) {
+        e = cudaFuncSetAttribute(sign_w_staged_kernel<P, SHARED, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev < 64) configured.fetch_or(uint64_t(1) << dev, std::memory_order_release);
     }
     KLaunch kl(KID_SIGN_W, st);
     sign_w_staged_kernel<P, SHARED, G><<<capped_grid((items + SG_WARPS - 1) / SG_WARPS, cap_per_sm), SG_WARPS * 32, SMEM, st>>>(j);
@@ -737,70 +635,8 @@ compact_kernel(const uint32_t* __restrict__ nact_dev, const uint32_t* __restrict
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Paired round kernel.  The Keccak stages (mask, ctilde) saturate the ALU pipe and touch almost no memory;
-// the arithmetic stages (sign_w, sign_z) live on the FMA pipe and on HBM latency and leave half the issue
-// slots idle.  Run back to back each wastes what the other needs, so a chunk is split into two WAYS whose
-// round loops are staggered by one stage, and every launch runs one Keccak stage of one way next to one
-// arithmetic stage of the other on the SAME SMs:
-//        launch 0: mask(A)   || sign_z(B)      launch 2: ctilde(A) || sign_w(B)
-//        launch 1: mask(B)   || sign_w(A)      launch 3: ctilde(B) || sign_z(A)
-// The kernel is persistent (5 CTAs per SM); its CTAs pull work units from two queues (one atomic per unit),
-// `kshare` of every 5 CTAs prefer the Keccak queue, the others the arithmetic queue, and a CTA whose queue has
-// run dry takes from the other one, so no SM idles while either stage has work left.
-// ------------------------------------------------------------------------------------------------
-struct PairJob {
-    int kstage;  // 0 none, 1 mask, 2 ctilde
-    int astage;  // 0 none, 1 sign_w, 2 sign_z
-    MaskJob mask;
-    CtildeJob ct;
-    SignWJob w;
-    SignZJob z;
-    uint32_t* queue;  // [2] zeroed unit counters: Keccak, arithmetic
-    int kshare;
-};
-constexpr int PAIR_CTAS_PER_SM = 5;
-
-template <class P, bool SHARED>
-__global__ void __launch_bounds__(SG_WARPS * 32, PAIR_CTAS_PER_SM) round_pair_kernel(PairJob pj)
-{
-    __shared__ __align__(16) unsigned char sm_raw[sizeof(SignWSmem<P>) * SG_WARPS > sizeof(SignSmem<P>) * SG_WARPS
-                                                      ? sizeof(SignWSmem<P>) * SG_WARPS
-                                                      : sizeof(SignSmem<P>) * SG_WARPS];
-    __shared__ uint32_t s_unit;
-    const size_t nk = pj.kstage == 1 ? mask_units<P>(pj.mask) : (pj.kstage == 2 ? ctilde_units<P>(pj.ct) : 0);
-    const size_t na = pj.astage == 1 ? sign_w_units<P>(pj.w) : (pj.astage == 2 ? sign_z_units<P>(pj.z) : 0);
-    const int prefer = (int)(blockIdx.x % PAIR_CTAS_PER_SM) < pj.kshare ? 0 : 1;
-    bool kdone = nk == 0, adone = na == 0;
-    while (!(kdone && adone)) {
-        const int r = prefer == 0 ? (kdone ? 1 : 0) : (adone ? 0 : 1);
-        __syncthreads();  // every thread is done with the previous unit (s_unit and the stage's shared memory)
-        if (threadIdx.x == 0) s_unit = atomicAdd(pj.queue + r, 1u);
-        __syncthreads();
-        const size_t u = s_unit;
-        if (r == 0) {
-            if (u >= nk) {
-                kdone = true;
-            } else if (pj.kstage == 1) {
-                mask_unit<P>(pj.mask, u);
-            } else {
-                ctilde_unit<P>(pj.ct, u);
-            }
-        } else {
-            if (u >= na) {
-                adone = true;
-            } else if (pj.astage == 1) {
-                sign_w_unit<P, SHARED>(pj.w, u, reinterpret_cast<SignWSmem<P>*>(sm_raw));
-            } else {
-                sign_z_unit<P, SHARED>(pj.z, u, reinterpret_cast<SignSmem<P>*>(sm_raw));
-            }
-        }
-    }
-}
-
-constexpr int CTL_WORDS = 16;       // SignWs::nact: [4 * way + buffer] active counts, [8] ctx error flag
+constexpr int CTL_WORDS = 16;       // SignWs::nact: [buffer] active counts of the two ping-pong lists, [8] ctx error flag
 constexpr int CTL_CTX_ERR = 8;
-constexpr int QUEUE_PAIRS = 2048;   // SignWs::queue: one (Keccak, arithmetic) counter pair per paired launch
 
 // ---- the rejection loop of one chunk, in three host phases ------------------------------------------------
 //   sign_begin   set-up kernels + the BULK rounds (while the expected number of live lanes is above `tail_lanes`)
@@ -814,7 +650,7 @@ constexpr int QUEUE_PAIRS = 2048;   // SignWs::queue: one (Keccak, arithmetic) c
 // parameter sets (FIPS 204 table 1: 4.25 / 5.1 / 3.85 expected iterations).
 template <class P>
 static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
-                                const uint8_t* rnd, size_t nA)
+                                const uint8_t* rnd)
 {
     constexpr int K = P::K, L = P::L;
     const SignWs& ws = r.ws;
@@ -826,7 +662,7 @@ static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, 
     {
         KLaunch kl(KID_SIGN_PREP, st);
         sign_prep_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, sk, sk_stride, md, rnd, ws.mu, ws.rhopp,
-                                                                        ws.kappa, ws.done, ws.act[0], ws.nact, nA,
+                                                                        ws.kappa, ws.done, ws.act[0], ws.nact,
                                                                         ctx_err, ws.kidx);
     }
     if (ws.keys_resident) return cudaGetLastError();  // A-hat and the s-hat rows come from a loaded key set
@@ -851,7 +687,7 @@ static int round_depth(const SignRun& r, size_t sz)
     return D;
 }
 
-// one round over (at most) sz live lanes of the un-paired loop
+// one round over (at most) sz live lanes
 template <class P>
 static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
 {
@@ -872,13 +708,9 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
     }
     cudaError_t ce = cudaSuccess;
     const SignWJob wj{nact, act, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, pos, ws.kidx, r.tail_slots};
-    if (tn.stage == 0) {
-        KLaunch kl(KID_SIGN_W, st);
-        if (shared) sign_w_kernel<P, true><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
-        else sign_w_kernel<P, false><<<warp_grid(sz * D), SG_WARPS * 32, 0, st>>>(wj);
-    } else {
+    {   // an even depth pairs the two candidates of a lane on one staged A-hat row (G = 2); an odd one stages per warp
         const int cap = arith_cap();
-        if (D % 2 == 0 && tn.stage == 2)
+        if (D % 2 == 0)
             ce = shared ? launch_sign_w_staged<P, true, 2>(st, wj, sz * D, cap) : launch_sign_w_staged<P, false, 2>(st, wj, sz * D, cap);
         else
             ce = shared ? launch_sign_w_staged<P, true, 1>(st, wj, sz * D, cap) : launch_sign_w_staged<P, false, 1>(st, wj, sz * D, cap);
@@ -935,137 +767,27 @@ static cudaError_t sign_rounds_until(cudaStream_t st, SignRun& r, double stop_at
     return cudaSuccess;
 }
 
-// Paired round loop (MLDSA_PAIR=1): synchronous, everything happens inside sign_begin.
-template <class P>
-static cudaError_t sign_paired_t(cudaStream_t st, SignRun& r, const uint8_t* sk, size_t sk_stride, const MsgDesc& md,
-                                 const uint8_t* rnd)
-{
-    const SignWs& ws = r.ws;
-    const size_t n = r.n;
-    const bool shared = r.shared;
-    const Tuning tn = tuning();
-    const int D = ws.depth;
-    const size_t nA = (n + 1) / 2;  // way A = lanes [0, nA), way B = [nA, n)
-    cudaError_t e = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
-    if (e != cudaSuccess) return e;
-    e = sign_setup_t<P>(st, r, sk, sk_stride, md, rnd, nA);
-    if (e != cudaSuccess) return e;
-    struct Way {
-        size_t lo, bound;
-        int cur = 0;
-        const uint32_t* nact(const SignWs& w, int way) const { return w.nact + 4 * way + cur; }
-    } way[2];
-    way[0].lo = 0, way[0].bound = nA;
-    way[1].lo = nA, way[1].bound = n - nA;
-    auto mask_job = [&](int v) { return MaskJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.rhopp, ws.kappa, ws.yraw, D, 0, 0}; };
-    auto ct_job = [&](int v) { return CtildeJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.mw1, ws.ctilde, ws.cmask, D}; };
-    auto w_job = [&](int v) { return SignWJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.A, ws.yraw, ws.w, ws.mw1, D, ws.mu, 0, ws.kidx, 0}; };
-    auto z_job = [&](int v) {
-        return SignZJob{way[v].nact(ws, v), ws.act[way[v].cur] + way[v].lo, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde,
-                        ws.cmask, ws.kappa, ws.done, ws.rhopp, r.sig, r.iters, D, 0, D, 0, ws.kidx, ws.keys_resident ? 0 : 1};
-    };
-    auto compact = [&](int v) -> cudaError_t {
-        Way& y = way[v];
-        uint32_t* nout = ws.nact + 4 * v + (y.cur ^ 1);
-        cudaError_t ce = cudaMemsetAsync(nout, 0, 4, st);
-        if (ce != cudaSuccess) return ce;
-        {
-            KLaunch kl(KID_COMPACT, st);
-            compact_kernel<<<(unsigned)((y.bound + 255) / 256) + 1, 256, 0, st>>>(y.nact(ws, v), ws.act[y.cur] + y.lo, ws.done,
-                                                                            ws.act[y.cur ^ 1] + y.lo, nout);
-        }
-        y.cur ^= 1;
-        return cudaGetLastError();
-    };
-    auto read_bounds = [&]() -> cudaError_t {  // refresh the host's view of both ways' active counts
-        publish_kernel<<<1, 32, 0, st>>>(ws.nact, ws.h_nact, CTL_WORDS);
-        cudaError_t ce = cudaStreamSynchronize(st);
-        if (ce != cudaSuccess) return ce;
-        for (int v = 0; v < 2; v++) way[v].bound = ws.h_nact[4 * v + way[v].cur];
-        return cudaSuccess;
-    };
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)(sms * PAIR_CTAS_PER_SM);
-    const int kshare = tn.kshare > 0 && tn.kshare < PAIR_CTAS_PER_SM ? tn.kshare : 2;
-    int qi = 0;
-    auto launch_pair = [&](int kstage, int kv, int astage, int av) -> cudaError_t {
-        if (qi == QUEUE_PAIRS) {  // recycle the counters (stream order: every earlier launch is done with them)
-            cudaError_t ce = cudaMemsetAsync(ws.queue, 0, QUEUE_PAIRS * 8, st);
-            if (ce != cudaSuccess) return ce;
-            qi = 0;
-        }
-        PairJob pj{};
-        pj.kstage = kstage;
-        pj.astage = astage;
-        if (kstage == 1) pj.mask = mask_job(kv);
-        if (kstage == 2) pj.ct = ct_job(kv);
-        if (astage == 1) pj.w = w_job(av);
-        if (astage == 2) pj.z = z_job(av);
-        pj.queue = ws.queue + 2 * qi++;
-        pj.kshare = kshare;
-        KLaunch kl(KID_ROUND_PAIR, st);
-        if (shared) round_pair_kernel<P, true><<<grid, SG_WARPS * 32, 0, st>>>(pj);
-        else round_pair_kernel<P, false><<<grid, SG_WARPS * 32, 0, st>>>(pj);
-        return cudaGetLastError();
-    };
-    bool pending_zb = false;  // way B's sign_z of the previous round rides with way A's next mask
-    int since_sync = 0;
-    while (way[0].bound > 0 || way[1].bound > 0 || pending_zb) {
-        e = launch_pair(way[0].bound ? 1 : 0, 0, pending_zb ? 2 : 0, 1);
-        if (e != cudaSuccess) return e;
-        if (pending_zb) {
-            e = compact(1);
-            if (e != cudaSuccess) return e;
-            pending_zb = false;
-        }
-        e = launch_pair(way[1].bound ? 1 : 0, 1, way[0].bound ? 1 : 0, 0);
-        if (e != cudaSuccess) return e;
-        e = launch_pair(way[0].bound ? 2 : 0, 0, way[1].bound ? 1 : 0, 1);
-        if (e != cudaSuccess) return e;
-        e = launch_pair(way[1].bound ? 2 : 0, 1, way[0].bound ? 2 : 0, 0);
-        if (e != cudaSuccess) return e;
-        if (way[0].bound) {
-            e = compact(0);
-            if (e != cudaSuccess) return e;
-        }
-        pending_zb = way[1].bound > 0;
-        r.rounds++;
-        if (++since_sync >= 4 || (way[0].bound + way[1].bound) < 4096) {
-            // (the counts lag: way B's are from before its pending sign_z, which only makes them larger)
-            e = read_bounds();
-            if (e != cudaSuccess) return e;
-            since_sync = 0;
-        }
-    }
-    if (ws.h_nact[CTL_CTX_ERR] != 0) {  // ctx too long (lib.rs:274)
-        r.ctx_err = true;
-        return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-}
-
 // expand_private for a key set (src/ml_dsa.rs:445-469): A-hat and s1-hat / s2-hat / t0-hat of nkeys packed secret keys
 template <class P>
 static cudaError_t sign_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
-                                      int32_t* t0h)
+                                      int32_t* t0h, bool with_A)
 {
     {
         KLaunch kl(KID_SIGN_KEY, st);
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
             nkeys, sk, P::SK_LEN, s1h, s2h, t0h);
     }
+    if (!with_A) return cudaGetLastError();  // the caller already holds this key's A-hat (e.g. from keygen)
     return launch_expand_a(st, P::K, P::L, sk, P::SK_LEN, nkeys, A);
 }
 cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
-                             int32_t* t0h)
+                             int32_t* t0h, bool with_A)
 {
     if (nkeys == 0) return cudaSuccess;
     switch (ps) {
-    case 44: return sign_expand_keys_t<Params<44>>(st, nkeys, sk, A, s1h, s2h, t0h);
-    case 65: return sign_expand_keys_t<Params<65>>(st, nkeys, sk, A, s1h, s2h, t0h);
-    case 87: return sign_expand_keys_t<Params<87>>(st, nkeys, sk, A, s1h, s2h, t0h);
+    case 44: return sign_expand_keys_t<Params<44>>(st, nkeys, sk, A, s1h, s2h, t0h, with_A);
+    case 65: return sign_expand_keys_t<Params<65>>(st, nkeys, sk, A, s1h, s2h, t0h, with_A);
+    case 87: return sign_expand_keys_t<Params<87>>(st, nkeys, sk, A, s1h, s2h, t0h, with_A);
     }
     return cudaErrorInvalidValue;
 }
@@ -1101,19 +823,10 @@ cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, siz
         return cudaSuccess;
     }
     cudaError_t e;
-    if (tuning().pair != 0 && n >= 8192 && !ws.keys_resident) {  // small batches are latency-bound: keep the plain loop
-        r.finished = true;
-        switch (ps) {
-        case 44: return sign_paired_t<Params<44>>(st, r, sk, sk_stride, md, rnd);
-        case 65: return sign_paired_t<Params<65>>(st, r, sk, sk_stride, md, rnd);
-        case 87: return sign_paired_t<Params<87>>(st, r, sk, sk_stride, md, rnd);
-        }
-        return cudaErrorInvalidValue;
-    }
     switch (ps) {
-    case 44: e = sign_setup_t<Params<44>>(st, r, sk, sk_stride, md, rnd, n); break;
-    case 65: e = sign_setup_t<Params<65>>(st, r, sk, sk_stride, md, rnd, n); break;
-    case 87: e = sign_setup_t<Params<87>>(st, r, sk, sk_stride, md, rnd, n); break;
+    case 44: e = sign_setup_t<Params<44>>(st, r, sk, sk_stride, md, rnd); break;
+    case 65: e = sign_setup_t<Params<65>>(st, r, sk, sk_stride, md, rnd); break;
+    case 87: e = sign_setup_t<Params<87>>(st, r, sk, sk_stride, md, rnd); break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

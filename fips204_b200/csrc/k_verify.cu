@@ -293,11 +293,13 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
 
 // expand_public (src/ml_dsa.rs:477-498) for nkeys packed public keys: A-hat, NTT(t1 * 2^d), tr = H(pk)
 template <class P>
-static cudaError_t verify_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr)
+static cudaError_t verify_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr,
+                                        bool with_A, bool with_tr)
 {
-    cudaError_t e = launch_expand_a(st, P::K, P::L, pk, P::PK_LEN, nkeys, A);
+    cudaError_t e = cudaSuccess;
+    if (with_A) e = launch_expand_a(st, P::K, P::L, pk, P::PK_LEN, nkeys, A);
     if (e != cudaSuccess) return e;
-    e = launch_shake256_rows(st, pk, P::PK_LEN, P::PK_LEN, nkeys, tr, 64, 64);
+    if (with_tr) e = launch_shake256_rows(st, pk, P::PK_LEN, P::PK_LEN, nkeys, tr, 64, 64);
     if (e != cudaSuccess) return e;
     {
         KLaunch kl(KID_T1HAT, st);
@@ -305,13 +307,14 @@ static cudaError_t verify_expand_keys_t(cudaStream_t st, size_t nkeys, const uin
     }
     return cudaGetLastError();
 }
-cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr)
+cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* pk, int32_t* A, int32_t* t1h, uint8_t* tr,
+                               bool with_A, bool with_tr)
 {
     if (nkeys == 0) return cudaSuccess;
     switch (ps) {
-    case 44: return verify_expand_keys_t<Params<44>>(st, nkeys, pk, A, t1h, tr);
-    case 65: return verify_expand_keys_t<Params<65>>(st, nkeys, pk, A, t1h, tr);
-    case 87: return verify_expand_keys_t<Params<87>>(st, nkeys, pk, A, t1h, tr);
+    case 44: return verify_expand_keys_t<Params<44>>(st, nkeys, pk, A, t1h, tr, with_A, with_tr);
+    case 65: return verify_expand_keys_t<Params<65>>(st, nkeys, pk, A, t1h, tr, with_A, with_tr);
+    case 87: return verify_expand_keys_t<Params<87>>(st, nkeys, pk, A, t1h, tr, with_A, with_tr);
     }
     return cudaErrorInvalidValue;
 }

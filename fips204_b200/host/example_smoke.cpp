@@ -1,5 +1,6 @@
 // Mirrors the reference's in-crate smoke test (src/lib.rs:503-551) through the C++ host mirror.
 //   g++ -std=c++17 -O2 example_smoke.cpp -L.. -lmldsa_b200 -Wl,-rpath,'$ORIGIN/..' -o example_smoke
+#include <algorithm>
 #include <cstdio>
 
 #include "fips204.hpp"
@@ -37,6 +38,14 @@ template <class M> static int run(const char* name, int want_pk0)
     std::vector<std::vector<uint8_t>> swapped{m2, m2, m1};
     auto w = pset.verify_batch(swapped, nullptr, flat.data(), idx);
     ok = ok && v[0] && v[1] && v[2] && !w[0] && w[1] && w[2];
+    // keys provisioned from seeds straight into resident sets, and the chained keygen -> sign -> verify pipeline
+    std::vector<uint8_t> xis(3 * 32, 0x11), pkb(3 * M::PK_LEN);
+    auto sets = M::keygen_to_keysets(3, xis.data(), pkb.data());
+    auto sigs2 = sets.first.sign_batch(msgs, nullptr, rnd.data());
+    auto v2 = sets.second.verify_batch(msgs, nullptr, flat.data());
+    ok = ok && std::equal(pk.bytes.begin(), pk.bytes.end(), pkb.begin()) && sigs2[0] == sig && sigs2[1] == sigs[1] && v2[0] && v2[1];
+    auto pr = M::pipeline_batch(3, xis.data(), msgs, rnd.data());
+    ok = ok && pr.ok[0] && pr.ok[1] && pr.ok[2] && pr.pk == pkb && std::equal(sig.begin(), sig.end(), pr.sig.begin());
     std::printf("%s: %s\n", name, ok ? "ok" : "FAILED");
     return ok ? 0 : 1;
 }

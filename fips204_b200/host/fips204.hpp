@@ -120,6 +120,8 @@ struct ParamSet {
     struct PrivateKeySet {
         mldsa_keyset* handle = nullptr;
         PrivateKeySet(size_t n, const uint8_t* sk, int dev = 0) { check(mldsa_sk_load(PS, dev, n, sk, &handle)); }
+        explicit PrivateKeySet(mldsa_keyset* adopted) : handle(adopted) {}  // from keygen_to_keysets
+        PrivateKeySet(PrivateKeySet&& o) noexcept : handle(o.handle) { o.handle = nullptr; }
         ~PrivateKeySet() { mldsa_keyset_free(handle); }
         PrivateKeySet(const PrivateKeySet&) = delete;
         PrivateKeySet& operator=(const PrivateKeySet&) = delete;
@@ -158,6 +160,8 @@ struct ParamSet {
     struct PublicKeySet {
         mldsa_keyset* handle = nullptr;
         PublicKeySet(size_t n, const uint8_t* pk, int dev = 0) { check(mldsa_pk_load(PS, dev, n, pk, &handle)); }
+        explicit PublicKeySet(mldsa_keyset* adopted) : handle(adopted) {}  // from keygen_to_keysets
+        PublicKeySet(PublicKeySet&& o) noexcept : handle(o.handle) { o.handle = nullptr; }
         ~PublicKeySet() { mldsa_keyset_free(handle); }
         PublicKeySet(const PublicKeySet&) = delete;
         PublicKeySet& operator=(const PublicKeySet&) = delete;
@@ -186,6 +190,40 @@ struct ParamSet {
     };
 
     // ---- the reference's types ----------------------------------------------------------------
+    // KG::keygen_from_seed for n seeds whose expanded keys stay on the device (mldsa_keygen_to_keyset): the packed
+    // public keys come back (pk: n x PK_LEN, may be nullptr), no packed secret key ever crosses PCIe.
+    static std::pair<PrivateKeySet, PublicKeySet> keygen_to_keysets(size_t n, const uint8_t* xi, uint8_t* pk, int dev = 0)
+    {
+        mldsa_keyset *s = nullptr, *p = nullptr;
+        check(mldsa_keygen_to_keyset(PS, dev, n, xi, pk, &s, &p));
+        return {PrivateKeySet(s), PublicKeySet(p)};
+    }
+    // keygen -> sign -> verify chained on the device (the flow of lib.rs:503-551 as one batch call, BASELINE config 5)
+    struct PipelineResult {
+        std::vector<uint8_t> pk, sig, ok;
+        double stage_ms[3] = {0, 0, 0};
+    };
+    static PipelineResult pipeline_batch(size_t n, const uint8_t* xi, const std::vector<Bytes>& msgs, const uint8_t* rnd,
+                                         const std::vector<int>& devs = {0}, int framing = 0)
+    {
+        if (msgs.size() != n) throw Error(MLDSA_E_PARAM, "pipeline_batch: msgs must have n entries");
+        std::vector<uint8_t> mb;
+        std::vector<uint64_t> mo(n + 1, 0);
+        for (size_t i = 0; i < n; i++) {
+            mb.insert(mb.end(), msgs[i].begin(), msgs[i].end());
+            mo[i + 1] = mb.size();
+        }
+        if (mb.empty()) mb.push_back(0);
+        PipelineResult r;
+        r.pk.resize(n * PK);
+        r.sig.resize(n * SIG);
+        r.ok.assign(n, 0);
+        check(mldsa_pipeline_batch_multi(PS, devs.data(), static_cast<int>(devs.size()), framing, n, xi, mb.data(), mo.data(),
+                                         nullptr, nullptr, rnd, r.pk.data(), nullptr, r.sig.data(), r.ok.data(), nullptr,
+                                         r.stage_ms));
+        return r;
+    }
+
     struct PublicKey {  // types.rs:35-41 (here: canonical bytes)
         std::array<uint8_t, PK> bytes{};
         static PublicKey try_from_bytes(const std::array<uint8_t, PK>& b) { return PublicKey{b}; }  // lib.rs:469

@@ -112,6 +112,24 @@ int mldsa_verify_batch_multi(int ps, const int* devs, int ndev, int framing, siz
                              size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx,
                              const uint32_t* ctx_off, const uint8_t* sig, uint8_t* ok);
 
+/* ---- chained pipeline (BASELINE config 5): keygen -> sign -> verify with keys and signatures resident ------------
+ * The reference's end-to-end flow (src/lib.rs:503-551: try_keygen, try_sign, verify) as ONE batch call: lane i derives
+ * (pk_i, sk_i) from xi[i], signs msgs[i] (ctx[i], rnd[i]) with sk_i and verifies the signature under pk_i.  Only xi,
+ * the messages / contexts and rnd cross PCIe on the way in; the packed pk, sig and verdicts on the way out (sk and the
+ * rejection-loop trip counts only if the pointers are given).  Between the stages everything stays in HBM, and A-hat --
+ * which the reference re-derives from rho in all three operations (src/ml_dsa.rs:78, :181, :360) -- is expanded once
+ * per key.  Bytes are those of mldsa_keygen_batch / mldsa_sign_batch / mldsa_verify_batch called one after the other.
+ * stage_ms: optional, 3 doubles: device time of the keygen / sign / verify stage (summed over the chunks; _multi: the
+ * slowest device per stage).  Return codes as mldsa_sign_batch. */
+int mldsa_pipeline_batch(int ps, int dev, int framing, size_t n, const uint8_t* xi, const uint8_t* msgs,
+                         const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* rnd,
+                         uint8_t* pk, uint8_t* sk /* optional */, uint8_t* sig, uint8_t* ok, uint32_t* iters /* optional */,
+                         double* stage_ms /* optional */);
+int mldsa_pipeline_batch_multi(int ps, const int* devs, int ndev, int framing, size_t n, const uint8_t* xi,
+                               const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off,
+                               const uint8_t* rnd, uint8_t* pk, uint8_t* sk, uint8_t* sig, uint8_t* ok, uint32_t* iters,
+                               double* stage_ms);
+
 /* ---- microbench / leaf entry points (BASELINE config 2) ----------------------------------
  * ntt: src/ntt.rs:14-76, raw-bit-exact representatives; intt: src/ntt.rs:85-161, canonical [0,q).
  * expand_a: out[i] = RejNTTPoly(seed34[i]), src/hashing.rs:111-146.  In place on n x 256 int32. */
@@ -157,6 +175,16 @@ int mldsa_verify_batch_keys(const mldsa_keyset* ks, int framing, size_t n, const
                             const uint64_t* msg_off, const uint8_t* ctx, const uint32_t* ctx_off, const uint8_t* sig,
                             uint8_t* ok);
 
+/* Device-side key provisioning: KG::keygen_from_seed (src/lib.rs:247-251, src/ml_dsa.rs:57-134) whose results are
+ * kept as EXPANDED keys in HBM (expand_private / expand_public, src/ml_dsa.rs:445-498) instead of being packed and
+ * shipped back: a signing service provisions n keys from n seeds and no packed secret key ever crosses PCIe (52 % of
+ * the bytes of a packed-key mldsa_sign_batch call).  xi: n x 32 host bytes.  pk: optional host output, n x PK_LEN (the
+ * public keys are what such a service publishes), NULL = none.  sk_set / pk_set: either may be NULL (not both); the
+ * sets are the same objects mldsa_sk_load / mldsa_pk_load build from the packed keys of mldsa_keygen_batch(xi) --
+ * signatures and verdicts are identical.  A-hat is expanded once and shared by construction of both sets. */
+int mldsa_keygen_to_keyset(int ps, int dev, size_t n, const uint8_t* xi, uint8_t* pk, mldsa_keyset** sk_set,
+                           mldsa_keyset** pk_set);
+
 /* HashML-DSA on resident key sets (try_hash_sign_with_rng src/lib.rs:310-342, hash_verify :391-411): ph as in
  * mldsa_hash_sign_batch (0 SHA-256, 1 SHA-512, 2 SHAKE128), the pre-hash runs on the device. */
 int mldsa_hash_sign_batch_keys(const mldsa_keyset* ks, int ph, size_t n, const uint32_t* key_idx, const uint8_t* msgs,
@@ -168,7 +196,7 @@ int mldsa_hash_verify_batch_keys(const mldsa_keyset* ks, int ph, size_t n, const
 
 /* ---- tuning / telemetry ------------------------------------------------------------------
  * Environment knobs (read once; the setters below override them): MLDSA_DEPTH, MLDSA_TAILDEPTH, MLDSA_TAILSLOTS,
- * MLDSA_KCAP, MLDSA_ACAP, MLDSA_STAGE, MLDSA_PAIR, MLDSA_KSHARE as documented at the setters; host pipelines:
+ * MLDSA_KCAP, MLDSA_ACAP as documented at the setters; host pipelines:
  * MLDSA_PLAN (chunk sizes of a large batch, e.g. "1,2,4,6,6,6,4,2,1"), MLDSA_TAIL (live lanes at which a sign chunk
  * hands over to the tail stream, default 16384), MLDSA_TAILPRIO (0: low-priority tail stream), MLDSA_NCAP (CTAs per
  * SM of the standalone NTT), MLDSA_TRACE=1 (device-side timeline of the host pipelines on stderr); test hook:
@@ -188,10 +216,6 @@ void mldsa_set_depth(int depth);
  * largest d in {4, 8, 16} with d <= tail_depth.  Results never depend on it (same argument as mldsa_set_depth).
  * Defaults MLDSA_TAILDEPTH / MLDSA_TAILSLOTS, else 8 / 32768; tail_depth <= depth switches it off. */
 void mldsa_set_tail(int tail_depth, int tail_slots);
-/* pair != 0 (MLDSA_PAIR, default 0: measured no gain while the arithmetic stages are latency-bound): a sign chunk of >= 8192 lanes runs as two half-chunks whose rejection loops are
- * staggered by one stage, each launch executing a Keccak stage of one half beside an arithmetic stage of the other on
- * the same SMs; kshare (1..4, default 2, MLDSA_KSHARE) = CTAs out of 5 per SM that prefer the Keccak queue. */
-void mldsa_set_pairing(int pair, int kshare);
 /* test hook for the ZeroizeOnDrop analogue (src/types.rs:19-41): number of non-zero bytes left in the device ranges
  * that held secret-derived data (staged xi / sk / rnd, rho', K, s1, s2 and their NTT images, y, w - c*s2, rho'')
  * during the most recent keygen or sign call on `dev`; *scanned_bytes (optional) = size of those ranges.  0 after

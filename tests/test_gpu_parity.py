@@ -621,15 +621,15 @@ print("ok")
 
 def test_multi_device_entry_points_split_contiguously(F):
     """mldsa_*_batch_multi: one host thread per listed device, contiguous lane ranges, disjoint output slices, ragged
-    message / ctx blobs addressed by absolute offsets.  Runs over every visible GPU -- or three shards on device 0 when
-    there is only one (the shards then serialise on the device context, the splitting logic is the same)."""
+    message / ctx blobs addressed by absolute offsets.  Three shards on device 0 (they serialise on the device context):
+    this pins the splitting logic on any box; test_gpu_round2.py::test_multi_entry_points_on_distinct_devices runs the
+    same entry points over every visible GPU and SKIPS when there is only one."""
     import ctypes as C
     from fips204_b200 import _lib
     L = _lib.lib()
     ps = 65
     m = F.PARAM_SETS[ps]
-    ndev = F.device_count()
-    devs = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    devs = [0, 0, 0]
     darr = (C.c_int * len(devs))(*devs)
     n = 1000 + 7
     xi = synth_block("md-xi", n, 32)
