@@ -151,7 +151,7 @@ def test_device_pointer_sign_leaves_no_partial_output_on_ctx_error(F):
     n = 300
     _, sk = O.keygen_batch(65, synth_block("dv-xi", n, 32))
     dev = torch.device("cuda", 0)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    t = lambda a: torch.from_numpy(np.array(a, copy=True)).to(dev)  # noqa: E731
     p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
     d_sk, d_rnd = t(sk), t(synth_rows("dv-r", n, 32))
     msg = t(synth_block("dv-m", n, 32))
@@ -190,7 +190,7 @@ def test_max_rounds_hook_leaves_no_signature_bytes(F):
     n = 2000
     _, sk = O.keygen_batch(44, synth_block("mr-xi", n, 32))
     dev = torch.device("cuda", 0)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    t = lambda a: torch.from_numpy(np.array(a, copy=True)).to(dev)  # noqa: E731
     p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
     d_sk, d_rnd, msg = t(sk), t(synth_rows("mr-r", n, 32)), t(synth_block("mr-m", n, 32))
     moff = torch.arange(0, 32 * (n + 1), 32, dtype=torch.int64, device=dev)
