@@ -14,7 +14,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libmldsa_b200.so"
 OBJ = HERE / "build"
-UNITS = ["k_common", "k_keygen", "k_verify", "k_sign", "k_probe", "engine"]
+UNITS = ["k_common", "k_keygen", "k_verify", "k_sign", "k_fused", "k_probe", "engine"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-O3", "-Xptxas", "-v"]

@@ -312,29 +312,30 @@ static size_t workspace_budget(size_t arena_bytes)
 }
 
 // ---- workspace carving per operation ------------------------------------------------------------
+// keygen keeps no A-hat (it is consumed as it is squeezed, k_fused.cu): seeds and the sampled s1 / s2 only
 static size_t keygen_ws_bytes(const PSInfo& p, size_t n)
 {
-    return pad256(n * 128) + pad256(n * (size_t)(p.K + p.L) * 256) + pad256(n * (size_t)p.K * p.L * 1024);
+    return pad256(n * 128) + pad256(n * (size_t)(p.K + p.L) * 256);
 }
 static KeygenWs keygen_carve(Carver& c, const PSInfo& p, size_t n)
 {
     KeygenWs w;
     w.seeds = c.take<uint8_t>(n * 128);
     w.s = c.take<int8_t>(n * (size_t)(p.K + p.L) * 256);
-    w.A = c.take<int32_t>(n * (size_t)p.K * p.L * 256);
+    w.A = nullptr;
     return w;
 }
-static size_t verify_ws_bytes(const PSInfo& p, size_t n, bool shared)
+// A-hat / t1-hat / tr of ONE key (the shared-key path); per-lane packed keys never materialise A-hat (k_fused.cu) and
+// resident key sets bring their own
+static size_t verify_ws_bytes(const PSInfo& p, size_t n)
 {
-    const size_t nk = shared ? 1 : n;
-    return pad256(nk * (size_t)p.K * p.L * 1024) + pad256((size_t)p.K * 1024) + pad256(64) +
+    return pad256((size_t)p.K * p.L * 1024) + pad256((size_t)p.K * 1024) + pad256(64) +
            pad256(n * (size_t)(64 + p.w1len)) + pad256(n * (size_t)SIB_BYTES) + pad256(n);
 }
-static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n, bool shared)
+static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n)
 {
-    const size_t nk = shared ? 1 : n;
     VerifyWs w;
-    w.A = c.take<int32_t>(nk * (size_t)p.K * p.L * 256);
+    w.A = c.take<int32_t>((size_t)p.K * p.L * 256);
     w.t1h = c.take<int32_t>((size_t)p.K * 256);
     w.tr = c.take<uint8_t>(64);
     w.mw1 = c.take<uint8_t>(n * (size_t)(64 + p.w1len));
@@ -429,15 +430,15 @@ static int verify_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size
     const auto t_start = std::chrono::steady_clock::now();
     auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     const bool shared = pk_stride == 0;
-    const size_t per_lane = (verify_ws_bytes(p, 1024, shared) - (shared ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
-    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + verify_ws_bytes(p, 0, shared), per_lane);
-    int rc = cx.reserve(arena_skip + verify_ws_bytes(p, chunk, shared), arena_skip);
+    const size_t per_lane = (verify_ws_bytes(p, 1024) - verify_ws_bytes(p, 0)) / 1024 + 1;
+    const size_t chunk = pick_chunk(cx.arena_bytes, n, arena_skip + verify_ws_bytes(p, 0), per_lane);
+    int rc = cx.reserve(arena_skip + verify_ws_bytes(p, chunk), arena_skip);
     if (rc) return rc;
     const double t_res = now_ms();
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
         Carver c(cx.arena + arena_skip);
-        VerifyWs ws = verify_carve(c, p, m, shared);
+        VerifyWs ws = verify_carve(c, p, m);
         MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
         CK(verify_run(ps, st, m, d_pk + pk_stride * lo, pk_stride, md, d_sig + p.sig * lo, d_ok + lo, ws));
     }
@@ -1308,10 +1309,8 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
     const size_t pk_lane = resident ? (key_idx ? 4 : 0) : p.pk;  // staged bytes per lane: packed pk, or a key index
     const size_t avg_msg = (size_t)((msg_off[n] - msg_off[0]) / n) + 1;
     const size_t avg_ctx = ctx_off ? (size_t)((ctx_off[n] - ctx_off[0]) / n) + 1 : 0;
-    // a resident key set brings its own A-hat / t1-hat / tr: the workspace is sized like the shared-key one
-    const bool small_ws = shared || resident;
-    const size_t fixed = verify_ws_bytes(p, 0, small_ws) + (shared ? NS * pad256(p.pk) : 0) + 65536;
-    const size_t ws_lane = (verify_ws_bytes(p, 1024, small_ws) - (small_ws ? verify_ws_bytes(p, 0, true) : 0)) / 1024 + 1;
+    const size_t fixed = verify_ws_bytes(p, 0) + (shared ? NS * pad256(p.pk) : 0) + 65536;
+    const size_t ws_lane = (verify_ws_bytes(p, 1024) - verify_ws_bytes(p, 0)) / 1024 + 1;
     const size_t io_lane = NS * ((shared ? 0 : pk_lane) + p.sig + 1 + 8 + 4 + avg_msg + avg_ctx + PREHASH_STRIDE + 8);
     const ChunkPlan pl = plan_chunks(cx->arena_bytes, n, fixed, ws_lane + io_lane, msg_off, ctx_off);
     const size_t C = pl.max_lanes, N = pl.nchunks();
@@ -1324,7 +1323,7 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
     const size_t set_bytes = pad256(pk_set) + pad256(C * p.sig) + pad256(C) + pad256((C + 1) * 8) +
                              pad256((C + 1) * 4) + pad256(pl.max_mbytes + 8) + pad256(pl.max_cbytes + 8) +
                              pad256(C * PREHASH_STRIDE) + pad256((C + 1) * 8);
-    rc = cx->reserve(NS * set_bytes + verify_ws_bytes(p, C, small_ws) + 4096);
+    rc = cx->reserve(NS * set_bytes + verify_ws_bytes(p, C) + 4096);
     if (rc) return rc;
     Carver c(cx->arena);
     for (auto& s : set) {
@@ -1381,7 +1380,7 @@ static int verify_host(int ps, int dev, int framing, int ph, size_t n, const uin
             cmo = s.po;
         }
         Carver wc(ws_base);
-        VerifyWs ws = verify_carve(wc, p, m, small_ws);
+        VerifyWs ws = verify_carve(wc, p, m);
         if (resident) {  // lanes [lo, lo + m) use keys key_idx[lo ..] -- or keys lo .. lo + m - 1 of the set
             const size_t k0 = key_idx ? 0 : lo;
             ws.keys_resident = true;
@@ -1834,7 +1833,7 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
     auto ws_bytes_for = [&](size_t C) {
         return pad256(C * 128) + pad256(C * KpL * 256) + pad256(C * KL * 1024) + pad256(C * (size_t)p.L * 1024) +
                2 * pad256(C * (size_t)p.K * 1024) + pad256(sign_ws_bytes(p, C, false, true)) + 4096 +
-               verify_ws_bytes(p, C, true) + pad256(C * (size_t)p.K * 1024) + pad256(C * 64);
+               verify_ws_bytes(p, C) + pad256(C * (size_t)p.K * 1024) + pad256(C * 64);
     };
     const size_t ws_lane = ws_bytes_for(1024) / 1024 + 1;
     const size_t io_lane = NS * (64 + p.pk + p.sk + p.sig + 1 + 4 + 8 + 4 + avg_msg + avg_ctx + 16);
@@ -1890,7 +1889,7 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
     sws.s2h = s2h;
     sws.t0h = t0h;
     c.take<uint8_t>(4096);
-    VerifyWs vws0 = verify_carve(c, p, C, true);
+    VerifyWs vws0 = verify_carve(c, p, C);
     int32_t* t1h = c.take<int32_t>(C * (size_t)p.K * 256);
     uint8_t* tr = c.take<uint8_t>(C * 64);
     uint8_t* const ws_end = cx->arena + c.off;
@@ -2049,16 +2048,7 @@ int mldsa_sk_to_pk_batch_dev(int ps, void* stream, size_t n, const uint8_t* d_sk
     DeviceCtx* cx = lock_current(lk, rc);
     if (!cx) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : cx->stream;
-    const size_t per_lane = (size_t)p.K * p.L * 1024 + 64;
-    const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, per_lane);
-    rc = cx->reserve(pad256(chunk * per_lane));
-    if (rc) return rc;
-    for (size_t lo = 0; lo < n; lo += chunk) {
-        const size_t m = n - lo < chunk ? n - lo : chunk;
-        KeygenWs ws{};
-        ws.A = reinterpret_cast<int32_t*>(cx->arena);
-        CK(sk_to_pk_run(ps, st, m, d_sk + p.sk * lo, d_pk + p.pk * lo, ws));
-    }
+    CK(launch_sk_to_pk_fused(ps, st, n, d_sk, d_pk));  // no scratch: A-hat is consumed as it is squeezed
     CK(cudaStreamSynchronize(st));
     prof_collect();
     return OK;
@@ -2073,15 +2063,13 @@ int mldsa_sk_to_pk_batch(int ps, int dev, size_t n, const uint8_t* sk, uint8_t* 
     DeviceCtx* cx = lock_ctx(dev, lk, rc);
     if (!cx) return rc;
     cudaStream_t st = cx->stream;
-    const size_t per_lane = (size_t)p.K * p.L * 1024 + p.sk + p.pk + 64;
+    const size_t per_lane = p.sk + p.pk + 64;
     const size_t chunk = pick_chunk(cx->arena_bytes, n, 0, per_lane);
-    rc = cx->reserve(pad256(chunk * p.sk) + pad256(chunk * p.pk) + pad256(chunk * (size_t)p.K * p.L * 1024));
+    rc = cx->reserve(pad256(chunk * p.sk) + pad256(chunk * p.pk));
     if (rc) return rc;
     Carver c(cx->arena);
     uint8_t* d_sk = c.take<uint8_t>(chunk * p.sk);
     uint8_t* d_pk = c.take<uint8_t>(chunk * p.pk);
-    KeygenWs ws{};
-    ws.A = c.take<int32_t>(chunk * (size_t)p.K * p.L * 256);
     cx->clear_secrets();
     cx->note_secret(d_sk, (n < chunk ? n : chunk) * p.sk);
     auto wipe = [&](int code) {  // the staged secret keys never outlive the call, whatever happened
@@ -2095,7 +2083,7 @@ int mldsa_sk_to_pk_batch(int ps, int dev, size_t n, const uint8_t* sk, uint8_t* 
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
         cudaError_t e = cudaMemcpyAsync(d_sk, sk + p.sk * lo, m * p.sk, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = sk_to_pk_run(ps, st, m, d_sk, d_pk, ws);
+        if (e == cudaSuccess) e = launch_sk_to_pk_fused(ps, st, m, d_sk, d_pk);
         if (e == cudaSuccess) e = cudaMemcpyAsync(pk + p.pk * lo, d_pk, m * p.pk, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_sk, 0, m * p.sk, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -89,21 +89,28 @@ struct MsgDesc {
     int framing;              // 0 external, 1 internal, 2 pre-hash (msgs already hold OID || PH(M))
 };
 
+// ---- k_fused.cu: ExpandA fused with the matrix-vector product (A-hat never written) ----
+// keygen arithmetic: pk and the sk fields rho, K, s1, s2, t0 from the seeds and the sampled s1 / s2 (src/ml_dsa.rs:78-98)
+cudaError_t launch_kg_fused(int ps, cudaStream_t st, size_t n, const uint8_t* seeds, const int8_t* s, uint8_t* pk, uint8_t* sk);
+// Signer::get_public_key (src/ml_dsa.rs:502-563): pk from packed sk
+cudaError_t launch_sk_to_pk_fused(int ps, cudaStream_t st, size_t n, const uint8_t* sk, uint8_t* pk);
+// verify under per-lane packed public keys: hints, z, w' = A z - c t1 2^d, UseHint, w1Encode (src/ml_dsa.rs:360-425)
+cudaError_t launch_verify_fused(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const uint8_t* sig,
+                                const uint8_t* cmask, uint8_t* mw1, uint8_t* pre_ok);
+
 // ---- k_keygen.cu ----
 struct KeygenWs {
     uint8_t* seeds;   // [n][128]  rho || rho' || K
     int8_t* s;        // [n][L+K][256]
-    int32_t* A;       // [n][K*L][256]
-    static size_t bytes_per_lane(int K, int L) { return 128 + (size_t)(K + L) * 256 + (size_t)K * L * 1024; }
+    int32_t* A;       // [n][K*L][256], or nullptr: A-hat is not kept (fused kernel); callers that go on to sign / verify
+                      // with the same keys (key sets, the chained pipeline) pass a buffer and reuse it
 };
 cudaError_t keygen_run(int ps, cudaStream_t st, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk,
                        const KeygenWs& ws);
-// pk from sk (Signer::get_public_key, src/ml_dsa.rs:502-563): only ws.A is used
-cudaError_t sk_to_pk_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, uint8_t* pk, const KeygenWs& ws);
 
 // ---- k_verify.cu ----
 struct VerifyWs {
-    int32_t* A;        // [nkeys][K*L][256]
+    int32_t* A;        // [K*L][256] of a shared key (per-lane packed keys: A-hat is never materialised, k_fused.cu)
     int32_t* t1h;      // [nkeys][K][256]   NTT(t1 * 2^d)   (only materialised for a shared key)
     uint8_t* tr;       // [nkeys][64]
     uint8_t* mw1;      // [n][64 + W1_LEN]  mu || w1'
@@ -112,10 +119,6 @@ struct VerifyWs {
     // Resident key set (mldsa_pk_load): A / t1h / tr point into the key set (per key), lane i uses key kidx[i] (nullptr: i)
     bool keys_resident = false;
     const uint32_t* kidx = nullptr;
-    static size_t bytes_per_lane(int K, int L, int w1len, bool shared)
-    {
-        return (shared ? 0 : (size_t)K * L * 1024 + 64) + 64 + w1len + SIB_BYTES + 8;
-    }
 };
 cudaError_t verify_run(int ps, cudaStream_t st, size_t n, const uint8_t* pk, size_t pk_stride, const MsgDesc& md,
                        const uint8_t* sig, uint8_t* ok, const VerifyWs& ws);

@@ -6,9 +6,10 @@
 // Pipeline over a chunk of lanes (one lane = one key):
 //   kg_seed      thread/lane   (rho, rho', K) = H(xi || k || l, 128)              ml_dsa.rs:68-74
 //   rej_bounded  thread/stream s1, s2 = RejBoundedPoly(rho' || LE16(r))            hashing.rs:158-213, 252-272
-//   expand_a     thread/stream A-hat                                               hashing.rs:225-239
-//   kg_arith     warp/lane     t = INTT(A-hat o NTT(s1)) + s2, Power2Round,
-//                              pkEncode / skEncode straight from registers         ml_dsa.rs:85-92, encodings.rs:18-152
+//   kg_fused     (k_fused.cu)  t = INTT(A-hat o NTT(s1)) + s2 with A-hat consumed as it is squeezed, Power2Round,
+//                              pkEncode / skEncode                                 hashing.rs:225-239, ml_dsa.rs:85-92
+//   -- or, when the caller keeps A-hat (key sets, the chained pipeline): expand_a (thread/stream) then kg_arith
+//      (warp/lane: the same arithmetic reading A-hat back), encodings.rs:18-152
 //   shake rows   thread/lane   tr = H(pk, 64) written into sk[64..128]             ml_dsa.rs:99-101
 #include "engine.h"
 #include "keccak.cuh"
@@ -175,87 +176,6 @@ kg_arith_kernel(size_t n, const uint8_t* __restrict__ seeds, const int8_t* __res
     }
 }
 
-// pk from sk: t1 = Power2Round(INTT(A-hat o NTT(s1)) + s2).high, s1/s2 unpacked from the sk bytes
-// (Signer::get_public_key -> private_to_public_key, src/ml_dsa.rs:502-563, then into_bytes).
-template <class P>
-__global__ void __launch_bounds__(KG_WARPS * 32)
-sk_to_pk_kernel(size_t n, const uint8_t* __restrict__ sk, const int32_t* __restrict__ Aall, uint8_t* __restrict__ pk)
-{
-    using LO = Layout<P>;
-    constexpr int K = P::K, L = P::L;
-    __shared__ __align__(16) int32_t tiles[KG_WARPS][NTT_TILE_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* tile = tiles[warp];
-    const size_t stride = (size_t)gridDim.x * KG_WARPS;
-    for (size_t ln = (size_t)blockIdx.x * KG_WARPS + warp; ln < n; ln += stride) {
-        const uint8_t* key = sk + ln * (size_t)P::SK_LEN;
-        const int32_t* A = Aall + ln * (size_t)(K * L) * 256;
-        uint8_t* pko = pk + ln * (size_t)P::PK_LEN;
-        pko[lane] = key[lane];  // rho
-        int32_t s1h[L][8];
-#pragma unroll
-        for (int l = 0; l < L; l++) {
-            uint32_t w[(P::ETABITS + 3) / 4];
-            load_span<P::ETABITS>(key + LO::SK_S1 + l * 32 * P::ETABITS + P::ETABITS * lane, w);
-#pragma unroll
-            for (int i = 0; i < 8; i++) s1h[l][i] = P::ETA - (int32_t)get_field<P::ETABITS>(w, i);
-            sntt_fwd_B2B(s1h[l], tile, lane);
-        }
-#pragma unroll 1
-        for (int k = 0; k < K; k++) {
-            int64_t acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = 0;
-#pragma unroll
-            for (int l = 0; l < L; l++) {
-                const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
-                const int4 x = __ldg(ap), y = __ldg(ap + 1);
-                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-#pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * s1h[l][i];
-            }
-            int32_t t[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = mont_reduce(acc[i]);
-            sntt_inv_B2B(t, tile, lane);
-            uint32_t w2[(P::ETABITS + 3) / 4], f1[8];
-            load_span<P::ETABITS>(key + LO::SK_S2 + k * 32 * P::ETABITS + P::ETABITS * lane, w2);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int32_t s2 = P::ETA - (int32_t)get_field<P::ETABITS>(w2, i);
-                const int32_t tt = freeze(t[i] + s2);
-                f1[i] = (uint32_t)((tt + (1 << (D - 1)) - 1) >> D);
-            }
-            uint32_t w1[3];
-            pack_fields<10>(f1, w1);
-            store_span<10>(pko + 32 + 320 * k + 10 * lane, w1);
-        }
-    }
-}
-
-template <class P>
-static cudaError_t sk_to_pk_run_t(cudaStream_t st, size_t n, const uint8_t* sk, uint8_t* pk, const KeygenWs& ws)
-{
-    cudaError_t e = launch_expand_a(st, P::K, P::L, sk, P::SK_LEN, n, ws.A);
-    if (e != cudaSuccess) return e;
-    {
-        KLaunch kl(KID_SK2PK, st);
-        sk_to_pk_kernel<P><<<capped_grid((n + KG_WARPS - 1) / KG_WARPS, arith_cap()), KG_WARPS * 32, 0, st>>>(n, sk, ws.A, pk);
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t sk_to_pk_run(int ps, cudaStream_t st, size_t n, const uint8_t* sk, uint8_t* pk, const KeygenWs& ws)
-{
-    if (n == 0) return cudaSuccess;
-    switch (ps) {
-    case 44: return sk_to_pk_run_t<Params<44>>(st, n, sk, pk, ws);
-    case 65: return sk_to_pk_run_t<Params<65>>(st, n, sk, pk, ws);
-    case 87: return sk_to_pk_run_t<Params<87>>(st, n, sk, pk, ws);
-    }
-    return cudaErrorInvalidValue;
-}
-
 template <class P>
 static cudaError_t keygen_run_t(cudaStream_t st, size_t n, const uint8_t* xi, uint8_t* pk, uint8_t* sk,
                                 const KeygenWs& ws)
@@ -271,10 +191,14 @@ static cudaError_t keygen_run_t(cudaStream_t st, size_t n, const uint8_t* xi, ui
         rej_bounded_kernel<P::ETA><<<(unsigned)((ns + RB_THREADS - 1) / RB_THREADS), RB_THREADS, 0, st>>>(
             ws.seeds, ns, K + L, ws.s);
     }
-    cudaError_t e = launch_expand_a(st, K, L, ws.seeds, 128, n, ws.A);
-    if (e != cudaSuccess) return e;
-    const unsigned grid = capped_grid((n + KG_WARPS - 1) / KG_WARPS, arith_cap());
-    {
+    cudaError_t e;
+    if (ws.A == nullptr) {  // A-hat consumed as it is squeezed (k_fused.cu)
+        e = launch_kg_fused(P::PS, st, n, ws.seeds, ws.s, pk, sk);
+        if (e != cudaSuccess) return e;
+    } else {                // A-hat kept for the caller (key sets, chained pipeline)
+        e = launch_expand_a(st, K, L, ws.seeds, 128, n, ws.A);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = capped_grid((n + KG_WARPS - 1) / KG_WARPS, arith_cap());
         KLaunch kl(KID_KG_ARITH, st);
         kg_arith_kernel<P><<<grid, KG_WARPS * 32, 0, st>>>(n, ws.seeds, ws.s, ws.A, pk, sk);
     }

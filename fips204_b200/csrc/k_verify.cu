@@ -3,7 +3,8 @@
 // sig_decode / pk_decode (src/encodings.rs:292-328, :55-80) folded in.
 //
 // Pipeline over a chunk of lanes (one lane = one (pk, message, signature)):
-//   [key prep]    expand_a per key; for a shared key also tr = H(pk) and NTT(t1 * 2^d), once
+//   [key prep]    one shared key: expand_a, tr = H(pk) and NTT(t1 * 2^d), once; resident key sets bring theirs;
+//                 per-lane packed keys: none -- verify_fused (k_fused.cu) squeezes A-hat inside the product
 //   verify_pre    thread/lane  tr (per-lane keys), mu = H(tr || M'), c = SampleInBall(c~) as bit masks
 //   verify_arith  warp/lane    hint decode + checks, z unpack + norm, NTTs,
 //                              w' = INTT(A-hat o z-hat - c-hat o t1-hat), UseHint, w1Encode
@@ -109,12 +110,12 @@ struct alignas(16) VerifySmem {
     alignas(16) int32_t zh[P::L][256];              // z-hat, NTT domain, natural order
 };
 
-// MODE 0: per-lane packed public keys (A-hat per lane in the workspace, t1-hat computed from the key bytes);
 // MODE 1: one shared key (A-hat, t1-hat cached once); MODE 2: resident key set (A-hat, t1-hat cached per key, lane
-// ln uses key kidx[ln] or ln) -- what the reference's PublicKey struct caches (src/types.rs:35-41).
+// ln uses key kidx[ln] or ln) -- what the reference's PublicKey struct caches (src/types.rs:35-41).  Per-lane packed
+// keys go through verify_fused_kernel (k_fused.cu), which never materialises A-hat.
 template <class P, int MODE>
 __global__ void __launch_bounds__(VF_WARPS * 32)
-verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, const uint8_t* __restrict__ sig,
+verify_arith_kernel(size_t n, const uint8_t* __restrict__ sig,
                     const int32_t* __restrict__ Aall, const int32_t* __restrict__ t1h_shared,
                     const uint8_t* __restrict__ cmask, uint8_t* __restrict__ mw1, uint8_t* __restrict__ pre_ok,
                     const uint32_t* __restrict__ kidx)
@@ -130,7 +131,6 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
     for (size_t ln = (size_t)blockIdx.x * VF_WARPS + warp; ln < n; ln += stride) {
         const uint8_t* sg = sig + ln * (size_t)P::SIG_LEN;
         const size_t key = MODE == 2 ? (kidx ? (size_t)kidx[ln] : ln) : ln;
-        const uint8_t* pkl = MODE == 0 ? pk + ln * pk_stride : pk;
         const int32_t* A = Aall + (SHARED ? 0 : key * (size_t)(K * L) * 256);
         const int32_t* t1h = t1h_shared + (MODE == 2 ? key * (size_t)K * 256 : 0);
         uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
@@ -206,13 +206,11 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ pk, size_t pk_stride, 
         for (int k = 0; k < K; k++) {
             if (!SHARED && k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
             int32_t t1v[8];
-            if (MODE != 0) {
+            {
                 const int4* tp = reinterpret_cast<const int4*>(t1h + 256 * k + 8 * lane);
                 const int4 x = __ldg(tp), y = __ldg(tp + 1);
                 t1v[0] = x.x; t1v[1] = x.y; t1v[2] = x.z; t1v[3] = x.w;
                 t1v[4] = y.x; t1v[5] = y.y; t1v[6] = y.z; t1v[7] = y.w;
-            } else {
-                load_t1_hat(pkl + 32 + 320 * k, t1v, tile, lane);
             }
             int64_t acc[8];
 #pragma unroll
@@ -260,9 +258,6 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
             KLaunch kl(KID_T1HAT, st);
             t1hat_kernel<P><<<1, 128, 0, st>>>(pk, ws.t1h);
         }
-    } else {
-        e = launch_expand_a(st, K, L, pk, pk_stride, n, ws.A);
-        if (e != cudaSuccess) return e;
     }
     {
         KLaunch kl(KID_VERIFY_PRE, st);
@@ -273,18 +268,17 @@ static cudaError_t verify_run_t(cudaStream_t st, size_t n, const uint8_t* pk, si
     // One shared key: few long-lived CTAs (measured at 2^20 lanes, ML-DSA-65: 16 per SM -> 10.9 ms, 192 per SM ->
     // 24.4 ms: the key's 36 KiB of A-hat / t1-hat stay hot in each SM's L1); per-lane keys: many short CTAs (no partly
     // empty last wave)
-    const unsigned grid = capped_grid((n + VF_WARPS - 1) / VF_WARPS, shared ? 16 : arith_cap());
-    {
+    // per-lane packed keys: A-hat is consumed as it is squeezed, never written (k_fused.cu)
+    if (!resident && !shared) {
+        e = launch_verify_fused(P::PS, st, n, pk, pk_stride, sig, ws.cmask, ws.mw1, ws.pre_ok);
+        if (e != cudaSuccess) return e;
+    } else {
+        const unsigned grid = capped_grid((n + VF_WARPS - 1) / VF_WARPS, shared ? 16 : arith_cap());
         KLaunch kl(KID_VERIFY_ARITH, st);
         if (resident)
-            verify_arith_kernel<P, 2><<<grid, VF_WARPS * 32, 0, st>>>(n, nullptr, 0, sig, ws.A, ws.t1h, ws.cmask, ws.mw1,
-                                                                      ws.pre_ok, ws.kidx);
-        else if (shared)
-            verify_arith_kernel<P, 1><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, ws.t1h, ws.cmask,
-                                                                      ws.mw1, ws.pre_ok, nullptr);
+            verify_arith_kernel<P, 2><<<grid, VF_WARPS * 32, 0, st>>>(n, sig, ws.A, ws.t1h, ws.cmask, ws.mw1, ws.pre_ok, ws.kidx);
         else
-            verify_arith_kernel<P, 0><<<grid, VF_WARPS * 32, 0, st>>>(n, pk, pk_stride, sig, ws.A, nullptr, ws.cmask,
-                                                                      ws.mw1, ws.pre_ok, nullptr);
+            verify_arith_kernel<P, 1><<<grid, VF_WARPS * 32, 0, st>>>(n, sig, ws.A, ws.t1h, ws.cmask, ws.mw1, ws.pre_ok, nullptr);
     }
     e = launch_ctilde(P::PS, st, n, nullptr, nullptr, 1, ws.mw1, /*verify*/ sig, ws.pre_ok, ok, nullptr, nullptr);
     if (e != cudaSuccess) return e;

@@ -218,11 +218,14 @@ __device__ __forceinline__ int32_t shoup_companion(int32_t z)
     constexpr int32_t G = (int32_t)(((int64_t)1 << 32) - F32);                  // (1 - frac) * 2^32 < 2^31
     return (int32_t)((uint32_t)z * 513u - (uint32_t)mulhi_noadd(z, G));
 }
+// a' = a + t is formed by the two IMADs of the Shoup product themselves (the addend rides along), b' = 2a - a' is one
+// three-input IADD3: one ALU-pipe instruction per butterfly instead of two, the FMA-pipe count unchanged.
 __device__ __forceinline__ void ct_bfly_s(int32_t& a, int32_t& b, int32_t z, int32_t zs)
 {
-    const int32_t t = shoup_mul(b, z, zs);
-    b = a - t;
-    a = a + t;
+    const int32_t qh = mulhi_noadd(b, zs);
+    const int32_t s = (int32_t)((uint32_t)b * (uint32_t)z + (uint32_t)a - (uint32_t)qh * (uint32_t)Q);
+    b = (int32_t)((uint32_t)a + (uint32_t)a - (uint32_t)s);
+    a = s;
 }
 __device__ __forceinline__ void gs_bfly_s(int32_t& a, int32_t& b, int32_t z, int32_t zs)
 {
