@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--ref-sample", type=int, default=0, help="lanes per step of the reference arm (0 = auto)")
     ap.add_argument("--no-verify-leg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[1], [2], [4] legs and the strong-scaling legs")
     return ap.parse_args()
 
 
@@ -145,11 +146,7 @@ class Clocks:
 def kernel_work(ps, n, total_iters, accepted):
     p = PARAMS[ps]
     K, L = p["K"], p["L"]
-    it = float(total_iters)
-    w = _kernel_work(ps, n, it, accepted)
-    # paired round launches: one Keccak stage (mask / ctilde) beside one arithmetic stage (sign_w / sign_z)
-    w["round_pair"] = tuple(sum(w[k][i] for k in ("mask", "sign_w", "ctilde", "sign_z")) for i in (0, 1))
-    return w
+    return _kernel_work(ps, n, float(total_iters), accepted)
 
 
 def _kernel_work(ps, n, it, accepted):
@@ -161,8 +158,9 @@ def _kernel_work(ps, n, it, accepted):
         "sign_key": (n * (L + 2 * K) * NTT_OPS, n * (p["sk"] - 128 + (L + 2 * K) * 1024)),
         "sign_prep": (n * 2 * KECCAK_F, n * (128 + MSG_LEN + 32 + 128)),
         "mask": (it * L * 5 * KECCAK_F, it * L * (66 + p["zbytes"])),
+        # A-hat: the two candidates of a lane (speculation depth 2) share ONE staged copy of every row
         "sign_w": (it * (L * NTT_OPS + K * INTT_OPS + K * L * 256 * MAC_OPS),
-                   it * (L * p["zbytes"] + K * L * 1024 + K * 1024 + p["w1"])),
+                   it * (L * p["zbytes"] + K * L * 1024 / 2 + K * 1024 + p["w1"] + 64)),
         "ctilde": (it * (p["ct_blocks"] + 1) * KECCAK_F, it * (64 + p["w1"] + 64 + 136)),
         "sign_z": (it * (NTT_OPS + (L + K) * (INTT_OPS + 256 * MAC_OPS)) + accepted * K * (INTT_OPS + 256 * MAC_OPS),
                    it * ((L + K) * 1024 + L * p["zbytes"] + 2 * K * 1024 + 200) + accepted * (K * 1024 + p["sig"])),
@@ -171,24 +169,41 @@ def _kernel_work(ps, n, it, accepted):
 
 
 def verify_work(ps, n, shared):
+    """(all algorithmic int32 ops, the Keccak part of them) of n verifies"""
     p = PARAMS[ps]
     K, L = p["K"], p["L"]
     kec = (1 + 1 + p["ct_blocks"]) + (0 if shared else K * L * 5 + p["tr_blocks"])
     ntt = (L + 1) + (0 if shared else K)
-    return n * (kec * KECCAK_F + ntt * NTT_OPS + K * INTT_OPS + (K * L + K) * 256 * MAC_OPS)
+    return (n * (kec * KECCAK_F + ntt * NTT_OPS + K * INTT_OPS + (K * L + K) * 256 * MAC_OPS), n * kec * KECCAK_F)
+
+
+# Kernels whose work is the Keccak permutation (LOP3 / SHF only): bounded by the ALU pipe, and their fraction of that
+# pipe's measured peak is a true utilisation figure.  The warp-per-lane arithmetic kernels are bounded by a mix of
+# issue, FMA pipe and latency: for them the line carries the pipe utilisations ncu measured (profiles/ncu_kernels.json,
+# written by tools/summarize_ncu.py from the committed --set full capture), not a ratio of model ops to a chosen peak.
+KECCAK_KERNELS = ("expand_a", "mask", "ctilde", "sign_prep", "rej_bounded", "kg_seed", "shake_rows", "verify_pre")
+PUBLISHED_US = {  # the reference's own figures: benches/README.md:16-26, one core of an Intel i7-7700K @ 4.2 GHz
+    "sign": {44: 226.32, 65: 352.89, 87: 385.05}, "verify": {44: 21.016, 65: 27.996, 87: 36.468},
+    "keygen": {44: 104.89, 65: 194.80, 87: 290.24}}
+
+
+def vs_published(op, ps, per_core_per_s):
+    """this host's per-core rate of the CPU baseline over the reference's published per-core rate (other hardware)"""
+    return per_core_per_s / (1e6 / PUBLISHED_US[op][ps])
 
 
 # ------------------------------------------------------------------------------------------------
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path, timed on the host cores.  The crate is Rust
     and cannot be built in this image (no rustc/cargo), so this is the CPU oracle port (kind 'port'),
-    one scalar instance per host core, on a bounded sample of the same workload."""
+    one instance per host core, on a bounded sample of the same workload."""
     if rank != 0:
         return
     import oracle_lib as O
     from synth import synth_block
+    build = O.use_native_build()
     cores = O.ncores()
-    sample = args.ref_sample or max(256, min(args.lanes, cores * 1024))  # ~0.7 s of work per step on every core
+    sample = args.ref_sample or max(256, min(args.lanes, cores * 1024))  # ~0.5 s of work per step on every core
     xi = synth_block("bench-xi", sample, 32)
     pk, sk = O.keygen_batch(args.ps, xi)
     msgs = [bytes(m) for m in synth_block("bench-msg", sample, MSG_LEN)]
@@ -208,12 +223,18 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": f"ML-DSA-{args.ps} signs/sec", "value": value, "unit": "signs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, sample),
+        # the SAME config object as the GPU arm (the workload is one and the same); what this arm actually times per step
+        # is `sample_lanes` lanes of it -- a per-operation CPU rate does not depend on the batch size
+        "config": workload_config(args, args.lanes), "sample_lanes": sample,
         "cpu_baseline": {"value": value, "unit": "signs/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} lanes/step of the same workload (distinct keys, 32-B msgs), "
-                                   f"all {cores} host threads, C oracle (reference crate needs rustc: absent)"},
+                                   f"all {cores} host threads, C oracle ({build}; the reference crate needs rustc: absent)",
+                         "per_core_us": 1e6 * cores / value,
+                         "vs_published_per_core": vs_published("sign", args.ps, value / cores),
+                         "published": f"{PUBLISHED_US['sign'][args.ps]} us per sign on one i7-7700K core (benches/README.md:21)"},
         "e2e": {"value": value, "unit": "signs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "verify": {"value": sample / tv, "unit": "verifies/s", "keys": "distinct"},
+        "verify": {"value": sample / tv, "unit": "verifies/s", "keys": "distinct", "per_core_us": 1e6 * cores * tv / sample,
+                   "vs_published_per_core": vs_published("verify", args.ps, sample / tv / cores)},
         "gpu_launches": 0, "mean_iters": float(iters.mean()),
     }
     _JSON_OUT.write(json.dumps(line) + "\n")
@@ -225,6 +246,166 @@ def workload_config(args, lanes):
                         f"{MSG_LEN}-byte messages, empty ctx, external framing",
             "lanes_per_gpu": lanes, "param_set": args.ps, "msg_len": MSG_LEN, "keys": "distinct",
             "l2": "inputs (>= 4 GB/step) exceed the 126 MB L2; no flush needed", "parallelism": f"batch-shard x{args.gpus}"}
+
+
+class Env:
+    """torch / library handles of one rank"""
+
+
+def rank_max(E, x):
+    """max over the ranks of a host float (device-timed or wall-clock seconds)"""
+    if E.world == 1:
+        return x
+    t = E.torch.tensor([x], dtype=E.torch.float64, device=E.dev)
+    E.dist.all_reduce(t, op=E.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(E):
+    if E.world > 1:
+        E.dist.barrier()
+    E.torch.cuda.synchronize()
+
+
+def timed_calls(E, fn, reps, warm=1):
+    """wall-clock seconds of each of `reps` calls, barrier on both sides, max over ranks"""
+    for _ in range(warm):
+        fn()
+    out = []
+    for _ in range(reps):
+        barrier(E)
+        t0 = time.perf_counter()
+        fn()
+        barrier(E)
+        out.append(rank_max(E, time.perf_counter() - t0))
+    return out
+
+
+def device_ms(E, fn, reps, warm=1):
+    """CUDA events on the launching stream around `reps` calls; ms per call, max over ranks"""
+    torch = E.torch
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(E)
+    a.record(E.stream)
+    for _ in range(reps):
+        fn()
+    b.record(E.stream)
+    barrier(E)
+    return rank_max(E, a.elapsed_time(b) / reps)
+
+
+def ncu_kernels():
+    f = ROOT / "profiles" / "ncu_kernels.json"
+    return json.load(open(f)) if f.exists() else {}
+
+
+def config_legs(E, args, n, peaks, hbm_peak):
+    """BASELINE configs[1], [2] and [4] on this rank's shard (driver-run, not only tools/bench_ops.py)."""
+    torch, L, dev, sh, check = E.torch, E.L, E.dev, E.sh, E.check
+    F = E.F
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC0F + E.rank)
+    out = {}
+    # ---- configs[1]: standalone NTT / INTT / expand_a, 2^20 ML-DSA polynomials on one GPU (int32 in place, 2 KiB of HBM
+    # traffic per polynomial for the transforms) -- every rank runs it on its own GPU, rank 0's figures are reported
+    npoly = 1 << 20
+    polys = torch.randint(0, 8380417, (npoly, 256), dtype=torch.int32, device=dev, generator=g)
+    seeds = torch.randint(0, 256, (npoly, 34), dtype=torch.uint8, device=dev, generator=g)
+    c1 = {"workload": "BASELINE configs[1]: NTT / INTT / expand_a microbench, 2^20 polynomials, 1 GPU", "polys": npoly}
+    for name, fn, ops, byts in (
+            ("ntt", lambda: check(L.mldsa_ntt_batch_dev(sh, npoly, ptr(polys))), NTT_OPS, 2048),
+            ("intt", lambda: check(L.mldsa_intt_batch_dev(sh, npoly, ptr(polys))), INTT_OPS, 2048),
+            ("expand_a", lambda: check(L.mldsa_expand_a_batch_dev(sh, npoly, ptr(seeds), ptr(polys))), 5 * KECCAK_F, 34 + 1024)):
+        if name == "intt":
+            polys.remainder_(8380417)
+        ms = device_ms(E, fn, 5, warm=2)
+        leg = {"ms": ms, "polys_per_s": npoly / (ms * 1e-3), "hbm_gbs": npoly * byts / (ms * 1e-3) / 1e9,
+               "hbm_frac": npoly * byts / (ms * 1e-3) / 1e9 / hbm_peak}
+        if name == "expand_a":
+            leg["alu_pipe_frac"] = npoly * ops / (ms * 1e-3) / peaks["alu_lop3_shf"]
+        c1[name] = leg
+    del polys, seeds
+    out["1"] = c1
+    # ---- configs[2]: ML-DSA-44 batched verify, n signatures under ONE public key (A-hat, tr, t1-hat cached once)
+    m44 = F.PARAM_SETS[44]
+    xi = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    msg = torch.randint(0, 256, (n, MSG_LEN), dtype=torch.uint8, device=dev, generator=g)
+    rnd = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    moff = torch.arange(n + 1, dtype=torch.int64, device=dev) * MSG_LEN
+    pk = torch.empty((1, m44.PK_LEN), dtype=torch.uint8, device=dev)
+    sk = torch.empty((1, m44.SK_LEN), dtype=torch.uint8, device=dev)
+    sig = torch.empty((n, m44.SIG_LEN), dtype=torch.uint8, device=dev)
+    ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+    check(L.mldsa_keygen_batch_dev(44, sh, 1, ptr(xi), ptr(pk), ptr(sk)))
+    check(L.mldsa_sign_batch_dev(44, sh, 0, n, ptr(sk), 0, ptr(msg), ptr(moff), None, None, ptr(rnd), ptr(sig), None))
+    sig[::8, 40] ^= 1  # SURVEY 8d config 3: a structured subset is corrupted; the verdict pattern is checked below
+    vfn = lambda: check(L.mldsa_verify_batch_dev(44, sh, 0, n, ptr(pk), 0, ptr(msg), ptr(moff), None, None, ptr(sig), ptr(ok)))  # noqa: E731
+    ms = device_ms(E, vfn, max(3, args.steps), warm=2)
+    okc = ok.cpu().numpy()
+    pattern_ok = bool((okc[::8] == 0).all() and okc.reshape(-1, 8)[:, 1:].all()) if n % 8 == 0 else None
+    vops, vkec = verify_work(44, n, True)
+    c2 = {"workload": "BASELINE configs[2]: ML-DSA-44 batched verify under one shared public key (cached A-hat)",
+          "lanes_per_gpu": n, "value": E.world * n / (ms * 1e-3), "unit": "verifies/s", "ms_per_step": ms,
+          "verdict_pattern_ok": pattern_ok, "algorithmic_int32_ops_per_verify": vops / n}
+    h_pk, h_msg, h_moff = pk.cpu().pin_memory(), msg.cpu().pin_memory(), moff.cpu().pin_memory()
+    h_sig, h_ok = sig.cpu().pin_memory(), torch.zeros(n, dtype=torch.uint8).pin_memory()
+    hv = lambda: check(L.mldsa_verify_batch(44, E.local, 0, n, ptr(h_pk), 0, ptr(h_msg), ptr(h_moff), None, None, ptr(h_sig), ptr(h_ok)))  # noqa: E731
+    vs = float(np.median(timed_calls(E, hv, 3)))
+    h2d = int(m44.PK_LEN + h_msg.numel() + h_moff.numel() * 8 + h_sig.numel())
+    c2["e2e"] = {"value": E.world * n / vs, "unit": "verifies/s", "ms_per_step": vs * 1e3, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": n, "h2d_gbs": h2d / vs / 1e9, "api": "mldsa_verify_batch (host pointers, pinned)"}
+    out["2"] = c2
+    del xi, msg, rnd, moff, pk, sk, sig, ok, h_pk, h_msg, h_moff, h_sig, h_ok
+    torch.cuda.empty_cache()
+    # ---- configs[4]: ML-DSA-87 keygen -> sign -> verify end to end with on-device packing, ONE batch of 2^20 lanes
+    # sharded over the ranks (n / world lanes each): only xi / msg / rnd go in, pk / sig / verdicts come out
+    m87 = F.PARAM_SETS[87]
+    npl = max(1, n // E.world)
+
+    def pinned(count, fill=None):
+        t = torch.empty(count, dtype=torch.uint8).pin_memory()
+        if fill is not None:
+            t.copy_(torch.randint(0, 256, (count,), dtype=torch.uint8, generator=fill))
+        return t
+
+    cg = torch.Generator()
+    cg.manual_seed(0x87 + E.rank)
+    p_xi, p_msg, p_rnd = pinned(npl * 32, cg), pinned(npl * MSG_LEN, cg), pinned(npl * 32, cg)
+    p_moff = (torch.arange(npl + 1, dtype=torch.int64) * MSG_LEN).pin_memory()
+    p_pk, p_sig, p_ok = pinned(npl * m87.PK_LEN), pinned(npl * m87.SIG_LEN), pinned(npl)
+    stage = (C.c_double * 3)()
+    pfn = lambda: check(L.mldsa_pipeline_batch(87, E.local, 0, npl, ptr(p_xi), ptr(p_msg), ptr(p_moff), None, None, ptr(p_rnd),  # noqa: E731
+                                                ptr(p_pk), None, ptr(p_sig), ptr(p_ok), None, stage))
+    ps_all = timed_calls(E, pfn, 3)
+    psec = float(np.median(ps_all))
+    all_ok = bool(p_ok.numpy().all())
+    sample_ok = None
+    if E.rank == 0:  # a sample of lanes against the CPU oracle: keys, signatures and verdicts, byte for byte
+        import oracle_lib as O
+        k = 64
+        idx = np.linspace(0, npl - 1, k).astype(np.int64)
+        xs = p_xi.numpy().reshape(npl, 32)[idx]
+        opk, osk = O.keygen_batch(87, xs)
+        osig, _ = O.sign_batch(87, osk, [bytes(x) for x in p_msg.numpy().reshape(npl, MSG_LEN)[idx]], p_rnd.numpy().reshape(npl, 32)[idx])
+        sample_ok = bool((opk == p_pk.numpy().reshape(npl, -1)[idx]).all() and (osig == p_sig.numpy().reshape(npl, -1)[idx]).all())
+    sm = [rank_max(E, float(x)) for x in stage]
+    out["4"] = {"workload": "BASELINE configs[4]: ML-DSA-87 keygen+sign+verify end to end, on-device packing, one batch sharded "
+                            "over the GPUs; keys and signatures stay in HBM between the stages, A-hat expanded once per key",
+                "lanes_total": npl * E.world, "lanes_per_gpu": npl, "value": E.world * npl / psec, "unit": "pipelines/s",
+                "ops_per_s": 3 * E.world * npl / psec, "ms_per_step": psec * 1e3, "step_ms_all": [round(x * 1e3, 2) for x in ps_all],
+                "stage_device_ms": {"keygen": sm[0], "sign": sm[1], "verify": sm[2]},
+                "stage_ops_per_s": {k: E.world * npl / (v * 1e-3) if v else None for k, v in zip(("keygen", "sign", "verify"), sm)},
+                "h2d_bytes_per_step": int(p_xi.numel() + p_msg.numel() + p_rnd.numel() + p_moff.numel() * 8),
+                "d2h_bytes_per_step": int(p_pk.numel() + p_sig.numel() + p_ok.numel()),
+                "pcie_bytes_equal_packed_sizes": True, "all_verdicts_true": all_ok, "oracle_sample_bit_exact": sample_ok,
+                "api": "mldsa_pipeline_batch (host pointers, pinned)", "scaling": "strong (2^20 lanes in total)"}
+    return out
 
 
 def main():
@@ -251,14 +432,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # host-side barrier for the leg one rank runs on every GPU
     L = _lib.lib()
     m = F.PARAM_SETS[args.ps]
     p = PARAMS[args.ps]
     n = args.lanes
     stream = torch.cuda.current_stream()
     sh = C.c_void_p(stream.cuda_stream)
+    E = Env()
+    E.torch, E.dist, E.F, E.L, E.check = torch, dist, F, L, _lib.check
+    E.rank, E.world, E.local, E.dev, E.stream, E.sh = rank, world, local, dev, stream, sh
 
     def ptr(t):
         return C.c_void_p(t.data_ptr())
@@ -281,14 +467,10 @@ def main():
         _lib.check(L.mldsa_sign_batch_dev(args.ps, sh, 0, n, ptr(d_sk), m.SK_LEN, ptr(d_msg), ptr(d_moff), None, None,
                                           ptr(d_rnd), ptr(d_sig), ptr(d_iters)))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- integer issue peak of this device (roofline denominator for an int32-issue-bound path)
+    # ---- integer issue peaks of this device, measured live (dependent-free instruction streams at full occupancy):
+    # the ALU pipe (LOP3 / SHF: what Keccak runs on) is the roofline denominator of the Keccak kernels
     peaks = {}
-    for mode, name in ((0, "alu_lop3_shf"), (1, "fma_imad"), (2, "both")):
+    for mode, name in ((0, "alu_lop3_shf"), (1, "fma_imad")):
         v = C.c_double()
         _lib.check(L.mldsa_int32_peak_probe(mode, C.byref(v)))
         peaks[name] = v.value
@@ -304,7 +486,7 @@ def main():
     L.mldsa_profile_enable(1)
     launches0 = L.mldsa_kernel_launches()
     clocks = Clocks(local, warm_s * args.steps)
-    barrier()
+    barrier(E)
     clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     rounds = 0
@@ -313,20 +495,16 @@ def main():
         sign_dev()
         b.record(stream)
         rounds += L.mldsa_last_sign_rounds()
-    barrier()
+    barrier(E)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     clk = clocks.stop()
     L.mldsa_profile_enable(0)
     launches = L.mldsa_kernel_launches() - launches0
-    total_ms = float(sum(step_ms))
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = rank_max(E, float(sum(step_ms)))
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
-    # per-kernel device time over the timed region
+    # ---- per-kernel device time over the timed region
     prof = {}
     for i in range(L.mldsa_profile_count()):
         ms, cnt = C.c_double(), C.c_uint64()
@@ -335,14 +513,24 @@ def main():
             prof[L.mldsa_profile_name(i).decode()] = (ms.value, cnt.value)
     iters_total = int(d_iters.to(torch.int64).sum().item())
     work = kernel_work(args.ps, n, iters_total, n)
+    ncu = ncu_kernels()
+    alu_peak = peaks["alu_lop3_shf"]
     kernels = {}
     for name, (ms, cnt) in prof.items():
         ops, byts = work.get(name, (0.0, 0.0))
-        kernels[name] = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
-                         "share": ms / (sum(v[0] for v in prof.values()) or 1.0),
-                         "int32_tops": ops / (ms / args.steps * 1e-3) / 1e12 if ms else None,
-                         "hbm_gbs": byts / (ms / args.steps * 1e-3) / 1e9 if ms else None}
-    top = max(prof, key=lambda k: prof[k][0]) if prof else None
+        per = ms / args.steps
+        k = {"ms_per_step": per, "launches_per_step": cnt / args.steps, "share": ms / (sum(v[0] for v in prof.values()) or 1.0),
+             "hbm_gbs_algorithmic": byts / (per * 1e-3) / 1e9 if per else None}
+        if name in KECCAK_KERNELS:
+            k["bound"] = "ALU pipe (Keccak: LOP3 / SHF)"
+            k["alu_pipe_frac"] = ops / (per * 1e-3) / alu_peak if per else None
+        else:
+            k["bound"] = "issue / FMA pipe / latency (see ncu)"
+        rec = ncu.get(f"{name}:{args.ps}")
+        if rec:
+            k["ncu"] = {x: rec[x] for x in ("issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_lsu_pct", "dram_pct", "source") if x in rec}
+        kernels[name] = k
+    top = max(prof, key=lambda kk: prof[kk][0]) if prof else None
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     if peaks_file.exists():
@@ -352,29 +540,32 @@ def main():
         tk = kernels[top]
         launches_top = prof[top][1] / args.steps
         ops, byts = work.get(top, (0.0, 0.0))
-        pipe = "alu_lop3_shf" if top in ("mask", "ctilde", "expand_a", "sign_prep") else "both"
+        tops = ops / (tk["ms_per_step"] * 1e-3) / 1e12
+        if top in KECCAK_KERNELS:
+            peak, peak_src, frac = alu_peak / 1e12, "measured live: ALU-pipe (LOP3 + SHF) issue probe", tops / (alu_peak / 1e12)
+        else:  # an arithmetic kernel on top: its utilisation is what ncu measured, not model ops over a chosen peak
+            rec = ncu.get(f"{top}:{args.ps}", {})
+            peak, peak_src = None, "ncu issue_active (profiles/ncu_kernels.json)"
+            frac = rec.get("issue_active_pct", 0.0) / 100.0 if rec else None
         roofline = {
-            "kernel": top, "bound": "int32",
-            "achieved": tk["int32_tops"], "peak": peaks[pipe] / 1e12, "unit": "Tops/s (algorithmic int32 ops)",
-            "frac": (tk["int32_tops"] or 0) / (peaks[pipe] / 1e12), "peak_source": f"measured live: {pipe} issue probe",
+            "kernel": top, "bound": "int32", "achieved": tops, "peak": peak, "unit": "Tops/s (algorithmic int32 ops)",
+            "frac": frac, "peak_source": peak_src,
             "avg_launch_ms": tk["ms_per_step"] / launches_top, "launches_per_step": launches_top,
             "algorithmic_ops_per_launch": ops / launches_top, "algorithmic_bytes_per_launch": byts / launches_top,
-            "hbm": {"bound": "hbm", "achieved": tk["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (tk["hbm_gbs"] or 0) / hbm_peak, "peak_source": hbm_src},
+            "hbm": {"bound": "hbm", "achieved": tk["hbm_gbs_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (tk["hbm_gbs_algorithmic"] or 0) / hbm_peak, "peak_source": hbm_src},
             "traffic": None,
         }
-        # DRAM bytes of that kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to
-        # this launch's lanes: dram__bytes_read.sum + dram__bytes_write.sum per launch
-        tf = ROOT / "profiles" / "ncu_traffic.json"
-        if tf.exists():
-            rec = json.load(open(tf)).get(f"{top}:{args.ps}")
-            if rec:
-                per_unit = (rec["dram_read_bytes"] + rec["dram_write_bytes"]) / rec["units"]
-                units_per_launch = {"expand_a": n}.get(top, iters_total / launches_top)
-                roofline["traffic"] = per_unit * units_per_launch
-                roofline["traffic_source"] = rec["source"]
-                roofline["traffic_over_algorithmic"] = roofline["traffic"] / (byts / launches_top) if byts else None
-    whole_ops = sum(v[0] for k, v in work.items() if k != "round_pair")
+        # DRAM bytes of that kernel from the committed ncu --set full capture, scaled to this launch's units
+        rec = ncu.get(f"{top}:{args.ps}")
+        if rec and rec.get("units"):
+            per_unit = (rec["dram_read_bytes"] + rec["dram_write_bytes"]) / rec["units"]
+            units_per_launch = {"expand_a": n, "sign_key": n}.get(top, iters_total / launches_top)
+            roofline["traffic"] = per_unit * units_per_launch
+            roofline["traffic_source"] = rec["source"]
+            roofline["traffic_over_algorithmic"] = roofline["traffic"] / (byts / launches_top) if byts else None
+    whole_ops = sum(v[0] for v in work.values())
+    keccak_ops = sum(work[k][0] for k in KECCAK_KERNELS if k in work)
 
     # ---- correctness guards outside the timed region: all signatures verify on the GPU, and a sample is
     # byte-identical to the CPU oracle
@@ -396,47 +587,22 @@ def main():
                 _lib.check(L.mldsa_sign_batch_dev(args.ps, sh, 0, n, ptr(d_sk), 0, ptr(d_msg), ptr(d_moff), None, None,
                                                   ptr(d_rnd), ptr(d_sig), None))
             stride = 0 if shared else m.PK_LEN
-            for _ in range(3):
-                _lib.check(L.mldsa_verify_batch_dev(args.ps, sh, 0, n, ptr(d_pk), stride, ptr(d_msg), ptr(d_moff),
-                                                    None, None, ptr(d_sig), ptr(d_ok)))
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            a.record(stream)
-            for _ in range(args.steps):
-                _lib.check(L.mldsa_verify_batch_dev(args.ps, sh, 0, n, ptr(d_pk), stride, ptr(d_msg), ptr(d_moff),
-                                                    None, None, ptr(d_sig), ptr(d_ok)))
-            b.record(stream)
-            barrier()
-            ms = a.elapsed_time(b) / args.steps
-            if world > 1:
-                t = torch.tensor([ms], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
+            vdev = lambda: _lib.check(L.mldsa_verify_batch_dev(args.ps, sh, 0, n, ptr(d_pk), stride, ptr(d_msg), ptr(d_moff),  # noqa: E731
+                                                               None, None, ptr(d_sig), ptr(d_ok)))
+            ms = device_ms(E, vdev, args.steps, warm=3)
             assert bool(d_ok.all().item())
-            vops = verify_work(args.ps, n, shared)
+            vops, vkec = verify_work(args.ps, n, shared)
             leg = {"keys": "shared" if shared else "distinct", "value": world * n / (ms * 1e-3),
-                   "unit": "verifies/s", "ms_per_step": ms,
-                   "int32_tops": vops / (ms * 1e-3) / 1e12, "frac_of_int32_peak": vops / (ms * 1e-3) / peaks["both"]}
+                   "unit": "verifies/s", "ms_per_step": ms, "algorithmic_int32_ops_per_verify": vops / n,
+                   # the Keccak part of the work over the ALU pipe's peak: a LOWER bound of that pipe's utilisation
+                   # (the arithmetic kernels use it too); the whole-leg pipe figures are in the ncu captures
+                   "keccak_alu_pipe_frac": vkec / (ms * 1e-3) / alu_peak}
             # the same leg end to end: host-pointer C-ABI call, pinned buffers, pk + msg + sig in, verdicts out
             h_sig.copy_(d_sig)
             torch.cuda.synchronize()
-
-            def verify_host():
-                _lib.check(L.mldsa_verify_batch(args.ps, local, 0, n, ptr(h_pk), stride, ptr(h_msg), ptr(h_moff), None,
-                                                None, ptr(h_sig), ptr(h_ok)))
-
-            verify_host()
-            barrier()
-            t0 = time.perf_counter()
-            vsteps = max(1, min(args.steps, 3))
-            for _ in range(vsteps):
-                verify_host()
-            barrier()
-            vs = (time.perf_counter() - t0) / vsteps
-            if world > 1:
-                t = torch.tensor([vs], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                vs = float(t.item())
+            vhost = lambda: _lib.check(L.mldsa_verify_batch(args.ps, local, 0, n, ptr(h_pk), stride, ptr(h_msg), ptr(h_moff), None,  # noqa: E731
+                                                            None, ptr(h_sig), ptr(h_ok)))
+            vs = float(np.median(timed_calls(E, vhost, max(1, min(args.steps, 3)))))
             assert bool(h_ok.all().item())
             h2d = int((m.PK_LEN if shared else h_pk.numel()) + h_msg.numel() + h_moff.numel() * 8 + h_sig.numel())
             leg["e2e"] = {"value": world * n / vs, "unit": "verifies/s", "ms_per_step": vs * 1e3,
@@ -452,6 +618,7 @@ def main():
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region
     h_sk = d_sk.cpu().pin_memory()
     h_rnd = d_rnd.cpu().pin_memory()
+    h_xi = d_xi.cpu().pin_memory()
     h_iters = torch.zeros(n, dtype=torch.int32).pin_memory()
 
     def sign_host():
@@ -459,22 +626,10 @@ def main():
                                       ptr(h_rnd), ptr(h_sig), ptr(h_iters)))
 
     del d_ok
-    sign_host()
     # every call is timed on its own (barrier on both sides); the reported step time is the MEDIAN of the calls:
     # on the shared boxes one call in five is 30-50 ms slower for host-side reasons (all samples are in the line)
     e2e_steps = max(3, args.steps)
-    e2e_samples = []
-    for _ in range(e2e_steps):
-        barrier()
-        t0 = time.perf_counter()
-        sign_host()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e_samples.append(dt)
+    e2e_samples = timed_calls(E, sign_host, e2e_steps)
     e2e_s = float(np.median(e2e_samples))
     check["e2e_equals_device_resident"] = bool(torch.equal(h_sig, d_sig.cpu()))
     e2e = {"value": world * n / e2e_s, "unit": "signs/s",
@@ -482,47 +637,83 @@ def main():
            "d2h_bytes_per_step": int(h_sig.numel() + h_iters.numel() * 4), "ms_per_step": e2e_s * 1e3,
            "steps": e2e_steps, "step_ms_all": [round(x * 1e3, 2) for x in e2e_samples], "statistic": "median of the steps",
            "host_buffers": "pinned", "api": "mldsa_sign_batch (host pointers)"}
+    e2e["h2d_gbs"] = e2e["h2d_bytes_per_step"] / e2e_s / 1e9
+    e2e["d2h_gbs"] = e2e["d2h_bytes_per_step"] / e2e_s / 1e9
 
-    # ---- the same batch with the keys resident on the device (mldsa_sk_load once, untimed): the
-    # reference's expanded PrivateKey.  Extra information, not the headline: the key expansion is outside the timed calls.
+    # ---- the byte-diet path: keys PROVISIONED ON THE DEVICE from their seeds (mldsa_keygen_to_keyset: expanded private
+    # keys stay in HBM, no packed secret key ever crosses PCIe), then signing moves rnd + message in and the signature
+    # out.  Provisioning is outside the timed calls (it is timed on its own); same bytes as the packed-key path.
     e2e_keys = None
     hks = C.c_void_p()
-    if not args.no_verify_leg and L.mldsa_sk_load(args.ps, local, n, ptr(h_sk), C.byref(hks)) != 0:
-        # (2^20 expanded ML-DSA-87 keys next to the cached 96 GiB arena do not fit in 180 GB: the leg is skipped)
-        e2e_keys, hks = {"unavailable": "key set + cached workspace exceed device memory"}, C.c_void_p()
+    if not args.no_verify_leg:
+        t0 = time.perf_counter()
+        rc = L.mldsa_keygen_to_keyset(args.ps, local, n, ptr(h_xi), None, C.byref(hks), None)
+        prov_s = time.perf_counter() - t0
+        if rc != 0:
+            # (2^20 expanded ML-DSA-87 keys next to the cached workspace do not fit in 180 GB: the leg is skipped)
+            e2e_keys, hks = {"unavailable": "key set + cached workspace exceed device memory"}, C.c_void_p()
     if hks:
-        ks_samples = []
-        for k in range(4):
-            barrier()
-            t0 = time.perf_counter()
-            _lib.check(L.mldsa_sign_batch_keys(hks, 0, n, None, ptr(h_msg), ptr(h_moff), None, None, ptr(h_rnd), ptr(h_sig),
-                                               ptr(h_iters)))
-            barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([dt], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            if k:
-                ks_samples.append(dt)
+        ks_fn = lambda: _lib.check(L.mldsa_sign_batch_keys(hks, 0, n, None, ptr(h_msg), ptr(h_moff), None, None, ptr(h_rnd), ptr(h_sig),  # noqa: E731
+                                                           ptr(h_iters)))
+        ks_samples = timed_calls(E, ks_fn, 3)
         L.mldsa_keyset_free(hks)
         check["resident_keys_equal_device_resident"] = bool(torch.equal(h_sig, d_sig.cpu()))
         ks_s = float(np.median(ks_samples))
         e2e_keys = {"value": world * n / ks_s, "unit": "signs/s", "ms_per_step": ks_s * 1e3,
+                    "step_ms_all": [round(x * 1e3, 2) for x in ks_samples],
                     "h2d_bytes_per_step": int(h_msg.numel() + h_rnd.numel() + h_moff.numel() * 8),
                     "d2h_bytes_per_step": int(h_sig.numel() + h_iters.numel() * 4),
-                    "api": "mldsa_sign_batch_keys (keys expanded once by mldsa_sk_load, outside the timed calls)"}
+                    "provisioning_ms": rank_max(E, prov_s) * 1e3, "provisioning_h2d_bytes": int(h_xi.numel()),
+                    "api": "mldsa_sign_batch_keys on a key set provisioned by mldsa_keygen_to_keyset(xi) (outside the timed calls)"}
+
+    # ---- strong-scaling reading of configs[3]: ONE batch of 2^20 lanes split over the ranks (n / world lanes each),
+    # end to end; and the same batch driven from ONE process over every GPU (mldsa_sign_batch_multi: one host thread per
+    # device) while the other ranks idle -- the in-process multi-GPU path a host crate would use
+    strong = None
+    if world > 1 and not args.no_configs:
+        ns = n // world
+        lo = 0  # every rank signs the first n / world lanes of its own shard
+        ss_fn = lambda: _lib.check(L.mldsa_sign_batch(args.ps, local, 0, ns, ptr(h_sk), m.SK_LEN, ptr(h_msg), ptr(h_moff), None, None,  # noqa: E731
+                                                      ptr(h_rnd), ptr(h_sig), ptr(h_iters)))
+        ss = timed_calls(E, ss_fn, 3)
+        sd_fn = lambda: _lib.check(L.mldsa_sign_batch_dev(args.ps, sh, 0, ns, ptr(d_sk), m.SK_LEN, ptr(d_msg), ptr(d_moff), None, None,  # noqa: E731
+                                                          ptr(d_rnd), ptr(d_sig), ptr(d_iters)))
+        sd_ms = device_ms(E, sd_fn, 3)
+        strong = {"lanes_total": ns * world, "lanes_per_gpu": ns,
+                  "device_resident": {"value": ns * world / (sd_ms * 1e-3), "unit": "signs/s", "ms_per_step": sd_ms},
+                  "e2e": {"value": ns * world / float(np.median(ss)), "unit": "signs/s", "ms_per_step": float(np.median(ss)) * 1e3,
+                          "step_ms_all": [round(x * 1e3, 2) for x in ss]}}
+        sign_dev()  # restore the full-batch signatures for the checks below
+        sign_host()
+        # one process, all GPUs
+        if torch.cuda.device_count() >= world:
+            dist.barrier(group=host_group)
+            if rank == 0:
+                devs = (C.c_int * world)(*range(world))
+                ip = []
+                for k in range(4):
+                    t0 = time.perf_counter()
+                    _lib.check(L.mldsa_sign_batch_multi(args.ps, devs, world, 0, n, ptr(h_sk), m.SK_LEN, ptr(h_msg), ptr(h_moff),
+                                                        None, None, ptr(h_rnd), ptr(h_sig), ptr(h_iters)))
+                    if k:
+                        ip.append(time.perf_counter() - t0)
+                check["inprocess_multi_equals_device_resident"] = bool(torch.equal(h_sig, d_sig.cpu()))
+                strong["e2e_inprocess"] = {"value": n / float(np.median(ip)), "unit": "signs/s", "lanes_total": n,
+                                           "ms_per_step": float(np.median(ip)) * 1e3, "step_ms_all": [round(x * 1e3, 2) for x in ip],
+                                           "api": f"mldsa_sign_batch_multi over {world} devices from one process (other ranks idle)"}
+            dist.barrier(group=host_group)
 
     cpu_baseline = None
     if rank == 0:
         import oracle_lib as O
-        ns = 256
-        idx = np.linspace(0, n - 1, ns).astype(np.int64)
+        ns_ = 256
+        idx = np.linspace(0, n - 1, ns_).astype(np.int64)
         osig, oit = O.sign_batch(args.ps, h_sk.numpy()[idx], [bytes(x) for x in h_msg.numpy()[idx]], h_rnd.numpy()[idx])
-        check["oracle_sample"] = ns
+        check["oracle_sample"] = ns_
         check["oracle_sample_bit_exact"] = bool((osig == h_sig.numpy()[idx]).all() and
                                                 (oit == h_iters.numpy()[idx].astype(np.uint32)).all())
         if world == 1 and not args.no_cpu_baseline:
+            build = O.use_native_build()
             cores = O.ncores()
             sample = max(256, cores * 64)
             sidx = np.arange(sample) % n
@@ -535,8 +726,18 @@ def main():
                 reps += 1
             dt = (time.perf_counter() - t0) / reps
             cpu_baseline = {"value": sample / dt, "unit": "signs/s", "cores": cores, "kind": "port",
-                            "sample": f"{sample} lanes of this workload x {reps} passes (~10 s), C oracle, "
-                                      f"one scalar instance per host thread"}
+                            "sample": f"{sample} lanes of this workload x {reps} passes (~10 s), C oracle ({build}), "
+                                      f"one instance per host thread",
+                            "per_core_us": 1e6 * cores * dt / sample,
+                            # the port against the crate it stands in for, per core (different CPUs: context, not a claim)
+                            "vs_published_per_core": vs_published("sign", args.ps, sample / dt / cores),
+                            "published": f"{PUBLISHED_US['sign'][args.ps]} us per sign on one i7-7700K core (benches/README.md:21)"}
+
+    del h_sk, h_rnd, h_xi, h_iters, h_sig, h_msg, h_moff, d_sk, d_pk, d_sig, d_xi, d_msg, d_rnd, d_moff, d_iters
+    torch.cuda.empty_cache()
+    configs = None
+    if not args.no_configs:
+        configs = config_legs(E, args, n, peaks, hbm_peak)
 
     if rank == 0:
         line = {
@@ -546,18 +747,20 @@ def main():
             "config": workload_config(args, n),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_resident_keys": e2e_keys,
             "gpu_launches": int(launches),
-            "clocks": clk, "verify": verify_obj,
+            "clocks": clk, "verify": verify_obj, "strong_scaling": strong, "configs": configs,
+            "step_ms_all": [round(x, 2) for x in step_ms],
             "sign": {"mean_iters": iters_total / n, "rounds_per_step": rounds / args.steps,
                      "algorithmic_int32_ops_per_sign": whole_ops / n,
-                     "whole_step_int32_tops": whole_ops / (ms_per_step * 1e-3) / 1e12 * 1.0,
-                     "whole_step_frac_of_int32_peak": whole_ops / (ms_per_step * 1e-3) / peaks["both"]},
+                     "whole_step_int32_tops": whole_ops / (ms_per_step * 1e-3) / 1e12,
+                     # Keccak work of the step over the ALU pipe's peak: the share of the step's time the pipe that bounds
+                     # 55 % of it would need at 100 % (always < 1; the arithmetic kernels' pipes are under kernels[*].ncu)
+                     "keccak_alu_pipe_frac_of_step": keccak_ops / (ms_per_step * 1e-3) / alu_peak},
             "int32_peaks_tops": {k: v / 1e12 for k, v in peaks.items()},
             "kernels": kernels, "check": check,
             # the only figures that are the reference's own (benches/README.md:16-26: one core of an i7-7700K @ 4.2 GHz,
             # pre-expanded keys); the cpu_baseline above is this repo's C oracle on the GPU box's host cores
-            "reference_published": {"sign_us": {"44": 226.32, "65": 352.89, "87": 385.05}[str(args.ps)],
-                                    "verify_us": {"44": 21.016, "65": 27.996, "87": 36.468}[str(args.ps)],
-                                    "keygen_us": {"44": 104.89, "65": 194.80, "87": 290.24}[str(args.ps)],
+            "reference_published": {"sign_us": PUBLISHED_US["sign"][args.ps], "verify_us": PUBLISHED_US["verify"][args.ps],
+                                    "keygen_us": PUBLISHED_US["keygen"][args.ps],
                                     "hardware": "Intel i7-7700K, 1 core", "source": "benches/README.md:16-26"},
         }
         _JSON_OUT.write(json.dumps(line) + "\n")

@@ -67,7 +67,16 @@ KLaunch::~KLaunch()
     if (g_profiling.load(std::memory_order_relaxed) && !t_events.empty() && t_events.back().id == id)
         cudaEventRecord(t_events.back().b, st);
 }
+// Called at the end of every entry point.  The event pairs recorded on this thread are folded into the totals LAZILY --
+// when a reader asks (mldsa_profile_get / _reset, same thread), when the thread is a worker about to exit, or when the
+// queue grows large -- so that a caller timing a call with its own events does not also time 200 cudaEventElapsedTime
+// calls made after the device has finished.
 void prof_collect()
+{
+    if (t_events.size() < 8192) return;
+    prof_collect_now();
+}
+void prof_collect_now()
 {
     if (t_events.empty()) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -495,10 +504,19 @@ static int sign_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size_t
         cx.note_sign_ws(ws, m, shared, p.K, p.L, p.zbits);
         MsgDesc md{d_msgs, d_msg_off + lo, d_ctx, d_ctx_off ? d_ctx_off + lo : nullptr, framing};
         SignRun run;
+        const bool trace = env_int("MLDSA_TRACE", 0) != 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
         cudaError_t e = sign_begin(ps, st, m, d_sk + sk_stride * lo, sk_stride, md, d_rnd + 32 * lo, d_sig + p.sig * lo,
                                    d_iters ? d_iters + lo : nullptr, ws, 0, &run);
+        const double t_begin = ms_since();
         if (e == cudaSuccess) e = sign_tail(st, &run);
+        const double t_tail = ms_since();
+        const int planned = run.rounds;
         if (e == cudaSuccess) e = sign_finish(&run);
+        if (trace)
+            fprintf(stderr, "[mldsa trace] sign chunk of %zu lanes: bulk enqueued at %.2f ms, tail at %.2f ms, finished at %.2f ms; "
+                    "%d planned rounds + %d straggler rounds\n", m, t_begin, t_tail, ms_since(), planned, run.rounds - planned);
         // Everything derived from the secret key or the mask (src/types.rs:19 ZeroizeOnDrop) is zeroed by
         // sign_z as each lane finishes; A-hat, mu||w1, c~ and the challenge are public.
         sign_wipe(ws, m, shared, e != cudaSuccess, st);
@@ -685,6 +703,7 @@ uint64_t mldsa_kernel_launches(void) { return g_launches.load(); }
 void mldsa_profile_enable(int on) { g_profiling.store(on ? 1 : 0); }
 void mldsa_profile_reset(void)
 {
+    prof_collect_now();
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int i = 0; i < KID_COUNT; i++) {
         g_prof_ms[i] = 0;
@@ -696,6 +715,7 @@ const char* mldsa_profile_name(int id) { return id >= 0 && id < KID_COUNT ? KERN
 int mldsa_profile_get(int id, double* ms, uint64_t* launches)
 {
     if (id < 0 || id >= KID_COUNT) return E_PARAM;
+    prof_collect_now();
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (ms) *ms = g_prof_ms[id];
     if (launches) *launches = g_prof_n[id];
@@ -2104,7 +2124,10 @@ static int run_sharded(const int* devs, int ndev, size_t n, Fn&& fn)
     std::vector<int> rcs((size_t)ndev, OK);
     for (int g = 0; g < ndev; g++) {
         const size_t lo = n * (size_t)g / (size_t)ndev, hi = n * (size_t)(g + 1) / (size_t)ndev;
-        th.emplace_back([&, g, lo, hi] { rcs[(size_t)g] = hi > lo ? fn(devs[g], lo, hi - lo) : OK; });
+        th.emplace_back([&, g, lo, hi] {
+            rcs[(size_t)g] = hi > lo ? fn(devs[g], lo, hi - lo) : OK;
+            prof_collect_now();  // this worker's event pairs die with the thread
+        });
     }
     for (auto& t : th) t.join();
     for (int rc : rcs)

@@ -28,7 +28,8 @@ struct KLaunch {  // scope one kernel launch: `{ KLaunch k(KID_X, st); kernel<<<
     KLaunch(int id, cudaStream_t st);
     ~KLaunch();
 };
-void prof_collect();  // fold finished event pairs into the per-kernel totals (call after a stream sync)
+void prof_collect();      // end of an entry point: bounds the queue of recorded event pairs (folding is lazy)
+void prof_collect_now();  // fold finished event pairs into the per-kernel totals (after a stream sync)
 
 // Launch tunables (mldsa_set_tuning / MLDSA_KCAP, MLDSA_ACAP): kcap / acap cap the CTAs per SM of the (grid-stride)
 // Keccak / arithmetic kernels (0 = default).

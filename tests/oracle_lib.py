@@ -27,6 +27,27 @@ def build(force=False):
 _lib = None
 
 
+def use_native_build():
+    """Switch this module to oracle/liboracle_native.so, compiled here and now with -march=native (bench.py's CPU
+    baseline: the oracle should run as fast as this host allows).  Returns the flags description; falls back to the
+    portable build if the compile fails."""
+    global _lib
+    native = ROOT / "oracle" / "liboracle_native.so"
+    try:
+        subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "-B", "liboracle_native.so"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        new = C.CDLL(str(native))
+    except (subprocess.CalledProcessError, OSError):
+        lib()
+        return "gcc -O3 -march=x86-64-v3 (portable build; native rebuild failed)"
+    new.oracle_mont_reduce.restype = C.c_int32
+    new.oracle_mont_reduce.argtypes = [C.c_int64]
+    new.oracle_zeta_mont.restype = C.c_int32
+    new.oracle_use_hint.restype = C.c_int32
+    _lib = new
+    return "gcc -O3 -march=native, built on this host"
+
+
 def lib():
     global _lib
     if _lib is None:

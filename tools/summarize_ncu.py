@@ -89,29 +89,52 @@ def full(rep, out):
     out.write("\n")
 
 
-def traffic(rep, tag, lanes, ps):
-    """profiles/ncu_traffic.json: DRAM bytes per launch of the kernels whose launch covers exactly `lanes` units
-    (expand_a: keys, sign_key: keys), read by bench.py for roofline.traffic."""
+KERNEL_KEYS = [  # kernel function name prefix -> the engine's kernel class (mldsa_profile_name), units per lane of a capture
+    ("expand_a_kernel", "expand_a", 1), ("sign_key_kernel", "sign_key", 1), ("sign_prep_kernel", "sign_prep", 1),
+    ("mask_kernel", "mask", 2), ("sign_w_staged_kernel", "sign_w", 2), ("ctilde_kernel", "ctilde", 2), ("sign_z_kernel", "sign_z", 2),
+    ("kg_fused_kernel", "kg_arith", 1), ("kg_arith_kernel", "kg_arith_materialised", 1), ("verify_fused_kernel", "verify_arith", 1),
+    ("verify_arith_kernel", "verify_arith_cached", 1), ("verify_pre_kernel", "verify_pre", 1), ("rej_bounded_kernel", "rej_bounded", 1),
+    ("shake_rows_kernel", "shake_rows", 1), ("ntt_kernel<(bool)0>", "ntt", 1), ("ntt_kernel<(bool)1>", "intt", 1),
+]
+UNIT_SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def kernels_json(rep, tag, lanes, ps):
+    """profiles/ncu_kernels.json: per kernel class, what ncu measured on the FIRST launch of the kernel in the capture
+    (sign rounds: the first round, every lane live, two candidates per lane): pipe utilisations, DRAM bytes, duration.
+    bench.py reads it for roofline.traffic and for the arithmetic kernels' pipe figures."""
     import json
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, data = rows[0], rows[2:]
-    dst = ROOT / "profiles" / "ncu_traffic.json"
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    dst = ROOT / "profiles" / "ncu_kernels.json"
     rec = json.load(open(dst)) if dst.exists() else {}
+
+    def val(r, name, scale=False):
+        i = hdr.index(name)
+        v = float(r[i].replace(",", ""))
+        return v * UNIT_SCALE.get(units[i], 1) if scale else v
+
+    seen = set()
     for r in data:
-        name = short(r[hdr.index("Kernel Name")])
-        for key in ("expand_a", "sign_key"):
-            if name.startswith(key):
-                rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
-                wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
-                u = hdr.index("dram__bytes_read.sum")
-                unit = rows[1][u]
-                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
-                wscale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[rows[1][hdr.index("dram__bytes_write.sum")]]
-                rec[f"{key}:{ps}"] = {"dram_read_bytes": rd * scale, "dram_write_bytes": wr * wscale, "units": lanes,
-                                      "source": f"profiles/{tag}.md (ncu --set full, {Path(rep).name}, {lanes} keys per launch)"}
-    json.dump(rec, open(dst, "w"), indent=1)
-    print(dst)
+        full_name = r[hdr.index("Kernel Name")].replace("mldsa::", "")
+        for prefix, key, per_lane in KERNEL_KEYS:
+            if prefix in full_name and key not in seen:
+                seen.add(key)
+                t_i = hdr.index("gpu__time_duration.sum")
+                t_ms = float(r[t_i].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[t_i], 1e-6)
+                rec[f"{key}:{ps}"] = {
+                    "kernel": full_name.split("(")[0][:80], "time_ms": t_ms, "lanes": lanes, "units": lanes * per_lane,
+                    "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "pipe_alu_pct": val(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                    "pipe_fma_pct": val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "pipe_lsu_pct": val(r, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                    "dram_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                    "dram_read_bytes": val(r, "dram__bytes_read.sum", True), "dram_write_bytes": val(r, "dram__bytes_write.sum", True),
+                    "regs": val(r, "launch__registers_per_thread"), "warp_inst": val(r, "smsp__inst_executed.sum"),
+                    "source": f"profiles/{tag}.md (ncu --set full --clock-control none, {Path(rep).name}, {lanes} lanes)"}
+    json.dump(rec, open(dst, "w"), indent=1, sort_keys=True)
+    print(dst, sorted(seen))
 
 
 if __name__ == "__main__":
@@ -120,10 +143,11 @@ if __name__ == "__main__":
     ap.add_argument("--launches")
     ap.add_argument("--rep")
     ap.add_argument("--note", default="")
-    ap.add_argument("--traffic-lanes", type=int, default=0, help="lanes per launch of the captured run: also write ncu_traffic.json")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes of the captured run: also update profiles/ncu_kernels.json")
     ap.add_argument("--ps", type=int, default=65)
     a = ap.parse_args()
     dst = ROOT / "profiles" / f"{a.tag}.md"
+    dst.parent.mkdir(parents=True, exist_ok=True)
     with open(dst, "w") as out:
         out.write(f"# ncu summary {a.tag}\n\n{a.note}\n\n")
         if a.launches:
@@ -131,5 +155,5 @@ if __name__ == "__main__":
         if a.rep:
             full(a.rep, out)
     print(dst)
-    if a.rep and a.traffic_lanes:
-        traffic(a.rep, a.tag, a.traffic_lanes, a.ps)
+    if a.rep and a.lanes:
+        kernels_json(a.rep, a.tag, a.lanes, a.ps)
