@@ -42,8 +42,6 @@ __host__ __device__ __forceinline__ int32_t freeze(int32_t a) { return caddq(red
 // helpers.rs:84-91 on a canonical input t in [0, q): centred representative in (-q/2, q/2]
 __host__ __device__ __forceinline__ int32_t center(int32_t t) { return t - ((((Q / 2) - t) >> 31) & Q); }
 
-constexpr int32_t F_MONT = 16382;      // 256^-1 * 2^32 mod q  (ntt.rs:88): plain inverse NTT
-constexpr int32_t F_MONT2 = 41978;     // 256^-1 * 2^64 mod q: inverse NTT of values carrying one 2^-32
 
 // high_low.rs:66-96 (decompose) for a canonical r in [0, q); returns r1, writes r0
 template <int32_t GAMMA2>

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict
             const int4* in = reinterpret_cast<const int4*>(g + 8 * lane);
             const int4 x = ldg_stream4(in), y = ldg_stream4(in + 1);
             v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-            ntt_inv_B2A<F_MONT>(v, tile, lane);
+            sntt_inv_B2A<true>(v, tile, lane);
 #pragma unroll
             for (int i = 0; i < 8; i++) stg_stream(g + 32 * i + lane, v[i]);
         }
@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict
 cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse)
 {
     if (n == 0) return cudaSuccess;
-    static const int ncap = getenv("MLDSA_NCAP") ? atoi(getenv("MLDSA_NCAP")) : 32;  // CTAs per SM (measured: 8 -> 0.513 ms, 32..64 -> 0.491 ms per 2^20 polynomials)
+    // CTAs per SM of the grid-stride loop (measured: 8 -> 0.513 ms, 32..64 -> 0.491 ms per 2^20 polynomials).
+    // Tried and measured slower (0.585 against 0.486 ms at the time): moving the polynomials with the TMA unit (one
+    // cp.async.bulk in, one out, two input slots per warp): the kernel is bound by instruction issue, not by its loads.
+    static const int ncap = getenv("MLDSA_NCAP") ? atoi(getenv("MLDSA_NCAP")) : 32;
     const unsigned grid = capped_grid((n + NTT_WARPS - 1) / NTT_WARPS, ncap);
     {
         KLaunch kl(inverse ? KID_INTT : KID_NTT, st);

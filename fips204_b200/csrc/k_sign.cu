@@ -33,6 +33,7 @@
 #include "pack.cuh"
 #include "sampling.cuh"
 #include "ctilde.cuh"
+#include "tma.cuh"
 
 namespace mldsa {
 
@@ -201,38 +202,6 @@ __device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (
 // HBM / L2 (ncu: 40 % of the un-staged kernel's stall samples were long-scoreboard waits on these loads).
 // With an even speculation depth the two candidates of a lane sit on neighbouring warps and SHARE the staged
 // row (G = 2): the row is fetched once for both, and whichever warp finishes its products last issues the next copy.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t atom_add_acq_rel_cta(uint32_t* p, uint32_t v)
-{
-    uint32_t old;
-    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-
 template <class P, int G>
 struct alignas(128) SignWStage {
     alignas(128) int32_t arow[SG_WARPS / G][P::L * 256];  // one staged row of A-hat per group of G warps

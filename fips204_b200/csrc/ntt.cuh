@@ -3,7 +3,8 @@
 //
 // Replaces src/ntt.rs:14-76 (ntt) and :85-161 (inv_ntt) of the reference.  The forward transform
 // is representative-exact with the reference (same signed Montgomery butterfly, same twiddle table,
-// no reductions between stages); the inverse returns canonical [0, q) like the reference.
+// no reductions between stages).  The inverse returns canonical [0, q) like the reference; since only
+// the residue of its output is defined, it runs on the Shoup butterflies of the fused kernels.
 //
 // Index bits 7..0 of a coefficient are split over three register layouts (t = lane, i = 0..7):
 //   A: idx = 32*i + t              bits 7,6,5 local  -> stages len = 128, 64, 32
@@ -18,23 +19,29 @@ namespace mldsa {
 
 #include "zetas.inc"
 
+__device__ __forceinline__ int32_t mulhi_noadd(int32_t a, int32_t b);
+
 constexpr int NTT_ROW = 36;
 constexpr int NTT_TILE_WORDS = 8 * NTT_ROW;  // 288 int32 = 1152 B per warp
 
+// t = mont_reduce(z * b) = hi(b z) - hi(lo(b zq) q) (ntt.rs:45) is never formed: both high products feed the two
+// three-input adds directly, a' = a + h1 - h2 (ntt.rs:51), b' = a - h1 + h2 (ntt.rs:48).  Same integers (two's
+// complement), but with a single use of each high product ptxas folds the subtraction into an IMAD.HI with a 64-bit
+// addend and pays three extra instructions per butterfly to build that register pair.
 __device__ __forceinline__ void ct_bfly(int32_t& a, int32_t& b, int32_t z, int32_t zq)
 {
-    const int32_t t = mont_mul_pre(b, z, zq);  // ntt.rs:45
-    b = a - t;                                 // ntt.rs:48
-    a = a + t;                                 // ntt.rs:51
+#ifdef __CUDA_ARCH__
+    const uint32_t lo = (uint32_t)b * (uint32_t)zq;
+    const uint32_t h1 = (uint32_t)mulhi_noadd(b, z), h2 = (uint32_t)mulhi_noadd((int32_t)lo, Q);
+    const uint32_t ua = (uint32_t)a;
+    a = (int32_t)(ua + h1 - h2);
+    b = (int32_t)(ua - h1 + h2);
+#else
+    const int32_t t = mont_mul_pre(b, z, zq);
+    b = a - t;
+    a = a + t;
+#endif
 }
-__device__ __forceinline__ void gs_bfly(int32_t& a, int32_t& b, int32_t z, int32_t zq)
-{
-    const int32_t t = a;                       // ntt.rs:124
-    a = t + b;                                 // ntt.rs:127
-    b = mont_mul_pre(t - b, z, zq);            // ntt.rs:130-133
-}
-
-
 // Per-lane twiddles of the B stage (len = 2, 1 forward / 1, 2 inverse) and per-row twiddles of the M stage
 // (len = 16, 8, 4 / 4, 8, 16) from the packed tables of zetas.inc: 3 + 4 contiguous 128-bit loads per transform.
 struct TwB { int2 za, zb, y0, y1, y2, y3; };
@@ -123,48 +130,6 @@ __device__ __forceinline__ void ntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int 
         ct_bfly(v[0], v[1], w.y0.x, w.y0.y); ct_bfly(v[2], v[3], w.y1.x, w.y1.y);
         ct_bfly(v[4], v[5], w.y2.x, w.y2.y); ct_bfly(v[6], v[7], w.y3.x, w.y3.y);
     }
-    __syncwarp();
-}
-
-// Inverse NTT.  In: v in layout B (NTT domain), |v| < q.  Out: v in layout A, canonical [0, q),
-// scaled by mont(F * .) -- F = F_MONT for a plain transform (ntt.rs:152-154), F_MONT2 when the input
-// carries a stray 2^-32 from an un-compensated Montgomery product.
-template <int32_t F>
-__device__ __forceinline__ void ntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane)
-{
-    {   // len = 1, 2   (twiddle index counts down: m = 2*nb - 1 - block, ntt.rs:112-118)
-        const TwB w = load_twB(ZMP_INV_BA, ZMP_INV_BY0, ZMP_INV_BY1, lane);
-        gs_bfly(v[0], v[1], w.y0.x, w.y0.y); gs_bfly(v[2], v[3], w.y1.x, w.y1.y);
-        gs_bfly(v[4], v[5], w.y2.x, w.y2.y); gs_bfly(v[6], v[7], w.y3.x, w.y3.y);
-        gs_bfly(v[0], v[2], w.za.x, w.za.y); gs_bfly(v[1], v[3], w.za.x, w.za.y);
-        gs_bfly(v[4], v[6], w.zb.x, w.zb.y); gs_bfly(v[5], v[7], w.zb.x, w.zb.y);
-    }
-    __syncwarp();
-    tile_store_B(tile, lane, v);
-    __syncwarp();
-    tile_load_M(tile, lane, v);
-    {   // len = 4, 8, 16
-        const TwM w = load_twM(ZMP_INV_M, lane);
-        gs_bfly(v[0], v[1], w.y0.x, w.y0.y); gs_bfly(v[2], v[3], w.y1.x, w.y1.y);
-        gs_bfly(v[4], v[5], w.y2.x, w.y2.y); gs_bfly(v[6], v[7], w.y3.x, w.y3.y);
-        gs_bfly(v[0], v[2], w.za.x, w.za.y); gs_bfly(v[1], v[3], w.za.x, w.za.y);
-        gs_bfly(v[4], v[6], w.zb.x, w.zb.y); gs_bfly(v[5], v[7], w.zb.x, w.zb.y);
-        gs_bfly(v[0], v[4], w.z8.x, w.z8.y); gs_bfly(v[1], v[5], w.z8.x, w.z8.y);
-        gs_bfly(v[2], v[6], w.z8.x, w.z8.y); gs_bfly(v[3], v[7], w.z8.x, w.z8.y);
-    }
-    tile_store_M(tile, lane, v);
-    __syncwarp();
-    tile_load_A(tile, lane, v);
-    // len = 32, 64, 128
-    gs_bfly(v[0], v[1], ZI7, ZI7Q); gs_bfly(v[2], v[3], ZI6, ZI6Q);
-    gs_bfly(v[4], v[5], ZI5, ZI5Q); gs_bfly(v[6], v[7], ZI4, ZI4Q);
-    gs_bfly(v[0], v[2], ZI3, ZI3Q); gs_bfly(v[1], v[3], ZI3, ZI3Q);
-    gs_bfly(v[4], v[6], ZI2, ZI2Q); gs_bfly(v[5], v[7], ZI2, ZI2Q);
-    gs_bfly(v[0], v[4], ZI1, ZI1Q); gs_bfly(v[1], v[5], ZI1, ZI1Q);
-    gs_bfly(v[2], v[6], ZI1, ZI1Q); gs_bfly(v[3], v[7], ZI1, ZI1Q);
-    constexpr int32_t FQ = (int32_t)((uint32_t)F * (uint32_t)QINV);
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = freeze(mont_mul_pre(v[i], F, FQ));
     __syncwarp();
 }
 
@@ -270,7 +235,10 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
 }
 
 // Inverse NTT WITHOUT the 1/256 scaling.  In: layout B, |v| < 2 q.  Out: layout A, canonical [0, q),
-// = 256 * INTT(v) mod q.
+// = 256 * INTT(v) mod q.  SCALE256 = true multiplies by 1/256 on the way out: the plain inverse transform,
+// canonical like the reference's (ntt.rs:85-161 returns full_reduce32 values, so only the residue matters and the
+// Shoup butterflies -- five instructions against the nine ptxas makes of the Montgomery form -- give the same output).
+template <bool SCALE256 = false>
 __device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane)
 {
     {
@@ -306,7 +274,7 @@ __device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int
     gs_bfly_s(v[0], v[4], ZSI1, ZSI1S); gs_bfly_s(v[1], v[5], ZSI1, ZSI1S);
     gs_bfly_s(v[2], v[6], ZSI1, ZSI1S); gs_bfly_s(v[3], v[7], ZSI1, ZSI1S);
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = freeze(v[i]);
+    for (int i = 0; i < 8; i++) v[i] = freeze(SCALE256 ? shoup_mul(v[i], SC_INV256, SC_INV256S) : v[i]);
     __syncwarp();
 }
 __device__ __forceinline__ void sntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int lane)
@@ -320,26 +288,6 @@ __device__ __forceinline__ void sntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int
 __device__ __forceinline__ void sntt_inv_B2B(int32_t (&v)[8], int32_t* tile, int lane)
 {
     sntt_inv_B2A(v, tile, lane);
-    tile_store_A(tile, lane, v);
-    __syncwarp();
-    tile_load_B(tile, lane, v);
-    __syncwarp();
-}
-
-// Convenience wrappers used by the fused kernels: coefficient-domain data lives in layout B
-// (lane-local bit packing), NTT-domain data too.
-__device__ __forceinline__ void ntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int lane)
-{
-    __syncwarp();
-    tile_store_B(tile, lane, v);
-    __syncwarp();
-    tile_load_A(tile, lane, v);
-    ntt_fwd_A2B(v, tile, lane);
-}
-template <int32_t F>
-__device__ __forceinline__ void ntt_inv_B2B(int32_t (&v)[8], int32_t* tile, int lane)
-{
-    ntt_inv_B2A<F>(v, tile, lane);
     tile_store_A(tile, lane, v);
     __syncwarp();
     tile_load_B(tile, lane, v);
