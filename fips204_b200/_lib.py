@@ -65,6 +65,7 @@ SIGNATURES = {
     "mldsa_sign_batch_keys": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mldsa_debug_secret_residue": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mldsa_debug_sampler_stream": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mldsa_kernel_launches": (C.c_uint64, []),
     "mldsa_last_sign_rounds": (C.c_int, []),
     "mldsa_profile_enable": (None, [C.c_int]),

@@ -2229,6 +2229,34 @@ int mldsa_expand_a_batch(int dev, size_t n, const uint8_t* seed34, int32_t* out)
     return n ? micro_host(dev, n, seed34, n * 34, out, n * 1024, 2) : OK;
 }
 
+// Test hooks for the rejection samplers' rare paths: the device parsers run over caller-supplied squeeze blocks.
+// which = 0: RejNTTPoly (src/hashing.rs:111-146): nblocks x 168 bytes per polynomial -> out = n x 256 int32 (zero-filled
+// first; coefficients the stream does not reach stay zero).  which = tau (39 / 49 / 60): SampleInBall (src/hashing.rs:
+// 43-100): nblocks x 136 bytes per challenge -> out = n x 64 bytes (256 "non-zero" bits, then 256 "negative" bits).
+int mldsa_debug_sampler_stream(int dev, int which, size_t n, const uint8_t* blocks, size_t nblocks, void* out)
+{
+    if (n == 0) return OK;
+    if (!blocks || !out || nblocks == 0 || (which != 0 && which != 39 && which != 49 && which != 60)) return E_PARAM;
+    std::unique_lock<std::mutex> lk;
+    int rc = OK;
+    DeviceCtx* cx = lock_ctx(dev, lk, rc);
+    if (!cx) return rc;
+    const size_t in_bytes = n * nblocks * (which == 0 ? 168 : SIB_BYTES), out_bytes = n * (which == 0 ? 1024 : CMASK_STRIDE);
+    rc = cx->reserve(pad256(in_bytes) + pad256(out_bytes));
+    if (rc) return rc;
+    cudaStream_t st = cx->stream;
+    Carver c(cx->arena);
+    uint8_t* d_in = c.take<uint8_t>(in_bytes);
+    uint8_t* d_out = c.take<uint8_t>(out_bytes);
+    CK(cudaMemcpyAsync(d_in, blocks, in_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_out, 0, out_bytes, st));
+    if (which == 0) CK(launch_rej_ntt_stream(st, d_in, nblocks, n, reinterpret_cast<int32_t*>(d_out)));
+    else CK(launch_sib_stream(st, d_in, nblocks, n, which, d_out));
+    CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OK;
+}
+
 int mldsa_shake_batch(int dev, int bits, size_t n, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len)
 {
     if ((bits != 128 && bits != 256) || (n && (!out || (in_len && !in))) || out_len == 0 || out_len > (1u << 20))

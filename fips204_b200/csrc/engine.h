@@ -75,6 +75,9 @@ cudaError_t launch_expand_a(cudaStream_t st, int K, int L, const uint8_t* rho, s
 // out[i][256] = RejNTTPoly(seed34[i])                          (src/hashing.rs:111-146)
 cudaError_t launch_expand_a_seed34(cudaStream_t st, const uint8_t* seeds, size_t n, int32_t* out);
 cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse);
+// test hooks: the rejection samplers' parsers over caller-supplied squeeze blocks (see k_common.cu)
+cudaError_t launch_rej_ntt_stream(cudaStream_t st, const uint8_t* blocks, size_t nblocks, size_t n, int32_t* out);
+cudaError_t launch_sib_stream(cudaStream_t st, const uint8_t* blocks, size_t nblocks, size_t n, int tau, uint8_t* cmask);
 // generic thread-per-message SHAKE256(in_i) -> out_i[outlen<=136] (tr = H(pk), test hook for the sponge)
 cudaError_t launch_shake256_rows(cudaStream_t st, const uint8_t* in, size_t in_stride, size_t in_len, size_t n,
                                  uint8_t* out, size_t out_stride, int out_len);

@@ -30,7 +30,10 @@ namespace mldsa {
 constexpr int EA_THREADS = 128;
 constexpr int EA_ROW = 64;  // words per thread: 3 carried + 56 candidates, rounded up to whole int4s
 
-template <bool SEED34>
+// SYNTH (test hook, mldsa_debug_rej_ntt_stream): the squeeze blocks come from a caller-supplied byte stream
+// (rho_stride / 168 blocks of 168 bytes per polynomial) instead of the permutation, so that a test can force the
+// parser through more blocks than SHAKE128 ever will (a 6th block has p ~ 1e-39).
+template <bool SEED34, bool SYNTH = false>
 __global__ void __launch_bounds__(EA_THREADS, 4)
 expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstreams, int KL, int L,
                 int32_t* __restrict__ out)
@@ -45,7 +48,7 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
     uint64_t a[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) a[i] = 0;
-    if (valid) {
+    if (valid && !SYNTH) {
         const size_t key = SEED34 ? q : q / KL;
         const int idx = SEED34 ? 0 : (int)(q % KL);
         uint32_t w[9];
@@ -61,8 +64,24 @@ expand_a_kernel(const uint8_t* __restrict__ rho, size_t rho_stride, size_t nstre
     int4* dst = reinterpret_cast<int4*>(out + (valid ? q : 0) * 256);  // next group of four to write
     int quads_left = valid ? 64 : 0;
     int have = 0;  // coefficients waiting at the head of the row (0..3 between blocks)
+    size_t synth_blk = 0;
     while (__any_sync(0xffffffffu, quads_left > 0)) {
-        keccak_f1600(a);
+        if (SYNTH) {
+            if (valid && (synth_blk + 1) * 168 <= rho_stride) {
+                const uint8_t* bp = rho + q * rho_stride + synth_blk * 168;
+#pragma unroll
+                for (int i = 0; i < 21; i++) {
+                    uint64_t w = 0;
+                    for (int k = 0; k < 8; k++) w |= (uint64_t)bp[8 * i + k] << (8 * k);
+                    a[i] = w;
+                }
+            } else {
+                quads_left = 0;  // stream exhausted: whatever was not produced stays unwritten
+            }
+            synth_blk++;
+        } else {
+            keccak_f1600(a);
+        }
         // The A-hat that feeds the fused kernels is stored prescaled by 2^32 / 256 mod q (the Montgomery factor of
         // the matrix-vector accumulator and the 1/256 of the un-scaled inverse NTT; see ntt.cuh).  These multiplies
         // sit on the FMA pipe, which this ALU-bound kernel leaves idle.  The microbench entry point (SEED34)
@@ -181,6 +200,42 @@ __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict
             for (int i = 0; i < 8; i++) stg_stream(g + 32 * i + lane, v[i]);
         }
     }
+}
+
+// test hook: RejNTTPoly's parser over caller-supplied squeeze blocks (nblocks x 168 bytes per polynomial)
+cudaError_t launch_rej_ntt_stream(cudaStream_t st, const uint8_t* blocks, size_t nblocks, size_t n, int32_t* out)
+{
+    if (n == 0) return cudaSuccess;
+    expand_a_kernel<true, true><<<(unsigned)((n + EA_THREADS - 1) / EA_THREADS), EA_THREADS, 0, st>>>(blocks, nblocks * 168, n, 1, 1, out);
+    return cudaGetLastError();
+}
+
+// test hook: SampleInBall's walk (sampling.cuh: SibWalk, src/hashing.rs:43-100) over caller-supplied squeeze blocks of
+// H(c~) (nblocks x 136 bytes per challenge): the first 8 bytes are the sign bits, the rest the rejection-sampled indices
+__global__ void __launch_bounds__(128) sib_stream_kernel(const uint8_t* __restrict__ blocks, size_t nblocks, size_t n, int tau,
+                                                         uint8_t* __restrict__ cmask)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SibWalk walk;
+    walk.init(tau);
+    uint64_t blk[17];
+    for (size_t b = 0; b < nblocks; b++) {
+        const uint8_t* bp = blocks + (i * nblocks + b) * SIB_BYTES;
+        for (int k = 0; k < 17; k++) {
+            uint64_t w = 0;
+            for (int j = 0; j < 8; j++) w |= (uint64_t)bp[8 * k + j] << (8 * j);
+            blk[k] = w;
+        }
+        if (walk.consume(blk, tau)) break;
+    }
+    walk.store(cmask + i * (size_t)CMASK_STRIDE);
+}
+cudaError_t launch_sib_stream(cudaStream_t st, const uint8_t* blocks, size_t nblocks, size_t n, int tau, uint8_t* cmask)
+{
+    if (n == 0) return cudaSuccess;
+    sib_stream_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(blocks, nblocks, n, tau, cmask);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse)

@@ -228,6 +228,13 @@ void mldsa_debug_set_max_rounds(int rounds);
 /* test hook: chunk sizes (lanes) the host pipelines use for an n-lane call when `cap` lanes fit the workspace; returns
  * the number of chunks (0 = plain chunks of `cap`), writes at most max_out of them.  Needs no device. */
 size_t mldsa_debug_chunk_plan(size_t n, size_t cap, size_t* out, size_t max_out);
+/* test hook for the rare paths of the rejection samplers: the device parsers run over caller-supplied squeeze blocks
+ * instead of SHAKE output.  which = 0: RejNTTPoly (src/hashing.rs:111-146, CoeffFromThreeBytes src/conversion.rs:40-61),
+ * nblocks x 168 bytes per polynomial, out = n x 256 int32 (coefficients the stream does not reach stay 0) -- forces the
+ * 6th, 7th ... squeeze block that SHAKE128 yields with p ~ 1e-39.  which = tau (39 / 49 / 60): SampleInBall
+ * (src/hashing.rs:43-100), nblocks x 136 bytes per challenge, out = n x 64 bytes (256 "non-zero" bits, then 256
+ * "negative" bits) -- forces the walk into a second squeeze block. */
+int mldsa_debug_sampler_stream(int dev, int which, size_t n, const uint8_t* blocks, size_t nblocks, void* out);
 /* kernels launched by this library since process start (all devices) */
 uint64_t mldsa_kernel_launches(void);
 /* rejection-loop rounds executed by the most recent sign call on this thread */

@@ -1,0 +1,182 @@
+"""Rare paths of the rejection samplers.
+
+* RejBoundedPoly's third SHAKE256 block (eta = 4, p ~ 1e-5 per polynomial) and the all-one-block / all-two-block keys of
+  eta = 2: seeds found offline by tests/golden/find_rare_seeds.py (committed with the script).  The CPU part checks the
+  fixture against hashlib and pins the oracle on those seeds; the GPU part compares the engine's keygen with the oracle.
+* RejNTTPoly's 6th+ squeeze block (p ~ 1e-39) and SampleInBall's second block (p < 1e-12) cannot be found by search:
+  the device parsers are fed crafted squeeze blocks through mldsa_debug_sampler_stream and compared with a direct
+  restatement of src/conversion.rs:40-61 / src/hashing.rs:43-100 over the same bytes (and with the C oracle's
+  SampleInBall on real SHAKE output, to pin the restatement itself)."""
+import ctypes as C
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+Q = 8380417
+RARE = json.loads((Path(__file__).resolve().parent / "golden" / "rare_seeds.json").read_text())
+CASES = [(65, "65_third_block"), (44, "44_all_one_block"), (44, "44_all_two_blocks"), (87, "87_all_two_blocks")]
+
+
+def _seeds(key):
+    return np.frombuffer(b"".join(bytes.fromhex(e["xi"]) for e in RARE[key]), np.uint8).reshape(-1, 32)
+
+
+@pytest.mark.parametrize("ps,key", CASES)
+def test_fixture_seeds_take_the_rare_path(ps, key):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("find_rare_seeds", Path(__file__).resolve().parent / "golden" / "find_rare_seeds.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for e in RARE[key]:
+        nb = mod.blocks_needed(ps, bytes.fromhex(e["xi"]))
+        assert nb == e["blocks"]
+        if key.endswith("third_block"):
+            assert max(nb) >= 3
+        elif key.endswith("one_block"):
+            assert max(nb) == 1
+        else:
+            assert min(nb) == 2
+    # the oracle signs and verifies with such keys (its own RejBoundedPoly walked the same blocks)
+    xi = _seeds(key)
+    pk, sk = O.keygen_batch(ps, xi)
+    msgs = [b"rare"] * len(xi)
+    sig, _ = O.sign_batch(ps, sk, msgs, np.zeros((len(xi), 32), np.uint8))
+    assert O.verify_batch(ps, pk, msgs, sig).all()
+
+
+def _sample_in_ball_stream(tau, stream):
+    """src/hashing.rs:43-100 over a raw byte stream: 8 bytes of signs, then rejection-sampled indices"""
+    c = [0] * 256
+    signs = int.from_bytes(stream[:8], "little")
+    pos = 8
+    for i in range(256 - tau, 256):
+        while True:
+            j = stream[pos]
+            pos += 1
+            if j <= i:
+                break
+        c[i] = c[j]
+        c[j] = 1 - 2 * ((signs >> (i + tau - 256)) & 1)
+    return c, pos
+
+
+def test_sample_in_ball_restatement_equals_oracle():
+    for tau, clen in ((39, 32), (49, 48), (60, 64)):
+        for k in range(50):
+            ct = hashlib.shake_256(b"sib" + bytes([tau, k])).digest(clen)
+            want = (C.c_int32 * 256)()
+            O.lib().oracle_sample_in_ball(tau, (C.c_uint8 * clen).from_buffer_copy(ct), C.c_size_t(clen), want)
+            got, _ = _sample_in_ball_stream(tau, hashlib.shake_256(ct).digest(136 * 4))
+            assert list(want) == got
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ps,key", CASES)
+def test_keygen_on_rare_seeds_equals_oracle(ps, key):
+    import fips204_b200 as F
+    m = F.PARAM_SETS[ps]
+    xi = _seeds(key)
+    # the rare lanes sit among ordinary ones, at warp boundaries and in the middle of a warp
+    rng = np.random.default_rng(ps)
+    allxi = rng.integers(0, 256, size=(300, 32), dtype=np.uint8)
+    slots = [0, 31, 32, 77, 128, 299][:len(xi)]
+    allxi[slots] = xi
+    pk, sk = m.keygen_batch(allxi)
+    opk, osk = O.keygen_batch(ps, allxi)
+    assert (pk == opk).all() and (sk == osk).all()
+    out = m.pipeline_batch(allxi, [b"x"] * 300, np.zeros((300, 32), np.uint8), want_sk=True)  # the A-hat keeping keygen path
+    assert (out["pk"] == opk).all() and (out["sk"] == osk).all() and out["ok"].all()
+
+
+@pytest.mark.gpu
+def test_rej_ntt_parser_beyond_five_blocks():
+    """CoeffFromThreeBytes over crafted squeeze blocks: streams that need 6, 7 and 9 blocks (many candidates >= q),
+    a stream that ends exactly on a block boundary, and ordinary random blocks; 200 streams so that the slow streams
+    share warps with fast ones (a finished stream must ignore the extra blocks its warp still runs)."""
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(6)
+    n, nblocks = 200, 14
+    blocks = rng.integers(0, 256, size=(n, nblocks, 168), dtype=np.uint8)
+    for i in range(n):
+        kind = i % 5
+        if kind in (1, 2, 3):  # make a share of the 3-byte candidates >= q: bytes 0xFF 0xFF 0x7F -> 0x7FFFFF
+            frac = (0.15, 0.30, 0.45)[kind - 1]
+            cand = blocks[i].reshape(-1, 3)
+            hit = rng.random(cand.shape[0]) < frac
+            cand[hit] = (0xFF, 0xFF, 0x7F)
+        if kind == 4:  # exactly 256 accepted candidates in the first 5 blocks minus none to spare: 280 candidates, 24 rejected
+            cand = blocks[i].reshape(-1, 3)
+            cand[:, 2] &= 0x3F  # everything < q ...
+            rej = rng.choice(280, size=24, replace=False)
+            cand[rej] = (0xFF, 0xFF, 0xFF)  # ... except 24 of the first 280
+    out = np.zeros((n, 256), np.int32)
+    _lib.check(L.mldsa_debug_sampler_stream(0, 0, n, blocks.ctypes.data, nblocks, out.ctypes.data))
+    used = []
+    for i in range(n):
+        raw = blocks[i].reshape(-1, 3).astype(np.int64)
+        z = ((raw[:, 2] & 0x7F) << 16) | (raw[:, 1] << 8) | raw[:, 0]
+        acc = z[z < Q]
+        assert acc.size >= 256
+        assert (out[i] == acc[:256]).all(), i
+        idx256 = np.nonzero(z < Q)[0][255]
+        used.append(idx256 // 56 + 1)
+    assert max(used) >= 9 and 6 in used and 7 in used and min(used) == 5
+    assert used[4] == 5  # the boundary case consumed exactly five blocks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tau", [39, 49, 60])
+def test_sample_in_ball_second_and_third_block(tau):
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(tau)
+    n, nblocks = 96, 4
+    blocks = rng.integers(0, 256, size=(n, nblocks, 136), dtype=np.uint8)
+    for i in range(n):
+        kind = i % 4
+        flat = blocks[i].reshape(-1)
+        if kind == 1:    # mostly rejected indices in the first block: the walk continues in the second
+            flat[8:136] = rng.integers(250, 256, size=128)
+        elif kind == 2:  # ... and in the second: a third block
+            flat[8:272] = 255
+        elif kind == 3:  # the walk ends on the last byte of the first block
+            seq = list(range(256 - tau, 256))  # j = i is always accepted
+            flat[8:136] = 255
+            flat[136 - tau:136] = seq
+    out = np.zeros((n, 64), np.uint8)
+    _lib.check(L.mldsa_debug_sampler_stream(0, tau, n, blocks.ctypes.data, nblocks, out.ctypes.data))
+    blocks_used = []
+    for i in range(n):
+        c, pos = _sample_in_ball_stream(tau, bytes(blocks[i].reshape(-1)))
+        nz = np.unpackbits(out[i, :32], bitorder="little")
+        sg = np.unpackbits(out[i, 32:], bitorder="little")
+        got = [int(a) - 2 * int(a & b) for a, b in zip(nz, sg)]
+        assert got == c, (tau, i)
+        assert sum(1 for v in c if v) == tau
+        blocks_used.append((pos + 135) // 136)
+    assert 2 in blocks_used and 3 in blocks_used and blocks_used[3] == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["sign", "keygen"])
+def test_fixed_work_secret_kernels_show_no_class_dependent_timing(op, tmp_path):
+    """dudect-style two-class timing (tools/ct_probe.py; the reference's harness: dudect/src/main.rs:30-56): for the
+    kernels that touch secret data with a fixed amount of work, Welch's |t| between the classes stays below dudect's
+    threshold of 5.  A reduced run (1 500 launches per class); the committed profiles hold the 10^4-launch runs of all
+    three parameter sets."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "ct.json"
+    r = subprocess.run([sys.executable, str(root / "tools" / "ct_probe.py"), "--op", op, "--ps", "65", "--lanes", "16384",
+                        "--reps", "1500", "--json", str(out)], capture_output=True, text=True, timeout=900, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(out.read_text())
+    assert res["worst_abs_t_fixed"] < 5.0, res

@@ -23,7 +23,18 @@ Classes (messages and rnd are the same in every class; only the keys differ):
 Calls of the three classes are interleaved in random order.  Output: per kernel, mean device time per class and
 Welch's t for A vs B and A vs R.
 
-    python tools/ct_probe.py [--lanes 16384] [--reps 300] [--ps 65] [--out profiles/ct_probe.md]
+--op keygen does the same for key generation, the other half of the reference's harness (dudect/src/main.rs:48-52 times
+keygen + sign together).  The classes are the seeds themselves (A: every lane xi = 0xAA.., B: 0x55.., R: random xi):
+
+  kg_seed      (rho, rho', K) = H(xi || k || l)              touches xi
+  rej_bounded  s1, s2 = RejBoundedPoly(rho' || r)            touches rho'; the number of SHAKE256 blocks a stream needs
+                                                             depends on it -- the reference's own expand_s has the
+                                                             same data-dependent loop (hashing.rs:158-213): carve-out
+  kg_arith     NTT(s1), A-hat o s1-hat (A-hat squeezed from the PUBLIC rho), INTT, + s2, Power2Round, packing
+                                                             touches s1, s2, t0
+  shake_rows   tr = H(pk)                                    public data
+
+    python tools/ct_probe.py [--op sign|keygen] [--lanes 16384] [--reps 300] [--ps 65] [--out profiles/ct_probe.md] [--json f]
 """
 import argparse
 import ctypes as C
@@ -45,6 +56,8 @@ ap.add_argument("--lanes", type=int, default=16384)
 ap.add_argument("--reps", type=int, default=300)
 ap.add_argument("--ps", type=int, default=65)
 ap.add_argument("--out", default="")
+ap.add_argument("--op", default="sign", choices=["sign", "keygen"])
+ap.add_argument("--json", default="")
 a = ap.parse_args()
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
@@ -64,21 +77,30 @@ def keys_from(xi):
     return sk
 
 
-sk_a = keys_from(torch.full((1, 32), 0xAA, dtype=torch.uint8, device=dev)).repeat(n, 1).contiguous()
-sk_b = keys_from(torch.full((1, 32), 0x55, dtype=torch.uint8, device=dev)).repeat(n, 1).contiguous()
-sk_r = keys_from(torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g))
-classes = {"A": sk_a, "B": sk_b, "R": sk_r}
+xi_a = torch.full((n, 32), 0xAA, dtype=torch.uint8, device=dev)
+xi_b = torch.full((n, 32), 0x55, dtype=torch.uint8, device=dev)
+xi_r = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+if a.op == "sign":
+    classes = {"A": keys_from(xi_a[:1]).repeat(n, 1).contiguous(), "B": keys_from(xi_b[:1]).repeat(n, 1).contiguous(),
+               "R": keys_from(xi_r)}
+else:
+    classes = {"A": xi_a, "B": xi_b, "R": xi_r}
+    kg_pk = torch.empty((n, m.PK_LEN), dtype=torch.uint8, device=dev)
+    kg_sk = torch.empty((n, m.SK_LEN), dtype=torch.uint8, device=dev)
 msg = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
 rnd = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
 moff = torch.arange(n + 1, dtype=torch.int64, device=dev) * 32
 sig = torch.empty((n, m.SIG_LEN), dtype=torch.uint8, device=dev)
-KERNELS = ["sign_key", "sign_prep", "mask", "sign_w", "ctilde", "sign_z"]
+KERNELS = ["sign_key", "sign_prep", "mask", "sign_w", "ctilde", "sign_z"] if a.op == "sign" else ["kg_seed", "rej_bounded", "kg_arith", "shake_rows"]
 
 
 def one(sk):
     L.mldsa_profile_reset()
-    rc = L.mldsa_sign_batch_dev(a.ps, sh, 0, n, p(sk), m.SK_LEN, p(msg), p(moff), None, None, p(rnd), p(sig), None)
-    assert rc in (0, -5), rc  # -5: stopped after one round with lanes still live (the hook's documented outcome)
+    if a.op == "sign":
+        rc = L.mldsa_sign_batch_dev(a.ps, sh, 0, n, p(sk), m.SK_LEN, p(msg), p(moff), None, None, p(rnd), p(sig), None)
+        assert rc in (0, -5), rc  # -5: stopped after one round with lanes still live (the hook's documented outcome)
+    else:
+        _lib.check(L.mldsa_keygen_batch_dev(a.ps, sh, n, p(sk), p(kg_pk), p(kg_sk)))
     out = {}
     for i in range(L.mldsa_profile_count()):
         ms, cnt = C.c_double(), C.c_uint64()
@@ -90,7 +112,8 @@ def one(sk):
     return out
 
 
-L.mldsa_debug_set_max_rounds(1)
+if a.op == "sign":
+    L.mldsa_debug_set_max_rounds(1)
 L.mldsa_profile_enable(1)
 try:
     for c in classes.values():  # warm-up
@@ -119,29 +142,49 @@ def welch(x, y):
     return (x.mean() - y.mean()) / math.sqrt(x.var(ddof=1) / len(x) + y.var(ddof=1) / len(y))
 
 
-lines = [f"# GPU two-class timing probe: ML-DSA-{a.ps}, {n} lanes per launch, {a.reps} launches per class", "",
-         "`python tools/ct_probe.py` (method in its docstring; dudect convention: |t| > 5 rejects constant time).",
-         "Device time of ONE launch over all lanes, first round of the rejection loop only; classes A / B = every lane signs",
-         "with the key from xi = 0xAA.. / 0x55.., R = distinct random keys; same messages and rnd in all classes.", "",
+if a.op == "sign":
+    head = ["Device time of ONE launch over all lanes, first round of the rejection loop only; classes A / B = every lane signs",
+            "with the key from xi = 0xAA.. / 0x55.., R = distinct random keys; same messages and rnd in all classes."]
+    what = {"sign_key": "s1, s2, t0", "sign_prep": "K", "mask": "rho''", "sign_w": "y", "ctilde": "(public: w1)",
+            "sign_z": "s-hat rows; early exit on the rejection pattern (carve-out)"}
+    carve = ("sign_z", "ctilde")
+else:
+    head = ["Device time of ONE launch over all lanes; classes A / B = every lane generates the key of xi = 0xAA.. / 0x55..,",
+            "R = distinct random seeds."]
+    what = {"kg_seed": "xi", "rej_bounded": "rho'; SHAKE256 blocks per stream depend on it (carve-out, as in the reference)",
+            "kg_arith": "s1, s2, t0 (A-hat from the public rho)", "shake_rows": "(public: pk)"}
+    carve = ("rej_bounded", "shake_rows")
+lines = [f"# GPU two-class timing probe: ML-DSA-{a.ps} {a.op}, {n} lanes per launch, {a.reps} launches per class", "",
+         "`python tools/ct_probe.py` (method in its docstring; dudect convention: |t| > 5 rejects constant time)."] + head + ["",
          "| kernel | secret input | mean A (us) | mean B (us) | mean R (us) | t (A vs B) | t (A vs R) |", "|---|---|---:|---:|---:|---:|---:|"]
-what = {"sign_key": "s1, s2, t0", "sign_prep": "K", "mask": "rho''", "sign_w": "y", "ctilde": "(public: w1)",
-        "sign_z": "s-hat rows; early exit on the rejection pattern (carve-out)"}
 res = {}
 for k in KERNELS:
     ma, mb, mr = (float(crop(samples[c][k]).mean()) for c in "ABR")
     tab, tar = welch(samples["A"][k], samples["B"][k]), welch(samples["A"][k], samples["R"][k])
     res[k] = (tab, tar)
     lines.append(f"| `{k}` | {what[k]} | {ma:.2f} | {mb:.2f} | {mr:.2f} | {tab:+.2f} | {tar:+.2f} |")
-fixed = [k for k in KERNELS if k not in ("sign_z", "ctilde")]
+fixed = [k for k in KERNELS if k not in carve]
 worst = max(abs(t) for k in fixed for t in res[k])
-lines += ["", f"Largest |t| over the fixed-work kernels that touch secret data ({', '.join(fixed)}): **{worst:.2f}**.",
-          "`ctilde` works on public data only: its SampleInBall walk rejects candidates j > i drawn from H(c~) exactly like",
-          "the reference's loop (src/hashing.rs:43-100), so its time follows the challenge bytes, which are part of the",
-          "signature.  `sign_z` stops at the first failed norm check, so its time follows the rejection pattern of the",
-          "batch, which differs between keys; that is the reference's documented exception (the loop trip count is not",
-          "constant time, src/lib.rs:85-89, traits.rs:128-132), not a data-dependent instruction or address inside the",
-          "arithmetic."]
+lines += ["", f"Largest |t| over the fixed-work kernels that touch secret data ({', '.join(fixed)}): **{worst:.2f}**."]
+if a.op == "sign":
+    lines += ["`ctilde` works on public data only: its SampleInBall walk rejects candidates j > i drawn from H(c~) exactly like",
+              "the reference's loop (src/hashing.rs:43-100), so its time follows the challenge bytes, which are part of the",
+              "signature.  `sign_z` stops at the first failed norm check, so its time follows the rejection pattern of the",
+              "batch, which differs between keys; that is the reference's documented exception (the loop trip count is not",
+              "constant time, src/lib.rs:85-89, traits.rs:128-132), not a data-dependent instruction or address inside the",
+              "arithmetic."]
+else:
+    lines += ["`rej_bounded` squeezes SHAKE256(rho' || r) until it has 256 accepted nibbles: how many blocks that takes depends",
+              "on rho', exactly like the reference's loop (src/hashing.rs:158-213); with every lane on the same seed (classes",
+              "A, B) all warps take the same number of blocks, with random seeds (R) the mix differs.  `shake_rows` hashes the",
+              "public key."]
 text = "\n".join(lines) + "\n"
 print(text)
 if a.out:
-    Path(a.out).write_text(text)
+    Path(a.out).parent.mkdir(parents=True, exist_ok=True)
+    with open(a.out, "a") as f:
+        f.write(text + "\n")
+if a.json:
+    import json
+    Path(a.json).write_text(json.dumps({"op": a.op, "ps": a.ps, "lanes": n, "reps": a.reps, "fixed": fixed, "worst_abs_t_fixed": worst,
+                                        "t": {k: list(v) for k, v in res.items()}}))
