@@ -589,7 +589,7 @@ static std::vector<size_t> plan_sizes(size_t n, size_t cap)
     // Chunks ramp up and down in units of 32 768 lanes (1, 2, 4, then at most 6 units = 196 608 lanes, mirrored at the
     // end): the exposed pipeline fill (first copy-in) and drain (last tail + copy-out) are one unit's worth, the bulk
     // rounds of a 32 768-lane chunk are as efficient as those of a large one (161 ns per lane, timeline in
-    // profiles/r06_e2e_timeline.md), and a chunk's latency-bound tail hides under the next chunk's bulk.  2^20 lanes:
+    // profiles/round1/r06_e2e_timeline.md), and a chunk's latency-bound tail hides under the next chunk's bulk.  2^20 lanes:
     // 1-2-4-6-6-6-4-2-1; 2^17 lanes: 1-2-1; below two units: one chunk.  MLDSA_PLAN overrides the shape with explicit
     // proportions ("1,3,4,4,3,1" = sixteenths).
     constexpr size_t UNIT = 32768;
@@ -1858,7 +1858,7 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
     const size_t ws_lane = ws_bytes_for(1024) / 1024 + 1;
     const size_t io_lane = NS * (64 + p.pk + p.sk + p.sig + 1 + 4 + 8 + 4 + avg_msg + avg_ctx + 16);
     const size_t cap = pick_chunk(cx->arena_bytes, n, ws_bytes_for(0) + 65536, ws_lane + io_lane);
-    // chunks of >= 32768 lanes (as efficient as large ones, profiles/r06_e2e_timeline.md), at least ~8 per call so that
+    // chunks of >= 32768 lanes (as efficient as large ones, profiles/round1/r06_e2e_timeline.md), at least ~8 per call so that
     // the copy-out of chunk i hides under the stages of chunk i + 1
     size_t C = n;
     if (n >= 65536) C = std::max<size_t>(32768, (n + 7) / 8);

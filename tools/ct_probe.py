@@ -20,8 +20,9 @@ Classes (messages and rnd are the same in every class; only the keys differ):
   A: all n lanes sign with the key generated from xi = 0xAA..AA      (the reference's "left" seed)
   B: all n lanes sign with the key generated from xi = 0x55..55      (the reference's "right" seed)
   R: n distinct random keys (fixed-vs-random)
-Calls of the three classes are interleaved in random order.  Output: per kernel, mean device time per class and
-Welch's t for A vs B and A vs R.
+  A': the bytes of class A once more, in a different device allocation (CONTROL: what separates A from A' is not data)
+Calls of the classes are interleaved in random order.  Output: per kernel, mean device time per class and
+Welch's t for A vs B, A vs R and the control A vs A'.
 
 --op keygen does the same for key generation, the other half of the reference's harness (dudect/src/main.rs:48-52 times
 keygen + sign together).  The classes are the seeds themselves (A: every lane xi = 0xAA.., B: 0x55.., R: random xi):
@@ -85,8 +86,11 @@ if a.op == "sign":
                "R": keys_from(xi_r)}
 else:
     classes = {"A": xi_a, "B": xi_b, "R": xi_r}
-    kg_pk = torch.empty((n, m.PK_LEN), dtype=torch.uint8, device=dev)
-    kg_sk = torch.empty((n, m.SK_LEN), dtype=torch.uint8, device=dev)
+# CONTROL: the SAME bytes as class A in a different allocation.  Whatever separates A from A' is not the data: buffer
+# placement (DRAM pages / L2 sets), or drift of the box -- the floor any A-vs-B figure has to be read against.
+classes["A'"] = classes["A"].clone()
+kg_pk = torch.empty((n, m.PK_LEN), dtype=torch.uint8, device=dev)
+kg_sk = torch.empty((n, m.SK_LEN), dtype=torch.uint8, device=dev)
 msg = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
 rnd = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
 moff = torch.arange(n + 1, dtype=torch.int64, device=dev) * 32
@@ -156,16 +160,20 @@ else:
     carve = ("rej_bounded", "shake_rows")
 lines = [f"# GPU two-class timing probe: ML-DSA-{a.ps} {a.op}, {n} lanes per launch, {a.reps} launches per class", "",
          "`python tools/ct_probe.py` (method in its docstring; dudect convention: |t| > 5 rejects constant time)."] + head + ["",
-         "| kernel | secret input | mean A (us) | mean B (us) | mean R (us) | t (A vs B) | t (A vs R) |", "|---|---|---:|---:|---:|---:|---:|"]
+         "| kernel | secret input | mean A (us) | mean B (us) | mean R (us) | t (A vs B) | t (A vs R) | control: t (A vs A') |",
+         "|---|---|---:|---:|---:|---:|---:|---:|"]
 res = {}
 for k in KERNELS:
     ma, mb, mr = (float(crop(samples[c][k]).mean()) for c in "ABR")
     tab, tar = welch(samples["A"][k], samples["B"][k]), welch(samples["A"][k], samples["R"][k])
-    res[k] = (tab, tar)
-    lines.append(f"| `{k}` | {what[k]} | {ma:.2f} | {mb:.2f} | {mr:.2f} | {tab:+.2f} | {tar:+.2f} |")
+    tctl = welch(samples["A"][k], samples["A'"][k])
+    res[k] = (tab, tar, tctl)
+    lines.append(f"| `{k}` | {what[k]} | {ma:.2f} | {mb:.2f} | {mr:.2f} | {tab:+.2f} | {tar:+.2f} | {tctl:+.2f} |")
 fixed = [k for k in KERNELS if k not in carve]
-worst = max(abs(t) for k in fixed for t in res[k])
-lines += ["", f"Largest |t| over the fixed-work kernels that touch secret data ({', '.join(fixed)}): **{worst:.2f}**."]
+worst = max(abs(t) for k in fixed for t in res[k][:2])
+worst_ctl = max(abs(res[k][2]) for k in fixed)
+lines += ["", f"Largest |t| over the fixed-work kernels that touch secret data ({', '.join(fixed)}): **{worst:.2f}**; "
+              f"largest |t| of the same kernels between class A and its byte-identical copy A': **{worst_ctl:.2f}**."]
 if a.op == "sign":
     lines += ["`ctilde` works on public data only: its SampleInBall walk rejects candidates j > i drawn from H(c~) exactly like",
               "the reference's loop (src/hashing.rs:43-100), so its time follows the challenge bytes, which are part of the",
@@ -186,5 +194,5 @@ if a.out:
         f.write(text + "\n")
 if a.json:
     import json
-    Path(a.json).write_text(json.dumps({"op": a.op, "ps": a.ps, "lanes": n, "reps": a.reps, "fixed": fixed, "worst_abs_t_fixed": worst,
+    Path(a.json).write_text(json.dumps({"op": a.op, "ps": a.ps, "lanes": n, "reps": a.reps, "fixed": fixed, "worst_abs_t_fixed": worst, "worst_abs_t_control": worst_ctl,
                                         "t": {k: list(v) for k, v in res.items()}}))
