@@ -103,10 +103,9 @@ class Clocks:
                 time.sleep(0.002)
             if self.stop_flag:
                 return
-            try:
+            try:  # clock + reasons only: every extra NVML query inside the region stalls the GPU again
                 self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
-                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)),
-                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1e3))
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)), None))
             except Exception:
                 return
 
@@ -123,8 +122,12 @@ class Clocks:
                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
             reasons = sorted({k for _, r, _ in self.samples for k, b in bits.items() if r & b})
             sm = [s[0] for s in self.samples]
+            try:
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3  # right after the region (the average NVML keeps)
+            except Exception:
+                power = None
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
-                    "samples": len(sm), "power_w": max((s[2] for s in self.samples), default=None),
+                    "samples": len(sm), "power_w": power,
                     "sampler": "NVML in-process, at 1/3 and 2/3 of the timed region (a clock query stalls the GPU ~10 ms)"}
         if self.proc:
             self.proc.terminate()
