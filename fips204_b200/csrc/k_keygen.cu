@@ -33,20 +33,21 @@ __global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict_
 }
 
 // RejBoundedPoly: one thread per SHAKE256 stream; nibbles are parsed out of the state registers
-// (CoeffFromHalfByte, src/conversion.rs:80-111), accepted values appended to the thread's row of a
-// shared tile, rows flushed by the warp.  Output: int8 coefficients in [-eta, eta].
+// (CoeffFromHalfByte, src/conversion.rs:80-111) and the accepted values appended to the thread's own row of a
+// shared tile; after every squeeze block the thread moves its complete groups of sixteen to their final place
+// with 128-bit stores and carries the rest to the head of the row (the scheme of expand_a: no warp-cooperative
+// flush, whose 32 x (2 shuffles + copy loop) per block cost this ALU-bound kernel 30 % of its instructions).
+// Output: int8 coefficients in [-eta, eta].
 constexpr int RB_THREADS = 128;
-constexpr int RB_ROW = 276;  // 272 nibbles per block + pad; 69 words (odd) per row
+constexpr int RB_ROW = 288;  // bytes per thread: <= 15 carried + 272 nibbles of a block, as whole int4s
 
 template <int ETA>
 __global__ void __launch_bounds__(RB_THREADS, 4)
 rej_bounded_kernel(const uint8_t* __restrict__ seeds, size_t nstreams, int KL /* K + L */, int8_t* __restrict__ out)
 {
-    __shared__ __align__(16) int8_t tile_all[RB_THREADS / 32][32 * RB_ROW];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int8_t* tile = tile_all[warp];
+    __shared__ __align__(16) int8_t tile_all[RB_THREADS * RB_ROW];
+    int8_t* row = tile_all + threadIdx.x * RB_ROW;  // private to this thread: no barriers needed
     const size_t q = (size_t)blockIdx.x * RB_THREADS + threadIdx.x;
-    const size_t qbase = q - lane;
     const bool valid = q < nstreams;
 
     uint64_t a[25];
@@ -61,11 +62,11 @@ rej_bounded_kernel(const uint8_t* __restrict__ seeds, size_t nstreams, int KL /*
         a[8] = (uint64_t)(idx | (0x1Fu << 16));  // LE16(idx) then SHAKE pad
         a[16] = 0x8000000000000000ULL;           // byte 135 of the 136-byte rate
     }
-    int j = valid ? 0 : 256;
-    while (__any_sync(0xffffffffu, j < 256)) {
+    int4* dst = reinterpret_cast<int4*>(out + (valid ? q : 0) * 256);  // next group of sixteen to write
+    int groups_left = valid ? 16 : 0;
+    int have = 0;  // coefficients waiting at the head of the row (0..15 between blocks)
+    while (__any_sync(0xffffffffu, groups_left > 0)) {
         keccak_f1600(a);
-        int cnt = 0;
-        int8_t* row = tile + lane * RB_ROW;
 #pragma unroll
         for (int wi = 0; wi < 34; wi++) {
             const uint32_t w = (wi & 1) ? (uint32_t)(a[wi >> 1] >> 32) : (uint32_t)a[wi >> 1];
@@ -73,24 +74,26 @@ rej_bounded_kernel(const uint8_t* __restrict__ seeds, size_t nstreams, int KL /*
             for (int nb = 0; nb < 8; nb++) {
                 const int b = (int)((w >> (4 * nb)) & 15);
                 if (ETA == 2) {
-                    if (b < 15) row[cnt++] = (int8_t)(2 - (b - 5 * ((b * 205) >> 10)));
+                    if (b < 15) row[have++] = (int8_t)(2 - (b - 5 * ((b * 205) >> 10)));
                 } else {
-                    if (b < 9) row[cnt++] = (int8_t)(4 - b);
+                    if (b < 9) row[have++] = (int8_t)(4 - b);
                 }
             }
         }
-        if (j >= 256) cnt = 0;
-        __syncwarp();
-        for (int s = 0; s < 32; s++) {
-            const int n_s = __shfl_sync(0xffffffffu, cnt, s);
-            const int j_s = __shfl_sync(0xffffffffu, j, s);
-            int8_t* dst = out + (qbase + s) * 256 + j_s;
-            const int lim = min(n_s, 256 - j_s);
-            for (int c = lane; c < lim; c += 32) dst[c] = tile[s * RB_ROW + c];
-        }
-        j += cnt;
-        __syncwarp();
+        const int ng = min(have >> 4, groups_left);
+        const int4* src = reinterpret_cast<const int4*>(row);
+#pragma unroll
+        for (int k = 0; k < RB_ROW / 16 - 1; k++)
+            if (k < ng) dst[k] = src[k];
+        const int4 tail = src[have >> 4];  // the incomplete group (a finished stream parks garbage there)
+        dst += ng;
+        groups_left -= ng;
+        have &= 15;
+        *reinterpret_cast<int4*>(row) = tail;
     }
+    // the row held secret coefficients: leave nothing of them in shared memory
+#pragma unroll
+    for (int k = 0; k < RB_ROW / 16; k++) reinterpret_cast<int4*>(row)[k] = make_int4(0, 0, 0, 0);
 }
 
 constexpr int KG_WARPS = 4;

@@ -4,6 +4,7 @@
 cd "$(dirname "$0")/.."
 PS=${1:-65}
 M=smsp__inst_executed.sum,smsp__thread_inst_executed.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,lts__t_sectors.sum
+mkdir -p gpurun_out
 OUT=gpurun_out/ct_trace_${PS}.txt
 : > $OUT
 for op in sign keygen; do
