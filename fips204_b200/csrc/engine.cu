@@ -1780,7 +1780,10 @@ int mldsa_keygen_to_keyset(int ps, int dev, size_t n, const uint8_t* xi, uint8_t
     cx->note_secret(seeds, first * 128);
     cx->note_secret(sbuf, first * KpL * 256);
     int32_t* const A_all = sks ? sks->A : pks->A;
-    CK(cudaStreamSynchronize(cx->s_out));
+    {
+        const cudaError_t e0 = cudaStreamSynchronize(cx->s_out);
+        if (e0 != cudaSuccess) return fail(cuda_fail(e0, "keygen_to_keyset"));
+    }
     size_t i = 0;
     for (size_t lo = 0; lo < n; lo += chunk, i++) {
         const size_t m = n - lo < chunk ? n - lo : chunk;
@@ -1956,8 +1959,11 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
         CK(cudaEventRecord(cx->ev_in[i % NS], cx->s_in));
         return OK;
     };
-    CK(cudaStreamSynchronize(cx->s_in));
-    CK(cudaStreamSynchronize(cx->s_out));
+    {
+        cudaError_t e0 = cudaStreamSynchronize(cx->s_in);
+        if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(cx->s_out);
+        if (e0 != cudaSuccess) return bail(cuda_fail(e0, "pipeline"));
+    }
     t_last_rounds = 0;
     if ((rc = copy_in(0))) return bail(rc);
     for (size_t i = 0; i < N; i++) {
