@@ -1,10 +1,12 @@
 """ctypes binding of the C-ABI library (include/mldsa_b200.h).  There is NO CPU fallback: if the CUDA
 library is missing or a call fails, an exception is raised."""
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-SO_PATH = HERE / "libmldsa_b200.so"
+# MLDSA_B200_LIB: an A/B build of the same library (fips204_b200/build.py build_variant) for tools/ probes
+SO_PATH = Path(os.environ["MLDSA_B200_LIB"]) if os.environ.get("MLDSA_B200_LIB") else HERE / "libmldsa_b200.so"
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)

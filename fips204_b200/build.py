@@ -58,5 +58,38 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(name, defs, units=None):
+    """A/B builds for tools/ (never loaded by the package itself unless MLDSA_B200_LIB names one):
+    fips204_b200/variants/libmldsa_b200_<name>.so compiled with extra -D flags.  Only `units` are recompiled with
+    the flags; the other objects come from the regular build."""
+    build()
+    vdir = HERE / "variants"
+    odir = OBJ / f"v_{name}"
+    vdir.mkdir(exist_ok=True)
+    odir.mkdir(exist_ok=True)
+    units = units or UNITS
+    objs = []
+    for u in UNITS:
+        if u in units:
+            o = odir / f"{u}.o"
+            r = subprocess.run([NVCC, *FLAGS, *defs, "-c", str(CSRC / f"{u}.cu"), "-o", str(o)], capture_output=True, text=True)
+            (odir / f"{u}.log").write_text(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {u} ({name}):\n{r.stderr}")
+            objs.append(str(o))
+        else:
+            objs.append(str(OBJ / f"{u}.o"))
+    out = vdir / f"libmldsa_b200_{name}.so"
+    r = subprocess.run([NVCC, "-shared", "-o", str(out), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC", "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:  # python -m fips204_b200.build --variant NAME unit[,unit] -DX=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 3:]], sys.argv[i + 2].split(",")))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -213,9 +213,7 @@ struct DeviceCtx {
     void note_sign_ws(const SignWs& w, size_t n, bool shared, int K, int L, int zbits)
     {
         const size_t nk = shared ? 1 : n, D = (size_t)w.depth;
-        note_secret(w.s1h, nk * (size_t)L * 1024);
-        note_secret(w.s2h, nk * (size_t)K * 1024);
-        note_secret(w.t0h, nk * (size_t)K * 1024);
+        note_secret(w.sh, nk * (size_t)(2 * K + L) * 1024);
         note_secret(w.w, n * D * K * 1024);                 // w - c*s2
         note_secret(w.yraw, n * D * L * 32 * (size_t)zbits);  // y
         note_secret(w.rhopp, n * 64);
@@ -286,7 +284,7 @@ struct KeySet {
     size_t n = 0, bytes = 0;
     uint8_t* base = nullptr;
     bool is_public = false;   // false: secret keys (sign), true: public keys (verify)
-    int32_t *A = nullptr, *s1h = nullptr, *s2h = nullptr, *t0h = nullptr;
+    int32_t *A = nullptr, *sh = nullptr;  // sh: [n][2K+L][256] s2-hat, s1-hat, t0-hat (SignWs::sh)
     uint8_t* mini = nullptr;  // secret keys: [n][128] rho || K || tr
     int32_t* t1h = nullptr;   // public keys: [n][K][256] NTT(t1 * 2^d), the reference's t1_d2_hat_mont (src/types.rs:40)
     uint8_t* tr = nullptr;    // public keys: [n][64]
@@ -356,7 +354,7 @@ static VerifyWs verify_carve(Carver& c, const PSInfo& p, size_t n)
 static size_t sign_ws_bytes(const PSInfo& p, size_t n, bool shared, bool resident = false)
 {
     const size_t nk = resident ? 0 : (shared ? 1 : n), D = (size_t)tuning().depth;
-    return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)p.L * 1024) + 2 * pad256(nk * (size_t)p.K * 1024) +
+    return pad256(nk * (size_t)p.K * p.L * 1024) + pad256(nk * (size_t)(2 * p.K + p.L) * 1024) +
            pad256(n * D * p.K * 1024) + pad256(n * D * p.L * 32 * p.zbits) + pad256(n * D * (64 + p.w1len)) +
            2 * pad256(n * 64) + 2 * pad256(n * D * 64) + pad256(n * 4) + pad256(n) + 2 * pad256(n * 4) + pad256(64);
 }
@@ -366,9 +364,7 @@ static SignWs sign_carve(Carver& c, const PSInfo& p, size_t n, bool shared, uint
     SignWs w;
     w.depth = (int)D;
     w.A = c.take<int32_t>(nk * (size_t)p.K * p.L * 256);
-    w.s1h = c.take<int32_t>(nk * (size_t)p.L * 256);
-    w.s2h = c.take<int32_t>(nk * (size_t)p.K * 256);
-    w.t0h = c.take<int32_t>(nk * (size_t)p.K * 256);
+    w.sh = c.take<int32_t>(nk * (size_t)(2 * p.K + p.L) * 256);
     w.w = c.take<int32_t>(n * D * p.K * 256);
     w.yraw = c.take<uint8_t>(n * D * p.L * 32 * p.zbits);
     w.mw1 = c.take<uint8_t>(n * D * (64 + p.w1len));
@@ -461,14 +457,14 @@ static int verify_core(DeviceCtx& cx, cudaStream_t st, int ps, int framing, size
 }
 
 // secrets of a sign workspace that the kernels do not zero themselves: the shared key's s-hat rows, and
-// everything when a run stopped early (s1-hat .. yraw are contiguous in the carve)
+// everything when a run stopped early (the s-hat rows .. yraw are contiguous in the carve)
 static void sign_wipe(const SignWs& ws, size_t m, bool shared, bool failed, cudaStream_t st)
 {
     if (failed) {
-        cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.mw1 - (uint8_t*)ws.s1h), st);
+        cudaMemsetAsync(ws.sh, 0, (size_t)((uint8_t*)ws.mw1 - (uint8_t*)ws.sh), st);
         cudaMemsetAsync(ws.rhopp, 0, m * 64, st);
     } else if (shared) {
-        cudaMemsetAsync(ws.s1h, 0, (size_t)((uint8_t*)ws.w - (uint8_t*)ws.s1h), st);
+        cudaMemsetAsync(ws.sh, 0, (size_t)((uint8_t*)ws.w - (uint8_t*)ws.sh), st);
     }
 }
 
@@ -1193,9 +1189,7 @@ static int sign_host(int ps, int dev, int framing, int ph, size_t n, const uint8
             ws.keys_resident = true;
             ws.kidx = key_idx ? reinterpret_cast<const uint32_t*>(s.sk) : nullptr;
             ws.A = ks->A + k0 * (size_t)p.K * p.L * 256;
-            ws.s1h = ks->s1h + k0 * (size_t)p.L * 256;
-            ws.s2h = ks->s2h + k0 * (size_t)p.K * 256;
-            ws.t0h = ks->t0h + k0 * (size_t)p.K * 256;
+            ws.sh = ks->sh + k0 * (size_t)(2 * p.K + p.L) * 256;
             key_rows = ks->mini + k0 * 128;
             cx->note_secret(ws.w, m * (size_t)ws.depth * p.K * 1024);
             cx->note_secret(ws.yraw, m * (size_t)ws.depth * p.L * 32 * p.zbits);
@@ -1475,9 +1469,8 @@ int mldsa_sk_load(int ps, int dev, size_t n, const uint8_t* sk, mldsa_keyset** o
     ks->ps = ps;
     ks->dev = dev;
     ks->n = n;
-    const size_t a_b = pad256(n * (size_t)p.K * p.L * 1024), s1_b = pad256(n * (size_t)p.L * 1024),
-                 s2_b = pad256(n * (size_t)p.K * 1024), mini_b = pad256(n * 128);
-    ks->bytes = a_b + s1_b + 2 * s2_b + mini_b;
+    const size_t a_b = pad256(n * (size_t)p.K * p.L * 1024), sh_b = pad256(n * (size_t)(2 * p.K + p.L) * 1024), mini_b = pad256(n * 128);
+    ks->bytes = a_b + sh_b + mini_b;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ks->base), ks->bytes);
     if (e != cudaSuccess) {
         delete ks;
@@ -1485,9 +1478,7 @@ int mldsa_sk_load(int ps, int dev, size_t n, const uint8_t* sk, mldsa_keyset** o
     }
     Carver c(ks->base);
     ks->A = c.take<int32_t>(n * (size_t)p.K * p.L * 256);
-    ks->s1h = c.take<int32_t>(n * (size_t)p.L * 256);
-    ks->s2h = c.take<int32_t>(n * (size_t)p.K * 256);
-    ks->t0h = c.take<int32_t>(n * (size_t)p.K * 256);
+    ks->sh = c.take<int32_t>(n * (size_t)(2 * p.K + p.L) * 256);
     ks->mini = c.take<uint8_t>(n * 128);
     // packed keys pass through the arena in chunks (two staging buffers: copy-in of chunk i+1 under the kernels of i)
     size_t chunk = pick_chunk(cx->arena_bytes, n, 65536, 2 * p.sk);
@@ -1518,8 +1509,8 @@ int mldsa_sk_load(int ps, int dev, size_t n, const uint8_t* sk, mldsa_keyset** o
         if (e == cudaSuccess) e = cudaEventRecord(cx->ev_in[i & 1], cx->s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, cx->ev_in[i & 1], 0);
         if (e == cudaSuccess)
-            e = sign_expand_keys(ps, st, m, d_sk, ks->A + lo * (size_t)p.K * p.L * 256, ks->s1h + lo * (size_t)p.L * 256,
-                                 ks->s2h + lo * (size_t)p.K * 256, ks->t0h + lo * (size_t)p.K * 256);
+            e = sign_expand_keys(ps, st, m, d_sk, ks->A + lo * (size_t)p.K * p.L * 256,
+                                 ks->sh + lo * (size_t)(2 * p.K + p.L) * 256);
         if (e == cudaSuccess)  // rho || K || tr: the first 128 bytes of every packed key (src/encodings.rs:168-176)
             e = cudaMemcpy2DAsync(ks->mini + 128 * lo, 128, d_sk, p.sk, 128, m, cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_sk, 0, m * p.sk, st);
@@ -1685,7 +1676,7 @@ static KeySet* keyset_new(const PSInfo& p, int ps, int dev, size_t n, bool is_pu
     ks->n = n;
     ks->is_public = is_public;
     const size_t a_b = pad256(n * (size_t)p.K * p.L * 1024), k_b = pad256(n * (size_t)p.K * 1024);
-    ks->bytes = is_public ? a_b + k_b + pad256(n * 64) : a_b + pad256(n * (size_t)p.L * 1024) + 2 * k_b + pad256(n * 128);
+    ks->bytes = is_public ? a_b + k_b + pad256(n * 64) : a_b + pad256(n * (size_t)(2 * p.K + p.L) * 1024) + pad256(n * 128);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ks->base), ks->bytes);
     if (e != cudaSuccess) {
         delete ks;
@@ -1698,9 +1689,7 @@ static KeySet* keyset_new(const PSInfo& p, int ps, int dev, size_t n, bool is_pu
         ks->t1h = c.take<int32_t>(n * (size_t)p.K * 256);
         ks->tr = c.take<uint8_t>(n * 64);
     } else {
-        ks->s1h = c.take<int32_t>(n * (size_t)p.L * 256);
-        ks->s2h = c.take<int32_t>(n * (size_t)p.K * 256);
-        ks->t0h = c.take<int32_t>(n * (size_t)p.K * 256);
+        ks->sh = c.take<int32_t>(n * (size_t)(2 * p.K + p.L) * 256);
         ks->mini = c.take<uint8_t>(n * 128);
     }
     return ks;
@@ -1794,8 +1783,7 @@ int mldsa_keygen_to_keyset(int ps, int dev, size_t n, const uint8_t* xi, uint8_t
         KeygenWs ws{seeds, sbuf, A_all + lo * KL * 256};  // A-hat is written once, straight into the key set
         if (e == cudaSuccess) e = keygen_run(ps, st, m, s.xi, s.pk, s.sk, ws);
         if (e == cudaSuccess && sks) {
-            e = sign_expand_keys(ps, st, m, s.sk, nullptr, sks->s1h + lo * (size_t)p.L * 256, sks->s2h + lo * (size_t)p.K * 256,
-                                 sks->t0h + lo * (size_t)p.K * 256, /*with_A*/ false);
+            e = sign_expand_keys(ps, st, m, s.sk, nullptr, sks->sh + lo * (size_t)(2 * p.K + p.L) * 256, /*with_A*/ false);
             if (e == cudaSuccess)  // rho || K || tr rows (src/encodings.rs:168-176)
                 e = cudaMemcpy2DAsync(sks->mini + 128 * lo, 128, s.sk, p.sk, 128, m, cudaMemcpyDeviceToDevice, st);
         }
@@ -1902,15 +1890,11 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
     kws.seeds = c.take<uint8_t>(C * 128);
     kws.s = c.take<int8_t>(C * KpL * 256);
     kws.A = c.take<int32_t>(C * KL * 256);
-    int32_t* s1h = c.take<int32_t>(C * (size_t)p.L * 256);
-    int32_t* s2h = c.take<int32_t>(C * (size_t)p.K * 256);
-    int32_t* t0h = c.take<int32_t>(C * (size_t)p.K * 256);
+    int32_t* sh = c.take<int32_t>(C * (size_t)(2 * p.K + p.L) * 256);
     SignWs sws = sign_carve(c, p, C, false, cx->mailbox, /*resident*/ true);
     sws.keys_resident = true;  // A-hat and the s-hat rows are this pipeline's own arrays, wiped after the stage
     sws.A = kws.A;
-    sws.s1h = s1h;
-    sws.s2h = s2h;
-    sws.t0h = t0h;
+    sws.sh = sh;
     c.take<uint8_t>(4096);
     VerifyWs vws0 = verify_carve(c, p, C);
     int32_t* t1h = c.take<int32_t>(C * (size_t)p.K * 256);
@@ -1981,9 +1965,7 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
         cx->note_secret(s.sk, m * p.sk);
         cx->note_secret(kws.seeds, m * 128);
         cx->note_secret(kws.s, m * KpL * 256);
-        cx->note_secret(s1h, m * (size_t)p.L * 1024);
-        cx->note_secret(s2h, m * (size_t)p.K * 1024);
-        cx->note_secret(t0h, m * (size_t)p.K * 1024);
+        cx->note_secret(sh, m * (size_t)(2 * p.K + p.L) * 1024);
         cx->note_secret(sws.w, m * (size_t)sws.depth * p.K * 1024);
         cx->note_secret(sws.yraw, m * (size_t)sws.depth * p.L * 32 * p.zbits);
         cx->note_secret(sws.rhopp, m * 64);
@@ -1995,7 +1977,7 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
         if (e == cudaSuccess) e = cudaMemsetAsync(kws.s, 0, m * KpL * 256, B);
         mark(1);
         // ---- stage 2: sign (src/ml_dsa.rs:153-337) with the packed keys where keygen left them
-        if (e == cudaSuccess) e = sign_expand_keys(ps, B, m, s.sk, nullptr, s1h, s2h, t0h, /*with_A*/ false);
+        if (e == cudaSuccess) e = sign_expand_keys(ps, B, m, s.sk, nullptr, sh, /*with_A*/ false);
         if (e != cudaSuccess) return bail(cuda_fail(e, "pipeline keygen"));
         const MsgDesc md{s.m - msg_off[lo], s.mo, ctx_off ? s.c - ctx_off[lo] : nullptr, ctx_off ? s.co : nullptr, framing};
         SignRun run;
@@ -2006,7 +1988,7 @@ static int pipeline_host(int ps, int dev, int framing, size_t n, const uint8_t* 
         e = sign_finish(&run);  // the one host wait of a chunk
         if (e != cudaSuccess) return bail(run.ctx_err ? E_CTX : (run.incomplete ? E_UNSUPPORTED : cuda_fail(e, "pipeline sign")));
         t_last_rounds += run.rounds;
-        e = cudaMemsetAsync(s1h, 0, (size_t)((uint8_t*)sws.w - (uint8_t*)s1h), B);  // s1-hat, s2-hat, t0-hat (contiguous)
+        e = cudaMemsetAsync(sh, 0, (size_t)((uint8_t*)sws.w - (uint8_t*)sh), B);  // s2-hat, s1-hat, t0-hat (contiguous)
         if (e == cudaSuccess) e = cudaMemsetAsync(s.rnd, 0, m * 32, B);
         mark(2);
         // ---- stage 3: verify (src/ml_dsa.rs:351-437) under the public keys keygen wrote

@@ -134,9 +134,8 @@ cudaError_t verify_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint
 // ---- k_sign.cu ----
 struct SignWs {
     int32_t* A;        // [nkeys][K*L][256]
-    int32_t* s1h;      // [nkeys][L][256]
-    int32_t* s2h;      // [nkeys][K][256]
-    int32_t* t0h;      // [nkeys][K][256]
+    int32_t* sh;       // [nkeys][2K+L][256]: s2-hat (K rows), s1-hat (L rows), t0-hat (K rows) of a key, contiguous and in
+                       // the order sign_z consumes them (one running row pointer per candidate)
     int depth;         // D = candidates per lane and round
     int32_t* w;        // [n][D][K][256]
     uint8_t* yraw;     // [n][D][L][32*ZBITS]
@@ -150,7 +149,7 @@ struct SignWs {
     uint32_t* act[2];  // [n] active lane lists (ping-pong)
     uint32_t* nact;    // [16] device control words: [buffer] active counts, [8] ctx error flag
     uint32_t* h_nact;  // mapped pinned host mirror of the 16 control words (written by publish_kernel)
-    // Resident key set (mldsa_sk_load): A / s1h / s2h / t0h point into the key set, the `sk` passed to sign_begin is
+    // Resident key set (mldsa_sk_load): A / sh point into the key set, the `sk` passed to sign_begin is
     // its 128-byte rho || K || tr rows, lane i uses key kidx[i] (nullptr: i), and nothing of the keys is wiped.
     bool keys_resident = false;
     const uint32_t* kidx = nullptr;
@@ -190,8 +189,8 @@ cudaError_t sign_begin(int ps, cudaStream_t st, size_t n, const uint8_t* sk, siz
                        SignRun* run);
 cudaError_t sign_tail(cudaStream_t st, SignRun* run);
 // expand_private (src/ml_dsa.rs:445-469) for nkeys packed secret keys: A-hat, s1-hat, s2-hat, t0-hat
-cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
-                             int32_t* t0h, bool with_A = true);
+cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* sh,
+                             bool with_A = true);
 cudaError_t sign_finish(SignRun* run);
 
 }  // namespace mldsa

@@ -34,7 +34,19 @@ __host__ __device__ __forceinline__ int32_t mont_mul(int32_t a, int32_t b)
     return MLDSA_MULHI(a, b) - MLDSA_MULHI(t, Q);
 }
 // helpers.rs:61-67: into (-q, q) for |a| < 2143289344
-__host__ __device__ __forceinline__ int32_t reduce32(int32_t a) { return a - ((a + (1 << 22)) >> 23) * Q; }
+__host__ __device__ __forceinline__ int32_t reduce32(int32_t a)
+{
+#if defined(__CUDA_ARCH__) && defined(RED_ALU)
+    // t q = (t << 23) - (t << 13) + t on the ALU pipe (the FMA-heavy pipe is what bounds the arithmetic kernels)
+    const uint32_t t = (uint32_t)((a + (1 << 22)) >> 23);
+    uint32_t r;
+    asm("{\n\t.reg .u32 s13, s23, u;\n\tshl.b32 s13, %2, 13;\n\tshl.b32 s23, %2, 23;\n\tsub.u32 u, s13, %2;\n\tsub.u32 u, u, s23;\n\tadd.u32 %0, %1, u;\n\t}"
+        : "=r"(r) : "r"((uint32_t)a), "r"(t));
+    return (int32_t)r;
+#else
+    return a - ((a + (1 << 22)) >> 23) * Q;
+#endif
+}
 // add q if negative
 __host__ __device__ __forceinline__ int32_t caddq(int32_t a) { return a + ((a >> 31) & Q); }
 // helpers.rs:70-76: canonical [0, q)

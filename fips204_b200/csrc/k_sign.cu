@@ -73,17 +73,17 @@ constexpr int SG_WARPS = 4;
 #define SG_MINB 6   // sign_w: its shared memory (y-hat rows, staged A-hat row, NTT tile: 8.8 KB per warp) admits 6 CTAs per SM
 #endif
 #ifndef SZ_MINB
-#define SZ_MINB 6
+#define SZ_MINB 5   // sign_z: 96 registers hold the early loads of the w row / y without spills (6: 80 registers, 30.0 ms; 5: 29.5 ms)
 #endif
 #ifndef SK_MINB
 #define SK_MINB 10  // sign_key: 48 registers
 #endif
 
-// s1-hat, s2-hat, t0-hat (plain NTT domain) for every key.  warp per key.
+// s2-hat, s1-hat, t0-hat for every key: rows [0, K), [K, K + L), [K + L, 2K + L) of the key's block of sh
+// (SignWs::sh: the order sign_z walks them).  warp per key.
 template <class P>
 __global__ void __launch_bounds__(SG_WARPS * 32, SK_MINB)
-sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, int32_t* __restrict__ s1h,
-                int32_t* __restrict__ s2h, int32_t* __restrict__ t0h)
+sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, int32_t* __restrict__ sh)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
@@ -93,8 +93,9 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
     const size_t stride = (size_t)gridDim.x * SG_WARPS;
     for (size_t kn = (size_t)blockIdx.x * SG_WARPS + warp; kn < nkeys; kn += stride) {
         const uint8_t* key = sk + kn * sk_stride;
+        int32_t* const rows = sh + kn * (size_t)(2 * K + L) * 256;
 #pragma unroll 1
-        for (int p = 0; p < L + 2 * K; p++) {
+        for (int p = 0; p < L + 2 * K; p++) {  // in the packed key's order: s1, s2, t0
             int32_t v[8];
             int32_t* dst;
             if (p < L + K) {  // BitUnpack(eta, eta): s = eta - field            (encodings.rs:185-198)
@@ -102,13 +103,13 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
                 load_span<P::ETABITS>(key + LO::SK_S1 + p * 32 * P::ETABITS + P::ETABITS * lane, w);
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = P::ETA - (int32_t)get_field<P::ETABITS>(w, i);
-                dst = p < L ? s1h + (kn * L + p) * 256 : s2h + (kn * K + (p - L)) * 256;
+                dst = rows + (p < L ? K + p : p - L) * 256;
             } else {          // BitUnpack(2^12 - 1, 2^12): t0 = 2^12 - field     (encodings.rs:203-210)
                 uint32_t w[4];
                 load_span<13>(key + LO::SK_T0 + (p - L - K) * 416 + 13 * lane, w);
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = (1 << (D - 1)) - (int32_t)get_field<13>(w, i);
-                dst = t0h + (kn * K + (p - L - K)) * 256;
+                dst = rows + p * 256;  // row K + L + (p - L - K)
             }
             sntt_fwd_B2B(v, tile, lane);
             // prescaled by 1/256: the inverse transforms of c*s1, c*s2, c*t0 in sign_z do not scale
@@ -137,13 +138,14 @@ struct SignWJob {
     size_t cap;            // as MaskJob::cap
 };
 struct SignZJob {
-    const uint32_t* nact; const uint32_t* act; const int32_t* s1h; const int32_t* s2h; const int32_t* t0h;
+    const uint32_t* nact; const uint32_t* act; const int32_t* sh;  // SignWs::sh
     const uint8_t* yraw; int32_t* w; const uint8_t* ctilde; const uint8_t* cmask; uint32_t* kappa; uint8_t* done;
     uint8_t* rhopp; uint8_t* sig; uint32_t* iters; int depth;
     int pos; int depth0; size_t tail_slots;  // pos = 1: the lane's stale slots of the carved depth0 are zeroed on accept
                                              // too, unless they lie in the shared tail region [0, tail_slots)
     const uint32_t* kidx;  // resident key set: key of lane ln = kidx[ln] (nullptr: ln)
-    int wipe_keys;         // 1: s1-hat / s2-hat / t0-hat belong to this call and are zeroed when the lane is accepted
+    int wipe_keys;         // 1: the key's s-hat rows belong to this call and are zeroed when the lane is accepted
+    int zero;              // 0, but only the host knows: pins the butterfly adds of the inverse transform to the ALU pipe (ntt.cuh)
 };
 
 // ExpandMask: one thread per (active lane, r) SHAKE256 stream; the squeezed bytes ARE the packed y.
@@ -202,10 +204,15 @@ __device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (
 // HBM / L2 (ncu: 40 % of the un-staged kernel's stall samples were long-scoreboard waits on these loads).
 // With an even speculation depth the two candidates of a lane sit on neighbouring warps and SHARE the staged
 // row (G = 2): the row is fetched once for both, and whichever warp finishes its products last issues the next copy.
+#ifndef SW_YREG
+#define SW_YREG 0   // rows of y-hat a warp keeps in registers instead of shared memory during the matrix-vector product
+#endif
+template <class P>
+struct SwYreg { static constexpr int N = SW_YREG < P::L ? SW_YREG : P::L; };
 template <class P, int G>
 struct alignas(128) SignWStage {
     alignas(128) int32_t arow[SG_WARPS / G][P::L * 256];  // one staged row of A-hat per group of G warps
-    alignas(16) int32_t yh[SG_WARPS][P::L][256];
+    alignas(16) int32_t yh[SG_WARPS][P::L - SwYreg<P>::N > 0 ? P::L - SwYreg<P>::N : 1][256];
     alignas(16) int32_t tile[SG_WARPS][NTT_TILE_WORDS];
     alignas(8) uint64_t full[SG_WARPS / G];
     uint32_t cnt[SG_WARPS / G];
@@ -268,6 +275,8 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
         release_and_fetch(0);
         uint32_t yw[2][(P::ZBITS + 3) / 4];  // packed y of the next polynomial is in flight during an NTT
         load_span<P::ZBITS>(yp + P::ZBITS * lane, yw[0]);
+        constexpr int YR = SwYreg<P>::N;
+        int32_t yreg[YR > 0 ? YR : 1][8];
 #pragma unroll
         for (int l = 0; l < L; l++) {
             if (l + 1 < L) load_span<P::ZBITS>(yp + (l + 1) * 32 * P::ZBITS + P::ZBITS * lane, yw[(l + 1) & 1]);
@@ -283,7 +292,12 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
                     y[i + 4] = x;
                 }
             }
-            row_store(sm.yh[warp][l], lane, y);  // only this lane reads these words back
+            if (l < YR) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) yreg[l][i] = y[i];
+            } else {
+                row_store(sm.yh[warp][l - YR], lane, y);  // only this lane reads these words back
+            }
         }
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
@@ -298,7 +312,12 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
                 const int4 x = ap[swz], y = ap[1 - swz];
                 const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
                 int32_t yv[8];
-                row_load(sm.yh[warp][l], lane, yv);
+                if (l < YR) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) yv[i] = yreg[l][i];
+                } else {
+                    row_load(sm.yh[warp][l - YR], lane, yv);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * yv[i];
             }
@@ -369,9 +388,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L;
     const uint32_t* __restrict__ act = j.act;
-    const int32_t* __restrict__ s1h_all = j.s1h;
-    const int32_t* __restrict__ s2h_all = j.s2h;
-    const int32_t* __restrict__ t0h_all = j.t0h;
+    const int32_t* __restrict__ sh_all = j.sh;
     const uint8_t* __restrict__ yraw = j.yraw;
     int32_t* __restrict__ wall = j.w;
     const uint8_t* __restrict__ ctilde = j.ctilde;
@@ -384,6 +401,10 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
     const int depth = j.depth;
     const size_t nact = *j.nact;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifndef SZ_Z0
+#define SZ_Z0 1
+#endif
+    const int32_t z0 = SZ_Z0 ? j.zero : 0;
     SignSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
     uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
@@ -410,13 +431,9 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
         }
         rej = false;
         int hcount = 0;
-        // operand row of step p: s2-hat[p], then s1-hat[p - K], then t0-hat[p - K - L]
-        auto row_ptr = [&](int p) {
-            const int32_t* r = p < K ? s2h_all + (kn * K + p) * 256
-                                     : (p < K + L ? s1h_all + (kn * L + (p - K)) * 256 : t0h_all + (kn * K + (p - K - L)) * 256);
-            return reinterpret_cast<const int4*>(r + 8 * lane);
-        };
-        int4 nx0 = __ldg(row_ptr(0)), nx1 = __ldg(row_ptr(0) + 1);  // in flight during the forward NTT of c
+        // operand row of step p: s2-hat[p], then s1-hat[p - K], then t0-hat[p - K - L] -- consecutive rows of the key's block
+        const int4* rp = reinterpret_cast<const int4*>(sh_all + kn * (size_t)(2 * K + L) * 256 + 8 * lane);
+        int4 nx0 = __ldg(rp), nx1 = __ldg(rp + 1);  // in flight during the forward NTT of c
         // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240) centred, with its Shoup companion
         int32_t ch[8], chs[8];
         load_c_layoutA(cmask + slot * (size_t)CMASK_STRIDE, lane, ch);
@@ -432,24 +449,35 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
             const int idx = phase == 0 ? p : (phase == 1 ? p - K : p - K - L);
             const int32_t sv[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
             if (p + 1 < 2 * K + L) {  // the next step's operand row loads while this step's inverse NTT runs
-                nx0 = __ldg(row_ptr(p + 1));
-                nx1 = __ldg(row_ptr(p + 1) + 1);
+                rp += 64;
+                nx0 = __ldg(rp);
+                nx1 = __ldg(rp + 1);
             }
             // the w rows of a candidate are contiguous: pull the next one into L2
             if (phase == 0 && lane < 8 && idx + 1 < K)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wl + 256 * (idx + 1)) + 128 * lane));
             if (phase == 1 && lane < 5 && idx + 1 < L)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + (idx + 1) * 32 * P::ZBITS + 128 * lane));
+            // What the checks after the inverse transform consume -- the w row (phases 0 and 2) or the packed y
+            // polynomial (phase 1) -- is requested BEFORE the transform: issued after it, these loads were the largest
+            // single stall of the kernel (ncu source page: 9 % of the not-issued samples on their first uses).
+            int4 wx = make_int4(0, 0, 0, 0), wy = wx;
+            uint32_t yw[(P::ZBITS + 3) / 4];
+            int4* const wp = reinterpret_cast<int4*>(wl + 256 * idx + 8 * lane);
+            if (phase == 1) {
+                load_span<P::ZBITS>(yp + idx * 32 * P::ZBITS + P::ZBITS * lane, yw);
+            } else {
+                wx = wp[0];
+                wy = wp[1];
+            }
             int32_t t[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) t[i] = shoup_mul(sv[i], ch[i], chs[i]);  // s-hat rows are prescaled by 1/256
-            sntt_inv_B2B(t, tile, lane);  // c*s2[idx] / c*s1[idx] / c*t0[idx], canonical
+            sntt_inv_B2B(t, tile, lane, z0);  // c*s2[idx] / c*s1[idx] / c*t0[idx], canonical
 
             bool bad = false;
             if (phase == 0) {
                 // r0 = LowBits(w - c*s2), ||r0||inf < gamma2 - beta              ml_dsa.rs:253-260, 268-272
-                int4* wp = reinterpret_cast<int4*>(wl + 256 * idx + 8 * lane);
-                const int4 wx = wp[0], wy = wp[1];
                 const int32_t wv[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
                 int32_t v[8];
 #pragma unroll
@@ -466,12 +494,11 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
                 }
             } else if (phase == 1) {
                 // z = y + c*s1, ||z||inf < gamma1 - beta                          ml_dsa.rs:243-250, 263-265
-                int32_t y[8];
-                load_y<P>(yp + idx * 32 * P::ZBITS, lane, y);
                 uint32_t f[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int32_t z = center(freeze(y[i] + t[i]));                 // z mod+- q (ml_dsa.rs:334-335)
+                    const int32_t y = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(yw, i);  // BitUnpack(gamma1 - 1, gamma1)
+                    const int32_t z = center(freeze(y + t[i]));                    // z mod+- q (ml_dsa.rs:334-335)
                     bad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;
                     f[i] = (uint32_t)(P::GAMMA1 - z);                              // BitPack(z, gamma1 - 1, gamma1)
                 }
@@ -491,8 +518,6 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
                 }
             } else {
                 // ||c*t0||inf < gamma2; h = MakeHint(-ct0, w - cs2 + ct0)          ml_dsa.rs:288-319
-                const int4* wp = reinterpret_cast<const int4*>(wl + 256 * idx + 8 * lane);
-                const int4 wx = wp[0], wy = wp[1];
                 const int32_t v[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
                 uint32_t hbits = 0;
 #pragma unroll
@@ -554,11 +579,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
             warp_zero16(const_cast<uint8_t*>(yraw) + ln * (size_t)j.depth0 * (L * 32 * P::ZBITS), j.depth0 * L * 32 * P::ZBITS, lane);
         }
         warp_zero16(rhopp + ln * 64, 64, lane);
-        if (!SHARED && j.wipe_keys) {
-            warp_zero16(const_cast<int32_t*>(s1h_all) + kn * (size_t)L * 256, L * 1024, lane);
-            warp_zero16(const_cast<int32_t*>(s2h_all) + kn * (size_t)K * 256, K * 1024, lane);
-            warp_zero16(const_cast<int32_t*>(t0h_all) + kn * (size_t)K * 256, K * 1024, lane);
-        }
+        if (!SHARED && j.wipe_keys) warp_zero16(const_cast<int32_t*>(sh_all) + kn * (size_t)(2 * K + L) * 256, (2 * K + L) * 1024, lane);
         __syncwarp();
     }
 }
@@ -638,7 +659,7 @@ static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, 
     {
         KLaunch kl(KID_SIGN_KEY, st);
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
-            nkeys, sk, sk_stride, ws.s1h, ws.s2h, ws.t0h);
+            nkeys, sk, sk_stride, ws.sh);
     }
     return launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
 }
@@ -690,8 +711,8 @@ static cudaError_t sign_round_t(cudaStream_t st, SignRun& r, size_t sz)
                        pos ? r.tail_slots : ~size_t(0));
     if (ce != cudaSuccess) return ce;
     {
-        const SignZJob zj{nact, act, ws.s1h, ws.s2h, ws.t0h, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done, ws.rhopp,
-                          r.sig, r.iters, D, pos, ws.depth, r.tail_slots, ws.kidx, ws.keys_resident ? 0 : 1};
+        const SignZJob zj{nact, act, ws.sh, ws.yraw, ws.w, ws.ctilde, ws.cmask, ws.kappa, ws.done, ws.rhopp,
+                          r.sig, r.iters, D, pos, ws.depth, r.tail_slots, ws.kidx, ws.keys_resident ? 0 : 1, 0};
         KLaunch kl(KID_SIGN_Z, st);
         if (shared) sign_z_kernel<P, true><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(zj);
         else sign_z_kernel<P, false><<<warp_grid(sz), SG_WARPS * 32, 0, st>>>(zj);
@@ -738,25 +759,23 @@ static cudaError_t sign_rounds_until(cudaStream_t st, SignRun& r, double stop_at
 
 // expand_private for a key set (src/ml_dsa.rs:445-469): A-hat and s1-hat / s2-hat / t0-hat of nkeys packed secret keys
 template <class P>
-static cudaError_t sign_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
-                                      int32_t* t0h, bool with_A)
+static cudaError_t sign_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* sh, bool with_A)
 {
     {
         KLaunch kl(KID_SIGN_KEY, st);
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
-            nkeys, sk, P::SK_LEN, s1h, s2h, t0h);
+            nkeys, sk, P::SK_LEN, sh);
     }
     if (!with_A) return cudaGetLastError();  // the caller already holds this key's A-hat (e.g. from keygen)
     return launch_expand_a(st, P::K, P::L, sk, P::SK_LEN, nkeys, A);
 }
-cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* s1h, int32_t* s2h,
-                             int32_t* t0h, bool with_A)
+cudaError_t sign_expand_keys(int ps, cudaStream_t st, size_t nkeys, const uint8_t* sk, int32_t* A, int32_t* sh, bool with_A)
 {
     if (nkeys == 0) return cudaSuccess;
     switch (ps) {
-    case 44: return sign_expand_keys_t<Params<44>>(st, nkeys, sk, A, s1h, s2h, t0h, with_A);
-    case 65: return sign_expand_keys_t<Params<65>>(st, nkeys, sk, A, s1h, s2h, t0h, with_A);
-    case 87: return sign_expand_keys_t<Params<87>>(st, nkeys, sk, A, s1h, s2h, t0h, with_A);
+    case 44: return sign_expand_keys_t<Params<44>>(st, nkeys, sk, A, sh, with_A);
+    case 65: return sign_expand_keys_t<Params<65>>(st, nkeys, sk, A, sh, with_A);
+    case 87: return sign_expand_keys_t<Params<87>>(st, nkeys, sk, A, sh, with_A);
     }
     return cudaErrorInvalidValue;
 }

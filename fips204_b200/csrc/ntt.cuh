@@ -17,6 +17,10 @@
 
 namespace mldsa {
 
+// per-lane packed twiddles of one transform direction (generated into zetas.inc): B stage .ba / .y0 / .y1 by lane,
+// M stage .m by lane >> 2
+struct TwPack { int4 ba[32]; int4 y0[32]; int4 y1[32]; int4 m[8][4]; };
+
 #include "zetas.inc"
 
 __device__ __forceinline__ int32_t mulhi_noadd(int32_t a, int32_t b);
@@ -46,15 +50,16 @@ __device__ __forceinline__ void ct_bfly(int32_t& a, int32_t& b, int32_t z, int32
 // (len = 16, 8, 4 / 4, 8, 16) from the packed tables of zetas.inc: 3 + 4 contiguous 128-bit loads per transform.
 struct TwB { int2 za, zb, y0, y1, y2, y3; };
 struct TwM { int2 z8, za, zb, y0, y1, y2, y3; };
-__device__ __forceinline__ TwB load_twB(const int4* BA, const int4* BY0, const int4* BY1, int lane)
+__device__ __forceinline__ TwB load_twB(const TwPack& T, int lane)
 {
-    const int4 a = __ldg(BA + lane), b = __ldg(BY0 + lane), c = __ldg(BY1 + lane);
+    const int4* p = T.ba + lane;  // .y0[lane] and .y1[lane] are 32 and 64 vectors further on
+    const int4 a = __ldg(p), b = __ldg(p + 32), c = __ldg(p + 64);
     return TwB{make_int2(a.x, a.y), make_int2(a.z, a.w), make_int2(b.x, b.y), make_int2(b.z, b.w), make_int2(c.x, c.y),
                make_int2(c.z, c.w)};
 }
-__device__ __forceinline__ TwM load_twM(const int4 (*M)[4], int lane)
+__device__ __forceinline__ TwM load_twM(const TwPack& T, int lane)
 {
-    const int4* p = M[lane >> 2];
+    const int4* p = T.m[lane >> 2];
     const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
     return TwM{make_int2(a.x, a.y), make_int2(a.z, a.w), make_int2(b.x, b.y), make_int2(b.z, b.w), make_int2(c.x, c.y),
                make_int2(c.z, c.w), make_int2(d.x, d.y)};
@@ -112,7 +117,7 @@ __device__ __forceinline__ void ntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int 
     __syncwarp();
     tile_load_M(tile, lane, v);
     {   // len = 16, 8, 4
-        const TwM w = load_twM(ZMP_FWD_M, lane);
+        const TwM w = load_twM(ZMP_FWD, lane);
         ct_bfly(v[0], v[4], w.z8.x, w.z8.y); ct_bfly(v[1], v[5], w.z8.x, w.z8.y);
         ct_bfly(v[2], v[6], w.z8.x, w.z8.y); ct_bfly(v[3], v[7], w.z8.x, w.z8.y);
         ct_bfly(v[0], v[2], w.za.x, w.za.y); ct_bfly(v[1], v[3], w.za.x, w.za.y);
@@ -124,7 +129,7 @@ __device__ __forceinline__ void ntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int 
     __syncwarp();
     tile_load_B(tile, lane, v);
     {   // len = 2, 1
-        const TwB w = load_twB(ZMP_FWD_BA, ZMP_FWD_BY0, ZMP_FWD_BY1, lane);
+        const TwB w = load_twB(ZMP_FWD, lane);
         ct_bfly(v[0], v[2], w.za.x, w.za.y); ct_bfly(v[1], v[3], w.za.x, w.za.y);
         ct_bfly(v[4], v[6], w.zb.x, w.zb.y); ct_bfly(v[5], v[7], w.zb.x, w.zb.y);
         ct_bfly(v[0], v[1], w.y0.x, w.y0.y); ct_bfly(v[2], v[3], w.y1.x, w.y1.y);
@@ -192,11 +197,17 @@ __device__ __forceinline__ void ct_bfly_s(int32_t& a, int32_t& b, int32_t z, int
     b = (int32_t)((uint32_t)a + (uint32_t)a - (uint32_t)s);
     a = s;
 }
-__device__ __forceinline__ void gs_bfly_s(int32_t& a, int32_t& b, int32_t z, int32_t zs)
+// z0: a register that holds 0 at run time but is opaque to ptxas (a kernel argument).  As a third addend it pins the
+// butterfly's sum and difference to IADD3 on the ALU pipe.  Left to itself ptxas turns part of them into IMAD.IADD
+// (an add on the FMA-heavy pipe) wherever its per-function pipe balance says so -- e.g. 51 of the 64 adds of the
+// inverse transform inside sign_z, a kernel that is bound by exactly that pipe (ncu: fmaheavy 75 %, ALU 47 %).
+// The literal 0 (the default) folds away and leaves the choice to ptxas, which is right for the kernels that run
+// beside Keccak warps (ALU-bound).
+__device__ __forceinline__ void gs_bfly_s(int32_t& a, int32_t& b, int32_t z, int32_t zs, int32_t z0 = 0)
 {
     const int32_t t = a;
-    a = t + b;
-    b = shoup_mul(t - b, z, zs);
+    a = t + b + z0;
+    b = shoup_mul(t - b + z0, z, zs);
 }
 
 // Forward NTT, layout A -> layout B, output = NTT(v) mod q as representatives in (-|in| - 10 q, |in| + 10 q).
@@ -213,7 +224,7 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
     __syncwarp();
     tile_load_M(tile, lane, v);
     {
-        const TwM w = load_twM(ZSP_FWD_M, lane);
+        const TwM w = load_twM(ZSP_FWD, lane);
         ct_bfly_s(v[0], v[4], w.z8.x, w.z8.y); ct_bfly_s(v[1], v[5], w.z8.x, w.z8.y);
         ct_bfly_s(v[2], v[6], w.z8.x, w.z8.y); ct_bfly_s(v[3], v[7], w.z8.x, w.z8.y);
         ct_bfly_s(v[0], v[2], w.za.x, w.za.y); ct_bfly_s(v[1], v[3], w.za.x, w.za.y);
@@ -225,7 +236,7 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
     __syncwarp();
     tile_load_B(tile, lane, v);
     {
-        const TwB w = load_twB(ZSP_FWD_BA, ZSP_FWD_BY0, ZSP_FWD_BY1, lane);
+        const TwB w = load_twB(ZSP_FWD, lane);
         ct_bfly_s(v[0], v[2], w.za.x, w.za.y); ct_bfly_s(v[1], v[3], w.za.x, w.za.y);
         ct_bfly_s(v[4], v[6], w.zb.x, w.zb.y); ct_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
         ct_bfly_s(v[0], v[1], w.y0.x, w.y0.y); ct_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
@@ -239,27 +250,27 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
 // canonical like the reference's (ntt.rs:85-161 returns full_reduce32 values, so only the residue matters and the
 // Shoup butterflies -- five instructions against the nine ptxas makes of the Montgomery form -- give the same output).
 template <bool SCALE256 = false>
-__device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane)
+__device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane, int32_t z0 = 0)
 {
     {
-        const TwB w = load_twB(ZSP_INV_BA, ZSP_INV_BY0, ZSP_INV_BY1, lane);
-        gs_bfly_s(v[0], v[1], w.y0.x, w.y0.y); gs_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
-        gs_bfly_s(v[4], v[5], w.y2.x, w.y2.y); gs_bfly_s(v[6], v[7], w.y3.x, w.y3.y);
-        gs_bfly_s(v[0], v[2], w.za.x, w.za.y); gs_bfly_s(v[1], v[3], w.za.x, w.za.y);
-        gs_bfly_s(v[4], v[6], w.zb.x, w.zb.y); gs_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
+        const TwB w = load_twB(ZSP_INV, lane);
+        gs_bfly_s(v[0], v[1], w.y0.x, w.y0.y, z0); gs_bfly_s(v[2], v[3], w.y1.x, w.y1.y, z0);
+        gs_bfly_s(v[4], v[5], w.y2.x, w.y2.y, z0); gs_bfly_s(v[6], v[7], w.y3.x, w.y3.y, z0);
+        gs_bfly_s(v[0], v[2], w.za.x, w.za.y, z0); gs_bfly_s(v[1], v[3], w.za.x, w.za.y, z0);
+        gs_bfly_s(v[4], v[6], w.zb.x, w.zb.y, z0); gs_bfly_s(v[5], v[7], w.zb.x, w.zb.y, z0);
     }
     __syncwarp();
     tile_store_B(tile, lane, v);
     __syncwarp();
     tile_load_M(tile, lane, v);
     {
-        const TwM w = load_twM(ZSP_INV_M, lane);
-        gs_bfly_s(v[0], v[1], w.y0.x, w.y0.y); gs_bfly_s(v[2], v[3], w.y1.x, w.y1.y);
-        gs_bfly_s(v[4], v[5], w.y2.x, w.y2.y); gs_bfly_s(v[6], v[7], w.y3.x, w.y3.y);
-        gs_bfly_s(v[0], v[2], w.za.x, w.za.y); gs_bfly_s(v[1], v[3], w.za.x, w.za.y);
-        gs_bfly_s(v[4], v[6], w.zb.x, w.zb.y); gs_bfly_s(v[5], v[7], w.zb.x, w.zb.y);
-        gs_bfly_s(v[0], v[4], w.z8.x, w.z8.y); gs_bfly_s(v[1], v[5], w.z8.x, w.z8.y);
-        gs_bfly_s(v[2], v[6], w.z8.x, w.z8.y); gs_bfly_s(v[3], v[7], w.z8.x, w.z8.y);
+        const TwM w = load_twM(ZSP_INV, lane);
+        gs_bfly_s(v[0], v[1], w.y0.x, w.y0.y, z0); gs_bfly_s(v[2], v[3], w.y1.x, w.y1.y, z0);
+        gs_bfly_s(v[4], v[5], w.y2.x, w.y2.y, z0); gs_bfly_s(v[6], v[7], w.y3.x, w.y3.y, z0);
+        gs_bfly_s(v[0], v[2], w.za.x, w.za.y, z0); gs_bfly_s(v[1], v[3], w.za.x, w.za.y, z0);
+        gs_bfly_s(v[4], v[6], w.zb.x, w.zb.y, z0); gs_bfly_s(v[5], v[7], w.zb.x, w.zb.y, z0);
+        gs_bfly_s(v[0], v[4], w.z8.x, w.z8.y, z0); gs_bfly_s(v[1], v[5], w.z8.x, w.z8.y, z0);
+        gs_bfly_s(v[2], v[6], w.z8.x, w.z8.y, z0); gs_bfly_s(v[3], v[7], w.z8.x, w.z8.y, z0);
     }
     // five doubling levels done: |v| < 64 q.  Back under q so that the last three stay inside int32.
 #pragma unroll
@@ -267,14 +278,25 @@ __device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int
     tile_store_M(tile, lane, v);
     __syncwarp();
     tile_load_A(tile, lane, v);
-    gs_bfly_s(v[0], v[1], ZSI7, ZSI7S); gs_bfly_s(v[2], v[3], ZSI6, ZSI6S);
-    gs_bfly_s(v[4], v[5], ZSI5, ZSI5S); gs_bfly_s(v[6], v[7], ZSI4, ZSI4S);
-    gs_bfly_s(v[0], v[2], ZSI3, ZSI3S); gs_bfly_s(v[1], v[3], ZSI3, ZSI3S);
-    gs_bfly_s(v[4], v[6], ZSI2, ZSI2S); gs_bfly_s(v[5], v[7], ZSI2, ZSI2S);
-    gs_bfly_s(v[0], v[4], ZSI1, ZSI1S); gs_bfly_s(v[1], v[5], ZSI1, ZSI1S);
-    gs_bfly_s(v[2], v[6], ZSI1, ZSI1S); gs_bfly_s(v[3], v[7], ZSI1, ZSI1S);
+    gs_bfly_s(v[0], v[1], ZSI7, ZSI7S, z0); gs_bfly_s(v[2], v[3], ZSI6, ZSI6S, z0);
+    gs_bfly_s(v[4], v[5], ZSI5, ZSI5S, z0); gs_bfly_s(v[6], v[7], ZSI4, ZSI4S, z0);
+    gs_bfly_s(v[0], v[2], ZSI3, ZSI3S, z0); gs_bfly_s(v[1], v[3], ZSI3, ZSI3S, z0);
+    gs_bfly_s(v[4], v[6], ZSI2, ZSI2S, z0); gs_bfly_s(v[5], v[7], ZSI2, ZSI2S, z0);
+    if (SCALE256) {
+        // the 1/256 rides on the last level: the difference outputs get it through their twiddle (zeta / 256), the sum
+        // outputs through one product each -- 4 extra products per lane instead of 8
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = freeze(SCALE256 ? shoup_mul(v[i], SC_INV256, SC_INV256S) : v[i]);
+        for (int i = 0; i < 4; i++) {
+            const int32_t t = v[i];
+            v[i] = shoup_mul(t + v[i + 4], SC_INV256, SC_INV256S);
+            v[i + 4] = shoup_mul(t - v[i + 4], ZSI1_256, ZSI1_256S);
+        }
+    } else {
+        gs_bfly_s(v[0], v[4], ZSI1, ZSI1S, z0); gs_bfly_s(v[1], v[5], ZSI1, ZSI1S, z0);
+        gs_bfly_s(v[2], v[6], ZSI1, ZSI1S, z0); gs_bfly_s(v[3], v[7], ZSI1, ZSI1S, z0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = freeze(v[i]);
     __syncwarp();
 }
 __device__ __forceinline__ void sntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int lane)
@@ -285,9 +307,9 @@ __device__ __forceinline__ void sntt_fwd_B2B(int32_t (&v)[8], int32_t* tile, int
     tile_load_A(tile, lane, v);
     sntt_fwd_A2B(v, tile, lane);
 }
-__device__ __forceinline__ void sntt_inv_B2B(int32_t (&v)[8], int32_t* tile, int lane)
+__device__ __forceinline__ void sntt_inv_B2B(int32_t (&v)[8], int32_t* tile, int lane, int32_t z0 = 0)
 {
-    sntt_inv_B2A(v, tile, lane);
+    sntt_inv_B2A(v, tile, lane, z0);
     tile_store_A(tile, lane, v);
     __syncwarp();
     tile_load_B(tile, lane, v);
