@@ -69,9 +69,6 @@ sign_prep_kernel(size_t n, const uint8_t* __restrict__ sk, size_t sk_stride, Msg
 }
 
 constexpr int SG_WARPS = 4;
-#ifndef SG_MINB
-#define SG_MINB 6   // sign_w: its shared memory (y-hat rows, staged A-hat row, NTT tile: 8.8 KB per warp) admits 6 CTAs per SM
-#endif
 #ifndef SZ_MINB
 #define SZ_MINB 5   // sign_z: 96 registers hold the early loads of the w row / y without spills (6: 80 registers, 30.0 ms; 5: 29.5 ms)
 #endif
@@ -94,27 +91,42 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
     for (size_t kn = (size_t)blockIdx.x * SG_WARPS + warp; kn < nkeys; kn += stride) {
         const uint8_t* key = sk + kn * sk_stride;
         int32_t* const rows = sh + kn * (size_t)(2 * K + L) * 256;
+        // packed bytes of polynomial p (this lane's 8 coefficients): eta-bit fields of s1 / s2, 13-bit fields of t0
+        auto fetch = [&](int p, uint32_t (&w)[4]) {
+            if (p < L + K) {
+                uint32_t e[(P::ETABITS + 3) / 4];
+                load_span<P::ETABITS>(key + LO::SK_S1 + p * 32 * P::ETABITS + P::ETABITS * lane, e);
+#pragma unroll
+                for (int i = 0; i < (P::ETABITS + 3) / 4; i++) w[i] = e[i];
+            } else {
+                load_span<13>(key + LO::SK_T0 + (p - L - K) * 416 + 13 * lane, w);
+            }
+        };
+        uint32_t cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
+        fetch(0, cur);
 #pragma unroll 1
         for (int p = 0; p < L + 2 * K; p++) {  // in the packed key's order: s1, s2, t0
+            if (p + 1 < L + 2 * K) fetch(p + 1, nxt);  // in flight during this polynomial's transform
             int32_t v[8];
             int32_t* dst;
+            // The rows are stored prescaled by 1/256 (the inverse transforms of c*s1, c*s2, c*t0 in sign_z do not scale).
+            // 1/256 = -32736 mod q is small, so the factor goes onto the INPUT of the (linear) transform as part of the
+            // unpacking multiply-add -- |input| < 2^12 * 32736 = 16 q, well inside the transform's int32 range -- instead
+            // of eight modular products after it; sign_z's products take any int32 operand.
+            constexpr int32_t C256 = SC_INV256;  // centred representative of 1/256
+            static_assert(C256 > -(1 << 15) && C256 < (1 << 15), "1/256 mod q as a small centred constant");
             if (p < L + K) {  // BitUnpack(eta, eta): s = eta - field            (encodings.rs:185-198)
-                uint32_t w[(P::ETABITS + 3) / 4];
-                load_span<P::ETABITS>(key + LO::SK_S1 + p * 32 * P::ETABITS + P::ETABITS * lane, w);
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = P::ETA - (int32_t)get_field<P::ETABITS>(w, i);
+                for (int i = 0; i < 8; i++) v[i] = (P::ETA - (int32_t)get_field<P::ETABITS>(cur, i)) * C256;
                 dst = rows + (p < L ? K + p : p - L) * 256;
             } else {          // BitUnpack(2^12 - 1, 2^12): t0 = 2^12 - field     (encodings.rs:203-210)
-                uint32_t w[4];
-                load_span<13>(key + LO::SK_T0 + (p - L - K) * 416 + 13 * lane, w);
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = (1 << (D - 1)) - (int32_t)get_field<13>(w, i);
+                for (int i = 0; i < 8; i++) v[i] = ((1 << (D - 1)) - (int32_t)get_field<13>(cur, i)) * C256;
                 dst = rows + p * 256;  // row K + L + (p - L - K)
             }
-            sntt_fwd_B2B(v, tile, lane);
-            // prescaled by 1/256: the inverse transforms of c*s1, c*s2, c*t0 in sign_z do not scale
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = shoup_mul(v[i], SC_INV256, SC_INV256S);
+            for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+            sntt_fwd_B2B(v, tile, lane);
             int4* o = reinterpret_cast<int4*>(dst + 8 * lane);
             o[0] = make_int4(v[0], v[1], v[2], v[3]);
             o[1] = make_int4(v[4], v[5], v[6], v[7]);
@@ -204,11 +216,33 @@ __device__ __forceinline__ void load_y(const uint8_t* ypoly, int lane, int32_t (
 // HBM / L2 (ncu: 40 % of the un-staged kernel's stall samples were long-scoreboard waits on these loads).
 // With an even speculation depth the two candidates of a lane sit on neighbouring warps and SHARE the staged
 // row (G = 2): the row is fetched once for both, and whichever warp finishes its products last issues the next copy.
-#ifndef SW_YREG
-#define SW_YREG 0   // rows of y-hat a warp keeps in registers instead of shared memory during the matrix-vector product
+// sign_w occupancy, per parameter set.  The kernel is bound by latency and by the shared-memory data pipe together
+// (ncu: L1 data-pipe wavefronts 91 %, FMA-heavy pipe 67 %, issue 61 %), so what pays is more resident warps: YREG rows
+// of y-hat stay in registers instead of shared memory during the matrix-vector product (1 KiB of shared memory per
+// warp and 10 wavefronts per row of A-hat each), and MINB CTAs per SM bound the register allocation to match what
+// then fits.  Shared memory per warp: (L - YREG) KiB of y-hat + L / 2 KiB of the staged A-hat row + the NTT tile.
+// Measured, 2^20 lanes (YREG / CTAs per SM: ms): ML-DSA-65 0 / 6 35.64, 1 / 6 35.41, 2 / 5 35.57, 5 / 4 36.96, 1 / 7 34.93;
+// ML-DSA-87 0 / 4 44.58, 1 / 5 41.79, 2 / 5 41.16; ML-DSA-44 0 / 6 21.61, 0 / 7 21.58, 1 / 8 22.02 (spills), 1 / 7 21.27.
+#ifndef SW_YREG_44
+#define SW_YREG_44 1
+#define SW_MINB_44 7
 #endif
+#ifndef SW_YREG_65
+#define SW_YREG_65 1
+#define SW_MINB_65 7
+#endif
+#ifndef SW_YREG_87
+#define SW_YREG_87 2
+#define SW_MINB_87 5
+#endif
+template <int YREG_, int MINB_>
+struct SwTuneT { static constexpr int YREG = YREG_, MINB = MINB_; };
+template <class P> struct SwTune;
+template <> struct SwTune<Params<44>> : SwTuneT<SW_YREG_44, SW_MINB_44> {};
+template <> struct SwTune<Params<65>> : SwTuneT<SW_YREG_65, SW_MINB_65> {};
+template <> struct SwTune<Params<87>> : SwTuneT<SW_YREG_87, SW_MINB_87> {};
 template <class P>
-struct SwYreg { static constexpr int N = SW_YREG < P::L ? SW_YREG : P::L; };
+struct SwYreg { static constexpr int N = SwTune<P>::YREG < P::L ? SwTune<P>::YREG : P::L; };
 template <class P, int G>
 struct alignas(128) SignWStage {
     alignas(128) int32_t arow[SG_WARPS / G][P::L * 256];  // one staged row of A-hat per group of G warps
@@ -219,7 +253,7 @@ struct alignas(128) SignWStage {
 };
 
 template <class P, bool SHARED, int G>
-__global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(SignWJob j)
+__global__ void __launch_bounds__(SG_WARPS * 32, SwTune<P>::MINB) sign_w_staged_kernel(SignWJob j)
 {
     constexpr int K = P::K, L = P::L;
     constexpr uint32_t ROW_BYTES = L * 1024;
@@ -273,6 +307,10 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SG_MINB) sign_w_staged_kernel(S
             }
         };
         release_and_fetch(0);
+#ifdef SW_YPF
+        if (lane < (L - 1) * 32 * P::ZBITS / 128)  // the later y polynomials stream into L2 behind the first one
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 32 * P::ZBITS + 128 * lane));
+#endif
         uint32_t yw[2][(P::ZBITS + 3) / 4];  // packed y of the next polynomial is in flight during an NTT
         load_span<P::ZBITS>(yp + P::ZBITS * lane, yw[0]);
         constexpr int YR = SwYreg<P>::N;

@@ -135,6 +135,8 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ sig,
         const int32_t* t1h = t1h_shared + (MODE == 2 ? key * (size_t)K * 256 : 0);
         uint8_t* w1o = mw1 + ln * (size_t)(MU_BYTES + P::W1_LEN) + MU_BYTES;
         __syncwarp();
+        // the signature this warp handles next streams from HBM into L2 while this one is verified
+        if (ln + stride < n) warp_prefetch_l2(sig + (ln + stride) * (size_t)P::SIG_LEN, P::SIG_LEN, lane);
 
         // ---- HintBitUnpack with its three malformed-input exits (conversion.rs:357, :373, :398) ----
         uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);
@@ -172,16 +174,18 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ sig,
         }
 
         // ---- z = BitUnpack(gamma1 - 1, gamma1), ||z||inf check, z-hat (kept in shared memory) ----
+        // the packed bytes of polynomial l + 1 are in flight during the transform of polynomial l
         bool zbad = false;
-#pragma unroll 1
+        uint32_t zw[2][(P::ZBITS + 3) / 4];
+        load_span<P::ZBITS>(sg + LO::SIG_Z + P::ZBITS * lane, zw[0]);
+#pragma unroll
         for (int l = 0; l < L; l++) {
-            uint32_t w[(P::ZBITS + 3) / 4];
-            load_span<P::ZBITS>(sg + LO::SIG_Z + l * 32 * P::ZBITS + P::ZBITS * lane, w);
+            if (l + 1 < L) load_span<P::ZBITS>(sg + LO::SIG_Z + (l + 1) * 32 * P::ZBITS + P::ZBITS * lane, zw[(l + 1) & 1]);
             int32_t zv[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int32_t z = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(w, i);  // conversion.rs:250
-                zbad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;                   // ml_dsa.rs:434
+                const int32_t z = P::GAMMA1 - (int32_t)get_field<P::ZBITS>(zw[l & 1], i);  // conversion.rs:250
+                zbad |= (z < 0 ? -z : z) >= P::GAMMA1 - P::BETA;                           // ml_dsa.rs:434
                 zv[i] = z;
             }
             sntt_fwd_B2B(zv, tile, lane);

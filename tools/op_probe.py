@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """One device-resident operation, a few times (for ncu captures and quick A/B timing):
-    python tools/op_probe.py keygen|verify|sign|sk2pk [ps] [lanes] [reps]"""
+    python tools/op_probe.py keygen|verify|verify_shared|sign|sk2pk [ps] [lanes] [reps]"""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -35,11 +35,14 @@ ok = torch.zeros(n, dtype=torch.uint8, device=dev)
 _lib.check(L.mldsa_keygen_batch_dev(ps, sh, n, p(xi), p(pk), p(sk)))
 if op == "verify":
     _lib.check(L.mldsa_sign_batch_dev(ps, sh, 0, n, p(sk), m.SK_LEN, p(msg), p(moff), None, None, p(rnd), p(sig), None))
+if op == "verify_shared":  # every lane under key 0
+    _lib.check(L.mldsa_sign_batch_dev(ps, sh, 0, n, p(sk), 0, p(msg), p(moff), None, None, p(rnd), p(sig), None))
 fn = {
     "keygen": lambda: L.mldsa_keygen_batch_dev(ps, sh, n, p(xi), p(pk), p(sk)),
     "sk2pk": lambda: L.mldsa_sk_to_pk_batch_dev(ps, sh, n, p(sk), p(pk)),
     "sign": lambda: L.mldsa_sign_batch_dev(ps, sh, 0, n, p(sk), m.SK_LEN, p(msg), p(moff), None, None, p(rnd), p(sig), None),
     "verify": lambda: L.mldsa_verify_batch_dev(ps, sh, 0, n, p(pk), m.PK_LEN, p(msg), p(moff), None, None, p(sig), p(ok)),
+    "verify_shared": lambda: L.mldsa_verify_batch_dev(ps, sh, 0, n, p(pk), 0, p(msg), p(moff), None, None, p(sig), p(ok)),
 }[op]
 L.mldsa_profile_enable(1)
 for r in range(reps):
@@ -55,4 +58,6 @@ for r in range(reps):
         L.mldsa_profile_get(i, C.byref(ms), C.byref(cnt))
         if cnt.value:
             parts.append(f"{L.mldsa_profile_name(i).decode()} {ms.value:.2f}")
+    if op.startswith("verify"):
+        assert bool(ok.all()), "verify rejected valid signatures"
     print(f"{op}{ps} n={n}: {e0.elapsed_time(e1):.2f} ms  = {n / e0.elapsed_time(e1) / 1e3:.2f} M/s | " + "  ".join(parts), flush=True)

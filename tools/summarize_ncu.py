@@ -18,7 +18,12 @@ METRICS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active%"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "pipe_alu%"),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "pipe_fma%"),
+    # IMAD / IMAD.HI / IMAD.WIDE all issue to the FMA-HEAVY half of the FMA pipe (an IMAD.HI holds it 4 cycles): this,
+    # not pipe_fma%, is the arithmetic kernels' busiest math pipe
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy%"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "pipe_lsu%"),
+    # shared-memory + global wavefronts through the L1 data pipe (one per cycle and SM)
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1_wavefronts%"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
     ("dram__bytes_read.sum", "dram_rd"),
     ("dram__bytes_write.sum", "dram_wr"),
@@ -129,6 +134,8 @@ def kernels_json(rep, tag, lanes, ps):
                     "pipe_alu_pct": val(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                     "pipe_fma_pct": val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                     "pipe_lsu_pct": val(r, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                    "pipe_fmaheavy_pct": val(r, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                    "l1_wavefronts_pct": val(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                     "dram_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                     "dram_read_bytes": val(r, "dram__bytes_read.sum", True), "dram_write_bytes": val(r, "dram__bytes_write.sum", True),
                     "regs": val(r, "launch__registers_per_thread"), "warp_inst": val(r, "smsp__inst_executed.sum"),
