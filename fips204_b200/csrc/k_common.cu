@@ -28,7 +28,13 @@ namespace mldsa {
 // p ~ 1e-39 -- handled exactly, not assumed away.
 // ------------------------------------------------------------------------------------------------
 constexpr int EA_THREADS = 128;
-constexpr int EA_ROW = 64;  // words per thread: 3 carried + 56 candidates, rounded up to whole int4s
+// Words per thread: 3 carried + 56 candidates, rounded up to whole int4s = 60, then padded to 68 = 4 (mod 32).  With
+// rows 64 words apart every thread's word j sat in the SAME bank: each of the 56 candidate stores of a block was a
+// 32-way conflict and each 128-bit flush load an 8-way one (ncu: 9.5e9 bank conflicts per launch, the L1 data pipe at
+// 98 % of its wavefront peak -- the kernel was bound by it as much as by the ALU pipe, which sat at 91 %).  At 68 the
+// 128-bit loads of a quarter-warp cover all 32 banks and the 32-bit stores are 4-way conflicts (the minimum for rows of
+// contiguous int4s): ~280 instead of ~2 300 wavefronts per block and warp.
+constexpr int EA_ROW = 68;
 
 // SYNTH (test hook, mldsa_debug_rej_ntt_stream): the squeeze blocks come from a caller-supplied byte stream
 // (rho_stride / 168 blocks of 168 bytes per polynomial) instead of the permutation, so that a test can force the

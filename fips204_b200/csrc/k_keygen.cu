@@ -39,7 +39,10 @@ __global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict_
 // flush, whose 32 x (2 shuffles + copy loop) per block cost this ALU-bound kernel 30 % of its instructions).
 // Output: int8 coefficients in [-eta, eta].
 constexpr int RB_THREADS = 128;
-constexpr int RB_ROW = 288;  // bytes per thread: <= 15 carried + 272 nibbles of a block, as whole int4s
+// Bytes per thread: <= 15 carried + 272 nibbles of a block, as whole int4s = 288, padded to 304 = 76 words = 12 (mod 32):
+// the 128-bit flush loads of a quarter-warp then cover all 32 banks, the byte stores are 4-way conflicts (288 = 8 (mod
+// 32) words made them 8-way and the loads 2-way; see EA_ROW in k_common.cu).
+constexpr int RB_ROW = 304;
 
 template <int ETA>
 __global__ void __launch_bounds__(RB_THREADS, 4)
@@ -83,7 +86,7 @@ rej_bounded_kernel(const uint8_t* __restrict__ seeds, size_t nstreams, int KL /*
         const int ng = min(have >> 4, groups_left);
         const int4* src = reinterpret_cast<const int4*>(row);
 #pragma unroll
-        for (int k = 0; k < RB_ROW / 16 - 1; k++)
+        for (int k = 0; k < (15 + 272) / 16; k++)  // at most 17 complete groups per block
             if (k < ng) dst[k] = src[k];
         const int4 tail = src[have >> 4];  // the incomplete group (a finished stream parks garbage there)
         dst += ng;
