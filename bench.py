@@ -528,10 +528,11 @@ def main():
             k["bound"] = "ALU pipe (Keccak: LOP3 / SHF)"
             k["alu_pipe_frac"] = ops / (per * 1e-3) / alu_peak if per else None
         else:
-            k["bound"] = "issue / FMA pipe / latency (see ncu)"
+            k["bound"] = "latency + FMA-heavy pipe (IMAD / IMAD.HI) + L1 data-pipe wavefronts (see ncu)"
         rec = ncu.get(f"{name}:{args.ps}")
         if rec:
-            k["ncu"] = {x: rec[x] for x in ("issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_lsu_pct", "dram_pct", "source") if x in rec}
+            k["ncu"] = {x: rec[x] for x in ("issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_fmaheavy_pct", "pipe_lsu_pct",
+                                            "l1_wavefronts_pct", "dram_pct", "source") if x in rec}
         kernels[name] = k
     top = max(prof, key=lambda kk: prof[kk][0]) if prof else None
     peaks_file = ROOT / "MEASURED_PEAKS.json"

@@ -883,7 +883,7 @@ int mldsa_verify_batch_dev(int ps, void* stream, int framing, size_t n, const ui
 
 int mldsa_ntt_batch_dev(void* stream, size_t n, int32_t* d_polys)
 {
-    if (n && !d_polys) return E_PARAM;
+    if (n && (!d_polys || (reinterpret_cast<uintptr_t>(d_polys) & 31))) return E_PARAM;  // rows move as 256-bit vectors
     CK(launch_ntt((cudaStream_t)stream, d_polys, n, false));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     prof_collect();
@@ -891,7 +891,7 @@ int mldsa_ntt_batch_dev(void* stream, size_t n, int32_t* d_polys)
 }
 int mldsa_intt_batch_dev(void* stream, size_t n, int32_t* d_polys)
 {
-    if (n && !d_polys) return E_PARAM;
+    if (n && (!d_polys || (reinterpret_cast<uintptr_t>(d_polys) & 31))) return E_PARAM;
     CK(launch_ntt((cudaStream_t)stream, d_polys, n, true));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     prof_collect();

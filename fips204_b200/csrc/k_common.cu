@@ -34,7 +34,10 @@ constexpr int EA_THREADS = 128;
 // 98 % of its wavefront peak -- the kernel was bound by it as much as by the ALU pipe, which sat at 91 %).  At 68 the
 // 128-bit loads of a quarter-warp cover all 32 banks and the 32-bit stores are 4-way conflicts (the minimum for rows of
 // contiguous int4s): ~280 instead of ~2 300 wavefronts per block and warp.
-constexpr int EA_ROW = 68;
+#ifndef EA_ROW_WORDS
+#define EA_ROW_WORDS 68
+#endif
+constexpr int EA_ROW = EA_ROW_WORDS;
 
 // SYNTH (test hook, mldsa_debug_rej_ntt_stream): the squeeze blocks come from a caller-supplied byte stream
 // (rho_stride / 168 blocks of 168 bytes per polynomial) instead of the permutation, so that a test can force the
@@ -174,6 +177,27 @@ __device__ __forceinline__ void stg_stream4(int4* p, int4 v)
 {
     asm volatile("st.global.cs.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+// a lane's 8 coefficients (one 32-byte sector) in one 256-bit streaming access (pack.cuh: Row8)
+__device__ __forceinline__ void ldg_stream8(const int32_t* p, int32_t (&v)[8])
+{
+#ifndef NO_V8
+    asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+#else
+    const int4 x = ldg_stream4(reinterpret_cast<const int4*>(p)), y = ldg_stream4(reinterpret_cast<const int4*>(p) + 1);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+#endif
+}
+__device__ __forceinline__ void stg_stream8(int32_t* p, const int32_t (&v)[8])
+{
+#ifndef NO_V8
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+#else
+    stg_stream4(reinterpret_cast<int4*>(p), make_int4(v[0], v[1], v[2], v[3]));
+    stg_stream4(reinterpret_cast<int4*>(p) + 1, make_int4(v[4], v[5], v[6], v[7]));
+#endif
+}
 
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict__ polys, size_t n)
@@ -194,13 +218,9 @@ __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = ldg_stream(g + 32 * i + lane);
             ntt_fwd_A2B(v, tile, lane);
-            int4* o = reinterpret_cast<int4*>(g + 8 * lane);
-            stg_stream4(o, make_int4(v[0], v[1], v[2], v[3]));
-            stg_stream4(o + 1, make_int4(v[4], v[5], v[6], v[7]));
+            stg_stream8(g + 8 * lane, v);
         } else {
-            const int4* in = reinterpret_cast<const int4*>(g + 8 * lane);
-            const int4 x = ldg_stream4(in), y = ldg_stream4(in + 1);
-            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+            ldg_stream8(g + 8 * lane, v);
             sntt_inv_B2A<true>(v, tile, lane);
 #pragma unroll
             for (int i = 0; i < 8; i++) stg_stream(g + 32 * i + lane, v[i]);

@@ -148,11 +148,9 @@ kg_arith_kernel(size_t n, const uint8_t* __restrict__ seeds, const int8_t* __res
             for (int i = 0; i < 8; i++) acc[i] = 0;
 #pragma unroll
             for (int l = 0; l < L; l++) {
-                const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
-                const int4 x = __ldg(ap), y = __ldg(ap + 1);
-                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                const Row8 av = ldg_row8(A + (size_t)(k * L + l) * 256 + 8 * lane);  // read once: one 256-bit load
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * s1h[l][i];
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av.v[i] * s1h[l][i];
             }
             int32_t t[8];
 #pragma unroll

@@ -127,9 +127,7 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
 #pragma unroll
             for (int i = 0; i < 4; i++) cur[i] = nxt[i];
             sntt_fwd_B2B(v, tile, lane);
-            int4* o = reinterpret_cast<int4*>(dst + 8 * lane);
-            o[0] = make_int4(v[0], v[1], v[2], v[3]);
-            o[1] = make_int4(v[4], v[5], v[6], v[7]);
+            st_row8(dst + 8 * lane, v);
         }
     }
 }
@@ -372,9 +370,7 @@ __global__ void __launch_bounds__(SG_WARPS * 32, SwTune<P>::MINB) sign_w_staged_
                 }
             }
             sntt_inv_B2B(t, tile, lane);  // w[k], canonical (A-hat is prescaled by 2^32 / 256)
-            int4* o = reinterpret_cast<int4*>(wo + 256 * k + 8 * lane);
-            o[0] = make_int4(t[0], t[1], t[2], t[3]);
-            o[1] = make_int4(t[4], t[5], t[6], t[7]);
+            st_row8(wo + 256 * k + 8 * lane, t);
             uint32_t f[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -470,8 +466,16 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
         rej = false;
         int hcount = 0;
         // operand row of step p: s2-hat[p], then s1-hat[p - K], then t0-hat[p - K - L] -- consecutive rows of the key's block
-        const int4* rp = reinterpret_cast<const int4*>(sh_all + kn * (size_t)(2 * K + L) * 256 + 8 * lane);
-        int4 nx0 = __ldg(rp), nx1 = __ldg(rp + 1);  // in flight during the forward NTT of c
+        // (a shared key's rows stay hot in L1: 128-bit __ldg; per-lane keys stream: one 256-bit load)
+        const int32_t* rp = sh_all + kn * (size_t)(2 * K + L) * 256 + 8 * lane;
+        auto load_row = [&](const int32_t* r) {
+            if (!SHARED) return ldg_row8(r);
+            Row8 o;
+            const int4 x = __ldg(reinterpret_cast<const int4*>(r)), y = __ldg(reinterpret_cast<const int4*>(r) + 1);
+            o.v[0] = x.x; o.v[1] = x.y; o.v[2] = x.z; o.v[3] = x.w; o.v[4] = y.x; o.v[5] = y.y; o.v[6] = y.z; o.v[7] = y.w;
+            return o;
+        };
+        Row8 nx = load_row(rp);  // in flight during the forward NTT of c
         // c from the challenge masks, c-hat = NTT(c) (ml_dsa.rs:237-240) centred, with its Shoup companion
         int32_t ch[8], chs[8];
         load_c_layoutA(cmask + slot * (size_t)CMASK_STRIDE, lane, ch);
@@ -485,11 +489,10 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
         for (int p = 0; p < 2 * K + L && !rej; p++) {
             const int phase = p < K ? 0 : (p < K + L ? 1 : 2);
             const int idx = phase == 0 ? p : (phase == 1 ? p - K : p - K - L);
-            const int32_t sv[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+            const Row8 sv = nx;
             if (p + 1 < 2 * K + L) {  // the next step's operand row loads while this step's inverse NTT runs
-                rp += 64;
-                nx0 = __ldg(rp);
-                nx1 = __ldg(rp + 1);
+                rp += 256;
+                nx = load_row(rp);
             }
             // the w rows of a candidate are contiguous: pull the next one into L2
             if (phase == 0 && lane < 8 && idx + 1 < K)
@@ -499,37 +502,32 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
             // What the checks after the inverse transform consume -- the w row (phases 0 and 2) or the packed y
             // polynomial (phase 1) -- is requested BEFORE the transform: issued after it, these loads were the largest
             // single stall of the kernel (ncu source page: 9 % of the not-issued samples on their first uses).
-            int4 wx = make_int4(0, 0, 0, 0), wy = wx;
+            Row8 wrow{};
             uint32_t yw[(P::ZBITS + 3) / 4];
-            int4* const wp = reinterpret_cast<int4*>(wl + 256 * idx + 8 * lane);
+            int32_t* const wp = wl + 256 * idx + 8 * lane;
             if (phase == 1) {
                 load_span<P::ZBITS>(yp + idx * 32 * P::ZBITS + P::ZBITS * lane, yw);
             } else {
-                wx = wp[0];
-                wy = wp[1];
+                wrow = ld_row8(wp);
             }
             int32_t t[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = shoup_mul(sv[i], ch[i], chs[i]);  // s-hat rows are prescaled by 1/256
+            for (int i = 0; i < 8; i++) t[i] = shoup_mul(sv.v[i], ch[i], chs[i]);  // s-hat rows are prescaled by 1/256
             sntt_inv_B2B(t, tile, lane, z0);  // c*s2[idx] / c*s1[idx] / c*t0[idx], canonical
 
             bool bad = false;
             if (phase == 0) {
                 // r0 = LowBits(w - c*s2), ||r0||inf < gamma2 - beta              ml_dsa.rs:253-260, 268-272
-                const int32_t wv[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
                 int32_t v[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    v[i] = caddq(wv[i] - t[i]);  // w - cs2, canonical
+                    v[i] = caddq(wrow.v[i] - t[i]);  // w - cs2, canonical
                     int32_t r0;
                     decompose<P::GAMMA2>(v[i], r0);
                     bad |= (r0 < 0 ? -r0 : r0) >= P::GAMMA2 - P::BETA;
                 }
                 rej = __any_sync(0xffffffffu, bad);
-                if (!rej) {  // w is only ever needed as w - cs2 from here on
-                    wp[0] = make_int4(v[0], v[1], v[2], v[3]);
-                    wp[1] = make_int4(v[4], v[5], v[6], v[7]);
-                }
+                if (!rej) st_row8(wp, v);  // w is only ever needed as w - cs2 from here on
             } else if (phase == 1) {
                 // z = y + c*s1, ||z||inf < gamma1 - beta                          ml_dsa.rs:243-250, 263-265
                 uint32_t f[8];
@@ -556,7 +554,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
                 }
             } else {
                 // ||c*t0||inf < gamma2; h = MakeHint(-ct0, w - cs2 + ct0)          ml_dsa.rs:288-319
-                const int32_t v[8] = {wx.x, wx.y, wx.z, wx.w, wy.x, wy.y, wy.z, wy.w};
+                const int32_t (&v)[8] = wrow.v;
                 uint32_t hbits = 0;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {

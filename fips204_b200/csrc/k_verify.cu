@@ -75,9 +75,7 @@ t1hat_kernel(const uint8_t* __restrict__ pk, int32_t* __restrict__ t1h)
     for (int k = warp; k < P::K; k += 4) {
         int32_t v[8];
         load_t1_hat(pk + 32 + 320 * k, v, tiles[warp], lane);
-        int4* o = reinterpret_cast<int4*>(t1h + 256 * k + 8 * lane);
-        o[0] = make_int4(v[0], v[1], v[2], v[3]);
-        o[1] = make_int4(v[4], v[5], v[6], v[7]);
+        st_row8(t1h + 256 * k + 8 * lane, v);
     }
 }
 
@@ -94,9 +92,7 @@ t1hat_batch_kernel(size_t nkeys, const uint8_t* __restrict__ pk, int32_t* __rest
         const int k = (int)(q % P::K);
         int32_t v[8];
         load_t1_hat(pk + key * (size_t)P::PK_LEN + 32 + 320 * k, v, tiles[warp], lane);
-        int4* o = reinterpret_cast<int4*>(t1h + q * 256 + 8 * lane);
-        o[0] = make_int4(v[0], v[1], v[2], v[3]);
-        o[1] = make_int4(v[4], v[5], v[6], v[7]);
+        st_row8(t1h + q * 256 + 8 * lane, v);
     }
 }
 
@@ -209,25 +205,26 @@ verify_arith_kernel(size_t n, const uint8_t* __restrict__ sig,
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
             if (!SHARED && k + 2 < K) warp_prefetch_l2(A + (size_t)(k + 2) * L * 256, L * 1024, lane);
-            int32_t t1v[8];
-            {
-                const int4* tp = reinterpret_cast<const int4*>(t1h + 256 * k + 8 * lane);
-                const int4 x = __ldg(tp), y = __ldg(tp + 1);
-                t1v[0] = x.x; t1v[1] = x.y; t1v[2] = x.z; t1v[3] = x.w;
-                t1v[4] = y.x; t1v[5] = y.y; t1v[6] = y.z; t1v[7] = y.w;
-            }
+            // one shared key: its 36 KiB of A-hat / t1-hat stay hot in L1 (128-bit __ldg); a resident key set streams
+            // each lane's rows once (256-bit loads, pack.cuh)
+            auto load_row = [&](const int32_t* r) {
+                if (!SHARED) return ldg_row8(r);
+                Row8 o;
+                const int4 x = __ldg(reinterpret_cast<const int4*>(r)), y = __ldg(reinterpret_cast<const int4*>(r) + 1);
+                o.v[0] = x.x; o.v[1] = x.y; o.v[2] = x.z; o.v[3] = x.w; o.v[4] = y.x; o.v[5] = y.y; o.v[6] = y.z; o.v[7] = y.w;
+                return o;
+            };
+            const Row8 t1v = load_row(t1h + 256 * k + 8 * lane);
             int64_t acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = -(int64_t)ch[i] * t1v[i];
+            for (int i = 0; i < 8; i++) acc[i] = -(int64_t)ch[i] * t1v.v[i];
 #pragma unroll
             for (int l = 0; l < L; l++) {
-                const int4* ap = reinterpret_cast<const int4*>(A + (size_t)(k * L + l) * 256 + 8 * lane);
-                const int4 x = __ldg(ap), y = __ldg(ap + 1);
-                const int32_t av[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                const Row8 av = load_row(A + (size_t)(k * L + l) * 256 + 8 * lane);
                 int32_t zz[8];
                 row_load(sm.zh[l], lane, zz);
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av[i] * zz[i];
+                for (int i = 0; i < 8; i++) acc[i] += (int64_t)av.v[i] * zz[i];
             }
             int32_t t[8];
 #pragma unroll

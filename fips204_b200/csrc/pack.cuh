@@ -68,6 +68,46 @@ __device__ __forceinline__ void store_span(uint8_t* dst, const uint32_t (&w)[(NB
     }
 }
 
+// A lane's 8 coefficients (32 bytes, 32-byte aligned: one sector) in ONE 256-bit access (sm_100: LDG / STG .256).
+// As 2 x 128-bit each store instruction of a warp filled half of every sector it touched, i.e. two write requests per
+// sector towards L2 (ncu, sign_key: 33 GB leave L1 for 18 GB of rows).  Used for the streamed per-lane rows; rows that
+// are meant to stay hot in L1 (a shared key's A-hat / s-hat) keep the 128-bit __ldg path.  -DNO_V8: the old form.
+struct Row8 { int32_t v[8]; };
+__device__ __forceinline__ Row8 ld_row8(const int32_t* p)  // coherent (data this kernel also writes)
+{
+    Row8 r;
+#ifndef NO_V8
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+#else
+    const int4 x = reinterpret_cast<const int4*>(p)[0], y = reinterpret_cast<const int4*>(p)[1];
+    r.v[0] = x.x; r.v[1] = x.y; r.v[2] = x.z; r.v[3] = x.w; r.v[4] = y.x; r.v[5] = y.y; r.v[6] = y.z; r.v[7] = y.w;
+#endif
+    return r;
+}
+__device__ __forceinline__ Row8 ldg_row8(const int32_t* p)  // read-only for the lifetime of the kernel
+{
+    Row8 r;
+#ifndef NO_V8
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+#else
+    const int4 x = __ldg(reinterpret_cast<const int4*>(p)), y = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    r.v[0] = x.x; r.v[1] = x.y; r.v[2] = x.z; r.v[3] = x.w; r.v[4] = y.x; r.v[5] = y.y; r.v[6] = y.z; r.v[7] = y.w;
+#endif
+    return r;
+}
+__device__ __forceinline__ void st_row8(int32_t* p, const int32_t (&v)[8])
+{
+#ifndef NO_V8
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+#else
+    reinterpret_cast<int4*>(p)[0] = make_int4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<int4*>(p)[1] = make_int4(v[4], v[5], v[6], v[7]);
+#endif
+}
+
 // Warp-cooperative L2 prefetch of `bytes` starting at p (128-byte lines): the streamed per-lane operands
 // (rows of A-hat, s-hat, w) are pulled from HBM into L2 while the warp is busy with an NTT, so the
 // demand loads that follow see L2 latency instead of DRAM latency.

@@ -132,7 +132,8 @@ int mldsa_pipeline_batch_multi(int ps, const int* devs, int ndev, int framing, s
 
 /* ---- microbench / leaf entry points (BASELINE config 2) ----------------------------------
  * ntt: src/ntt.rs:14-76, raw-bit-exact representatives; intt: src/ntt.rs:85-161, canonical [0,q).
- * expand_a: out[i] = RejNTTPoly(seed34[i]), src/hashing.rs:111-146.  In place on n x 256 int32. */
+ * expand_a: out[i] = RejNTTPoly(seed34[i]), src/hashing.rs:111-146.  In place on n x 256 int32.
+ * Device pointers of the _dev forms: polynomials 32-byte aligned (-1 otherwise; cudaMalloc gives 256). */
 int mldsa_ntt_batch(int dev, size_t n, int32_t* polys);
 int mldsa_intt_batch(int dev, size_t n, int32_t* polys);
 int mldsa_expand_a_batch(int dev, size_t n, const uint8_t* seed34, int32_t* out);
