@@ -16,10 +16,10 @@ ncu --set full --clock-control none -k regex:"kg_fused|rej_bounded|shake_rows|ve
     -c 16 -o /tmp/prof_ops -f python tools/bench_ops.py --sets 65 --reps 1 > /dev/null 2>&1
 python tools/summarize_ncu.py $TAG/ops65 --rep /tmp/prof_ops.ncu-rep --lanes 1048576 --ps 65 \
     --note "\`tools/bench_ops.py --sets 65 --reps 1\` under \`ncu --set full --clock-control none\`: the NTT / INTT microbench (configs[1]), keygen (ExpandA fused with the matrix-vector product: kg_fused) and per-lane-key verify (verify_fused) at 2^20 lanes, ML-DSA-65; every kernel appears twice (warm-up + timed call)."
-ncu --set full --clock-control none -k regex:"verify_arith_kernel|verify_pre_kernel|ctilde_kernel" \
-    -c 3 -o /tmp/prof_vs -f python tools/op_probe.py verify_shared 65 1048576 1 > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:"verify_arith_kernel|verify_pre_kernel" \
+    -c 2 -o /tmp/prof_vs -f python tools/op_probe.py verify_shared 65 1048576 1 > /dev/null 2>&1
 python tools/summarize_ncu.py $TAG/verify_shared65 --rep /tmp/prof_vs.ncu-rep \
-    --note "\`tools/op_probe.py verify_shared 65 1048576 1\`: the three kernels of a verify under ONE shared public key (cached A-hat, tr, t1-hat: BASELINE configs[2]'s shape) at 2^20 lanes, ML-DSA-65."
+    --note "\`tools/op_probe.py verify_shared 65 1048576 1\`: verify_pre and verify_arith of a verify under ONE shared public key (cached A-hat, tr, t1-hat: BASELINE configs[2]'s shape) at 2^20 lanes, ML-DSA-65."
 ncu --set full --clock-control none -k regex:"kg_arith_kernel|verify_arith_kernel|t1hat|expand_a_kernel" \
     -c 4 -o /tmp/prof_pipe -f python tools/pipeline_probe.py 262144 1 87 > /dev/null 2>&1
 python tools/summarize_ncu.py $TAG/pipeline87 --rep /tmp/prof_pipe.ncu-rep --lanes 32768 --ps 87 \
