@@ -30,6 +30,7 @@
 #include "engine.h"
 #include "keccak.cuh"
 #include "ntt.cuh"
+#include "ntt16.cuh"
 #include "pack.cuh"
 #include "sampling.cuh"
 #include "ctilde.cuh"
@@ -128,6 +129,64 @@ sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, 
             for (int i = 0; i < 4; i++) cur[i] = nxt[i];
             sntt_fwd_B2B(v, tile, lane);
             st_row8(dst + 8 * lane, v);
+        }
+    }
+}
+
+// The same with two polynomials per warp (ntt16.cuh: a half-warp per polynomial, 16 coefficients per lane): 32 instead
+// of 48 shared-memory wavefronts per transform and one set of twiddle loads for both -- this kernel was at 93 % of the L1
+// data pipe's wavefront peak.  Half-warp h takes polynomial pp + h of the pair; an odd polynomial count leaves the
+// second half of the last pair transforming a duplicate that is not stored.
+#ifndef SK16_MINB
+#define SK16_MINB 6
+#endif
+template <class P>
+__global__ void __launch_bounds__(SG_WARPS * 32, SK16_MINB)
+sign_key16_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, int32_t* __restrict__ sh)
+{
+    using LO = Layout<P>;
+    constexpr int K = P::K, L = P::L, NP = L + 2 * K;
+    __shared__ __align__(16) int32_t tiles[SG_WARPS][T16_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, h = lane >> 4, t = lane & 15;
+    int32_t* tile = tiles[warp] + h * T16_POLY;
+    const size_t stride = (size_t)gridDim.x * SG_WARPS;
+    for (size_t kn = (size_t)blockIdx.x * SG_WARPS + warp; kn < nkeys; kn += stride) {
+        const uint8_t* key = sk + kn * sk_stride;
+        int32_t* const rows = sh + kn * (size_t)NP * 256;
+        // packed bytes of this lane's 16 coefficients of polynomial p: 2 * eta-bits bytes (s1 / s2) or 26 bytes (t0)
+        auto fetch = [&](int p, uint32_t (&w)[7]) {
+            if (p < L + K) {
+                uint32_t e[(2 * P::ETABITS + 3) / 4];
+                load_span<2 * P::ETABITS>(key + LO::SK_S1 + p * 32 * P::ETABITS + 2 * P::ETABITS * t, e);
+#pragma unroll
+                for (int i = 0; i < (2 * P::ETABITS + 3) / 4; i++) w[i] = e[i];
+            } else {
+                load_span<26>(key + LO::SK_T0 + (p - L - K) * 416 + 26 * t, w);
+            }
+        };
+        auto poly_of = [&](int pp) { return pp + h < NP ? pp + h : NP - 1; };
+        uint32_t cur[7] = {0, 0, 0, 0, 0, 0, 0}, nxt[7] = {0, 0, 0, 0, 0, 0, 0};
+        fetch(poly_of(0), cur);
+#pragma unroll 1
+        for (int pp = 0; pp < NP; pp += 2) {  // in the packed key's order: s1, s2, t0
+            const int p = poly_of(pp);
+            if (pp + 2 < NP) fetch(poly_of(pp + 2), nxt);  // in flight during this pair's transform
+            constexpr int32_t C256 = SC_INV256;  // 1/256 mod q, centred and small: rides on the unpacking multiply (see sign_key_kernel)
+            int32_t v[16];
+            int row;
+            if (p < L + K) {  // BitUnpack(eta, eta): s = eta - field            (encodings.rs:185-198)
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = (P::ETA - (int32_t)get_field<P::ETABITS>(cur, i)) * C256;
+                row = p < L ? K + p : p - L;
+            } else {          // BitUnpack(2^12 - 1, 2^12): t0 = 2^12 - field     (encodings.rs:203-210)
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = ((1 << (D - 1)) - (int32_t)get_field<13>(cur, i)) * C256;
+                row = p;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) cur[i] = nxt[i];
+            sntt16_fwd(v, tile, t);
+            if (pp + h < NP) st_row16(rows + row * 256 + 16 * t, v);
         }
     }
 }
@@ -694,8 +753,13 @@ static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, 
     if (ws.keys_resident) return cudaGetLastError();  // A-hat and the s-hat rows come from a loaded key set
     {
         KLaunch kl(KID_SIGN_KEY, st);
+#ifndef NO_SK16
+        sign_key16_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
+            nkeys, sk, sk_stride, ws.sh);
+#else
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
             nkeys, sk, sk_stride, ws.sh);
+#endif
     }
     return launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
 }
@@ -799,8 +863,13 @@ static cudaError_t sign_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8
 {
     {
         KLaunch kl(KID_SIGN_KEY, st);
+#ifndef NO_SK16
+        sign_key16_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
+            nkeys, sk, P::SK_LEN, sh);
+#else
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
             nkeys, sk, P::SK_LEN, sh);
+#endif
     }
     if (!with_A) return cudaGetLastError();  // the caller already holds this key's A-hat (e.g. from keygen)
     return launch_expand_a(st, P::K, P::L, sk, P::SK_LEN, nkeys, A);

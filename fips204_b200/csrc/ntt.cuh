@@ -18,8 +18,10 @@
 namespace mldsa {
 
 // per-lane packed twiddles of one transform direction (generated into zetas.inc): B stage .ba / .y0 / .y1 by lane,
-// M stage .m by lane >> 2
-struct TwPack { int4 ba[32]; int4 y0[32]; int4 y1[32]; int4 m[8][4]; };
+// M stage .m[vector][lane >> 2] (vector-major: a warp's load of one vector is a single 128-byte line)
+struct TwPack { int4 ba[32]; int4 y0[32]; int4 y1[32]; int4 m[4][8]; };
+// per-lane packed twiddles of the 16-coefficients-per-lane transforms (ntt16.cuh): vector j of lane t (t = lane & 15)
+struct Tw16 { int4 v[8][16]; };
 
 #include "zetas.inc"
 
@@ -59,8 +61,8 @@ __device__ __forceinline__ TwB load_twB(const TwPack& T, int lane)
 }
 __device__ __forceinline__ TwM load_twM(const TwPack& T, int lane)
 {
-    const int4* p = T.m[lane >> 2];
-    const int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    const int4* p = &T.m[0][lane >> 2];
+    const int4 a = __ldg(p), b = __ldg(p + 8), c = __ldg(p + 16), d = __ldg(p + 24);
     return TwM{make_int2(a.x, a.y), make_int2(a.z, a.w), make_int2(b.x, b.y), make_int2(b.z, b.w), make_int2(c.x, c.y),
                make_int2(c.z, c.w), make_int2(d.x, d.y)};
 }

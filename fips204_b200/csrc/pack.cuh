@@ -108,6 +108,24 @@ __device__ __forceinline__ void st_row8(int32_t* p, const int32_t (&v)[8])
 #endif
 }
 
+// 16 contiguous coefficients of a lane (ntt16.cuh, layout Y: 64 bytes = two sectors) as two 256-bit accesses
+__device__ __forceinline__ void st_row16(int32_t* p, const int32_t (&v)[16])
+{
+    const int32_t a[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+    const int32_t b[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+    st_row8(p, a);
+    st_row8(p + 8, b);
+}
+__device__ __forceinline__ void ld_row16(const int32_t* p, int32_t (&v)[16])
+{
+    const Row8 a = ld_row8(p), b = ld_row8(p + 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[i] = a.v[i];
+        v[8 + i] = b.v[i];
+    }
+}
+
 // Warp-cooperative L2 prefetch of `bytes` starting at p (128-byte lines): the streamed per-lane operands
 // (rows of A-hat, s-hat, w) are pulled from HBM into L2 while the warp is busy with an NTT, so the
 // demand loads that follow see L2 latency instead of DRAM latency.
