@@ -73,76 +73,23 @@ constexpr int SG_WARPS = 4;
 #ifndef SZ_MINB
 #define SZ_MINB 5   // sign_z: 96 registers hold the early loads of the w row / y without spills (6: 80 registers, 30.0 ms; 5: 29.5 ms)
 #endif
-#ifndef SK_MINB
-#define SK_MINB 10  // sign_key: 48 registers
-#endif
 
 // s2-hat, s1-hat, t0-hat for every key: rows [0, K), [K, K + L), [K + L, 2K + L) of the key's block of sh
-// (SignWs::sh: the order sign_z walks them).  warp per key.
+// (SignWs::sh: the order sign_z walks them).  Warp per key, TWO polynomials per warp (ntt16.cuh: a half-warp per
+// polynomial, 16 coefficients per lane): 32 instead of 48 shared-memory wavefronts per transform and one set of twiddle
+// loads for both -- with 8 coefficients per lane this kernel sat at 93 % of the L1 data pipe's wavefront peak (6.36 ms per
+// 2^20 ML-DSA-65 keys; now 6.17, ML-DSA-87 9.09 -> 8.20, ML-DSA-44 4.73 -> 4.00).  Half-warp h takes polynomial pp + h of
+// the pair; an odd polynomial count leaves the second half of the last pair transforming a duplicate that is not stored.
+// The rows are stored prescaled by 1/256 (the inverse transforms of c*s1, c*s2, c*t0 in sign_z do not scale): 1/256 =
+// -32736 mod q is small, so the factor goes onto the INPUT of the (linear) transform as part of the unpacking
+// multiply-add -- |input| < 2^12 * 32736 = 16 q, well inside the transform's int32 range -- instead of modular products
+// after it; sign_z's products take any int32 operand.
+#ifndef SK_MINB
+#define SK_MINB 6
+#endif
 template <class P>
 __global__ void __launch_bounds__(SG_WARPS * 32, SK_MINB)
 sign_key_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, int32_t* __restrict__ sh)
-{
-    using LO = Layout<P>;
-    constexpr int K = P::K, L = P::L;
-    __shared__ __align__(16) int32_t tiles[SG_WARPS][NTT_TILE_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* tile = tiles[warp];
-    const size_t stride = (size_t)gridDim.x * SG_WARPS;
-    for (size_t kn = (size_t)blockIdx.x * SG_WARPS + warp; kn < nkeys; kn += stride) {
-        const uint8_t* key = sk + kn * sk_stride;
-        int32_t* const rows = sh + kn * (size_t)(2 * K + L) * 256;
-        // packed bytes of polynomial p (this lane's 8 coefficients): eta-bit fields of s1 / s2, 13-bit fields of t0
-        auto fetch = [&](int p, uint32_t (&w)[4]) {
-            if (p < L + K) {
-                uint32_t e[(P::ETABITS + 3) / 4];
-                load_span<P::ETABITS>(key + LO::SK_S1 + p * 32 * P::ETABITS + P::ETABITS * lane, e);
-#pragma unroll
-                for (int i = 0; i < (P::ETABITS + 3) / 4; i++) w[i] = e[i];
-            } else {
-                load_span<13>(key + LO::SK_T0 + (p - L - K) * 416 + 13 * lane, w);
-            }
-        };
-        uint32_t cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
-        fetch(0, cur);
-#pragma unroll 1
-        for (int p = 0; p < L + 2 * K; p++) {  // in the packed key's order: s1, s2, t0
-            if (p + 1 < L + 2 * K) fetch(p + 1, nxt);  // in flight during this polynomial's transform
-            int32_t v[8];
-            int32_t* dst;
-            // The rows are stored prescaled by 1/256 (the inverse transforms of c*s1, c*s2, c*t0 in sign_z do not scale).
-            // 1/256 = -32736 mod q is small, so the factor goes onto the INPUT of the (linear) transform as part of the
-            // unpacking multiply-add -- |input| < 2^12 * 32736 = 16 q, well inside the transform's int32 range -- instead
-            // of eight modular products after it; sign_z's products take any int32 operand.
-            constexpr int32_t C256 = SC_INV256;  // centred representative of 1/256
-            static_assert(C256 > -(1 << 15) && C256 < (1 << 15), "1/256 mod q as a small centred constant");
-            if (p < L + K) {  // BitUnpack(eta, eta): s = eta - field            (encodings.rs:185-198)
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = (P::ETA - (int32_t)get_field<P::ETABITS>(cur, i)) * C256;
-                dst = rows + (p < L ? K + p : p - L) * 256;
-            } else {          // BitUnpack(2^12 - 1, 2^12): t0 = 2^12 - field     (encodings.rs:203-210)
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = ((1 << (D - 1)) - (int32_t)get_field<13>(cur, i)) * C256;
-                dst = rows + p * 256;  // row K + L + (p - L - K)
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) cur[i] = nxt[i];
-            sntt_fwd_B2B(v, tile, lane);
-            st_row8(dst + 8 * lane, v);
-        }
-    }
-}
-
-// The same with two polynomials per warp (ntt16.cuh: a half-warp per polynomial, 16 coefficients per lane): 32 instead
-// of 48 shared-memory wavefronts per transform and one set of twiddle loads for both -- this kernel was at 93 % of the L1
-// data pipe's wavefront peak.  Half-warp h takes polynomial pp + h of the pair; an odd polynomial count leaves the
-// second half of the last pair transforming a duplicate that is not stored.
-#ifndef SK16_MINB
-#define SK16_MINB 6
-#endif
-template <class P>
-__global__ void __launch_bounds__(SG_WARPS * 32, SK16_MINB)
-sign_key16_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride, int32_t* __restrict__ sh)
 {
     using LO = Layout<P>;
     constexpr int K = P::K, L = P::L, NP = L + 2 * K;
@@ -171,7 +118,8 @@ sign_key16_kernel(size_t nkeys, const uint8_t* __restrict__ sk, size_t sk_stride
         for (int pp = 0; pp < NP; pp += 2) {  // in the packed key's order: s1, s2, t0
             const int p = poly_of(pp);
             if (pp + 2 < NP) fetch(poly_of(pp + 2), nxt);  // in flight during this pair's transform
-            constexpr int32_t C256 = SC_INV256;  // 1/256 mod q, centred and small: rides on the unpacking multiply (see sign_key_kernel)
+            constexpr int32_t C256 = SC_INV256;  // centred representative of 1/256
+            static_assert(C256 > -(1 << 15) && C256 < (1 << 15), "1/256 mod q as a small centred constant");
             int32_t v[16];
             int row;
             if (p < L + K) {  // BitUnpack(eta, eta): s = eta - field            (encodings.rs:185-198)
@@ -753,13 +701,8 @@ static cudaError_t sign_setup_t(cudaStream_t st, SignRun& r, const uint8_t* sk, 
     if (ws.keys_resident) return cudaGetLastError();  // A-hat and the s-hat rows come from a loaded key set
     {
         KLaunch kl(KID_SIGN_KEY, st);
-#ifndef NO_SK16
-        sign_key16_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
-            nkeys, sk, sk_stride, ws.sh);
-#else
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
             nkeys, sk, sk_stride, ws.sh);
-#endif
     }
     return launch_expand_a(st, K, L, sk, sk_stride, nkeys, ws.A);
 }
@@ -863,13 +806,8 @@ static cudaError_t sign_expand_keys_t(cudaStream_t st, size_t nkeys, const uint8
 {
     {
         KLaunch kl(KID_SIGN_KEY, st);
-#ifndef NO_SK16
-        sign_key16_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
-            nkeys, sk, P::SK_LEN, sh);
-#else
         sign_key_kernel<P><<<capped_grid((nkeys + SG_WARPS - 1) / SG_WARPS, arith_cap()), SG_WARPS * 32, 0, st>>>(
             nkeys, sk, P::SK_LEN, sh);
-#endif
     }
     if (!with_A) return cudaGetLastError();  // the caller already holds this key's A-hat (e.g. from keygen)
     return launch_expand_a(st, P::K, P::L, sk, P::SK_LEN, nkeys, A);
