@@ -7,6 +7,7 @@
 #include "engine.h"
 #include "keccak.cuh"
 #include "ntt.cuh"
+#include "ntt16.cuh"
 #include "pack.cuh"
 #include "sampling.cuh"
 #include "sha2.cuh"
@@ -199,31 +200,53 @@ __device__ __forceinline__ void stg_stream8(int32_t* p, const int32_t (&v)[8])
 #endif
 }
 
+// Two polynomials per warp (ntt16.cuh: a half-warp per polynomial, 16 coefficients per lane): a transform between the two
+// global-memory-friendly layouts needs ONE shared-memory exchange (16 wavefronts per polynomial; the 8-per-lane kernel
+// needed two, and sat at 83 % of the L1 data pipe beside 77 % of the FMA-heavy pipe and 66 % of DRAM).
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_WARPS * 32) ntt_kernel(int32_t* __restrict__ polys, size_t n)
 {
-    __shared__ __align__(16) int32_t tiles[NTT_WARPS][NTT_TILE_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* tile = tiles[warp];
+    __shared__ __align__(16) int32_t tiles[NTT_WARPS][T16_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, h = lane >> 4, t = lane & 15;
+    int32_t* tile = tiles[warp] + h * T16_POLY;
+    const size_t npairs = (n + 1) / 2;
     const size_t stride = (size_t)gridDim.x * NTT_WARPS;
     const size_t first = (size_t)blockIdx.x * NTT_WARPS + warp;
-    // the warp's next two polynomials are pulled into L2 while it transforms the current one
-    if (lane < 8 && first + stride < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(polys + (first + stride) * 256 + 32 * lane));
-    for (size_t p = first; p < n; p += stride) {
-        int32_t* g = polys + p * 256;
-        if (lane < 8 && p + 2 * stride < n)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(polys + (p + 2 * stride) * 256 + 32 * lane));
-        int32_t v[8];
+    // the warp's next two pairs are pulled into L2 while it transforms the current one (2 KiB per pair: 16 lines)
+    auto prefetch = [&](size_t pair) {
+        if (lane < 16 && 2 * pair + (lane >> 3) < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(polys + pair * 512 + 32 * lane));
+    };
+    if (first + stride < npairs) prefetch(first + stride);
+    for (size_t pair = first; pair < npairs; pair += stride) {
+        if (pair + 2 * stride < npairs) prefetch(pair + 2 * stride);
+        const size_t p = 2 * pair + h;
+        const bool live = p < n;  // an odd count leaves the second half-warp of the last pair without a polynomial
+        int32_t* g = polys + (live ? p : 2 * pair) * 256;
+        int32_t v[16];
         if (!INVERSE) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = ldg_stream(g + 32 * i + lane);
-            ntt_fwd_A2B(v, tile, lane);
-            stg_stream8(g + 8 * lane, v);
+            for (int i = 0; i < 16; i++) v[i] = ldg_stream(g + 16 * i + t);  // layout X: 64 contiguous bytes per half-warp
+            ntt16_fwd_mont_X2Y(v, tile, t);
+            if (live) {
+                const int32_t lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+                const int32_t hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+                stg_stream8(g + 16 * t, lo);  // layout Y: 64 contiguous bytes per lane
+                stg_stream8(g + 16 * t + 8, hi);
+            }
         } else {
-            ldg_stream8(g + 8 * lane, v);
-            sntt_inv_B2A<true>(v, tile, lane);
+            int32_t lo[8], hi[8];
+            ldg_stream8(g + 16 * t, lo);
+            ldg_stream8(g + 16 * t + 8, hi);
 #pragma unroll
-            for (int i = 0; i < 8; i++) stg_stream(g + 32 * i + lane, v[i]);
+            for (int i = 0; i < 8; i++) {
+                v[i] = lo[i];
+                v[8 + i] = hi[i];
+            }
+            sntt16_inv_scaled_Y2X(v, tile, t);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) stg_stream(g + 16 * i + t, v[i]);
+            }
         }
     }
 }
@@ -267,11 +290,12 @@ cudaError_t launch_sib_stream(cudaStream_t st, const uint8_t* blocks, size_t nbl
 cudaError_t launch_ntt(cudaStream_t st, int32_t* polys, size_t n, bool inverse)
 {
     if (n == 0) return cudaSuccess;
-    // CTAs per SM of the grid-stride loop (measured: 8 -> 0.513 ms, 32..64 -> 0.491 ms per 2^20 polynomials).
+    // CTAs per SM of the grid-stride loop (measured, 16 coefficients per lane: 16 / 32 -> 0.376 ms, 64 -> 0.372 ms per 2^20
+    // polynomials).
     // Tried and measured slower (0.585 against 0.486 ms at the time): moving the polynomials with the TMA unit (one
     // cp.async.bulk in, one out, two input slots per warp): the kernel is bound by instruction issue, not by its loads.
-    static const int ncap = getenv("MLDSA_NCAP") ? atoi(getenv("MLDSA_NCAP")) : 32;
-    const unsigned grid = capped_grid((n + NTT_WARPS - 1) / NTT_WARPS, ncap);
+    static const int ncap = getenv("MLDSA_NCAP") ? atoi(getenv("MLDSA_NCAP")) : 64;
+    const unsigned grid = capped_grid(((n + 1) / 2 + NTT_WARPS - 1) / NTT_WARPS, ncap);  // a warp takes two polynomials at a time
     {
         KLaunch kl(inverse ? KID_INTT : KID_NTT, st);
         if (inverse) ntt_kernel<true><<<grid, NTT_WARPS * 32, 0, st>>>(polys, n);

@@ -1,10 +1,10 @@
 // ntt.cuh -- one warp per 256-coefficient polynomial, 8 coefficients per lane, staged through a
 // per-warp shared-memory tile so that every butterfly is register-local.
 //
-// Replaces src/ntt.rs:14-76 (ntt) and :85-161 (inv_ntt) of the reference.  The forward transform
-// is representative-exact with the reference (same signed Montgomery butterfly, same twiddle table,
-// no reductions between stages).  The inverse returns canonical [0, q) like the reference; since only
-// the residue of its output is defined, it runs on the Shoup butterflies of the fused kernels.
+// Replaces src/ntt.rs:14-76 (ntt) and :85-161 (inv_ntt) of the reference for the FUSED kernels, which need
+// results mod q only (Shoup butterflies below).  The standalone, representative-exact forward transform (the
+// reference's signed Montgomery butterfly ct_bfly, same twiddle table, no reductions between stages) and the
+// standalone inverse run with 16 coefficients per lane: ntt16.cuh.
 //
 // Index bits 7..0 of a coefficient are split over three register layouts (t = lane, i = 0..7):
 //   A: idx = 32*i + t              bits 7,6,5 local  -> stages len = 128, 64, 32
@@ -101,43 +101,6 @@ __device__ __forceinline__ void tile_store_B(int32_t* tile, int lane, const int3
     int4* p = reinterpret_cast<int4*>(tile + NTT_ROW * (lane >> 2) + 8 * (lane & 3));
     p[0] = make_int4(v[0], v[1], v[2], v[3]);
     p[1] = make_int4(v[4], v[5], v[6], v[7]);
-}
-
-// Forward NTT.  In: v in layout A (coefficient domain).  Out: v in layout B (NTT domain, the
-// reference's in-place array order).  Uses the warp's tile; ends with the tile free.
-__device__ __forceinline__ void ntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int lane)
-{
-    // len = 128, 64, 32: twiddles ZETA[1], ZETA[2..3], ZETA[4..7] are compile-time constants
-    ct_bfly(v[0], v[4], ZF1, ZF1Q); ct_bfly(v[1], v[5], ZF1, ZF1Q);
-    ct_bfly(v[2], v[6], ZF1, ZF1Q); ct_bfly(v[3], v[7], ZF1, ZF1Q);
-    ct_bfly(v[0], v[2], ZF2, ZF2Q); ct_bfly(v[1], v[3], ZF2, ZF2Q);
-    ct_bfly(v[4], v[6], ZF3, ZF3Q); ct_bfly(v[5], v[7], ZF3, ZF3Q);
-    ct_bfly(v[0], v[1], ZF4, ZF4Q); ct_bfly(v[2], v[3], ZF5, ZF5Q);
-    ct_bfly(v[4], v[5], ZF6, ZF6Q); ct_bfly(v[6], v[7], ZF7, ZF7Q);
-    __syncwarp();
-    tile_store_A(tile, lane, v);
-    __syncwarp();
-    tile_load_M(tile, lane, v);
-    {   // len = 16, 8, 4
-        const TwM w = load_twM(ZMP_FWD, lane);
-        ct_bfly(v[0], v[4], w.z8.x, w.z8.y); ct_bfly(v[1], v[5], w.z8.x, w.z8.y);
-        ct_bfly(v[2], v[6], w.z8.x, w.z8.y); ct_bfly(v[3], v[7], w.z8.x, w.z8.y);
-        ct_bfly(v[0], v[2], w.za.x, w.za.y); ct_bfly(v[1], v[3], w.za.x, w.za.y);
-        ct_bfly(v[4], v[6], w.zb.x, w.zb.y); ct_bfly(v[5], v[7], w.zb.x, w.zb.y);
-        ct_bfly(v[0], v[1], w.y0.x, w.y0.y); ct_bfly(v[2], v[3], w.y1.x, w.y1.y);
-        ct_bfly(v[4], v[5], w.y2.x, w.y2.y); ct_bfly(v[6], v[7], w.y3.x, w.y3.y);
-    }
-    tile_store_M(tile, lane, v);  // same addresses this lane just read
-    __syncwarp();
-    tile_load_B(tile, lane, v);
-    {   // len = 2, 1
-        const TwB w = load_twB(ZMP_FWD, lane);
-        ct_bfly(v[0], v[2], w.za.x, w.za.y); ct_bfly(v[1], v[3], w.za.x, w.za.y);
-        ct_bfly(v[4], v[6], w.zb.x, w.zb.y); ct_bfly(v[5], v[7], w.zb.x, w.zb.y);
-        ct_bfly(v[0], v[1], w.y0.x, w.y0.y); ct_bfly(v[2], v[3], w.y1.x, w.y1.y);
-        ct_bfly(v[4], v[5], w.y2.x, w.y2.y); ct_bfly(v[6], v[7], w.y3.x, w.y3.y);
-    }
-    __syncwarp();
 }
 
 // A polynomial row parked in shared memory by its owning warp (y-hat / z-hat between the NTT and the
@@ -248,10 +211,7 @@ __device__ __forceinline__ void sntt_fwd_A2B(int32_t (&v)[8], int32_t* tile, int
 }
 
 // Inverse NTT WITHOUT the 1/256 scaling.  In: layout B, |v| < 2 q.  Out: layout A, canonical [0, q),
-// = 256 * INTT(v) mod q.  SCALE256 = true multiplies by 1/256 on the way out: the plain inverse transform,
-// canonical like the reference's (ntt.rs:85-161 returns full_reduce32 values, so only the residue matters and the
-// Shoup butterflies -- five instructions against the nine ptxas makes of the Montgomery form -- give the same output).
-template <bool SCALE256 = false>
+// = 256 * INTT(v) mod q (callers fold the 1/256 into an operand; the standalone, scaled inverse is in ntt16.cuh).
 __device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int lane, int32_t z0 = 0)
 {
     {
@@ -284,19 +244,8 @@ __device__ __forceinline__ void sntt_inv_B2A(int32_t (&v)[8], int32_t* tile, int
     gs_bfly_s(v[4], v[5], ZSI5, ZSI5S, z0); gs_bfly_s(v[6], v[7], ZSI4, ZSI4S, z0);
     gs_bfly_s(v[0], v[2], ZSI3, ZSI3S, z0); gs_bfly_s(v[1], v[3], ZSI3, ZSI3S, z0);
     gs_bfly_s(v[4], v[6], ZSI2, ZSI2S, z0); gs_bfly_s(v[5], v[7], ZSI2, ZSI2S, z0);
-    if (SCALE256) {
-        // the 1/256 rides on the last level: the difference outputs get it through their twiddle (zeta / 256), the sum
-        // outputs through one product each -- 4 extra products per lane instead of 8
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int32_t t = v[i];
-            v[i] = shoup_mul(t + v[i + 4], SC_INV256, SC_INV256S);
-            v[i + 4] = shoup_mul(t - v[i + 4], ZSI1_256, ZSI1_256S);
-        }
-    } else {
-        gs_bfly_s(v[0], v[4], ZSI1, ZSI1S, z0); gs_bfly_s(v[1], v[5], ZSI1, ZSI1S, z0);
-        gs_bfly_s(v[2], v[6], ZSI1, ZSI1S, z0); gs_bfly_s(v[3], v[7], ZSI1, ZSI1S, z0);
-    }
+    gs_bfly_s(v[0], v[4], ZSI1, ZSI1S, z0); gs_bfly_s(v[1], v[5], ZSI1, ZSI1S, z0);
+    gs_bfly_s(v[2], v[6], ZSI1, ZSI1S, z0); gs_bfly_s(v[3], v[7], ZSI1, ZSI1S, z0);
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = freeze(v[i]);
     __syncwarp();

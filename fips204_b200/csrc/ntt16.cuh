@@ -151,6 +151,98 @@ __device__ __forceinline__ void sntt16_inv(int32_t (&v)[16], int32_t* tile, int 
     t16_load_Y(tile, t, v);
 }
 
+// ---- the standalone transforms of the microbench entry points (mldsa_ntt_batch / mldsa_intt_batch): ONE exchange each,
+// because their global accesses can use either layout (X: 64 contiguous bytes per half-warp and instruction; Y: 64
+// contiguous bytes per lane) ----
+
+// Forward NTT, representative-exact with src/ntt.rs:14-76: the reference's signed Montgomery butterfly in the reference's
+// order per coefficient, so every output is the very int32 the reference computes.  In: layout X.  Out: layout Y.
+#define T16_CTM(a, b, Z, ZQ) ct_bfly(v[a], v[b], Z, ZQ)
+__device__ __forceinline__ void ntt16_fwd_mont_X2Y(int32_t (&v)[16], int32_t* tile, int t)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) T16_CTM(i, i + 8, ZF1, ZF1Q);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { T16_CTM(i, i + 4, ZF2, ZF2Q); T16_CTM(i + 8, i + 12, ZF3, ZF3Q); }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        T16_CTM(i, i + 2, ZF4, ZF4Q); T16_CTM(i + 4, i + 6, ZF5, ZF5Q);
+        T16_CTM(i + 8, i + 10, ZF6, ZF6Q); T16_CTM(i + 12, i + 14, ZF7, ZF7Q);
+    }
+    T16_CTM(0, 1, ZF8, ZF8Q); T16_CTM(2, 3, ZF9, ZF9Q); T16_CTM(4, 5, ZF10, ZF10Q); T16_CTM(6, 7, ZF11, ZF11Q);
+    T16_CTM(8, 9, ZF12, ZF12Q); T16_CTM(10, 11, ZF13, ZF13Q); T16_CTM(12, 13, ZF14, ZF14Q); T16_CTM(14, 15, ZF15, ZF15Q);
+    __syncwarp();  // (the tile's previous readers: the other lanes' layout-Y loads of the last polynomial)
+    t16_store_X(tile, t, v);
+    __syncwarp();
+    t16_load_Y(tile, t, v);
+    const int4* q = &ZM16_FWD.v[0][t];
+    {
+        const int4 w0 = __ldg(q), w1 = __ldg(q + 16), w2 = __ldg(q + 32), w3 = __ldg(q + 48);
+#pragma unroll
+        for (int i = 0; i < 8; i++) T16_CTM(i, i + 8, w0.x, w0.y);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { T16_CTM(i, i + 4, w0.z, w0.w); T16_CTM(i + 8, i + 12, w1.x, w1.y); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            T16_CTM(i, i + 2, w1.z, w1.w); T16_CTM(i + 4, i + 6, w2.x, w2.y);
+            T16_CTM(i + 8, i + 10, w2.z, w2.w); T16_CTM(i + 12, i + 14, w3.x, w3.y);
+        }
+        T16_CTM(0, 1, w3.z, w3.w);
+    }
+    {
+        const int4 w4 = __ldg(q + 64), w5 = __ldg(q + 80), w6 = __ldg(q + 96), w7 = __ldg(q + 112);
+        T16_CTM(2, 3, w4.x, w4.y); T16_CTM(4, 5, w4.z, w4.w); T16_CTM(6, 7, w5.x, w5.y); T16_CTM(8, 9, w5.z, w5.w);
+        T16_CTM(10, 11, w6.x, w6.y); T16_CTM(12, 13, w6.z, w6.w); T16_CTM(14, 15, w7.x, w7.y);
+    }
+}
+#undef T16_CTM
+
+// Inverse NTT WITH the 1/256, canonical output like the reference's (src/ntt.rs:85-161 returns full_reduce32 values, so
+// only the residue is defined and the Shoup butterflies apply).  In: layout Y, canonical or |v| < 2 q.  Out: layout X.
+// The 1/256 rides on the last level: difference outputs through the twiddle zeta / 256, sum outputs one product each.
+__device__ __forceinline__ void sntt16_inv_scaled_Y2X(int32_t (&v)[16], int32_t* tile, int t)
+{
+    constexpr int32_t z0 = 0;
+    const int4* q = &ZS16_INV.v[0][t];
+    {
+        const int4 w0 = __ldg(q), w1 = __ldg(q + 16), w2 = __ldg(q + 32), w3 = __ldg(q + 48);
+        T16_GS(0, 1, w0.x, w0.y); T16_GS(2, 3, w0.z, w0.w); T16_GS(4, 5, w1.x, w1.y); T16_GS(6, 7, w1.z, w1.w);
+        T16_GS(8, 9, w2.x, w2.y); T16_GS(10, 11, w2.z, w2.w); T16_GS(12, 13, w3.x, w3.y); T16_GS(14, 15, w3.z, w3.w);
+    }
+    {
+        const int4 w4 = __ldg(q + 64), w5 = __ldg(q + 80), w6 = __ldg(q + 96), w7 = __ldg(q + 112);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            T16_GS(i, i + 2, w4.x, w4.y); T16_GS(i + 4, i + 6, w4.z, w4.w);
+            T16_GS(i + 8, i + 10, w5.x, w5.y); T16_GS(i + 12, i + 14, w5.z, w5.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { T16_GS(i, i + 4, w6.x, w6.y); T16_GS(i + 8, i + 12, w6.z, w6.w); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) T16_GS(i, i + 8, w7.x, w7.y);
+    }
+    v[0] = reduce32(v[0]);
+    __syncwarp();  // (the tile's previous readers: the other lanes' layout-X loads of the last polynomial)
+    t16_store_Y(tile, t, v);
+    __syncwarp();
+    t16_load_X(tile, t, v);
+    T16_GS(0, 1, ZSI15, ZSI15S); T16_GS(2, 3, ZSI14, ZSI14S); T16_GS(4, 5, ZSI13, ZSI13S); T16_GS(6, 7, ZSI12, ZSI12S);
+    T16_GS(8, 9, ZSI11, ZSI11S); T16_GS(10, 11, ZSI10, ZSI10S); T16_GS(12, 13, ZSI9, ZSI9S); T16_GS(14, 15, ZSI8, ZSI8S);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        T16_GS(i, i + 2, ZSI7, ZSI7S); T16_GS(i + 4, i + 6, ZSI6, ZSI6S);
+        T16_GS(i + 8, i + 10, ZSI5, ZSI5S); T16_GS(i + 12, i + 14, ZSI4, ZSI4S);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { T16_GS(i, i + 4, ZSI3, ZSI3S); T16_GS(i + 8, i + 12, ZSI2, ZSI2S); }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int32_t a = v[i];
+        v[i] = freeze(shoup_mul(a + v[i + 8], SC_INV256, SC_INV256S));
+        v[i + 8] = freeze(shoup_mul(a - v[i + 8], ZSI1_256, ZSI1_256S));
+    }
+}
+
 #undef T16_CT
 #undef T16_GS
 
