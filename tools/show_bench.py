@@ -14,7 +14,10 @@ for leg in (d.get("verify") or {}).get("legs", []):
 if d.get("verify"):
     print("verify:", [(l["keys"], round(l["value"])) for l in d["verify"]["legs"]])
 for k, v in sorted(d.get("kernels", {}).items(), key=lambda kv: -kv[1]["ms_per_step"]):
-    print(f"  {k:12s} {v['ms_per_step']:8.2f} ms {v['share'] * 100:5.1f}%  {v['int32_tops'] or 0:6.2f} Tops  {v['hbm_gbs'] or 0:7.0f} GB/s")
+    ncu = v.get("ncu") or {}
+    util = (f"ALU pipe {v['alu_pipe_frac'] * 100:5.1f}% of peak" if v.get("alu_pipe_frac") else
+            f"ncu: fmaheavy {ncu.get('pipe_fmaheavy_pct', 0):.0f}%  L1 wavefronts {ncu.get('l1_wavefronts_pct', 0):.0f}%  issue {ncu.get('issue_active_pct', 0):.0f}%")
+    print(f"  {k:12s} {v['ms_per_step']:8.2f} ms {v['share'] * 100:5.1f}%  {util}")
 print("roofline:", {k: d["roofline"][k] for k in ("kernel", "achieved", "peak", "frac")} if d.get("roofline") else None)
 print("sign:", d.get("sign"))
 print("peaks:", d.get("int32_peaks_tops"), "cpu:", d.get("cpu_baseline", {}) and d["cpu_baseline"].get("value"))
