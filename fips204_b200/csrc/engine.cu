@@ -590,7 +590,7 @@ static std::vector<size_t> plan_sizes(size_t n, size_t cap)
     // proportions ("1,3,4,4,3,1" = sixteenths).
     constexpr size_t UNIT = 32768;
     std::vector<size_t> sizes;  // lanes per chunk
-    if (const char* pe = getenv("MLDSA_PLAN")) {
+    if (const char* pe = getenv("MLDSA_PLAN"); pe && *pe) {  // (an empty value counts as unset)
         std::vector<size_t> f;
         size_t total = 0;
         for (const char* q = pe; *q;) {
