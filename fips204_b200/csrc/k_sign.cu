@@ -442,10 +442,7 @@ __device__ __forceinline__ void sign_z_unit(const SignZJob& j, size_t unit, Sign
     const int depth = j.depth;
     const size_t nact = *j.nact;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#ifndef SZ_Z0
-#define SZ_Z0 1
-#endif
-    const int32_t z0 = SZ_Z0 ? j.zero : 0;
+    const int32_t z0 = j.zero;  // 0, opaque to ptxas: keeps the inverse transform's adds on the ALU pipe (ntt.cuh: gs_bfly_s)
     SignSmem<P>& sm = sm_all[warp];
     int32_t* tile = sm.tile;
     uint8_t* hb = reinterpret_cast<uint8_t*>(sm.stage);

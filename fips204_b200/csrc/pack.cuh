@@ -116,16 +116,6 @@ __device__ __forceinline__ void st_row16(int32_t* p, const int32_t (&v)[16])
     st_row8(p, a);
     st_row8(p + 8, b);
 }
-__device__ __forceinline__ void ld_row16(const int32_t* p, int32_t (&v)[16])
-{
-    const Row8 a = ld_row8(p), b = ld_row8(p + 8);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        v[i] = a.v[i];
-        v[8 + i] = b.v[i];
-    }
-}
-
 // Warp-cooperative L2 prefetch of `bytes` starting at p (128-byte lines): the streamed per-lane operands
 // (rows of A-hat, s-hat, w) are pulled from HBM into L2 while the warp is busy with an NTT, so the
 // demand loads that follow see L2 latency instead of DRAM latency.
