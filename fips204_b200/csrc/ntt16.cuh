@@ -10,7 +10,8 @@
 // per-lane twiddles of the Y levels (1 + 2 + 4 + 8 entries from index 16 + t, 32 + 2t, 64 + 4t, 128 + 8t of the plain
 // tables; mirrored for the inverse) come from per-lane packed copies, eight 128-bit loads serving both polynomials of
 // the warp; and every level offers 8 independent butterflies per lane instead of 4.
-// Index maps and twiddle indices were checked against a direct transform with a Python model before any of this ran.
+// Index maps, twiddle indices and the packed tables are checked against a direct transform by a Python model of this
+// file (tests/test_ntt16_tables.py, no GPU needed).
 //
 // Same arithmetic as ntt.cuh (src/ntt.rs:14-161 mod q): ct_bfly_s / gs_bfly_s, results mod q as lazily reduced int32.
 #pragma once
