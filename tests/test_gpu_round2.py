@@ -284,3 +284,22 @@ def test_key_sets_live_on_their_own_device(F):
     assert pks.verify_batch(msgs, sig).all()
     sks.free()
     pks.free()
+
+
+def test_ntt_device_entry_points_want_32_byte_aligned_polynomials(F):
+    """The standalone transforms move a lane's coefficients as 256-bit vectors: a device pointer that is not 32-byte
+    aligned is a parameter error (-1, include/mldsa_b200.h), not a misaligned-address fault; an aligned one works."""
+    torch = pytest.importorskip("torch")
+    from fips204_b200 import _lib
+    L = _lib.lib()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    polys = (synth_block("ntt-al", 3, 1024).view(np.uint32).astype(np.int64) % 8380417).astype(np.int32).reshape(3, 256)
+    buf = torch.zeros(3 * 256 + 8, dtype=torch.int32, device=dev)
+    sh = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for fn in (L.mldsa_ntt_batch_dev, L.mldsa_intt_batch_dev):
+        for off in (1, 4):  # 4 and 16 bytes past an aligned address
+            assert fn(sh, 3, C.c_void_p(buf.data_ptr() + 4 * off)) == -1
+    buf[:768] = torch.from_numpy(polys.reshape(-1)).to(dev)
+    assert L.mldsa_ntt_batch_dev(sh, 3, C.c_void_p(buf.data_ptr())) == 0
+    assert (buf[:768].cpu().numpy().reshape(3, 256) == O.ntt_batch(polys)).all()
